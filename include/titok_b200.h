@@ -1,0 +1,161 @@
+/*
+ * titok_b200.h -- C ABI of libtitok_b200.so: the sm_100a kernels behind the TiTok-Video tokenizer
+ * hot path (encode -> quantize -> decode).
+ *
+ * The reference (NilanEkanayake/TiTok-Video) is pure Python/PyTorch and has NO native interface;
+ * each entry point below replaces the chain of library kernels that one stretch of the reference's
+ * Python launches. The "replaces" notes cite reference files (relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked "host".
+ *   - bf16 tensors are row-major with an explicit leading dimension in ELEMENTS (ld*), 16-byte aligned.
+ *   - the caller owns every buffer; nothing is allocated or freed; all work is enqueued on `stream`
+ *     (no internal synchronisation) so calls can be captured into a CUDA graph.
+ *   - return value: 0 on success, negative ttk_status otherwise; never throws. There is no CPU or
+ *     non-sm_100 fallback: a device that is not compute capability 10.x returns TTK_ERR_ARCH.
+ */
+#ifndef TITOK_B200_H_
+#define TITOK_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* ttk_stream_t; /* == cudaStream_t */
+
+enum ttk_status {
+  TTK_OK = 0,
+  TTK_ERR_BAD_ARG = -1,
+  TTK_ERR_BAD_SHAPE = -2,
+  TTK_ERR_ALIGNMENT = -3,
+  TTK_ERR_ARCH = -4,
+  TTK_ERR_CUDA = -5,
+  TTK_ERR_DRIVER = -6,
+  TTK_ERR_WORKSPACE = -7
+};
+
+const char* ttk_strerror(int status);
+int ttk_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Quantizer: model/quantizer/fsq.py
+ * FSQ constants are HOST arrays of D (<= 8) entries, computed by the caller exactly as
+ * FSQ.bound / FSQ.quantize compute them (fsq.py:78-90): half_l, offset, shift, half_width; basis and
+ * levels are FSQ._basis / FSQ._levels (fsq.py:63-67).
+ * ------------------------------------------------------------------------------------------- */
+
+/* FSQ.forward (fsq.py:123-135). dtype 0 = bf16, 1 = fp32. codes has z's dtype, indices are int32. */
+int ttk_fsq_fwd(const void* z, void* codes, int32_t* indices, int64_t n, int dtype, int D, const float* half_l,
+                const float* offset, const float* shift, const float* half_width, const int32_t* basis,
+                const int32_t* levels, ttk_stream_t stream);
+
+/* Backward of FSQ.forward through round_ste (fsq.py:48-51): dz = dcodes*half_l*(1-tanh^2(z+shift))/half_width */
+int ttk_fsq_bwd(const void* z, const void* dcodes, void* dz, int64_t n, int dtype, int D, const float* half_l,
+                const float* offset, const float* shift, const float* half_width, const int32_t* basis,
+                const int32_t* levels, ttk_stream_t stream);
+
+/* FSQ.indices_to_codes (fsq.py:96-103,111-121). idx_dtype 0 = int32, 1 = int64; out_dtype 0 = bf16, 1 = fp32. */
+int ttk_fsq_indices_to_codes(const void* idx, int idx_dtype, void* codes, int out_dtype, int64_t n, int D,
+                             const float* half_width, const int32_t* basis, const int32_t* levels,
+                             ttk_stream_t stream);
+
+/* torch.bincount of CodebookLogger.get_scores (train_utils/codebook_logging.py:20-24), on device:
+ * counts[K] (uint32) += histogram(idx[n]). */
+int ttk_hist_u32(const int32_t* idx, int64_t n, int K, uint32_t* counts, ttk_stream_t stream);
+
+/* usage / entropy of CodebookLogger.get_scores (codebook_logging.py:26-29), on device.
+ * out[3] doubles: #non-zero bins, entropy in nats, total count. */
+int ttk_codebook_stats(const uint32_t* counts, int K, double* out, ttk_stream_t stream);
+
+/* Generic VQ (BASELINE.json north_star): idx[n] = argmin_k ||z_n - c_k||^2 over a [K,D] bf16 codebook, the
+ * oracle being torch.cdist(z, C).argmin(-1) (for FSQ: C = FSQ.implicit_codebook, fsq.py:75-76).
+ * The codebook is augmented once: cb_aug [K, ttk_vq_aug_dim(D)] = [-2c | 3-term bf16 split of |c|^2 | 0].
+ * z is [N,D] bf16 with row pitch ldz (multiple of 8 elements). best (optional) = |c|^2 - 2 z.c of the winner. */
+int ttk_vq_aug_dim(int D);
+int ttk_vq_prepare_codebook(const void* codebook, int64_t ldc, int K, int D, void* cb_aug, int64_t lda,
+                            ttk_stream_t stream);
+int ttk_vq_argmin(const void* z, int64_t ldz, const void* cb_aug, int64_t lda, int64_t N, int K, int D, int32_t* idx,
+                  float* best, ttk_stream_t stream);
+/* zq[n] = C[idx[n]] (16-byte gather, D % 8 == 0) and, if loss_sum != NULL, loss_sum[0] += sum ||zq - z||^2
+ * (numerator of the commitment / codebook loss of a learned-codebook VQ; the reference's FSQ has no such loss). */
+int ttk_vq_gather_loss(const void* z, int64_t ldz, const void* codebook, int64_t ldc, const int32_t* idx, int64_t N,
+                       int D, void* zq, int64_t ldq, float* loss_sum, ttk_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Linear layers (tcgen05 GEMMs).  C[M,N] = A[M,K] @ W[N,K]^T, bf16 in, fp32 accumulate, bf16 out.
+ * ------------------------------------------------------------------------------------------- */
+
+/* nn.Linear (blocks.py:49,67,125,143; transformer.py:45,83). bias bf16 [N] or NULL. out_row_map int32 [M]
+ * or NULL (scatter rows; negative = skip). w_is_kn != 0: W given as [K,N] row-major. */
+int ttk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, const void* bias,
+                  void* out, int64_t ldo, const int32_t* out_row_map, int w_is_kn, ttk_stream_t stream);
+
+/* Attn.to_qkv + split + apply_rotary_emb(q), (k) (transformer.py:85-98, rope.py:19-27).
+ * rope: fp32 [M,60] (cos,sin) of the 30 rotated complex lanes per token (RoPE.forward, rope.py:57-71).
+ * out [M, 2*width+2*gqa] = [rope(q) | gate | rope(k) | v]. */
+int ttk_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int K, int width, int gqa,
+                      const float* rope, void* out, int64_t ldo, ttk_stream_t stream);
+
+/* GEGLU.w12 + chunk + gelu(gate)*x (transformer.py:47-52). W12 [2*inner, K]; out [M, inner]. */
+int ttk_gemm_geglu(const void* A, int64_t lda, const void* W12, int64_t ldw, int M, int inner, int K, void* out,
+                   int64_t ldo, ttk_stream_t stream);
+
+/* out_proj / w3 (N = 256) fused with the residual or KEEL update and the next pre-norm
+ * (transformer.py:128-130,141-145). mode 0: x' = x + y; mode 1: x' = RMSNorm(alpha*x + y)*w_post.
+ * x_out = x'; xn_out (optional) = RMSNorm(x')*w_next. Norm weights fp32 [256]. */
+int ttk_gemm_resid_norm256(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int K, const void* x,
+                           int64_t ldx, int mode, float alpha, const float* w_post, const float* w_next, void* x_out,
+                           void* xn_out, int64_t ldo, ttk_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention: flash_attn_varlen_func(...) * sigmoid(gate) (transformer.py:100-103).
+ * qkv is the output of ttk_gemm_qkv_rope. work: device array of n_work 48-byte records
+ * {q_row0[2], q_valid[2], q_head[2], kv_head, kv_row0, kv_len, pad[3]} (int32) built by the host planner
+ * from cu_seqlens (blocks.py:81-83). out [M, width].
+ * ------------------------------------------------------------------------------------------- */
+int ttk_attn_varlen_fwd(const void* qkv, int64_t ld, int M, int width, int gqa, const void* work, int n_work,
+                        float softmax_scale, void* out, int64_t ldo, ttk_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row kernels (width in {256,512,768,1024}; norm weights fp32 [width]; mask_token fp32 [1]).
+ * ------------------------------------------------------------------------------------------- */
+
+/* flash_attn.ops.triton.layer_norm.RMSNorm forward (eps 1e-5). */
+int ttk_rmsnorm_fwd(const void* x, int64_t ldx, const float* w, void* y, int64_t ldy, int M, int width,
+                    ttk_stream_t stream);
+
+/* Residual / KEEL update + next pre-norm, unfused form of ttk_gemm_resid_norm256 (any width). */
+int ttk_resid_norm(const void* x, const void* y, void* x_out, void* xn_out, const float* w_post, const float* w_next,
+                   float alpha, int mode, int M, int width, int64_t ld, ttk_stream_t stream);
+
+/* TiTokEncoder embed (blocks.py:95-97). src_row int32 [M]: >= 0 row of proj (patch), < 0 latent row. */
+int ttk_enc_embed(const void* proj, int64_t ldp, const int32_t* src_row, const float* mask_token, const float* w_t,
+                  const float* w_p, const float* w_next, void* x_out, void* xn_out, int M, int width, int64_t ld,
+                  ttk_stream_t stream);
+
+/* TiTokDecoder embed (blocks.py:164-167). src_row int32 [M]: >= 0 latent token index into codes, < 0 patch row.
+ * w_in bf16 [width, token_size], b_in bf16 [width]. */
+int ttk_dec_embed(const void* codes, int token_size, const int32_t* src_row, const void* w_in, const void* b_in,
+                  const float* mask_token, const float* w_t, const float* w_p, const float* w_next, void* x_out,
+                  void* xn_out, int M, int width, int64_t ld, ttk_stream_t stream);
+
+/* Encoder head + quantizer (blocks.py:101-103 -> titok.py:49 -> fsq.py:123-135).
+ * w_out bf16 [token_size, width], b_out bf16 [token_size]. Outputs z/codes bf16 [T, token_size], idx int32 [T]. */
+int ttk_enc_head_fsq(const void* x, int64_t ld, const int32_t* latent_row, const float* w_post, int pre_normed,
+                     const void* w_out, const void* b_out, int token_size, void* z_out, void* codes_out,
+                     int32_t* idx_out, int T, int width, const float* half_l, const float* offset, const float* shift,
+                     const float* half_width, const int32_t* basis, const int32_t* levels, ttk_stream_t stream);
+
+/* patch_rearrange / unpatch_rearrange (model/base/utils.py:26-51) with feature order (c p0 p1 p2).
+ * geom int64 [G,4] = {element offset of the patch origin in the flat clip buffer, W, H*W, T*H*W}. P2 must be 8. */
+int ttk_patchify(const void* clips, const int64_t* geom, int C, int P0, int P1, int P2, void* patches, int64_t ldp,
+                 int64_t G, ttk_stream_t stream);
+int ttk_unpatchify(const void* proj, int64_t ldp, const int32_t* patch_row, const int64_t* geom, int C, int P0,
+                   int P1, int P2, void* clips, int64_t G, ttk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TITOK_B200_H_ */

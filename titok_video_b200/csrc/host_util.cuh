@@ -1,0 +1,31 @@
+// Host-side helpers shared by the C-ABI launchers: TMA tensor-map encoding through the
+// driver entry point (no link-time dependency on libcuda), device checks, launch error mapping.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace ttk {
+
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                             CUtensorMapFloatOOBfill);
+
+PFN_tensorMapEncodeTiled get_encode_fn();
+
+// 2-D bf16 row-major tensor [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols],
+// SWIZZLE_128B, out-of-bounds elements read as zero.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols = 64);
+
+int check_device_sm100();
+int num_sms();
+
+inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? TTK_OK : TTK_ERR_CUDA; }
+inline int launch_status() { return cuda_status(cudaGetLastError()); }
+
+}  // namespace ttk

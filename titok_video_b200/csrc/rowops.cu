@@ -1,0 +1,416 @@
+// Bandwidth-bound row kernels of the TiTok encoder / decoder: one warp per packed token row,
+// 16-byte vector loads/stores, warp-shuffle reductions, fp32 math with bf16 rounding at the
+// reference's op boundaries.
+//
+//   rmsnorm / resid_norm   flash-attn RMSNorm (fp32, eps 1e-5, weight only) and the residual / KEEL
+//                          updates of ResidualAttentionBlock.forward (transformer.py:126-146)
+//   enc_embed              TiTokEncoder.forward embed (blocks.py:95-97)
+//   dec_embed              TiTokDecoder.forward embed (blocks.py:164-167)
+//   enc_head_fsq           latent gather -> ln_post -> proj_out -> FSQ (blocks.py:101-103, fsq.py:123-135)
+//   patchify / unpatchify  einops rearranges of model/base/utils.py:26-51 (feature order permuted to
+//                          (c p0 p1 p2) so both sides move 16-byte runs; weights are permuted to match)
+#include "common.cuh"
+#include "fsq.cuh"
+#include "host_util.cuh"
+
+namespace ttk {
+
+constexpr int ROW_WARPS = 8;  // warps (rows) per CTA
+constexpr float RMS_EPS = 1e-5f;
+
+// Each lane owns NV vectors of 8 consecutive bf16: element index (i*256 + lane*8 + e).
+template <int NV>
+struct RowVec {
+  float v[NV * 8];
+  __device__ __forceinline__ void load(const __nv_bfloat16* row, int lane) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint4 r = ldg16(row + i * 256 + lane * 8);
+      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[i * 8 + 2 * e] = bf16_lo(rr[e]);
+        v[i * 8 + 2 * e + 1] = bf16_hi(rr[e]);
+      }
+    }
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* row, int lane) const {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      stg16(row + i * 256 + lane * 8,
+            make_uint4(pack_bf16x2(v[i * 8], v[i * 8 + 1]), pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]),
+                       pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]), pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7])));
+  }
+  __device__ __forceinline__ float sumsq() const {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) s += v[i] * v[i];
+    return warp_sum(s);
+  }
+  // v = bf16(v * rstd * w)   (the RMSNorm output is stored in the activation dtype)
+  __device__ __forceinline__ void norm(const float* w, int lane, float rstd) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 w0 = *reinterpret_cast<const float4*>(w + i * 256 + lane * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(w + i * 256 + lane * 8 + 4);
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i * 8 + e] = bf16r(v[i * 8 + e] * rstd * ww[e]);
+    }
+  }
+};
+
+__device__ __forceinline__ float rstd_of(float sumsq, int width) {
+  return 1.0f / sqrtf(sumsq / static_cast<float>(width) + RMS_EPS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = RMSNorm(x) * w
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32) rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                                                                 const float* __restrict__ w,
+                                                                 __nv_bfloat16* __restrict__ y, int64_t ldy, int M) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  RowVec<NV> r;
+  r.load(x + row * ldx, lane);
+  r.norm(w, lane, rstd_of(r.sumsq(), NV * 256));
+  r.store(y + row * ldy, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// mode 0: x' = x + y                         (layer 0, transformer.py:128-130)
+// mode 1: x' = RMSNorm(alpha*x + y) * w_post (KEEL, transformer.py:141-145)
+// xn = RMSNorm(x') * w_next (optional)       (pre-norm of the next sub-layer / ln_post)
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+resid_norm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                  __nv_bfloat16* __restrict__ x_out, __nv_bfloat16* __restrict__ xn_out,
+                  const float* __restrict__ w_post, const float* __restrict__ w_next, float alpha, int mode, int M,
+                  int64_t ld) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  RowVec<NV> a, b;
+  a.load(x + row * ld, lane);
+  b.load(y + row * ld, lane);
+#pragma unroll
+  for (int i = 0; i < NV * 8; ++i) {
+    const float xa = (mode == 1) ? bf16r(a.v[i] * alpha) : a.v[i];
+    a.v[i] = bf16r(xa + b.v[i]);
+  }
+  if (mode == 1) a.norm(w_post, lane, rstd_of(a.sumsq(), NV * 256));
+  a.store(x_out + row * ld, lane);
+  if (xn_out) {
+    a.norm(w_next, lane, rstd_of(a.sumsq(), NV * 256));
+    a.store(xn_out + row * ld, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Encoder embed. src_row[r] >= 0: patch row, v = bf16(proj[src_row[r]] + mask_token) -> ln_pre_p
+//                src_row[r] <  0: latent row, v = mask_token (constant row)            -> ln_pre_t
+// x[r] = norm ; xn[r] = RMSNorm(x[r]) * w_next
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+enc_embed_kernel(const __nv_bfloat16* __restrict__ proj, int64_t ldp, const int32_t* __restrict__ src_row,
+                 const float* __restrict__ mask_token, const float* __restrict__ w_t, const float* __restrict__ w_p,
+                 const float* __restrict__ w_next, __nv_bfloat16* __restrict__ x_out,
+                 __nv_bfloat16* __restrict__ xn_out, int M, int64_t ld) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float mt = bf16r(mask_token[0]);  // mask_token.to(dtype)
+  const int src = src_row[row];
+  RowVec<NV> a;
+  if (src >= 0) {
+    a.load(proj + src * ldp, lane);
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) a.v[i] = bf16r(a.v[i] + mt);
+    a.norm(w_p, lane, rstd_of(a.sumsq(), NV * 256));
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) a.v[i] = mt;
+    a.norm(w_t, lane, rstd_of(a.sumsq(), NV * 256));
+  }
+  a.store(x_out + row * ld, lane);
+  if (xn_out) {
+    a.norm(w_next, lane, rstd_of(a.sumsq(), NV * 256));
+    a.store(xn_out + row * ld, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decoder embed. src_row[r] >= 0: latent row, v = bf16(bf16(codes[src] @ Win^T + b) + mask_token) -> ln_pre_t
+//                src_row[r] <  0: patch row,  v = mask_token                                     -> ln_pre_p
+// Win is [width, TS] bf16 (nn.Linear(token_size, width)), TS <= 8.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+dec_embed_kernel(const __nv_bfloat16* __restrict__ codes, int TS, const int32_t* __restrict__ src_row,
+                 const __nv_bfloat16* __restrict__ w_in, const __nv_bfloat16* __restrict__ b_in,
+                 const float* __restrict__ mask_token, const float* __restrict__ w_t, const float* __restrict__ w_p,
+                 const float* __restrict__ w_next, __nv_bfloat16* __restrict__ x_out,
+                 __nv_bfloat16* __restrict__ xn_out, int M, int64_t ld) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float mt = bf16r(mask_token[0]);
+  const int src = src_row[row];
+  RowVec<NV> a;
+  if (src >= 0) {
+    float cv[FSQ_MAX_D];
+#pragma unroll
+    for (int k = 0; k < FSQ_MAX_D; ++k) cv[k] = (k < TS) ? __bfloat162float(codes[static_cast<int64_t>(src) * TS + k]) : 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int n = i * 256 + lane * 8 + e;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < FSQ_MAX_D; ++k)
+          if (k < TS) acc = fmaf(cv[k], __bfloat162float(w_in[n * TS + k]), acc);
+        acc += __bfloat162float(b_in[n]);
+        a.v[i * 8 + e] = bf16r(bf16r(acc) + mt);
+      }
+    }
+    a.norm(w_t, lane, rstd_of(a.sumsq(), NV * 256));
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) a.v[i] = mt;
+    a.norm(w_p, lane, rstd_of(a.sumsq(), NV * 256));
+  }
+  a.store(x_out + row * ld, lane);
+  if (xn_out) {
+    a.norm(w_next, lane, rstd_of(a.sumsq(), NV * 256));
+    a.store(xn_out + row * ld, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Encoder head: for latent token t: tok = RMSNorm(x[latent_row[t]]) * w_post ; z = bf16(tok @ Wout^T + b)
+// then FSQ on z.float(). Wout is [TS, width] bf16. Outputs z [T,TS] bf16, codes [T,TS] bf16, idx [T] int32.
+// If pre_normed != 0, x already holds RMSNorm(x) * w_post (fused upstream).
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+enc_head_fsq_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const int32_t* __restrict__ latent_row,
+                    const float* __restrict__ w_post, int pre_normed, const __nv_bfloat16* __restrict__ w_out,
+                    const __nv_bfloat16* __restrict__ b_out, int TS, __nv_bfloat16* __restrict__ z_out,
+                    __nv_bfloat16* __restrict__ codes_out, int32_t* __restrict__ idx_out, int T,
+                    const __grid_constant__ FsqConsts c) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const int row = latent_row[t];
+  RowVec<NV> a;
+  a.load(x + row * ld, lane);
+  if (!pre_normed) a.norm(w_post, lane, rstd_of(a.sumsq(), NV * 256));
+  float zk[FSQ_MAX_D];
+#pragma unroll
+  for (int k = 0; k < FSQ_MAX_D; ++k) {
+    float acc = 0.f;
+    if (k < TS) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const uint4 r = ldg16(w_out + static_cast<int64_t>(k) * (NV * 256) + i * 256 + lane * 8);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc = fmaf(a.v[i * 8 + 2 * e], bf16_lo(rr[e]), acc);
+          acc = fmaf(a.v[i * 8 + 2 * e + 1], bf16_hi(rr[e]), acc);
+        }
+      }
+      acc = warp_sum(acc);
+    }
+    zk[k] = acc;
+  }
+  if (lane == 0) {
+    float idx = 0.f;
+#pragma unroll
+    for (int k = 0; k < FSQ_MAX_D; ++k) {
+      if (k < TS) {
+        const float z = bf16r(zk[k] + __bfloat162float(b_out[k]));
+        z_out[static_cast<int64_t>(t) * TS + k] = __float2bfloat16_rn(z);
+        const float code = fsq_quantize_dim(z, c, k, idx);
+        codes_out[static_cast<int64_t>(t) * TS + k] = __float2bfloat16_rn(code);
+      }
+    }
+    idx_out[t] = static_cast<int32_t>(idx);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// patchify: clips (flat bf16 buffer, each clip [3,T,H,W]) -> patches [G, 3*P0*P1*P2] with feature order
+// (c, p0, p1, p2). geom[g] = {element offset of (c=0,t0,h0,w0), W, H*W, T*H*W}. One thread per 8-element
+// run along W (P2 == 8).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) patchify_kernel(const __nv_bfloat16* __restrict__ clips,
+                                                       const int64_t* __restrict__ geom, int C, int P0, int P1,
+                                                       __nv_bfloat16* __restrict__ patches, int64_t ldp, int64_t G) {
+  const int runs = C * P0 * P1;  // 16-byte runs per patch
+  const int64_t total = G * runs;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t g = i / runs;
+    const int rr = static_cast<int>(i - g * runs);
+    const int c = rr / (P0 * P1);
+    const int p0 = (rr / P1) % P0;
+    const int p1 = rr % P1;
+    const int64_t* ge = geom + g * 4;
+    const int64_t src = ge[0] + c * ge[3] + p0 * ge[2] + p1 * ge[1];
+    stg16(patches + g * ldp + rr * 8, ldg16_stream(clips + src));
+  }
+}
+
+// unpatchify: rows of `proj` ([*, ldp], feature order (c,p0,p1,p2)) for the patch rows -> clips.
+// patch_row[g] = row of proj holding patch g.
+__global__ void __launch_bounds__(256) unpatchify_kernel(const __nv_bfloat16* __restrict__ proj, int64_t ldp,
+                                                         const int32_t* __restrict__ patch_row,
+                                                         const int64_t* __restrict__ geom, int C, int P0, int P1,
+                                                         __nv_bfloat16* __restrict__ clips, int64_t G) {
+  const int runs = C * P0 * P1;
+  const int64_t total = G * runs;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t g = i / runs;
+    const int rr = static_cast<int>(i - g * runs);
+    const int c = rr / (P0 * P1);
+    const int p0 = (rr / P1) % P0;
+    const int p1 = rr % P1;
+    const int64_t* ge = geom + g * 4;
+    const int64_t dst = ge[0] + c * ge[3] + p0 * ge[2] + p1 * ge[1];
+    stg16(clips + dst, ldg16_stream(proj + static_cast<int64_t>(patch_row[g]) * ldp + rr * 8));
+  }
+}
+
+int fsq_make_consts(FsqConsts& c, int D, const float* half_l, const float* offset, const float* shift,
+                    const float* half_width, const int32_t* basis, const int32_t* levels);
+
+}  // namespace ttk
+
+using namespace ttk;
+
+#define TTK_DISPATCH_NV(width, ...)            \
+  switch ((width) / 256) {                     \
+    case 1: { constexpr int NV = 1; __VA_ARGS__; break; } \
+    case 2: { constexpr int NV = 2; __VA_ARGS__; break; } \
+    case 3: { constexpr int NV = 3; __VA_ARGS__; break; } \
+    case 4: { constexpr int NV = 4; __VA_ARGS__; break; } \
+    default: return TTK_ERR_BAD_SHAPE;         \
+  }
+
+static inline int row_grid(int M) { return (M + ROW_WARPS - 1) / ROW_WARPS; }
+static inline bool width_ok(int width) { return width > 0 && width % 256 == 0 && width <= 1024; }
+
+extern "C" {
+
+int ttk_rmsnorm_fwd(const void* x, int64_t ldx, const float* w, void* y, int64_t ldy, int M, int width,
+                    cudaStream_t stream) {
+  if (!x || !w || !y) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (!width_ok(width) || ldx % 8 || ldy % 8) return TTK_ERR_BAD_SHAPE;
+  if (M <= 0) return TTK_OK;
+  TTK_DISPATCH_NV(width, rmsnorm_kernel<NV><<<row_grid(M), ROW_WARPS * 32, 0, stream>>>(
+                             static_cast<const __nv_bfloat16*>(x), ldx, w, static_cast<__nv_bfloat16*>(y), ldy, M));
+  return launch_status();
+}
+
+int ttk_resid_norm(const void* x, const void* y, void* x_out, void* xn_out, const float* w_post, const float* w_next,
+                   float alpha, int mode, int M, int width, int64_t ld, cudaStream_t stream) {
+  if (!x || !y || !x_out) return TTK_ERR_BAD_ARG;
+  if ((mode == 1 && !w_post) || (xn_out && !w_next)) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (!width_ok(width) || ld % 8) return TTK_ERR_BAD_SHAPE;
+  if (M <= 0) return TTK_OK;
+  TTK_DISPATCH_NV(width, resid_norm_kernel<NV><<<row_grid(M), ROW_WARPS * 32, 0, stream>>>(
+                             static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(y),
+                             static_cast<__nv_bfloat16*>(x_out), static_cast<__nv_bfloat16*>(xn_out), w_post, w_next,
+                             alpha, mode, M, ld));
+  return launch_status();
+}
+
+int ttk_enc_embed(const void* proj, int64_t ldp, const int32_t* src_row, const float* mask_token, const float* w_t,
+                  const float* w_p, const float* w_next, void* x_out, void* xn_out, int M, int width, int64_t ld,
+                  cudaStream_t stream) {
+  if (!proj || !src_row || !mask_token || !w_t || !w_p || !x_out) return TTK_ERR_BAD_ARG;
+  if (xn_out && !w_next) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (!width_ok(width) || ld % 8 || ldp % 8) return TTK_ERR_BAD_SHAPE;
+  if (M <= 0) return TTK_OK;
+  TTK_DISPATCH_NV(width, enc_embed_kernel<NV><<<row_grid(M), ROW_WARPS * 32, 0, stream>>>(
+                             static_cast<const __nv_bfloat16*>(proj), ldp, src_row, mask_token, w_t, w_p, w_next,
+                             static_cast<__nv_bfloat16*>(x_out), static_cast<__nv_bfloat16*>(xn_out), M, ld));
+  return launch_status();
+}
+
+int ttk_dec_embed(const void* codes, int token_size, const int32_t* src_row, const void* w_in, const void* b_in,
+                  const float* mask_token, const float* w_t, const float* w_p, const float* w_next, void* x_out,
+                  void* xn_out, int M, int width, int64_t ld, cudaStream_t stream) {
+  if (!codes || !src_row || !w_in || !b_in || !mask_token || !w_t || !w_p || !x_out) return TTK_ERR_BAD_ARG;
+  if (xn_out && !w_next) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (!width_ok(width) || ld % 8 || token_size < 1 || token_size > FSQ_MAX_D) return TTK_ERR_BAD_SHAPE;
+  if (M <= 0) return TTK_OK;
+  TTK_DISPATCH_NV(width, dec_embed_kernel<NV><<<row_grid(M), ROW_WARPS * 32, 0, stream>>>(
+                             static_cast<const __nv_bfloat16*>(codes), token_size, src_row,
+                             static_cast<const __nv_bfloat16*>(w_in), static_cast<const __nv_bfloat16*>(b_in),
+                             mask_token, w_t, w_p, w_next, static_cast<__nv_bfloat16*>(x_out),
+                             static_cast<__nv_bfloat16*>(xn_out), M, ld));
+  return launch_status();
+}
+
+int ttk_enc_head_fsq(const void* x, int64_t ld, const int32_t* latent_row, const float* w_post, int pre_normed,
+                     const void* w_out, const void* b_out, int token_size, void* z_out, void* codes_out,
+                     int32_t* idx_out, int T, int width, const float* half_l, const float* offset, const float* shift,
+                     const float* half_width, const int32_t* basis, const int32_t* levels, cudaStream_t stream) {
+  if (!x || !latent_row || !w_out || !b_out || !z_out || !codes_out || !idx_out) return TTK_ERR_BAD_ARG;
+  if (!pre_normed && !w_post) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (!width_ok(width) || ld % 8) return TTK_ERR_BAD_SHAPE;
+  FsqConsts c;
+  if (int e = fsq_make_consts(c, token_size, half_l, offset, shift, half_width, basis, levels)) return e;
+  if (T <= 0) return TTK_OK;
+  TTK_DISPATCH_NV(width, enc_head_fsq_kernel<NV><<<row_grid(T), ROW_WARPS * 32, 0, stream>>>(
+                             static_cast<const __nv_bfloat16*>(x), ld, latent_row, w_post, pre_normed,
+                             static_cast<const __nv_bfloat16*>(w_out), static_cast<const __nv_bfloat16*>(b_out),
+                             token_size, static_cast<__nv_bfloat16*>(z_out), static_cast<__nv_bfloat16*>(codes_out),
+                             idx_out, T, c));
+  return launch_status();
+}
+
+// geom: device int64 [G,4] = {offset, W, H*W, T*H*W} per patch. Requires P2 == 8 (16-byte runs).
+int ttk_patchify(const void* clips, const int64_t* geom, int C, int P0, int P1, int P2, void* patches, int64_t ldp,
+                 int64_t G, cudaStream_t stream) {
+  if (!clips || !geom || !patches) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (P2 != 8 || C < 1 || P0 < 1 || P1 < 1 || ldp % 8) return TTK_ERR_BAD_SHAPE;
+  if (G <= 0) return TTK_OK;
+  const int64_t total = G * C * P0 * P1;
+  const int64_t blocks = (total + 255) / 256;
+  const int grid = static_cast<int>(blocks < 32LL * num_sms() ? blocks : 32LL * num_sms());
+  patchify_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(clips), geom, C, P0, P1,
+                                            static_cast<__nv_bfloat16*>(patches), ldp, G);
+  return launch_status();
+}
+
+int ttk_unpatchify(const void* proj, int64_t ldp, const int32_t* patch_row, const int64_t* geom, int C, int P0, int P1,
+                   int P2, void* clips, int64_t G, cudaStream_t stream) {
+  if (!proj || !patch_row || !geom || !clips) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (P2 != 8 || C < 1 || P0 < 1 || P1 < 1 || ldp % 8) return TTK_ERR_BAD_SHAPE;
+  if (G <= 0) return TTK_OK;
+  const int64_t total = G * C * P0 * P1;
+  const int64_t blocks = (total + 255) / 256;
+  const int grid = static_cast<int>(blocks < 32LL * num_sms() ? blocks : 32LL * num_sms());
+  unpatchify_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(proj), ldp, patch_row, geom, C, P0,
+                                              P1, static_cast<__nv_bfloat16*>(clips), G);
+  return launch_status();
+}
+
+}  // extern "C"

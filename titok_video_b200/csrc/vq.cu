@@ -1,0 +1,420 @@
+// Generic vector-quantizer lookup on the tensor cores: idx[n] = argmin_k ||z_n - c_k||^2.
+//
+// BASELINE.json's north_star asks for the distance computation ||z||^2 - 2 z.C^T + ||c||^2 as a
+// tcgen05 / TMEM GEMM fed by TMA with the argmin fused into the epilogue, so that the [N, K] distance
+// matrix never reaches HBM. The reference's own quantizer is FSQ (model/quantizer/fsq.py), whose
+// indices equal torch.cdist(z, FSQ.implicit_codebook).argmin(-1) (fsq.py:75-76 builds that buffer);
+// that cdist/argmin expression is the oracle for this kernel.
+//
+// Formulation: ||z||^2 is constant per row and dropped. The codebook is pre-augmented ONCE
+// (ttk_vq_prepare_codebook):   c'_k = [ -2 c_k , hi(|c_k|^2), mid(|c_k|^2), lo(|c_k|^2), 0.. ]  (bf16)
+// where hi+mid+lo is an exact 3-term bf16 split of the fp32 squared norm, and the A tile gets three
+// columns of ones patched in shared memory after its TMA load. The tensor core then produces
+//   S'[n,k] = |c_k|^2 - 2 z_n.c_k        (fp32, exact products)
+// directly, and the epilogue is a pure running (min, argmin) over TMEM columns: ~0.6 ALU ops/element.
+//
+// One persistent CTA per SM; a CTA owns 128 rows of z at a time and streams the whole codebook.
+//   warp 0      B producer: codebook tiles [256 codes x 64] through a TMA ring
+//   warp 1      MMA issuer: S'[128 x 256] per codebook tile, accumulators double-buffered in TMEM
+//   warp 2      TMEM allocator
+//   warp 3      A producer: z tile (all of D, resident for the whole codebook sweep) + ones patch
+//   warps 4-11  epilogue: thread == row, two warps per TMEM lane quarter split the 256 columns
+#include "common.cuh"
+#include "host_util.cuh"
+
+namespace ttk {
+
+constexpr int VQ_BM = 128;
+constexpr int VQ_BN = 256;
+constexpr int VQ_BK = 64;
+constexpr int VQ_A_KB_BYTES = VQ_BM * VQ_BK * 2;  // 16 KB per 64-wide k block of the z tile
+constexpr int VQ_B_BYTES = VQ_BN * VQ_BK * 2;     // 32 KB per ring stage
+constexpr int VQ_MAX_KB = 5;                      // D + 3 <= 320
+constexpr int VQ_SMEM_BUDGET = 220 * 1024;
+
+struct VqParams {
+  int64_t N;
+  int K, D, DA;  // DA = augmented feature count (multiple of 8)
+  int num_kb;    // ceil(DA / 64)
+  int a_bufs;    // 1 or 2
+  int b_stages;
+  int num_m_tiles, num_n_tiles;
+  int32_t* idx;
+  float* best;
+};
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// running (min, argmin) over one 32-column chunk held in registers
+__device__ __forceinline__ void vq_chunk_update(const uint32_t (&v)[32], int col0, int K, float& best, int& best_i) {
+  float f[32];
+  if (col0 + 32 <= K) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = (col0 + i < K) ? __uint_as_float(v[i]) : INFINITY;
+  }
+  float m[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) m[i] = fmin3(f[3 * i], f[3 * i + 1], f[3 * i + 2]);
+  m[10] = fminf(f[30], f[31]);
+  const float a = fmin3(m[0], m[1], m[2]), b = fmin3(m[3], m[4], m[5]), c = fmin3(m[6], m[7], m[8]);
+  const float mm = fminf(fmin3(a, b, c), fminf(m[9], m[10]));
+  if (mm < best) {  // rare after the first few chunks; strict '<' keeps the first minimum (argmin tie rule)
+    best = mm;
+    int bi = 31;
+#pragma unroll
+    for (int i = 30; i >= 0; --i)
+      if (f[i] == mm) bi = i;
+    best_i = col0 + bi;
+  }
+}
+
+__global__ void __launch_bounds__(384, 1)
+vq_argmin_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmC, const VqParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                               // [a_bufs][num_kb][128 x 64]
+  uint8_t* sB = sA + p.a_bufs * p.num_kb * VQ_A_KB_BYTES;           // [b_stages][256 x 64]
+  uint8_t* tail = sB + p.b_stages * VQ_B_BYTES;
+  float* m_best = reinterpret_cast<float*>(tail);                   // [128] merge buffer
+  int* m_idx = reinterpret_cast<int*>(tail + 512);                  // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 1024);
+  uint64_t* a_full = bars;          // [2]
+  uint64_t* a_ready = bars + 2;     // [2]
+  uint64_t* a_empty = bars + 4;     // [2]
+  uint64_t* t_full = bars + 6;      // [2]
+  uint64_t* t_empty = bars + 8;     // [2]
+  uint64_t* b_full = bars + 10;     // [b_stages <= 8]
+  uint64_t* b_empty = bars + 18;    // [b_stages <= 8]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 26);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmZ);
+    tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_ready[s], 1);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&t_full[s], 1);
+      mbar_init(&t_empty[s], 8);
+    }
+    for (int s = 0; s < p.b_stages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== codebook (B) producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x) {
+        for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&b_full[stage], VQ_B_BYTES);
+            tma_load_2d(sB + stage * VQ_B_BYTES, &tmC, &b_full[stage], kb * VQ_BK, nt * VQ_BN);
+            if (++stage == p.b_stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ===================== z (A) producer + ones patch =====================
+    int it = 0;
+    for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x, ++it) {
+      const int ab = (p.a_bufs == 2) ? (it & 1) : 0;
+      const uint32_t ph = (p.a_bufs == 2) ? ((it >> 1) & 1) : (it & 1);
+      uint8_t* a = sA + ab * p.num_kb * VQ_A_KB_BYTES;
+      if (lane == 0) {
+        mbar_wait(&a_empty[ab], ph ^ 1);
+        mbar_arrive_expect_tx(&a_full[ab], p.num_kb * VQ_A_KB_BYTES);
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          tma_load_2d(a + kb * VQ_A_KB_BYTES, &tmZ, &a_full[ab], kb * VQ_BK, mt * VQ_BM);
+      }
+      __syncwarp();
+      mbar_wait(&a_full[ab], ph);
+      // columns D, D+1, D+2 of every row := 1.0 (they multiply the hi/mid/lo norm terms of c')
+      for (int e = lane; e < VQ_BM * 3; e += 32) {
+        const int r = e / 3;
+        const int col = p.D + (e - r * 3);
+        const int kb = col >> 6;
+        const int cc = col & 63;
+        uint8_t* dst = a + kb * VQ_A_KB_BYTES + sw128_offset(r, cc >> 3) + (cc & 7) * 2;
+        *reinterpret_cast<unsigned short*>(dst) = 0x3f80;  // bf16(1.0)
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_ready[ab]);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(VQ_BM, VQ_BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      int it = 0;
+      for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x, ++it) {
+        const int ab = (p.a_bufs == 2) ? (it & 1) : 0;
+        const uint32_t ph = (p.a_bufs == 2) ? ((it >> 1) & 1) : (it & 1);
+        const uint32_t a_addr = smem_u32(sA + ab * p.num_kb * VQ_A_KB_BYTES);
+        mbar_wait(&a_ready[ab], ph);
+        for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+          mbar_wait(&t_empty[as], aphase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * VQ_BN;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&b_full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = a_addr + kb * VQ_A_KB_BYTES;
+            const uint32_t sb = smem_u32(sB + stage * VQ_B_BYTES);
+            const int rem = p.DA - kb * VQ_BK;
+            const int ksteps = rem >= VQ_BK ? 4 : (rem + 15) / 16;
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16_ss(d_tmem, umma_smem_desc_sw128(sa + k * 32, 1024, 0),
+                           umma_smem_desc_sw128(sb + k * 32, 1024, 0), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&b_empty[stage]);
+            if (kb == p.num_kb - 1) umma_commit(&t_full[as]);
+            if (++stage == p.b_stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          if (++as == 2) {
+            as = 0;
+            aphase ^= 1;
+          }
+        }
+        umma_commit(&a_empty[ab]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue: running argmin =====================
+    const int quarter = warp & 3;
+    const int chalf = (warp - 4) >> 2;
+    const int r = quarter * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x) {
+      float best = INFINITY;
+      int best_i = 0;
+      for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+        mbar_wait(&t_full[as], aphase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * VQ_BN + chalf * 128;
+        const int colbase = nt * VQ_BN + chalf * 128;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 64) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32b_x32(t_row + c0, v0);
+          tmem_ld_32x32b_x32(t_row + c0 + 32, v1);
+          tmem_ld_wait();
+          if (colbase + c0 < p.K) vq_chunk_update(v0, colbase + c0, p.K, best, best_i);
+          if (colbase + c0 + 32 < p.K) vq_chunk_update(v1, colbase + c0 + 32, p.K, best, best_i);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+      // merge the two column halves of each row (lower index wins ties)
+      if (chalf == 1) {
+        m_best[r] = best;
+        m_idx[r] = best_i;
+      }
+      named_bar_sync(1, 256);
+      if (chalf == 0) {
+        const float ob = m_best[r];
+        const int oi = m_idx[r];
+        if (ob < best || (ob == best && oi < best_i)) {
+          best = ob;
+          best_i = oi;
+        }
+        const int64_t row = static_cast<int64_t>(mt) * VQ_BM + r;
+        if (row < p.N) {
+          p.idx[row] = best_i;
+          if (p.best) p.best[row] = best;
+        }
+      }
+      named_bar_sync(1, 256);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// c'_k = [-2 c_k | hi, mid, lo of |c_k|^2 | 0..]; one warp per code.
+__global__ void __launch_bounds__(256) vq_prepare_kernel(const __nv_bfloat16* __restrict__ cb, int64_t ldc, int K,
+                                                         int D, __nv_bfloat16* __restrict__ out, int64_t lda,
+                                                         int DA) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (k >= K) return;
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float c = __bfloat162float(cb[k * ldc + d]);
+    s = fmaf(c, c, s);
+    out[k * lda + d] = __float2bfloat16_rn(-2.0f * c);
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    const float hi = bf16r(s);
+    const float r1 = s - hi;
+    const float mid = bf16r(r1);
+    const float lo = bf16r(r1 - mid);
+    out[k * lda + D] = __float2bfloat16_rn(hi);
+    out[k * lda + D + 1] = __float2bfloat16_rn(mid);
+    out[k * lda + D + 2] = __float2bfloat16_rn(lo);
+  }
+  for (int d = D + 3 + lane; d < DA; d += 32) out[k * lda + d] = __float2bfloat16_rn(0.f);
+}
+
+// zq[n] = C[idx[n]]; optional loss_sum += sum (zq - z)^2. One thread per 8-element run.
+__global__ void __launch_bounds__(256) vq_gather_kernel(const __nv_bfloat16* __restrict__ z, int64_t ldz,
+                                                        const __nv_bfloat16* __restrict__ cb, int64_t ldc,
+                                                        const int32_t* __restrict__ idx, int64_t N, int D8,
+                                                        __nv_bfloat16* __restrict__ zq, int64_t ldq,
+                                                        float* __restrict__ loss_sum) {
+  float acc = 0.f;
+  const int64_t total = N * D8;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t n = i / D8;
+    const int c = static_cast<int>(i - n * D8);
+    const uint4 q = ldg16(cb + static_cast<int64_t>(idx[n]) * ldc + c * 8);
+    stg16(zq + n * ldq + c * 8, q);
+    if (loss_sum) {
+      const uint4 a = ldg16_stream(z + n * ldz + c * 8);
+      const uint32_t qq[4] = {q.x, q.y, q.z, q.w}, aa[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d0 = bf16_lo(qq[e]) - bf16_lo(aa[e]);
+        const float d1 = bf16_hi(qq[e]) - bf16_hi(aa[e]);
+        acc += d0 * d0 + d1 * d1;
+      }
+    }
+  }
+  if (loss_sum) {
+    __shared__ float part[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      float v = part[threadIdx.x];
+      for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+      if (threadIdx.x == 0) atomicAdd(loss_sum, v);
+    }
+  }
+}
+
+}  // namespace ttk
+
+using namespace ttk;
+
+extern "C" {
+
+// Number of bf16 columns of the augmented codebook for feature dim D.
+int ttk_vq_aug_dim(int D) { return ((D + 3 + 7) / 8) * 8; }
+
+// codebook [K, D] bf16 (row pitch ldc) -> cb_aug [K, ttk_vq_aug_dim(D)] bf16 (row pitch lda).
+int ttk_vq_prepare_codebook(const void* codebook, int64_t ldc, int K, int D, void* cb_aug, int64_t lda,
+                            cudaStream_t stream) {
+  if (!codebook || !cb_aug) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  const int DA = ttk_vq_aug_dim(D);
+  if (K <= 0 || D <= 0 || lda < DA) return TTK_ERR_BAD_SHAPE;
+  vq_prepare_kernel<<<(K + 7) / 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(codebook), ldc, K, D,
+                                                     static_cast<__nv_bfloat16*>(cb_aug), lda, DA);
+  return launch_status();
+}
+
+// z [N, D] bf16 with row pitch ldz (multiple of 8 elements); cb_aug from ttk_vq_prepare_codebook.
+// idx[N] int32 = argmin_k ||z_n - c_k||^2 (first minimum); best (optional) = |c|^2 - 2 z.c of the winner.
+int ttk_vq_argmin(const void* z, int64_t ldz, const void* cb_aug, int64_t lda, int64_t N, int K, int D, int32_t* idx,
+                  float* best, cudaStream_t stream) {
+  if (!z || !cb_aug || !idx) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  const int DA = ttk_vq_aug_dim(D);
+  const int num_kb = (DA + VQ_BK - 1) / VQ_BK;
+  if (N <= 0) return TTK_OK;
+  if (K <= 0 || D <= 0 || num_kb > VQ_MAX_KB || N > (int64_t(1) << 31) - VQ_BM) return TTK_ERR_BAD_SHAPE;
+  VqParams p{};
+  p.N = N;
+  p.K = K;
+  p.D = D;
+  p.DA = DA;
+  p.num_kb = num_kb;
+  const int a_one = num_kb * VQ_A_KB_BYTES;
+  p.a_bufs = (2 * a_one + 3 * VQ_B_BYTES <= VQ_SMEM_BUDGET) ? 2 : 1;
+  int bs = (VQ_SMEM_BUDGET - p.a_bufs * a_one) / VQ_B_BYTES;
+  if (bs > 6) bs = 6;
+  if (bs < 2) return TTK_ERR_BAD_SHAPE;
+  p.b_stages = bs;
+  p.num_m_tiles = static_cast<int>((N + VQ_BM - 1) / VQ_BM);
+  p.num_n_tiles = (K + VQ_BN - 1) / VQ_BN;
+  p.idx = idx;
+  p.best = best;
+  CUtensorMap tmZ, tmC;
+  // inner extent = true D for z (columns >= D read as zero, then patched with ones), DA for the codebook
+  if (int e = make_tmap_bf16_2d(&tmZ, z, static_cast<uint64_t>(N), D, ldz, VQ_BM)) return e;
+  if (int e = make_tmap_bf16_2d(&tmC, cb_aug, K, DA, lda, VQ_BN)) return e;
+  const int smem = p.a_bufs * a_one + p.b_stages * VQ_B_BYTES + 1024 + 256 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+        cudaSuccess)
+      return TTK_ERR_CUDA;
+    attr_done = true;
+  }
+  const int grid = p.num_m_tiles < num_sms() ? p.num_m_tiles : num_sms();
+  vq_argmin_kernel<<<grid, 384, smem, stream>>>(tmZ, tmC, p);
+  return launch_status();
+}
+
+// D must be a multiple of 8 (pad). codebook is the ORIGINAL [K, D] bf16 codebook.
+int ttk_vq_gather_loss(const void* z, int64_t ldz, const void* codebook, int64_t ldc, const int32_t* idx, int64_t N,
+                       int D, void* zq, int64_t ldq, float* loss_sum, cudaStream_t stream) {
+  if (!codebook || !idx || !zq || (loss_sum && !z)) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (D <= 0 || D % 8 || ldc % 8 || ldq % 8 || (z && ldz % 8)) return TTK_ERR_BAD_SHAPE;
+  if (N <= 0) return TTK_OK;
+  const int64_t total = N * (D / 8);
+  const int64_t blocks = (total + 255) / 256;
+  const int grid = static_cast<int>(blocks < 16LL * num_sms() ? blocks : 16LL * num_sms());
+  vq_gather_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(z), ldz,
+                                             static_cast<const __nv_bfloat16*>(codebook), ldc, idx, N, D / 8,
+                                             static_cast<__nv_bfloat16*>(zq), ldq, loss_sum);
+  return launch_status();
+}
+
+}  // extern "C"
