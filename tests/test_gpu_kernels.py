@@ -1,0 +1,519 @@
+"""Per-kernel parity on the B200: every entry point of libtitok_b200.so is called through the C ABI and compared
+with the CPU oracle (oracle/titok_oracle.py) on the same seeded inputs.
+
+Tolerances. Integer / index outputs: bit-exact (FSQ, histogram, gathers), or exact modulo stated near-ties (VQ).
+bf16 GEMM-class outputs: the products are exact in fp32, only the accumulation order differs from the oracle's,
+so results agree to ~1 bf16 ulp: |d| <= 2^-7 * |ref| + small absolute term.
+"""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import from_bits, load_golden
+from oracle import titok_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+DEV = "cuda"
+
+
+def lib():
+    from titok_video_b200 import _lib
+
+    return _lib
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def ST():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_KEEP = []
+
+
+def G(t):
+    """Pointer to a CUDA copy of `t` that stays alive until the end of the test. (A temporary created inline in the
+    argument list would be freed -- and its block reused by the next temporary -- before the asynchronous kernel
+    reads it.)"""
+    if t is None:
+        return ctypes.c_void_p(0)
+    d = t.to(DEV)
+    _KEEP.append(d)
+    return ctypes.c_void_p(d.data_ptr())
+
+
+@pytest.fixture(autouse=True)
+def _release_keepalive():
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
+
+
+def randn(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(BF)
+
+
+def close_bf16(out, ref, ulps=2.0, atol=None, what=""):
+    """out (cuda bf16) vs ref (cpu fp32, bf16-valued)."""
+    o = out.float().cpu()
+    scale = ref.abs().max().item() + 1e-20
+    atol = (2.0 ** -8) * scale * 0.05 if atol is None else atol
+    d = (o - ref).abs()
+    tol = ulps * (2.0 ** -8) * ref.abs() + atol
+    bad = (d > tol)
+    assert torch.isfinite(o).all(), f"{what}: non-finite output"
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} outside {ulps} bf16 ulp; max|d|={d.max().item():.4g} "
+                           f"scale={scale:.4g} first bad={torch.nonzero(bad)[:4].tolist()}")
+
+
+# --------------------------------------------------------------------------------------------------
+# GEMMs
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,bias", [(128, 128, 64, False), (300, 256, 256, True), (1000, 768, 256, True),
+                                        (517, 256, 704, False), (256, 768, 768, True), (77, 40, 128, True),
+                                        (5676, 256, 768, True)])
+def test_gemm_store(M, N, K, bias):
+    A, W = randn(M, K, seed=1), randn(N, K, seed=2, scale=0.1)
+    b = randn(N, seed=3) if bias else None
+    ref = O.linear(A.float(), W, b)
+    out = torch.full((M, N), float("nan"), dtype=BF, device=DEV)
+    Ad, Wd = A.to(DEV), W.to(DEV)
+    bd = b.to(DEV) if bias else None
+    lib().call("ttk_gemm_bf16", P(Ad), K, P(Wd), K, M, N, K, P(bd), P(out), N, P(None), 0, ST())
+    torch.cuda.synchronize()
+    close_bf16(out, ref, what=f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_store_row_map_and_ld():
+    M, N, K = 200, 256, 128
+    A, W = randn(M, K, seed=4), randn(N, K, seed=5, scale=0.1)
+    ref = O.linear(A.float(), W)
+    g = torch.Generator().manual_seed(0)
+    rmap = torch.randperm(M + 50, generator=g)[:M].to(torch.int32)
+    rmap[7] = -1
+    out = torch.zeros((M + 50, N + 64), dtype=BF, device=DEV)
+    lib().call("ttk_gemm_bf16", G(A), K, G(W), K, M, N, K, P(None), P(out), N + 64, G(rmap), 0,
+               ST())
+    torch.cuda.synchronize()
+    o = out.cpu().float()
+    keep = rmap >= 0
+    close_bf16(out[rmap[keep].long().to(DEV), :N], ref[keep], what="row-mapped gemm")
+    assert o[:, N:].abs().max() == 0
+    untouched = torch.ones(M + 50, dtype=torch.bool)
+    untouched[rmap[keep].long()] = False
+    assert o[untouched].abs().max() == 0
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (300, 256, 256), (129, 64, 192)])
+def test_gemm_weight_given_as_kn(M, N, K):
+    """B operand with N contiguous (MN-major UMMA descriptor) -- the layout the attention kernel uses for V."""
+    A, Wkn = randn(M, K, seed=6), randn(K, N, seed=7, scale=0.1)
+    ref = O.r(A.float() @ Wkn.float())
+    out = torch.empty((M, N), dtype=BF, device=DEV)
+    lib().call("ttk_gemm_bf16", G(A), K, G(Wkn), N, M, N, K, P(None), P(out), N, P(None), 1, ST())
+    torch.cuda.synchronize()
+    close_bf16(out, ref, what="gemm kn")
+
+
+@pytest.mark.parametrize("M,width,gqa", [(300, 256, 128), (1892, 256, 128), (200, 768, 256)])
+def test_gemm_qkv_rope(M, width, gqa):
+    K = width
+    A, W = randn(M, K, seed=8), randn(2 * width + 2 * gqa, K, seed=9, scale=0.08)
+    cos, sin = O.rope_cos_sin([3, 10, 10], M - 300 if M > 300 else 0)
+    cos, sin = cos[:M], sin[:M]
+    if cos.shape[0] < M:  # tile the table for the large case
+        rep = (M + cos.shape[0] - 1) // cos.shape[0]
+        cos, sin = cos.repeat(rep, 1)[:M], sin.repeat(rep, 1)[:M]
+    rope = torch.stack([cos, sin], dim=-1).reshape(M, 60).contiguous()
+    qkv = O.linear(A.float(), W)
+    q, gate, k, v = qkv.split([width, width, gqa, gqa], dim=-1)
+    q = O.apply_rope(q.reshape(M, -1, 64), cos, sin).reshape(M, -1)
+    k = O.apply_rope(k.reshape(M, -1, 64), cos, sin).reshape(M, -1)
+    ref = torch.cat([q, gate, k, v], dim=-1)
+    out = torch.empty((M, 2 * width + 2 * gqa), dtype=BF, device=DEV)
+    lib().call("ttk_gemm_qkv_rope", G(A), K, G(W), K, M, K, width, gqa, G(rope), P(out),
+               out.stride(0), ST())
+    torch.cuda.synchronize()
+    # the rotation is done on bf16-rounded GEMM outputs: a 1-ulp difference of an input moves the output by ~1 ulp of it
+    close_bf16(out, ref, ulps=3.0, atol=2.0 ** -8 * ref.abs().max().item() * 0.5, what="qkv+rope")
+
+
+@pytest.mark.parametrize("M,inner,K", [(300, 704, 256), (1000, 1376, 512), (64, 704, 256)])
+def test_gemm_geglu(M, inner, K):
+    A, W = randn(M, K, seed=10), randn(2 * inner, K, seed=11, scale=0.1)
+    h = O.linear(A.float(), W)
+    val, gate = h.chunk(2, dim=-1)
+    ref = O.r(O.r(O.gelu_erf(gate)) * val)
+    out = torch.empty((M, inner), dtype=BF, device=DEV)
+    lib().call("ttk_gemm_geglu", G(A), K, G(W), K, M, inner, K, P(out), inner, ST())
+    torch.cuda.synchronize()
+    close_bf16(out, ref, ulps=4.0, atol=2.0 ** -8 * ref.abs().max().item() * 0.5, what="geglu")
+
+
+def _resid_ref(x, y, mode, alpha, w_post, w_next):
+    if mode == 0:
+        xn = O.r(x + y)
+    else:
+        xn = O.rmsnorm(O.r(O.r(alpha * x) + y), w_post)
+    return xn, O.rmsnorm(xn, w_next)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("M,K", [(300, 256), (1000, 704)])
+def test_gemm_resid_norm256(mode, M, K):
+    A, W = randn(M, K, seed=12), randn(256, K, seed=13, scale=0.1)
+    x = randn(M, 256, seed=14)
+    g = torch.Generator().manual_seed(15)
+    w_post = 1 + 0.1 * torch.randn(256, generator=g)
+    w_next = 1 + 0.1 * torch.randn(256, generator=g)
+    y = O.linear(A.float(), W)
+    ref_x, ref_xn = _resid_ref(x.float(), y, mode, 8.0, w_post, w_next)
+    xo = torch.empty((M, 256), dtype=BF, device=DEV)
+    xno = torch.empty((M, 256), dtype=BF, device=DEV)
+    lib().call("ttk_gemm_resid_norm256", G(A), K, G(W), K, M, K, G(x), 256, mode, 8.0,
+               G(w_post), G(w_next), P(xo), P(xno), 256, ST())
+    torch.cuda.synchronize()
+    close_bf16(xo, ref_x, ulps=3.0, atol=2.0 ** -8 * ref_x.abs().max().item() * 0.5, what="resid x")
+    close_bf16(xno, ref_xn, ulps=4.0, atol=2.0 ** -8 * ref_xn.abs().max().item() * 0.5, what="resid xn")
+
+
+# --------------------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seq_lens,hq,hkv", [([128], 4, 2), ([200, 64, 513], 4, 2), ([1892, 576], 4, 2),
+                                               ([300, 129], 12, 4), ([257], 8, 2)])
+def test_attn_varlen(seq_lens, hq, hkv):
+    from titok_video_b200.plan import attn_work_list
+
+    width, gqa = hq * 64, hkv * 64
+    M = sum(seq_lens)
+    qkv = randn(M, 2 * width + 2 * gqa, seed=20, scale=1.0)
+    starts = np.concatenate([[0], np.cumsum(seq_lens)[:-1]]).tolist()
+    work = torch.from_numpy(attn_work_list(starts, seq_lens, hq, hkv))
+    q, gate, k, v = qkv.float().split([width, width, gqa, gqa], dim=-1)
+    ref = torch.empty(M, width)
+    for s0, sl in zip(starts, seq_lens):
+        o = O.attention(q[s0:s0 + sl].reshape(sl, hq, 64), k[s0:s0 + sl].reshape(sl, hkv, 64),
+                        v[s0:s0 + sl].reshape(sl, hkv, 64)).reshape(sl, width)
+        ref[s0:s0 + sl] = O.r(o * O.r(torch.sigmoid(gate[s0:s0 + sl])))
+    out = torch.full((M, width), float("nan"), dtype=BF, device=DEV)
+    qd = qkv.to(DEV)
+    lib().call("ttk_attn_varlen_fwd", P(qd), qd.stride(0), M, width, gqa, G(work), work.shape[0], 0.125, P(out),
+               width, ST())
+    torch.cuda.synchronize()
+    o = out.float().cpu()
+    assert torch.isfinite(o).all()
+    d = (o - ref).abs()
+    # P is rounded to bf16 before P.V (as in flash-attention): errors ~2^-9 relative to the value scale
+    tol = 2e-2 * ref.abs() + 6e-3 * ref.abs().max()
+    assert (d <= tol).all(), f"attention max|d|={d.max().item():.4g} scale={ref.abs().max().item():.4g} bad={int((d > tol).sum())}"
+    assert d.mean().item() < 2e-3 * ref.abs().max().item()
+
+
+# --------------------------------------------------------------------------------------------------
+# row kernels
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("width", [256, 512, 768, 1024])
+def test_rmsnorm_and_resid_norm(width):
+    M = 333
+    x, y = randn(M, width, seed=30), randn(M, width, seed=31)
+    g = torch.Generator().manual_seed(32)
+    w1 = 1 + 0.1 * torch.randn(width, generator=g)
+    w2 = 1 + 0.1 * torch.randn(width, generator=g)
+    out = torch.empty((M, width), dtype=BF, device=DEV)
+    lib().call("ttk_rmsnorm_fwd", G(x), width, G(w1), P(out), width, M, width, ST())
+    close_bf16(out, O.rmsnorm(x.float(), w1), ulps=1.0, what="rmsnorm")
+    for mode in (0, 1):
+        rx, rxn = _resid_ref(x.float(), y.float(), mode, 8.0, w1, w2)
+        xo = torch.empty((M, width), dtype=BF, device=DEV)
+        xno = torch.empty((M, width), dtype=BF, device=DEV)
+        lib().call("ttk_resid_norm", G(x), G(y), P(xo), P(xno), G(w1), G(w2), 8.0, mode,
+                   M, width, width, ST())
+        close_bf16(xo, rx, ulps=1.5, what=f"resid_norm x mode {mode}")  # rstd may differ in its last bit
+        close_bf16(xno, rxn, ulps=2.5, what=f"resid_norm xn mode {mode}")
+
+
+def test_patchify_unpatchify_roundtrip_and_layout():
+    from titok_video_b200.engine import patch_feature_perm
+    from titok_video_b200.plan import make_plan
+
+    shapes, tcs, patch = [(8, 32, 48), (4, 16, 24), (16, 168, 168)], [3, 0, 7], (4, 8, 8)
+    clips = O.make_clips(shapes, 0)
+    pl = make_plan(shapes, tcs, patch)
+    flat = torch.cat([c.reshape(-1) for c in clips]).to(DEV)
+    patches = torch.empty((pl.G, 768), dtype=BF, device=DEV)
+    geom = torch.from_numpy(pl.geom).to(DEV)
+    lib().call("ttk_patchify", P(flat), P(geom), 3, 4, 8, 8, P(patches), 768, pl.G, ST())
+    ref = torch.cat([O.patchify(c.float(), patch) for c in clips], dim=0)  # reference feature order
+    perm = patch_feature_perm(patch, 3)
+    assert torch.equal(patches.float().cpu(), ref[:, perm]), "patchify is a pure permutation: must be bit-exact"
+    # scatter back through a row map (rows = packed rows)
+    rows = torch.zeros((pl.M, 768), dtype=BF, device=DEV)
+    prow = torch.from_numpy(pl.patch_row).to(DEV)
+    rows[prow.long()] = patches
+    out = torch.zeros_like(flat)
+    lib().call("ttk_unpatchify", P(rows), 768, P(prow), P(geom), 3, 4, 8, 8, P(out), pl.G, ST())
+    assert torch.equal(out, flat)
+
+
+def _fsq_consts(levels, device="cpu"):
+    import titok_video_b200 as T
+
+    return T.FSQ(list(levels))._consts(torch.device(device))
+
+
+def test_enc_dec_embed_and_head():
+    from titok_video_b200.plan import make_plan
+
+    width, ts = 256, 5
+    shapes, tcs = [(8, 32, 32), (4, 16, 24)], [5, 2]
+    pl = make_plan(shapes, tcs, (4, 8, 8))
+    g = torch.Generator().manual_seed(40)
+    proj = randn(pl.G, width, seed=41)
+    mt = torch.tensor([0.37])
+    w_t, w_p, w_n = [1 + 0.1 * torch.randn(width, generator=g) for _ in range(3)]
+    mtb = O.r(mt)
+    # encoder embed
+    ref = torch.empty(pl.M, width)
+    lat = O.rmsnorm(mtb.expand(1, width).clone(), w_t)
+    ref[torch.from_numpy(pl.latent_row).long()] = lat
+    ref[torch.from_numpy(pl.patch_row).long()] = O.rmsnorm(O.r(proj.float() + mtb), w_p)
+    xo = torch.empty((pl.M, width), dtype=BF, device=DEV)
+    xno = torch.empty((pl.M, width), dtype=BF, device=DEV)
+    lib().call("ttk_enc_embed", G(proj), width, G(torch.from_numpy(pl.enc_src_row)), G(mt),
+               G(w_t), G(w_p), G(w_n), P(xo), P(xno), pl.M, width, width, ST())
+    close_bf16(xo, ref, ulps=1.0, what="enc_embed x")
+    close_bf16(xno, O.rmsnorm(ref, w_n), ulps=1.5, what="enc_embed xn")
+    # decoder embed
+    codes = (torch.randint(-2, 3, (pl.T, ts), generator=g).float() / 2).to(BF)
+    w_in, b_in = randn(width, ts, seed=42, scale=0.3), randn(width, seed=43, scale=0.1)
+    ref = torch.empty(pl.M, width)
+    ref[torch.from_numpy(pl.latent_row).long()] = O.rmsnorm(O.r(O.linear(codes.float(), w_in, b_in) + mtb), w_t)
+    ref[torch.from_numpy(pl.patch_row).long()] = O.rmsnorm(mtb.expand(1, width).clone(), w_p)
+    lib().call("ttk_dec_embed", G(codes), ts, G(torch.from_numpy(pl.dec_src_row)), G(w_in),
+               G(b_in), G(mt), G(w_t), G(w_p), G(w_n), P(xo), P(xno), pl.M,
+               width, width, ST())
+    close_bf16(xo, ref, ulps=1.5, what="dec_embed x")
+    # encoder head + FSQ
+    levels = [7, 5, 5, 5, 5]
+    x = randn(pl.M, width, seed=44, scale=2.0)
+    w_out, b_out = randn(ts, width, seed=45, scale=0.15), randn(ts, seed=46, scale=0.1)
+    tok = O.rmsnorm(x.float()[torch.from_numpy(pl.latent_row).long()], w_n)
+    z_ref = O.linear(tok, w_out, b_out)
+    z = torch.empty((pl.T, ts), dtype=BF, device=DEV)
+    cd = torch.empty((pl.T, ts), dtype=BF, device=DEV)
+    idx = torch.empty((pl.T,), dtype=torch.int32, device=DEV)
+    lib().call("ttk_enc_head_fsq", G(x), width, G(torch.from_numpy(pl.latent_row)), G(w_n), 0,
+               G(w_out), G(b_out), ts, P(z), P(cd), P(idx), pl.T, width, *_fsq_consts(levels), ST())
+    close_bf16(z, z_ref, ulps=2.0, what="enc head z")
+    codes_o, idx_o, _ = O.fsq_forward(z.float().cpu(), levels)  # FSQ of the kernel's own z must be exact
+    assert torch.equal(idx.cpu(), idx_o)
+    assert torch.equal(cd.float().cpu(), O.r(codes_o))
+
+
+# --------------------------------------------------------------------------------------------------
+# quantizer
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_fsq_against_reference_vectors(tag):
+    """Bit-exact against vectors produced by the reference's FSQ (tests/golden/fsq_kat.npz)."""
+    import titok_video_b200 as T
+
+    kat = load_golden("fsq_kat")
+    levels = kat[f"{tag}_levels"].tolist()
+    q = T.FSQ(levels).to(DEV)
+    assert q.codebook_size == int(kat[f"{tag}_codebook_size"])
+    assert q._basis.cpu().tolist() == kat[f"{tag}_basis"].tolist()
+    assert torch.equal(q.implicit_codebook.cpu(), torch.from_numpy(kat[f"{tag}_implicit_codebook"]))
+    z = torch.from_numpy(kat[f"{tag}_z"])
+    codes, d = q(z.to(DEV))
+    ref_idx = torch.from_numpy(kat[f"{tag}_indices"])
+    ref_codes = torch.from_numpy(kat[f"{tag}_codes"])
+    # stated epsilon: an index may differ only where bound(z) is within eps_b of a rounding boundary
+    # (tanh on the GPU vs the CPU that generated the vectors can differ by an ulp)
+    _, _, bounded = O.fsq_forward(z, levels)
+    gap = O.fsq_boundary_gap(bounded)
+    hl = max(levels) * 0.5
+    eps_b = 4 * 2.0 ** -24 * hl
+    neq = d["indices"].cpu() != ref_idx
+    assert not (neq & (gap > eps_b)).any(), f"{int(neq.sum())} index mismatches away from boundaries"
+    assert torch.equal(codes.cpu()[~neq], ref_codes[~neq])
+    assert int(neq.sum()) <= 2
+    # bf16 input path
+    zb = z.to(BF)
+    codes_b, db = q(zb.to(DEV))
+    neq_b = db["indices"].cpu() != torch.from_numpy(kat[f"{tag}_indices_bf16"])
+    _, _, bounded_b = O.fsq_forward(zb.float(), levels)
+    assert not (neq_b & (O.fsq_boundary_gap(bounded_b) > eps_b)).any()
+    assert torch.equal(codes_b.cpu()[~neq_b], from_bits(kat[f"{tag}_codes_bf16_bits"])[~neq_b])
+    # indices -> codes, int32 and int64
+    i2c = torch.from_numpy(kat[f"{tag}_i2c"])
+    assert torch.equal(q.indices_to_codes(ref_idx.to(DEV)).cpu(), i2c)
+    assert torch.equal(q.indices_to_codes(ref_idx.to(DEV).long()).cpu(), i2c)
+    # round trip: indices_to_codes(forward(z).indices) == forward(z).codes
+    assert torch.equal(q.indices_to_codes(d["indices"]).cpu(), codes.cpu())
+
+
+def test_fsq_large_and_ragged_sizes():
+    import titok_video_b200 as T
+
+    q = T.FSQ([7, 5, 5, 5, 5]).to(DEV)
+    for n in (0, 1, 1023, 1025, 2 ** 20 + 3):
+        g = torch.Generator().manual_seed(n)
+        z = (torch.randn((n, 5), generator=g) * 2).to(BF)
+        codes, d = q(z.to(DEV))
+        assert codes.shape == (n, 5) and d["indices"].shape == (n,)
+        if n:
+            c_ref, i_ref, bounded = O.fsq_forward(z.float(), [7, 5, 5, 5, 5])
+            neq = d["indices"].cpu() != i_ref
+            assert not (neq & (O.fsq_boundary_gap(bounded) > 1e-6)).any()
+            assert int(neq.sum()) <= max(2, n // 100000)
+            # property at full size: the decoded codes re-encode to the same indices (idempotence)
+            c2, d2 = q(codes)
+            assert torch.equal(d2["indices"], d["indices"])
+
+
+def test_fsq_backward_ste():
+    import titok_video_b200 as T
+
+    levels = [8, 8, 8, 6, 5]
+    q = T.FSQ(levels).to(DEV)
+    g = torch.Generator().manual_seed(1)
+    z = (torch.randn((4096, 5), generator=g) * 1.5)
+    zc = z.to(DEV).requires_grad_(True)
+    codes, _ = q(zc)
+    w = torch.randn((4096, 5), generator=g)
+    (codes * w.to(DEV)).sum().backward()
+    zr = z.clone().requires_grad_(True)
+    lv, basis, half_l, offset, shift, hw = O.fsq_constants(levels)
+    b = (zr + shift).tanh() * half_l - offset
+    cr = (b + (b.round() - b).detach()) / hw
+    (cr * w).sum().backward()
+    assert torch.allclose(zc.grad.cpu(), zr.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_histogram_and_stats():
+    from scipy.stats import entropy
+
+    for K, n in [(4375, 300000), (16, 1000), (65536, 200000), (15360, 7)]:
+        g = torch.Generator().manual_seed(K)
+        idx = torch.randint(0, K, (n,), generator=g, dtype=torch.int32)
+        idx[::3] = idx[0]
+        cnt = torch.zeros(K, dtype=torch.int32, device=DEV)
+        lib().call("ttk_hist_u32", G(idx), n, K, P(cnt), ST())
+        ref = torch.bincount(idx.long(), minlength=K)
+        assert torch.equal(cnt.cpu().long(), ref)
+        out = torch.empty(3, dtype=torch.float64, device=DEV)
+        lib().call("ttk_codebook_stats", P(cnt), K, P(out), ST())
+        nz, ent, tot = out.cpu().tolist()
+        f = ref.double().numpy()
+        assert nz == float((ref > 0).sum()) and tot == float(n)
+        assert abs(ent - entropy(f / f.sum())) < 1e-9
+
+
+def test_codebook_logger_matches_reference_vector():
+    import titok_video_b200 as T
+
+    kat = load_golden("fsq_kat")
+    lens = kat["logger_lens"].tolist()
+    flat = torch.from_numpy(kat["logger_samples"])
+    samples = list(torch.split(flat, lens))
+    for dev in ("cpu", DEV):
+        lg = T.CodebookLogger(16)
+        lg([s.to(dev) for s in samples])
+        sc = lg.get_scores()
+        assert abs(float(sc["codebook/usage_percent"]) - float(kat["logger_usage"])) < 1e-4
+        assert abs(float(sc["codebook/entropy"]) - float(kat["logger_entropy"])) < 1e-5
+        assert lg.codebook_indices == []
+
+
+# --------------------------------------------------------------------------------------------------
+# generic VQ: tensor-core distance + fused argmin
+# --------------------------------------------------------------------------------------------------
+def _vq_run(z, cb):
+    N, D = z.shape
+    K = cb.shape[0]
+    DA = lib().fn("ttk_vq_aug_dim")(D)
+    D8 = (D + 7) // 8 * 8
+    zp = torch.zeros((N, D8), dtype=BF, device=DEV)
+    zp[:, :D] = z.to(DEV)
+    cbd = cb.to(DEV).contiguous()
+    aug = torch.empty((K, DA), dtype=BF, device=DEV)
+    lib().call("ttk_vq_prepare_codebook", P(cbd), D, K, D, P(aug), DA, ST())
+    idx = torch.full((N,), -1, dtype=torch.int32, device=DEV)
+    best = torch.empty((N,), dtype=torch.float32, device=DEV)
+    lib().call("ttk_vq_argmin", P(zp), D8, P(aug), DA, N, K, D, P(idx), P(best), ST())
+    torch.cuda.synchronize()
+    return idx.cpu(), best.cpu()
+
+
+@pytest.mark.parametrize("N,K,D", [(1000, 256, 16), (4096, 1024, 64), (3000, 4096, 128), (2048, 1000, 5),
+                                   (5000, 4375, 5), (1500, 777, 256), (300, 16384, 32)])
+def test_vq_argmin(N, K, D):
+    g = torch.Generator().manual_seed(N + K + D)
+    z = (torch.randn((N, D), generator=g) * 2).to(BF)
+    if (K, D) == (4375, 5):
+        import titok_video_b200 as T
+
+        cb = T.FSQ([7, 5, 5, 5, 5]).implicit_codebook.to(BF)
+    else:
+        cb = torch.randn((K, D), generator=g).to(BF)
+    idx, best = _vq_run(z, cb)
+    ref_idx, gap = O.vq_argmin(z, cb)
+    assert (idx >= 0).all() and (idx < K).all()
+    neq = idx != ref_idx
+    # stated near-tie criterion: top-2 squared-distance gap below 2^-18 * (|z|^2 + max|c|^2)
+    scale = z.float().pow(2).sum(-1) + cb.float().pow(2).sum(-1).max()
+    assert not (neq & (gap > 2.0 ** -18 * scale)).any(), f"{int(neq.sum())} mismatches, some with a clear gap"
+    assert neq.float().mean().item() < 1e-3
+    # the reported score is |c|^2 - 2 z.c of the chosen code
+    c = cb.float()[idx.long()]
+    want = c.pow(2).sum(-1) - 2 * (z.float() * c).sum(-1)
+    assert torch.allclose(best, want, rtol=1e-4, atol=1e-3)
+
+
+def test_vq_matches_fsq_indices():
+    """cdist/argmin over FSQ.implicit_codebook reproduces FSQ's indices (product code)."""
+    import titok_video_b200 as T
+
+    q = T.FSQ([7, 5, 5, 5, 5]).to(DEV)
+    g = torch.Generator().manual_seed(11)
+    z = (torch.randn((20000, 5), generator=g) * 2).to(BF)
+    codes, d = q(z.to(DEV))
+    idx, _ = _vq_run(codes.cpu(), q.implicit_codebook.cpu().to(BF))
+    # codes are exact grid points up to bf16 rounding of k/3, k/2: nearest codeword is the code itself
+    assert (idx == d["indices"].cpu()).float().mean().item() > 0.999
+
+
+def test_vq_gather_and_loss():
+    N, K, D = 5000, 512, 64
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn((N, D), generator=g).to(BF)
+    cb = torch.randn((K, D), generator=g).to(BF)
+    idx = torch.randint(0, K, (N,), generator=g, dtype=torch.int32)
+    zq = torch.empty((N, D), dtype=BF, device=DEV)
+    loss = torch.zeros(1, dtype=torch.float32, device=DEV)
+    lib().call("ttk_vq_gather_loss", G(z), D, G(cb), D, G(idx), N, D, P(zq), D, P(loss), ST())
+    ref = cb[idx.long()]
+    assert torch.equal(zq.cpu(), ref)
+    want = (ref.float() - z.float()).pow(2).sum().item()
+    assert abs(loss.item() - want) / want < 1e-4
+
+
+def test_bad_arguments_return_errors_not_crashes():
+    L = lib()
+    x = torch.zeros((8, 256), dtype=BF, device=DEV)
+    w = torch.ones(256, device=DEV)
+    assert L.fn("ttk_rmsnorm_fwd")(P(None), 256, P(w), P(x), 256, 8, 256, ST()) == -1
+    assert L.fn("ttk_rmsnorm_fwd")(P(x), 256, P(w), P(x), 256, 8, 200, ST()) == -2
+    assert L.fn("ttk_gemm_bf16")(P(x), 255, P(x), 256, 8, 8, 256, P(None), P(x), 256, P(None), 0, ST()) == -3
+    with pytest.raises(L.TitokB200Error):
+        L.call("ttk_patchify", P(x), P(x), 3, 4, 8, 4, P(x), 768, 1, ST())

@@ -1,0 +1,149 @@
+"""Host-side logic (no GPU): the packing planner, attention work list, weight layout permutation, config loader,
+module / state-dict layout and clip sharding."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, build_model
+from oracle import titok_oracle as O
+from titok_video_b200 import plan as P
+from titok_video_b200.config import AttrDict, load_config, tiny_config
+
+
+def test_plan_layout_matches_reference_packing():
+    shapes, tcs = [(8, 32, 48), (4, 16, 24), (16, 168, 168)], [3, 0, 128]
+    pl = P.make_plan(shapes, tcs, (4, 8, 8))
+    gs = [2 * 4 * 6, 1 * 2 * 3, 4 * 21 * 21]
+    assert (pl.G, pl.T, pl.M) == (sum(gs), 131, sum(gs) + 131)
+    # cu_seqlens = cumsum(grid + tokens)  (blocks.py:81-83)
+    assert pl.cu_seqlens.tolist() == [0, gs[0] + 3, gs[0] + 3 + gs[1], pl.M]
+    # the reference's mask: per clip token_count ones then grid_size zeros (blocks.py:85-86)
+    mask = np.concatenate([np.r_[np.ones(t, bool), np.zeros(g, bool)] for t, g in zip(tcs, gs)])
+    assert np.array_equal(pl.enc_src_row < 0, mask) and np.array_equal(pl.dec_src_row >= 0, mask)
+    assert np.array_equal(np.nonzero(mask)[0], pl.latent_row) and np.array_equal(np.nonzero(~mask)[0], pl.patch_row)
+    assert np.array_equal(pl.enc_src_row[~mask], np.arange(pl.G)) and np.array_equal(pl.dec_src_row[mask], np.arange(pl.T))
+    assert pl.clip_offset == (0, 3 * 8 * 32 * 48, 3 * 8 * 32 * 48 + 3 * 4 * 16 * 24)
+
+
+def test_plan_geometry_reproduces_patchify():
+    """Gathering 16-byte runs at geom offsets == the oracle's einops-equivalent patchify, up to the feature
+    permutation (c p0 p1 p2) <- (p0 p1 p2 c)."""
+    from titok_video_b200.engine import patch_feature_perm
+
+    shapes, tcs, patch = [(8, 16, 24), (4, 32, 8)], [2, 5], (4, 8, 8)
+    clips = O.make_clips(shapes, 0)
+    pl = P.make_plan(shapes, tcs, patch)
+    flat = torch.cat([c.reshape(-1) for c in clips]).float()
+    rows = torch.empty(pl.G, 768)
+    for g in range(pl.G):
+        off, W, HW, THW = pl.geom[g].tolist()
+        for c in range(3):
+            for p0 in range(4):
+                for p1 in range(8):
+                    src = off + c * THW + p0 * HW + p1 * W
+                    rows[g, c * 256 + p0 * 64 + p1 * 8:c * 256 + p0 * 64 + p1 * 8 + 8] = flat[src:src + 8]
+    ref = torch.cat([O.patchify(c.float(), patch) for c in clips])
+    perm = patch_feature_perm(patch, 3)
+    assert torch.equal(rows, ref[:, perm])
+    assert sorted(perm.tolist()) == list(range(768))
+
+
+def test_rope_ids_and_table():
+    ids = P.rope_ids((2, 3, 4), 3)
+    assert ids.shape == (3 + 24, 3)
+    assert ids[:3].tolist() == [[0, 0, 0], [1, 1, 1], [2, 2, 2]]  # latent j -> (j,j,j)
+    assert ids[3].tolist() == [3, 3, 3] and ids[4].tolist() == [3, 3, 4] and ids[3 + 4].tolist() == [3, 4, 3]
+    assert ids[-1].tolist() == [1 + 3, 2 + 3, 3 + 3]
+    inv = P.rope_inv_freqs()
+    assert inv.shape == (10,) and abs(inv[0] - math.pi / 2) < 1e-15 and abs(inv[-1] - 10000 * math.pi / 2) < 1e-9
+    tab = P.rope_table(ids, inv)
+    assert tab.shape == (27, 60) and tab.dtype == np.float32
+    cos, sin = O.rope_cos_sin((2, 3, 4), 3)
+    assert np.allclose(tab.reshape(27, 30, 2)[..., 0], cos.numpy(), atol=1e-6)
+    assert np.allclose(tab.reshape(27, 30, 2)[..., 1], sin.numpy(), atol=1e-6)
+    # lane index = freq*3 + axis: lane 1 uses axis 1 with the lowest frequency
+    assert abs(tab[4, 2 * 2] - math.cos(inv[0] * 4)) < 1e-6  # row 4 = patch (0,0,1)+3 -> axis2 id 4, lane 2
+
+
+@pytest.mark.parametrize("hq,hkv", [(4, 2), (8, 2), (12, 4), (16, 4)])
+def test_attention_work_list_covers_every_query_tile_once(hq, hkv):
+    seq = [1892, 576, 130, 128, 1]
+    starts = np.concatenate([[0], np.cumsum(seq)[:-1]]).tolist()
+    w = P.attn_work_list(starts, seq, hq, hkv)
+    assert w.dtype == np.int32 and w.shape[1] == 12
+    seen = {}
+    ratio = hq // hkv
+    for r in w.tolist():
+        q_row0, q_valid, q_head, kv_head, kv_row0, kv_len = r[0:2], r[2:4], r[4:6], r[6], r[7], r[8]
+        assert kv_row0 in starts and kv_len == seq[starts.index(kv_row0)]
+        for t in range(2):
+            if q_valid[t] == 0:
+                continue
+            assert q_head[t] // ratio == kv_head  # GQA mapping: q head h reads kv head h // ratio
+            assert kv_row0 <= q_row0[t] < kv_row0 + kv_len and (q_row0[t] - kv_row0) % 128 == 0
+            assert q_valid[t] == min(128, kv_row0 + kv_len - q_row0[t])
+            key = (q_row0[t], q_head[t])
+            assert key not in seen
+            seen[key] = 1
+    want = sum(((s + 127) // 128) * hq for s in seq)
+    assert len(seen) == want
+    assert w[:, 8].tolist() == sorted(w[:, 8].tolist(), reverse=True)  # longest sequences first
+
+
+def test_plan_rejects_bad_shapes():
+    with pytest.raises(ValueError):
+        P.make_plan([(8, 30, 32)], [4], (4, 8, 8))
+    with pytest.raises(ValueError):
+        P.make_plan([(8, 32, 32)], [4, 5], (4, 8, 8))
+    with pytest.raises(ValueError):
+        P.make_plan([(32, 32)], [4], (8, 8))
+    pl = P.make_plan([(4, 8, 8)], [0], (4, 8, 8))  # zero latent tokens is a legal (if useless) request
+    assert (pl.M, pl.T, pl.G) == (1, 0, 1)
+
+
+def test_config_schema_accepts_reference_yaml():
+    cfg = load_config(os.path.join(ROOT, "configs", "tiny.yaml"))
+    m = cfg.tokenizer.model
+    assert m.patch_size == [4, 8, 8] and m.fsq_levels == [7, 5, 5, 5, 5] and m.encoder_size == "tiny"
+    assert cfg.training.sampling.train_seq_len == 6144
+    assert isinstance(cfg, AttrDict) and tiny_config().tokenizer.model.decoder_size == "tiny"
+    ref_yaml = "/root/reference/configs/tiny.yaml"
+    if os.path.exists(ref_yaml):  # the reference's own file, verbatim
+        c2 = load_config(ref_yaml)
+        assert c2.tokenizer.model.fsq_levels == m.fsq_levels and c2.tokenizer.model.patch_size == m.patch_size
+
+
+def test_module_layout_and_model_dims():
+    from titok_video_b200.model.base.utils import geglu_inner_dim, get_model_dims
+
+    assert get_model_dims("tiny") == (256, 4, [4, 2], 4.0)
+    assert get_model_dims("small") == (512, 8, [8, 2], 4.0)
+    assert get_model_dims("base") == (768, 12, [12, 4], 4.0)
+    assert get_model_dims("large") == (1024, 24, [16, 4], 4.0)
+    assert [geglu_inner_dim(w) for w in (256, 512, 768, 1024)] == [704, 1376, 2048, 2752]
+    m = build_model(False)
+    sd = m.state_dict()
+    assert len(sd) == 76 and sum(v.numel() for v in sd.values()) == 6828295
+    assert sd["encoder.proj_in.weight"].shape == (256, 768) and sd["encoder.proj_out.weight"].shape == (5, 256)
+    assert sd["decoder.proj_in.weight"].shape == (256, 5) and sd["decoder.proj_out.weight"].shape == (768, 256)
+    assert sd["encoder.model_layers.attn_layer.3.to_qkv.weight"].shape == (768, 256)
+    assert sd["encoder.model_layers.ffd_layer.0.w12.weight"].shape == (1408, 256)
+    assert sd["encoder.model_layers.ffd_layer.0.w3.weight"].shape == (256, 704)
+    assert "encoder.model_layers.attn_post_ln.2.weight" in sd and "encoder.model_layers.attn_post_ln.3.weight" not in sd
+    assert sd["encoder.mask_token"].shape == (1, 1)
+    assert not any(k.startswith("quantize") for k in sd)  # FSQ buffers are non-persistent (fsq.py:64,67,76)
+    assert m.quantize.codebook_size == 4375 and m.quantize._basis.tolist() == [1, 7, 35, 175, 875]
+    assert m.encoder.model_layers.alpha == 8
+
+
+def test_shard_clips_balances_cost():
+    costs = [P.clip_cost(s, t, (4, 8, 8), 256, 4) for s, t in
+             [((16, 168, 168), 128), ((8, 128, 128), 64), ((16, 128, 168), 32), ((8, 168, 168), 1)] * 4]
+    parts = P.shard_clips(costs, 4)
+    assert sorted(i for p in parts for i in p) == list(range(16))
+    loads = [sum(costs[i] for i in p) for p in parts]
+    assert max(loads) / min(loads) < 1.15
+    assert P.shard_clips([1.0], 2) == [[0], []]

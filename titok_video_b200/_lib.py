@@ -1,0 +1,114 @@
+"""ctypes binding of libtitok_b200.so (include/titok_b200.h).
+
+The library is the product: there is no CPU or PyTorch fallback. If the shared object is missing the import of
+this module raises, and every call checks the returned ttk_status and raises RuntimeError(ttk_strerror).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtitok_b200.so")
+
+
+class TitokB200Error(RuntimeError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise TitokB200Error(
+            f"{LIB_PATH} not found: the CUDA extension has not been built. "
+            "Run `python -m titok_video_b200.build` (needs nvcc); there is no CPU fallback."
+        )
+    return ctypes.CDLL(LIB_PATH)
+
+
+_lib = _load()
+
+_vp, _i, _i64, _f = c_void_p, c_int, c_int64, c_float
+_fp = POINTER(c_float)
+_ip = POINTER(c_int32)
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/titok_b200.h exactly
+SIGNATURES = {
+    "ttk_strerror": [_i],
+    "ttk_version": [],
+    "ttk_fsq_fwd": [_vp, _vp, _vp, _i64, _i, _i, _fp, _fp, _fp, _fp, _ip, _ip, _vp],
+    "ttk_fsq_bwd": [_vp, _vp, _vp, _i64, _i, _i, _fp, _fp, _fp, _fp, _ip, _ip, _vp],
+    "ttk_fsq_indices_to_codes": [_vp, _i, _vp, _i, _i64, _i, _fp, _ip, _ip, _vp],
+    "ttk_hist_u32": [_vp, _i64, _i, _vp, _vp],
+    "ttk_codebook_stats": [_vp, _i, _vp, _vp],
+    "ttk_vq_aug_dim": [_i],
+    "ttk_vq_prepare_codebook": [_vp, _i64, _i, _i, _vp, _i64, _vp],
+    "ttk_vq_argmin": [_vp, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp],
+    "ttk_vq_gather_loss": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _i64, _vp, _vp],
+    "ttk_gemm_bf16": [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _i64, _vp, _i, _vp],
+    "ttk_gemm_qkv_rope": [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _vp],
+    "ttk_gemm_geglu": [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i64, _vp],
+    "ttk_gemm_resid_norm256": [_vp, _i64, _vp, _i64, _i, _i, _vp, _i64, _i, _f, _vp, _vp, _vp, _vp, _i64, _vp],
+    "ttk_attn_varlen_fwd": [_vp, _i64, _i, _i, _i, _vp, _i, _f, _vp, _i64, _vp],
+    "ttk_rmsnorm_fwd": [_vp, _i64, _vp, _vp, _i64, _i, _i, _vp],
+    "ttk_resid_norm": [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i64, _vp],
+    "ttk_enc_embed": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp],
+    "ttk_dec_embed": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp],
+    "ttk_enc_head_fsq": [_vp, _i64, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _fp, _fp, _fp, _fp, _ip, _ip, _vp],
+    "ttk_patchify": [_vp, _vp, _i, _i, _i, _i, _vp, _i64, _i64, _vp],
+    "ttk_unpatchify": [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp, _i64, _vp],
+}
+_RESTYPES = {"ttk_strerror": c_char_p}
+
+for _name, _args in SIGNATURES.items():
+    _fn = getattr(_lib, _name)  # AttributeError here == header/library mismatch: fail loudly
+    _fn.argtypes = _args
+    _fn.restype = _RESTYPES.get(_name, c_int)
+
+
+def strerror(status: int) -> str:
+    return _lib.ttk_strerror(int(status)).decode()
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        raise TitokB200Error(f"{what or 'libtitok_b200'} failed: {strerror(status)} (status {status})")
+
+
+def fn(name: str):
+    return getattr(_lib, name)
+
+
+LAUNCHES = 0  # kernels launched through call() since import (every kernel entry point launches exactly one)
+_PROFILER = None  # optional object with begin(name) / end(name, token), see bench.py
+
+
+def set_profiler(p) -> None:
+    global _PROFILER
+    _PROFILER = p
+
+
+def call(name: str, *args) -> None:
+    """Invoke an int-returning kernel entry point and raise on a non-zero status."""
+    global LAUNCHES
+    LAUNCHES += 1
+    if _PROFILER is None:
+        check(getattr(_lib, name)(*args), name)
+    else:
+        tok = _PROFILER.begin(name)
+        check(getattr(_lib, name)(*args), name)
+        _PROFILER.end(name, tok)
+
+
+def version() -> int:
+    return _lib.ttk_version()
+
+
+def float_array(values) -> "ctypes.Array":
+    vals = [float(v) for v in values]
+    return (c_float * len(vals))(*vals)
+
+
+def int_array(values) -> "ctypes.Array":
+    vals = [int(v) for v in values]
+    return (c_int32 * len(vals))(*vals)

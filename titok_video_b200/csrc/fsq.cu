@@ -236,6 +236,7 @@ extern "C" {
 int ttk_fsq_fwd(const void* z, void* codes, int32_t* indices, int64_t n, int dtype, int D, const float* half_l,
                 const float* offset, const float* shift, const float* half_width, const int32_t* basis,
                 const int32_t* levels, cudaStream_t stream) {
+  if (n <= 0) return TTK_OK;  // empty batch: nothing to do (empty tensors have null data pointers)
   if (!z || !codes || !indices) return TTK_ERR_BAD_ARG;
   if (int e = check_device_sm100()) return e;
   FsqConsts c;
@@ -258,6 +259,7 @@ int ttk_fsq_fwd(const void* z, void* codes, int32_t* indices, int64_t n, int dty
 int ttk_fsq_bwd(const void* z, const void* dcodes, void* dz, int64_t n, int dtype, int D, const float* half_l,
                 const float* offset, const float* shift, const float* half_width, const int32_t* basis,
                 const int32_t* levels, cudaStream_t stream) {
+  if (n <= 0) return TTK_OK;
   if (!z || !dcodes || !dz) return TTK_ERR_BAD_ARG;
   if (int e = check_device_sm100()) return e;
   FsqConsts c;
@@ -283,6 +285,7 @@ int ttk_fsq_bwd(const void* z, const void* dcodes, void* dz, int64_t n, int dtyp
 int ttk_fsq_indices_to_codes(const void* idx, int idx_dtype, void* codes, int out_dtype, int64_t n, int D,
                              const float* half_width, const int32_t* basis, const int32_t* levels,
                              cudaStream_t stream) {
+  if (n <= 0) return TTK_OK;
   if (!idx || !codes) return TTK_ERR_BAD_ARG;
   if (int e = check_device_sm100()) return e;
   FsqConsts c;
@@ -312,6 +315,7 @@ int ttk_fsq_indices_to_codes(const void* idx, int idx_dtype, void* codes, int ou
 // counts[K] (uint32, caller-zeroed or accumulated across calls) += histogram of idx[n]; values outside
 // [0, K) are ignored.
 int ttk_hist_u32(const int32_t* idx, int64_t n, int K, uint32_t* counts, cudaStream_t stream) {
+  if (n <= 0) return TTK_OK;
   if (!idx || !counts || K <= 0) return TTK_ERR_BAD_ARG;
   if (int e = check_device_sm100()) return e;
   if (n <= 0) return TTK_OK;

@@ -1,0 +1,304 @@
+"""Launch sequences of the sm_100a kernels for the TiTok encoder / decoder stacks.
+
+This is the only place that talks to libtitok_b200.so. PyTorch is used for device memory, the current CUDA
+stream and (optionally) CUDA-graph capture; all arithmetic happens in the library's kernels.
+
+Per forward the sequence is (reference call stack: model/titok.py:68-74 -> model/base/blocks.py:71-104,148-177
+-> model/base/transformer.py:126-146):
+
+  encoder: patchify -> proj_in GEMM -> embed rows (+pre-norm) -> L x [qkv GEMM+RoPE, attention*sigmoid(gate),
+           out_proj GEMM (+residual/KEEL+next norm), w12 GEMM+GEGLU, w3 GEMM (+residual/KEEL+next norm)]
+           -> latent head + FSQ
+  decoder: embed rows from codes -> L x [...] -> proj_out GEMM -> unpatchify
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .plan import PackedPlan, get_attn_work, make_plan
+
+_vp = ctypes.c_void_p
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return _vp(t.data_ptr()) if t is not None else _vp(0)
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(device: torch.device) -> None:
+    if device.type != "cuda":
+        raise _lib.TitokB200Error(
+            f"titok_video_b200 runs on CUDA sm_100a devices only (got tensors on '{device}'); there is no CPU path"
+        )
+
+
+# --------------------------------------------------------------------------------------------------
+# device-resident plan (metadata uploaded once) + workspace
+# --------------------------------------------------------------------------------------------------
+class DevicePlan:
+    def __init__(self, plan: PackedPlan, device: torch.device):
+        self.plan = plan
+        self.device = device
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
+        self.enc_src_row = up(plan.enc_src_row)
+        self.dec_src_row = up(plan.dec_src_row)
+        self.latent_row = up(plan.latent_row)
+        self.patch_row = up(plan.patch_row)
+        self.geom = up(plan.geom)
+        self.rope = up(plan.rope)
+        self._attn: Dict[Tuple[int, int], torch.Tensor] = {}
+        self.ws: Dict[str, torch.Tensor] = {}
+        self.graphs: Dict[tuple, "torch.cuda.CUDAGraph"] = {}
+
+    def attn_work(self, hq: int, hkv: int) -> torch.Tensor:
+        k = (hq, hkv)
+        if k not in self._attn:
+            w = get_attn_work(self.plan, hq, hkv)
+            self._attn[k] = torch.from_numpy(np.ascontiguousarray(w)).to(self.device)
+        return self._attn[k]
+
+    def buf(self, name: str, shape: Sequence[int], dtype=torch.bfloat16) -> torch.Tensor:
+        t = self.ws.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self.ws[name] = t
+        return t
+
+
+_PLAN_CACHE: Dict[tuple, DevicePlan] = {}
+_PLAN_CACHE_MAX = 64
+
+
+def get_device_plan(grids_px, token_counts, patch_size, channels, device) -> DevicePlan:
+    key = (tuple(tuple(int(v) for v in g) for g in grids_px), tuple(int(t) for t in token_counts),
+           tuple(int(p) for p in patch_size), int(channels), str(device))
+    dp = _PLAN_CACHE.get(key)
+    if dp is None:
+        if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+        dp = DevicePlan(make_plan(key[0], key[1], key[2], key[3]), device)
+        _PLAN_CACHE[key] = dp
+    return dp
+
+
+def clear_caches() -> None:
+    _PLAN_CACHE.clear()
+
+
+# --------------------------------------------------------------------------------------------------
+# prepared weights: bf16 GEMM operands, fp32 norm weights; refreshed in place when parameters change
+# --------------------------------------------------------------------------------------------------
+def patch_feature_perm(patch_size: Sequence[int], channels: int) -> torch.Tensor:
+    """perm[j_new] = j_ref with j_ref = ((p0*P1+p1)*P2+p2)*C + c (einops '(p0 p1 p2 c)', utils.py:26-34) and
+    j_new = ((c*P0+p0)*P1+p1)*P2+p2 (what patchify / unpatchify move as 16-byte runs)."""
+    P0, P1, P2 = patch_size
+    j = torch.arange(channels * P0 * P1 * P2)
+    p2 = j % P2
+    p1 = (j // P2) % P1
+    p0 = (j // (P2 * P1)) % P0
+    c = j // (P2 * P1 * P0)
+    return ((p0 * P1 + p1) * P2 + p2) * channels + c
+
+
+class PreparedStack:
+    """bf16 / fp32 device copies of one TiTokEncoder / TiTokDecoder's parameters in kernel layout."""
+
+    def __init__(self, module, kind: str):
+        self.kind = kind  # 'enc' | 'dec'
+        self.module = module
+        self.sig = None
+        self.t: Dict[str, torch.Tensor] = {}
+
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version, p.dtype) for p in self.module.parameters())
+
+    def _set(self, name: str, value: torch.Tensor, dtype) -> None:
+        cur = self.t.get(name)
+        if cur is not None and cur.shape == value.shape and cur.dtype == dtype and cur.device == value.device:
+            cur.copy_(value.detach())  # keep the address stable: captured CUDA graphs stay valid
+        else:
+            self.t[name] = value.detach().to(dtype, copy=True).contiguous()
+
+    @torch.no_grad()
+    def refresh(self) -> "PreparedStack":
+        sig = self._signature()
+        if sig == self.sig:
+            return self
+        m = self.module
+        bf, f32 = torch.bfloat16, torch.float32
+        perm = patch_feature_perm(m.patch_size_tuple, m.patch_channels).to(m.mask_token.device)
+        self._set("mask_token", m.mask_token.reshape(1), f32)
+        self._set("ln_pre_t", m.ln_pre_t.weight, f32)
+        self._set("ln_pre_p", m.ln_pre_p.weight, f32)
+        self._set("ln_post", m.ln_post.weight, f32)
+        if self.kind == "enc":
+            self._set("proj_in_w", m.proj_in.weight[:, perm], bf)
+            self._set("proj_in_b", m.proj_in.bias, bf)
+            self._set("proj_out_w", m.proj_out.weight, bf)
+            self._set("proj_out_b", m.proj_out.bias, bf)
+        else:
+            self._set("proj_in_w", m.proj_in.weight, bf)
+            self._set("proj_in_b", m.proj_in.bias, bf)
+            self._set("proj_out_w", m.proj_out.weight[perm, :], bf)
+            self._set("proj_out_b", m.proj_out.bias[perm], bf)
+        ml = m.model_layers
+        for i in range(m.num_layers):
+            a, f = ml.attn_layer[i], ml.ffd_layer[i]
+            self._set(f"pre_ln{i}", a.pre_ln.weight, f32)
+            self._set(f"to_qkv{i}", a.to_qkv.weight, bf)
+            self._set(f"out_proj{i}", a.out_proj.weight, bf)
+            self._set(f"ffn_norm{i}", f.norm.weight, f32)
+            self._set(f"w12_{i}", f.w12.weight, bf)
+            self._set(f"w3_{i}", f.w3.weight, bf)
+            if i > 0:
+                self._set(f"attn_post_ln{i}", ml.attn_post_ln[i - 1].weight, f32)
+                self._set(f"ffd_post_ln{i}", ml.ffd_post_ln[i - 1].weight, f32)
+        self.sig = sig
+        return self
+
+
+def prepared(module, kind: str) -> PreparedStack:
+    ps = module.__dict__.get("_ttk_prepared")
+    if ps is None or ps.kind != kind:
+        ps = PreparedStack(module, kind)
+        module.__dict__["_ttk_prepared"] = ps
+    return ps.refresh()
+
+
+# --------------------------------------------------------------------------------------------------
+# launch sequences
+# --------------------------------------------------------------------------------------------------
+FUSE_RESID_256 = os.environ.get("TTK_FUSE_RESID", "1") != "0"
+
+
+def _layers(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tensor) -> None:
+    """ResidualAttentionBlock.forward (transformer.py:126-146). x, xn are updated in place; on return xn holds
+    RMSNorm(x) * ln_post.weight for every packed row."""
+    M, w = x.shape
+    hq, hkv = m.heads
+    gqa = hkv * 64
+    inner = m.inner_dim
+    L = m.num_layers
+    alpha = float(2 * L)
+    st = _stream()
+    qkv = dp.buf("qkv", (M, 2 * w + 2 * gqa))
+    att = dp.buf("att", (M, w))
+    h = dp.buf("h", (M, inner))
+    y = None if (FUSE_RESID_256 and w == 256) else dp.buf("y", (M, w))
+    work = dp.attn_work(hq, hkv)
+    scale = 1.0 / math.sqrt(64.0)
+    T = W.t
+
+    def out_update(a: torch.Tensor, wmat: torch.Tensor, K: int, mode: int, w_post, w_next) -> None:
+        if y is None:
+            _lib.call("ttk_gemm_resid_norm256", _ptr(a), a.stride(0), _ptr(wmat), wmat.stride(0), M, K, _ptr(x),
+                      x.stride(0), mode, alpha, _ptr(w_post), _ptr(w_next), _ptr(x), _ptr(xn), x.stride(0), st)
+        else:
+            _lib.call("ttk_gemm_bf16", _ptr(a), a.stride(0), _ptr(wmat), wmat.stride(0), M, w, K, _vp(0), _ptr(y),
+                      y.stride(0), _vp(0), 0, st)
+            _lib.call("ttk_resid_norm", _ptr(x), _ptr(y), _ptr(x), _ptr(xn), _ptr(w_post), _ptr(w_next), alpha, mode,
+                      M, w, x.stride(0), st)
+
+    for i in range(L):
+        mode = 0 if i == 0 else 1
+        _lib.call("ttk_gemm_qkv_rope", _ptr(xn), xn.stride(0), _ptr(T[f"to_qkv{i}"]), w, M, w, w, gqa, _ptr(dp.rope),
+                  _ptr(qkv), qkv.stride(0), st)
+        _lib.call("ttk_attn_varlen_fwd", _ptr(qkv), qkv.stride(0), M, w, gqa, _ptr(work), work.shape[0], scale,
+                  _ptr(att), att.stride(0), st)
+        out_update(att, T[f"out_proj{i}"], w, mode, T.get(f"attn_post_ln{i}"), T[f"ffn_norm{i}"])
+        _lib.call("ttk_gemm_geglu", _ptr(xn), xn.stride(0), _ptr(T[f"w12_{i}"]), w, M, inner, w, _ptr(h), h.stride(0),
+                  st)
+        w_next = T[f"pre_ln{i + 1}"] if i + 1 < L else T["ln_post"]
+        out_update(h, T[f"w3_{i}"], inner, mode, T.get(f"ffd_post_ln{i}"), w_next)
+
+
+def encoder_launch(m, dp: DevicePlan, clips_flat: torch.Tensor, fsq_consts) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """TiTokEncoder.forward (+ FSQ.forward) on a flat bf16 clip buffer. Returns (z, codes, indices) workspace
+    tensors: z/codes bf16 [T, token_size], indices int32 [T]."""
+    W = prepared(m, "enc")
+    pl = dp.plan
+    M, G, Tn, w = pl.M, pl.G, pl.T, m.width
+    P0, P1, P2 = pl.patch_size
+    feat = pl.channels * P0 * P1 * P2
+    st = _stream()
+    patches = dp.buf("patches", (G, feat))
+    proj = dp.buf("proj", (G, w))
+    x = dp.buf("x", (M, w))
+    xn = dp.buf("xn", (M, w))
+    ts = m.token_size
+    z = dp.buf("z", (max(Tn, 1), ts))
+    codes = dp.buf("codes", (max(Tn, 1), ts))
+    idx = dp.buf("idx", (max(Tn, 1),), torch.int32)
+    T = W.t
+    _lib.call("ttk_patchify", _ptr(clips_flat), _ptr(dp.geom), pl.channels, P0, P1, P2, _ptr(patches), feat, G, st)
+    _lib.call("ttk_gemm_bf16", _ptr(patches), feat, _ptr(T["proj_in_w"]), feat, G, w, feat, _ptr(T["proj_in_b"]),
+              _ptr(proj), w, _vp(0), 0, st)
+    _lib.call("ttk_enc_embed", _ptr(proj), w, _ptr(dp.enc_src_row), _ptr(T["mask_token"]), _ptr(T["ln_pre_t"]),
+              _ptr(T["ln_pre_p"]), _ptr(T["pre_ln0"]), _ptr(x), _ptr(xn), M, w, w, st)
+    _layers(m, W, dp, x, xn)
+    half_l, offset, shift, half_width, basis, levels = fsq_consts
+    _lib.call("ttk_enc_head_fsq", _ptr(xn), w, _ptr(dp.latent_row), _ptr(T["ln_post"]), 1, _ptr(T["proj_out_w"]),
+              _ptr(T["proj_out_b"]), ts, _ptr(z), _ptr(codes), _ptr(idx), Tn, w, half_l, offset, shift, half_width,
+              basis, levels, st)
+    return z[:Tn], codes[:Tn], idx[:Tn]
+
+
+def decoder_launch(m, dp: DevicePlan, codes: torch.Tensor, out_flat: torch.Tensor) -> torch.Tensor:
+    """TiTokDecoder.forward: codes bf16 [T, token_size] -> out_flat bf16 [sum 3*T*H*W]."""
+    W = prepared(m, "dec")
+    pl = dp.plan
+    M, G, w = pl.M, pl.G, m.width
+    P0, P1, P2 = pl.patch_size
+    feat = pl.channels * P0 * P1 * P2
+    st = _stream()
+    x = dp.buf("x", (M, w))
+    xn = dp.buf("xn", (M, w))
+    rows = dp.buf("rows", (M, feat))
+    T = W.t
+    _lib.call("ttk_dec_embed", _ptr(codes), m.token_size, _ptr(dp.dec_src_row), _ptr(T["proj_in_w"]),
+              _ptr(T["proj_in_b"]), _ptr(T["mask_token"]), _ptr(T["ln_pre_t"]), _ptr(T["ln_pre_p"]), _ptr(T["pre_ln0"]),
+              _ptr(x), _ptr(xn), M, w, w, st)
+    _layers(m, W, dp, x, xn)
+    _lib.call("ttk_gemm_bf16", _ptr(xn), w, _ptr(T["proj_out_w"]), w, M, feat, w, _ptr(T["proj_out_b"]), _ptr(rows),
+              feat, _vp(0), 0, st)
+    _lib.call("ttk_unpatchify", _ptr(rows), feat, _ptr(dp.patch_row), _ptr(dp.geom), pl.channels, P0, P1, P2,
+              _ptr(out_flat), G, st)
+    return out_flat
+
+
+# --------------------------------------------------------------------------------------------------
+# helpers for the module layer
+# --------------------------------------------------------------------------------------------------
+def to_host_ints(v) -> List[int]:
+    """token_counts / grids as Python ints. A CUDA tensor costs one device sync (the reference syncs many
+    times per forward here, blocks.py:85-86); pass CPU tensors or lists to avoid it."""
+    if isinstance(v, torch.Tensor):
+        return v.detach().cpu().tolist()
+    return [(to_host_ints(e) if isinstance(e, (list, tuple, torch.Tensor)) else int(e)) for e in v]
+
+
+def flatten_clips(videos: Sequence[torch.Tensor], dp: DevicePlan, name: str = "clips_in") -> torch.Tensor:
+    """Concatenate the clips into the plan's static flat bf16 input buffer (one cat kernel)."""
+    buf = dp.buf(name, (dp.plan.total_numel,))
+    if len(videos) == 1 and videos[0].dtype == torch.bfloat16 and videos[0].is_contiguous():
+        buf.copy_(videos[0].reshape(-1))
+    else:
+        torch.cat([v.reshape(-1).to(torch.bfloat16) for v in videos], out=buf)
+    return buf
+
+
+def split_clips(flat: torch.Tensor, plan: PackedPlan) -> List[torch.Tensor]:
+    out = []
+    for off, n, g in zip(plan.clip_offset, plan.clip_numel, plan.grids_px):
+        out.append(flat[off:off + n].view(plan.channels, *g))
+    return out

@@ -1,0 +1,73 @@
+"""TiTok model facade with the API of the reference's model/titok.py:
+`TiTok(config)`, `.encoder/.quantize/.decoder`, `encode`, `decode`, `decode_indices`, `forward`.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import engine
+from .base.blocks import TiTokDecoder, TiTokEncoder
+from .base.utils import init_weights
+from .quantizer.fsq import FSQ
+
+
+class TiTok(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        conf = config.tokenizer.model
+        token_size = len(conf.fsq_levels)
+        self.encoder = TiTokEncoder(model_size=conf.encoder_size, patch_size=conf.patch_size, in_channels=3,
+                                    out_channels=token_size)
+        self.quantize = FSQ(levels=list(conf.fsq_levels))
+        self.decoder = TiTokDecoder(model_size=conf.decoder_size, patch_size=conf.patch_size, in_channels=token_size,
+                                    out_channels=3)
+        self.apply(init_weights)
+
+    # ---- titok.py:47-52 -------------------------------------------------------------------------
+    def encode(self, x: Sequence[torch.Tensor], token_counts, grids=None, split_indices: bool = False):
+        """x_q [sum(token_counts), token_size] in the clips' dtype, {'indices': int32 [sum(token_counts)]}.
+        split_indices=True returns a tuple of per-clip index tensors (the reference's intent; its own
+        torch.split call fails for tensor token_counts)."""
+        _, codes, idx, _ = self.encoder.forward_impl(x, token_counts, grids, fsq=self.quantize)
+        x_q = codes.clone().to(x[0].dtype)
+        indices = idx.clone()
+        if split_indices:
+            indices = torch.split(indices, engine.to_host_ints(token_counts), dim=0)
+        return x_q, {"indices": indices}
+
+    # ---- titok.py:54-62 -------------------------------------------------------------------------
+    def decode_indices(self, indices, grids, token_counts=None):
+        if token_counts is None:
+            assert type(indices) in [list, tuple]
+            token_counts = [int(t.shape[0]) for t in indices]
+            indices = torch.cat(list(indices), dim=0)
+        x_q = self.quantize.indices_to_codes(indices, out_dtype=torch.bfloat16)
+        return self.decoder(x_q, token_counts, grids)
+
+    # ---- titok.py:64-66 -------------------------------------------------------------------------
+    def decode(self, x, token_counts, grids):
+        return self.decoder(x, token_counts, grids)
+
+    # ---- titok.py:68-74 -------------------------------------------------------------------------
+    def forward(self, x: Sequence[torch.Tensor], token_counts):
+        """list of reconstructed clips [3,T,H,W] (input dtype) and {'indices': int32}."""
+        grids = [tuple(v.shape[1:]) for v in x]
+        tcs = engine.to_host_ints(token_counts)
+        _, codes, idx, dp = self.encoder.forward_impl(x, tcs, grids, fsq=self.quantize)
+        out, _ = self.decoder.forward_impl(codes, tcs, grids)
+        recon = engine.split_clips(out.clone().to(x[0].dtype), dp.plan)
+        return recon, {"indices": idx.clone()}
+
+    # ---- throughput path: no defensive copies, results live in the plan's workspace ---------------
+    @torch.no_grad()
+    def tokenize_reconstruct_(self, x: Sequence[torch.Tensor], token_counts):
+        """forward() without the output clones: the returned clips / indices alias workspace buffers that the next
+        call with the same shapes overwrites. Used by bench.py and batch jobs that consume results immediately."""
+        grids = [tuple(v.shape[1:]) for v in x]
+        _, codes, idx, dp = self.encoder.forward_impl(x, token_counts, grids, fsq=self.quantize)
+        out, _ = self.decoder.forward_impl(codes, token_counts, grids)
+        return engine.split_clips(out, dp.plan), {"indices": idx}

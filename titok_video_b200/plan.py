@@ -1,0 +1,201 @@
+"""Host-side metadata planner for a packed (variable-length) batch of clips.
+
+Everything TiTokEncoder.forward / TiTokDecoder.forward derive on the device with synchronising ops
+(reference model/base/blocks.py:72-89,154-162 and RoPE.forward, model/base/rope.py:57-71) is derived here from
+Python ints with numpy, once per (shapes, token_counts) signature, with zero device syncs:
+
+  * packed row layout: per clip, `token_count` latent rows followed by the patch rows (blocks.py:85-86)
+  * cu_seqlens (blocks.py:81-83)
+  * gather / scatter maps between packed rows, latent tokens and patches
+  * patch geometry for patchify / unpatchify (model/base/utils.py:26-51)
+  * the RoPE table: fp64 angles -> fp32 (cos, sin), 30 complex lanes per token (rope.py:40-54)
+  * the attention work list (pairs of 128-row query tiles sharing one K/V stream)
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+ATTN_TILE = 128
+ROPE_LANES_PER_AXIS = 10  # head_dim 64 // (3 axes * 2)
+
+
+@dataclass
+class PackedPlan:
+    # batch description (host ints)
+    grids_px: Tuple[Tuple[int, ...], ...]  # per clip (T, H, W) in pixels
+    grids: Tuple[Tuple[int, ...], ...]  # per clip (T/p0, H/p1, W/p2) in patches
+    token_counts: Tuple[int, ...]
+    patch_size: Tuple[int, ...]
+    channels: int
+    # derived sizes
+    M: int = 0  # packed rows
+    T: int = 0  # latent tokens
+    G: int = 0  # patches
+    seq_lens: Tuple[int, ...] = ()
+    clip_numel: Tuple[int, ...] = ()
+    clip_offset: Tuple[int, ...] = ()
+    total_numel: int = 0
+    # numpy metadata (uploaded by the engine)
+    cu_seqlens: np.ndarray = None  # int32 [B+1]
+    enc_src_row: np.ndarray = None  # int32 [M]: patch index or -1 (latent)
+    dec_src_row: np.ndarray = None  # int32 [M]: latent token index or -1 (patch)
+    latent_row: np.ndarray = None  # int32 [T]
+    patch_row: np.ndarray = None  # int32 [G]
+    geom: np.ndarray = None  # int64 [G,4]: offset, W, H*W, T*H*W
+    rope: np.ndarray = None  # float32 [M,60]
+    attn_work: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)  # (hq,hkv) -> int32 [n,12]
+
+    @property
+    def key(self):
+        return (self.grids_px, self.token_counts, self.patch_size, self.channels)
+
+
+def rope_inv_freqs(theta: float = 10000.0, n: int = ROPE_LANES_PER_AXIS) -> np.ndarray:
+    """theta ** linspace(0, 1, n) * pi / 2 in float64 (rope.py:42-45). Evaluated with torch on the host so the
+    ten frequencies are bit-identical to the reference's buffer (angles reach ~2.4e6 rad)."""
+    import torch
+
+    f = torch.pow(theta, torch.linspace(0.0, 1.0, n, dtype=torch.float64)) * torch.pi / 2.0
+    return f.numpy().copy()
+
+
+def rope_ids(grid: Sequence[int], token_count: int) -> np.ndarray:
+    """Position ids [token_count + prod(grid), len(grid)]: latent j -> (j,..,j); patch (a,b,c) -> (a,b,c)+token_count
+    with the last axis fastest (torch.cartesian_prod order, rope.py:61-66)."""
+    nd = len(grid)
+    tok = np.repeat(np.arange(token_count, dtype=np.float64)[:, None], nd, axis=1)
+    axes = np.meshgrid(*[np.arange(g, dtype=np.float64) for g in grid], indexing="ij")
+    pat = np.stack([a.reshape(-1) for a in axes], axis=-1) + float(token_count)
+    return np.concatenate([tok, pat], axis=0)
+
+
+def rope_table(ids: np.ndarray, inv_freqs: np.ndarray) -> np.ndarray:
+    """(cos, sin) pairs, float32 [L, n_freq*n_axes*2]; complex lane index = freq * n_axes + axis (interleaved
+    layout of rope.py:49-53); angles are formed in float64 and only the final cos/sin are rounded to float32
+    (apply_rotary_emb casts the complex128 table to complex64, rope.py:24)."""
+    ang = inv_freqs[None, :, None] * ids[:, None, :]  # [L, F, A]
+    ang = ang.reshape(ids.shape[0], -1)
+    out = np.empty((ids.shape[0], ang.shape[1], 2), dtype=np.float32)
+    out[..., 0] = np.cos(ang)
+    out[..., 1] = np.sin(ang)
+    return out.reshape(ids.shape[0], -1)
+
+
+def attn_work_list(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: int, hkv: int) -> np.ndarray:
+    """int32 [n, 12] records {q_row0[2], q_valid[2], q_head[2], kv_head, kv_row0, kv_len, pad[3]} (csrc/attn.cu).
+    Two query tiles per record share one kv head: two heads of the same group when the group size is even,
+    otherwise two consecutive row tiles of one head. Longest sequences first (LPT) to shorten the tail."""
+    ratio = hq // hkv
+    recs: List[List[int]] = []
+    for start, slen in zip(seq_starts, seq_lens):
+        n_tiles = (slen + ATTN_TILE - 1) // ATTN_TILE
+        if ratio % 2 == 0:
+            for ti in range(n_tiles):
+                r0 = start + ti * ATTN_TILE
+                valid = min(ATTN_TILE, slen - ti * ATTN_TILE)
+                for h in range(0, hq, 2):
+                    recs.append([r0, r0, valid, valid, h, h + 1, h // ratio, start, slen, 0, 0, 0])
+        else:
+            for h in range(hq):
+                for ti in range(0, n_tiles, 2):
+                    r0 = start + ti * ATTN_TILE
+                    v0 = min(ATTN_TILE, slen - ti * ATTN_TILE)
+                    if ti + 1 < n_tiles:
+                        r1 = r0 + ATTN_TILE
+                        v1 = min(ATTN_TILE, slen - (ti + 1) * ATTN_TILE)
+                    else:
+                        r1, v1 = r0, 0
+                    recs.append([r0, r1, v0, v1, h, h, h // ratio, start, slen, 0, 0, 0])
+    recs.sort(key=lambda r: -r[8])
+    return np.asarray(recs, dtype=np.int32).reshape(-1, 12)
+
+
+def make_plan(grids_px: Sequence[Sequence[int]], token_counts: Sequence[int], patch_size: Sequence[int],
+              channels: int = 3) -> PackedPlan:
+    patch_size = tuple(int(p) for p in patch_size)
+    grids_px = tuple(tuple(int(v) for v in g) for g in grids_px)
+    token_counts = tuple(int(t) for t in token_counts)
+    if len(grids_px) != len(token_counts):
+        raise ValueError("one token count per clip is required")
+    if len(patch_size) != 3:
+        raise ValueError("the CUDA path supports 3-D (T,H,W) patching only")
+    grids = []
+    for g in grids_px:
+        if len(g) != 3 or any(v <= 0 or v % p for v, p in zip(g, patch_size)):
+            raise ValueError(f"clip shape {g} is not a positive multiple of patch size {patch_size}")
+        grids.append(tuple(v // p for v, p in zip(g, patch_size)))
+    if any(t < 0 for t in token_counts):
+        raise ValueError("token counts must be non-negative")
+    plan = PackedPlan(grids_px=grids_px, grids=tuple(grids), token_counts=token_counts, patch_size=patch_size,
+                      channels=channels)
+
+    inv = rope_inv_freqs()
+    gsz = [int(np.prod(g)) for g in grids]
+    seq = [g + t for g, t in zip(gsz, token_counts)]
+    plan.seq_lens = tuple(seq)
+    plan.cu_seqlens = np.concatenate([[0], np.cumsum(seq)]).astype(np.int32)
+    plan.M, plan.T, plan.G = int(sum(seq)), int(sum(token_counts)), int(sum(gsz))
+    numel = [channels * t * h * w for (t, h, w) in grids_px]
+    plan.clip_numel = tuple(numel)
+    plan.clip_offset = tuple(int(v) for v in np.concatenate([[0], np.cumsum(numel)[:-1]]))
+    plan.total_numel = int(sum(numel))
+
+    enc_src = np.full(plan.M, -1, dtype=np.int32)
+    dec_src = np.full(plan.M, -1, dtype=np.int32)
+    latent_row = np.empty(plan.T, dtype=np.int32)
+    patch_row = np.empty(plan.G, dtype=np.int32)
+    geom = np.empty((plan.G, 4), dtype=np.int64)
+    rope = np.empty((plan.M, 2 * 3 * ROPE_LANES_PER_AXIS), dtype=np.float32)
+    row = tok = pat = 0
+    p0, p1, p2 = patch_size
+    for b, (g, tc) in enumerate(zip(grids, token_counts)):
+        T_, H_, W_ = grids_px[b]
+        ng = gsz[b]
+        latent_row[tok:tok + tc] = np.arange(row, row + tc)
+        dec_src[row:row + tc] = np.arange(tok, tok + tc)
+        patch_row[pat:pat + ng] = np.arange(row + tc, row + tc + ng)
+        enc_src[row + tc:row + tc + ng] = np.arange(pat, pat + ng)
+        d0, d1, d2 = np.meshgrid(np.arange(g[0]), np.arange(g[1]), np.arange(g[2]), indexing="ij")
+        off = plan.clip_offset[b] + (d0.reshape(-1) * p0) * (H_ * W_) + (d1.reshape(-1) * p1) * W_ + d2.reshape(-1) * p2
+        geom[pat:pat + ng, 0] = off
+        geom[pat:pat + ng, 1] = W_
+        geom[pat:pat + ng, 2] = H_ * W_
+        geom[pat:pat + ng, 3] = T_ * H_ * W_
+        rope[row:row + tc + ng] = rope_table(rope_ids(g, tc), inv)
+        row += tc + ng
+        tok += tc
+        pat += ng
+    plan.enc_src_row, plan.dec_src_row = enc_src, dec_src
+    plan.latent_row, plan.patch_row, plan.geom, plan.rope = latent_row, patch_row, geom, rope
+    return plan
+
+
+def get_attn_work(plan: PackedPlan, hq: int, hkv: int) -> np.ndarray:
+    k = (hq, hkv)
+    if k not in plan.attn_work:
+        plan.attn_work[k] = attn_work_list(plan.cu_seqlens[:-1].tolist(), plan.seq_lens, hq, hkv)
+    return plan.attn_work[k]
+
+
+def shard_clips(costs: Sequence[float], world_size: int) -> List[List[int]]:
+    """Greedy longest-processing-time partition of clip indices over ranks (balance by cost).
+    Returns, per rank, the sorted list of clip indices it owns."""
+    order = sorted(range(len(costs)), key=lambda i: -costs[i])
+    loads = [0.0] * world_size
+    out: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda j: (loads[j], j))
+        out[r].append(i)
+        loads[r] += costs[i]
+    return [sorted(o) for o in out]
+
+
+def clip_cost(grid_px: Sequence[int], token_count: int, patch_size: Sequence[int], width: int, layers: int) -> float:
+    """Forward FLOPs of one clip through one stack: linear part + quadratic attention part."""
+    g = math.prod(v // p for v, p in zip(grid_px, patch_size))
+    s = g + token_count
+    return layers * (s * 1605632.0 * (width / 256.0) ** 2 + 4.0 * s * s * width)
