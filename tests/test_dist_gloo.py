@@ -1,0 +1,91 @@
+"""world_size-2 `gloo` tests of the multi-GPU plumbing on CPU: clip sharding is a deterministic partition, the
+histogram all-reduce equals the single-process histogram, gathered indices come back in clip order. The per-rank
+"tokeniser" here is the CPU oracle's FSQ (the CUDA forward needs a GPU); the property under test -- a sharded job
+produces exactly the single-process result on the concatenated batch -- does not depend on which it is."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+LEVELS = [7, 5, 5, 5, 5]
+SHAPES = [(16, 168, 168), (8, 128, 128), (8, 168, 128), (16, 128, 128), (12, 136, 152)]
+TCS = [128, 64, 17, 1, 90]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _z_for_clip(i):
+    g = torch.Generator().manual_seed(100 + i)
+    return (torch.randn((TCS[i], 5), generator=g) * 2).to(torch.bfloat16)
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import titok_oracle as O
+    from titok_video_b200 import dist as D
+
+    owned = D.shard_batch(SHAPES, TCS)
+    local_idx = [O.fsq_forward(_z_for_clip(i).float(), LEVELS)[1] for i in owned]
+    counts = torch.zeros(4375, dtype=torch.int64)
+    for t in local_idx:
+        counts += torch.bincount(t.long(), minlength=4375)
+    D.allreduce_counts(counts)
+    gathered = D.gather_indices(local_idx, owned, len(SHAPES), dst=0)
+    torch.save({"owned": owned, "counts": counts, "gathered": gathered}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_job_equals_single_process(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
+    # partition
+    assert sorted(res[0]["owned"] + res[1]["owned"]) == list(range(len(SHAPES)))
+    assert not set(res[0]["owned"]) & set(res[1]["owned"])
+    # single-process result on the concatenated batch
+    from oracle import titok_oracle as O
+
+    ref = [O.fsq_forward(_z_for_clip(i).float(), LEVELS)[1] for i in range(len(SHAPES))]
+    ref_counts = torch.bincount(torch.cat(ref).long(), minlength=4375)
+    for r in range(world):
+        assert torch.equal(res[r]["counts"], ref_counts)
+    assert res[1]["gathered"] is None
+    for a, b in zip(res[0]["gathered"], ref):
+        assert torch.equal(a, b)
+
+
+def test_sharding_is_balanced_and_rank_independent():
+    from titok_video_b200.plan import clip_cost, shard_clips
+
+    costs = [clip_cost(s, t, (4, 8, 8), 256, 4) for s, t in zip(SHAPES * 4, TCS * 4)]
+    parts = shard_clips(costs, 8)
+    assert sorted(i for p in parts for i in p) == list(range(20))
+    loads = [sum(costs[i] for i in p) for p in parts]
+    assert max(loads) <= 1.5 * (sum(costs) / 8)
+
+
+def test_single_process_helpers_are_noops():
+    from titok_video_b200 import dist as D
+
+    assert D.shard_batch(SHAPES, TCS) == list(range(len(SHAPES)))
+    c = torch.arange(5)
+    assert D.allreduce_counts(c) is c
+    out = D.gather_indices([torch.tensor([1, 2]), torch.tensor([3])], [1, 0], 2)
+    assert out[0].tolist() == [3] and out[1].tolist() == [1, 2]

@@ -67,7 +67,9 @@ def close_bf16(out, ref, ulps=2.0, atol=None, what=""):
     scale = ref.abs().max().item() + 1e-20
     atol = (2.0 ** -8) * scale * 0.05 if atol is None else atol
     d = (o - ref).abs()
-    tol = ulps * (2.0 ** -8) * ref.abs() + atol
+    # one bf16 ulp of ref is 2^(floor(log2|ref|) - 7): between 2^-8 |ref| (top of a binade) and 2^-7 |ref| (bottom)
+    ulp = torch.exp2(torch.floor(torch.log2(ref.abs().clamp_min(1e-30))) - 7.0)
+    tol = ulps * ulp + atol
     bad = (d > tol)
     assert torch.isfinite(o).all(), f"{what}: non-finite output"
     assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} outside {ulps} bf16 ulp; max|d|={d.max().item():.4g} "

@@ -52,6 +52,12 @@ constexpr int AT_KV_BYTES = AT_BN * AT_D * 2;  // 16 KB
 constexpr int AT_P_BYTES = AT_BM * AT_BN * 2;  // 32 KB (two 64-key swizzle atoms)
 constexpr int AT_SMEM = 2 * AT_Q_BYTES + 2 * AT_KST * AT_KV_BYTES + 2 * AT_P_BYTES + 512 + 1024;
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -117,7 +123,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_ptr;
   // TMEM columns: S0 [0,128) S1 [128,256) PV0 [256,320) PV1 [320,384)
 
+  // Register re-distribution: the producer / MMA / allocator warpgroup needs few registers; each softmax
+  // thread keeps a 128-key score row plus its 64-wide fp32 output row live (12 warps x 168 = 4 x 40 + 8 x 232).
+  // (setmaxnreg sits at the top of each role branch so that ptxas allocates registers per role.)
+
   if (warp == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (elect_one()) {
       const uint32_t q_bytes = (act0 ? AT_Q_BYTES : 0) + (act1 ? AT_Q_BYTES : 0);
       mbar_arrive_expect_tx(q_full, q_bytes);
@@ -136,6 +147,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     __syncwarp();
   } else if (warp == 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);  // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_D, 0, 1);   // P (K-major) x V (MN-major)
@@ -203,7 +215,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int t = (warp - 4) >> 2;  // query tile of this softmax group
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row within the tile == TMEM lane
@@ -220,100 +235,80 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t par = j & 1;
-        // fold in P V of the previous kv tile (its MMA ran while we were idle / the other tile worked)
-        if (j > 0) {
-          mbar_wait(&pv_full[t], (j - 1) & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int c0 = 0; c0 < AT_D; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_pv + c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[c0 + i] += __uint_as_float(v[i]);
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&pv_empty[t]);
-        }
-
+        // ---- S(j): the whole 128-key row into registers with one wait, then hand S back to the tensor core
         mbar_wait(&s_full[t], par);
         tc_fence_after();
-        const int kv_valid = w.kv_len - j * AT_BN;  // >= 1; < 128 only for the last tile
-        // pass 1: row max
-        float m_tile = -INFINITY;
-#pragma unroll 1
-        for (int c0 = 0; c0 < AT_BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_s + c0, v);
-          tmem_ld_wait();
-          if (c0 + 32 <= kv_valid) {
+        uint32_t sv[AT_BN];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(v[i]));
-          } else {
+        for (int c0 = 0; c0 < AT_BN; c0 += 32)
+          tmem_ld_32x32b_x32(t_s + c0, *reinterpret_cast<uint32_t(*)[32]>(&sv[c0]));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[t]);  // S(j+1) = Q K(j+1)^T may now overwrite the accumulator
+
+        const int kv_valid = w.kv_len - j * AT_BN;  // >= 1; < 128 only for the clip's last kv tile
+        if (kv_valid < AT_BN) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c0 + i < kv_valid) m_tile = fmaxf(m_tile, __uint_as_float(v[i]));
-          }
+          for (int i = 0; i < AT_BN; ++i)
+            if (i >= kv_valid) sv[i] = 0xff800000u;  // -inf: exp2 -> 0, never the max
         }
+        float m_tile = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
+#pragma unroll
+        for (int i = 2; i < AT_BN; i += 2)
+          m_tile = fmax3(m_tile, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
         const float m_new = fmaxf(m_run, m_tile);
         const float alpha = ex2_approx((m_run - m_new) * c);  // 0 on the first tile
         const float mc = m_new * c;
-        // P buffer of kv tile j-1 must have been consumed by its P V MMA
-        if (j > 0) mbar_wait(&p_empty[t], (j - 1) & 1);
-        // pass 2: p = 2^(s*c - m*c), row sum, bf16 P -> swizzled smem (A operand of P V)
-        float l_tile = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < AT_BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_s + c0, v);
+
+        // ---- fold in P V of the previous kv tile (its MMA ran while the other query tile was busy)
+        if (j > 0) {
+          mbar_wait(&pv_full[t], (j - 1) & 1);
+          tc_fence_after();
+          uint32_t v[AT_D];
+          tmem_ld_32x32b_x32(t_pv, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld_32x32b_x32(t_pv + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
           tmem_ld_wait();
-          uint32_t pk[16];
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&pv_empty[t]);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0 = ex2_approx(__uint_as_float(v[2 * i]) * c - mc);
-            float p1 = ex2_approx(__uint_as_float(v[2 * i + 1]) * c - mc);
-            if (c0 + 2 * i >= kv_valid) p0 = 0.f;
-            if (c0 + 2 * i + 1 >= kv_valid) p1 = 0.f;
-            // the row sum uses the bf16-rounded probabilities that the P V product sees
-            const uint32_t pp = pack_bf16x2(p0, p1);
-            l_tile += bf16_lo(pp) + bf16_hi(pp);
-            pk[i] = pp;
-          }
-          uint8_t* atom = myP + (c0 >> 6) * (AT_BM * 128);
-          const uint32_t ch0 = (c0 & 63) >> 3;  // first 16-byte chunk of this 32-key group inside the atom
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(atom + sw128_offset(r, ch0 + q)) =
-                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          for (int i = 0; i < AT_D; ++i) o[i] = (o[i] + __uint_as_float(v[i])) * alpha;
         }
-        // S(j) fully read -> tensor core may overwrite it with S(j+1)
-        tc_fence_before();
+
+        // ---- P(j) = 2^(s*c - m*c) as bf16 into swizzled smem (A operand of P V); row sum in fp32
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < AT_BN; i += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), c, -mc));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), c, -mc));
+          l0 += p0;
+          l1 += p1;
+          sv[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        if (j > 0) mbar_wait(&p_empty[t], (j - 1) & 1);  // P V(j-1) has consumed the P buffer
+#pragma unroll
+        for (int q = 0; q < AT_BN / 8; ++q) {
+          uint8_t* atom = myP + (q >> 3) * (AT_BM * 128);
+          *reinterpret_cast<uint4*>(atom + sw128_offset(r, q & 7)) =
+              make_uint4(sv[4 * q], sv[4 * q + 1], sv[4 * q + 2], sv[4 * q + 3]);
+        }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&s_empty[t]);
-          mbar_arrive(&p_full[t]);
-        }
-        l_run = l_run * alpha + l_tile;
+        if (lane == 0) mbar_arrive(&p_full[t]);
+        l_run = l_run * alpha + (l0 + l1);
         m_run = m_new;
-        if (alpha != 1.0f) {
-#pragma unroll
-          for (int i = 0; i < AT_D; ++i) o[i] *= alpha;
-        }
       }
       // last P V
       {
         mbar_wait(&pv_full[t], (n_kv - 1) & 1);
         tc_fence_after();
+        uint32_t v[AT_D];
+        tmem_ld_32x32b_x32(t_pv, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld_32x32b_x32(t_pv + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tmem_ld_wait();
 #pragma unroll
-        for (int c0 = 0; c0 < AT_D; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_pv + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[c0 + i] += __uint_as_float(v[i]);
-        }
+        for (int i = 0; i < AT_D; ++i) o[i] += __uint_as_float(v[i]);
       }
       // epilogue: out = bf16(O / l) * bf16(sigmoid(gate))
       const int qv = w.q_valid[t];

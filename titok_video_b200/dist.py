@@ -1,0 +1,74 @@
+"""Multi-GPU plumbing: one process per GPU, clips sharded across ranks, no data-path collective.
+
+Clips never interact (attention is block-diagonal over cu_seqlens, norms are per row, FSQ per vector), so the
+tokenizer shards by clip. The only collectives are bookkeeping:
+  * codebook-usage histogram: one all-reduce(SUM) of [K] counts (the reference keeps per-rank statistics)
+  * optional gather of the per-clip index tensors to one rank (tokenise-to-disk jobs)
+`torch.distributed` (NCCL on the GPU box, gloo in the CPU tests) is used as plumbing only.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .plan import clip_cost, shard_clips
+
+
+def _world(group=None) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_batch(shapes: Sequence[Sequence[int]], token_counts: Sequence[int], patch_size=(4, 8, 8), width: int = 256,
+                layers: int = 4, group=None) -> List[int]:
+    """Indices of the clips this rank owns. Deterministic on every rank (pure function of the shapes): greedy
+    longest-processing-time balancing by forward FLOPs (linear + quadratic attention term)."""
+    rank, world = _world(group)
+    costs = [clip_cost(s, t, patch_size, width, layers) for s, t in zip(shapes, token_counts)]
+    return shard_clips(costs, world)[rank]
+
+
+def allreduce_counts(counts: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum a [K] histogram over ranks in place (no-op for a single process)."""
+    _, world = _world(group)
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
+def gather_indices(local: Sequence[torch.Tensor], owned: Sequence[int], n_clips: int, dst: int = 0,
+                   group=None) -> Optional[List[torch.Tensor]]:
+    """Collect per-clip index tensors on rank `dst` in the original clip order. `local[i]` belongs to clip
+    `owned[i]`. Returns the list on `dst`, None elsewhere. One padded all_gather (indices are a few KB per clip)."""
+    rank, world = _world(group)
+    if world == 1:
+        out = [None] * n_clips
+        for t, i in zip(local, owned):
+            out[i] = t
+        return out
+    dev = local[0].device if len(local) else torch.device("cpu")
+    lens = torch.tensor([t.numel() for t in local] + [0] * (n_clips - len(local)), dtype=torch.int64, device=dev)
+    ids = torch.tensor(list(owned) + [-1] * (n_clips - len(owned)), dtype=torch.int64, device=dev)
+    meta = torch.stack([ids, lens])  # [2, n_clips]
+    metas = [torch.empty_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    max_len = int(max(int(m[1].sum()) for m in metas))
+    flat = torch.zeros(max(max_len, 1), dtype=torch.int32, device=dev)
+    if len(local):
+        cat = torch.cat([t.reshape(-1).to(torch.int32) for t in local])
+        flat[:cat.numel()] = cat
+    flats = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(flats, flat, group=group)
+    if rank != dst:
+        return None
+    out: List[Optional[torch.Tensor]] = [None] * n_clips
+    for m, f in zip(metas, flats):
+        off = 0
+        for cid, ln in zip(m[0].tolist(), m[1].tolist()):
+            if cid >= 0:
+                out[cid] = f[off:off + ln].clone()
+                off += ln
+    return out
