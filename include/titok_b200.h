@@ -92,6 +92,10 @@ int ttk_vq_gather_loss(const void* z, int64_t ldz, const void* codebook, int64_t
 int ttk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, const void* bias,
                   void* out, int64_t ldo, const int32_t* out_row_map, int w_is_kn, ttk_stream_t stream);
 
+/* Development aid (not used by the product path): buf = device int64 [148][64], zeroed by the caller, or NULL to
+ * switch off. GEMM launches after this call record clock64 stamps of their producer / MMA / epilogue pipelines. */
+int ttk_debug_set_trace(void* buf);
+
 /* Attn.to_qkv + split + apply_rotary_emb(q), (k) (transformer.py:85-98, rope.py:19-27).
  * rope: fp32 [M,60] (cos,sin) of the 30 rotated complex lanes per token (RoPE.forward, rope.py:57-71).
  * out [M, 2*width+2*gqa] = [rope(q) | gate | rope(k) | v]. */

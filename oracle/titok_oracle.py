@@ -274,6 +274,18 @@ def vq_argmin(z: torch.Tensor, codebook: torch.Tensor, chunk: int = 8192):
 # ------------------------------------------------------------------------------------------------
 # deterministic weights / inputs shared by tests, golden generation and the bench
 # ------------------------------------------------------------------------------------------------
+def codebook_scores(samples: Sequence[torch.Tensor], codebook_size: int) -> Tuple[float, float]:
+    """(usage %, entropy in nats) of the reference CodebookLogger.get_scores
+    (train_utils/codebook_logging.py:13-35): FIFO window of the last `codebook_size` SAMPLES (:13-17), sum of
+    per-sample bincounts, nonzero fraction, scipy-style entropy of the normalised frequencies (sum p ln(1/p), p > 0)."""
+    freq = torch.zeros(codebook_size, dtype=torch.float64)
+    for s_ in list(samples)[-codebook_size:]:
+        freq += torch.bincount(s_.reshape(-1).to(torch.int64), minlength=codebook_size)[:codebook_size].double()
+    usage = float((freq > 0).sum()) / codebook_size * 100.0
+    p = freq[freq > 0] / freq.sum()
+    return usage, float(-(p * p.log()).sum())
+
+
 def stress_init_(sd: Dict[str, torch.Tensor], seed: int = 1) -> Dict[str, torch.Tensor]:
     """the reference init (std 0.02) maps every latent to one code; the stress init draws every 2-D
     weight from N(0, (2/sqrt(fan_in))^2) so that tokens spread over the codebook. In place, deterministic."""

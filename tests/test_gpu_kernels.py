@@ -378,9 +378,14 @@ def test_fsq_large_and_ragged_sizes():
             neq = d["indices"].cpu() != i_ref
             assert not (neq & (O.fsq_boundary_gap(bounded) > 1e-6)).any()
             assert int(neq.sum()) <= max(2, n // 100000)
-            # property at full size: the decoded codes re-encode to the same indices (idempotence)
-            c2, d2 = q(codes)
-            assert torch.equal(d2["indices"], d["indices"])
+            # properties at full size: indices_to_codes inverts the index map exactly (fsq.py:111-121), and the
+            # codes lie on the level grid (code * half_width is an integer in [-half_width, half_width]).
+            # (FSQ.forward is NOT idempotent on its own codes: tanh(1) * 3.003 rounds to 2, not 3, for a 7-level dim.)
+            assert torch.equal(q.indices_to_codes(d["indices"]).to(codes.dtype), codes)
+            hw = torch.tensor([3, 2, 2, 2, 2], dtype=torch.float32, device=DEV)
+            lv = codes.float() * hw
+            # codes are bf16 here (2/3 * 3 = 2.0039): on the grid up to one bf16 rounding of level / half_width
+            assert bool(((lv - lv.round()).abs() <= 2.0 ** -7).all()) and bool((lv.round().abs() <= hw).all())
 
 
 def test_fsq_backward_ste():

@@ -21,7 +21,7 @@ def _load() -> ctypes.CDLL:
     if not os.path.exists(LIB_PATH):
         raise TitokB200Error(
             f"{LIB_PATH} not found: the CUDA extension has not been built. "
-            "Run `python -m titok_video_b200.build` (needs nvcc); there is no CPU fallback."
+            "Run `python titok_video_b200/build.py` (needs nvcc); there is no CPU fallback."
         )
     return ctypes.CDLL(LIB_PATH)
 
@@ -46,6 +46,7 @@ SIGNATURES = {
     "ttk_vq_argmin": [_vp, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp],
     "ttk_vq_gather_loss": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _i64, _vp, _vp],
     "ttk_gemm_bf16": [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _i64, _vp, _i, _vp],
+    "ttk_debug_set_trace": [_vp],
     "ttk_gemm_qkv_rope": [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _vp],
     "ttk_gemm_geglu": [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i64, _vp],
     "ttk_gemm_resid_norm256": [_vp, _i64, _vp, _i64, _i, _i, _vp, _i64, _i, _f, _vp, _vp, _vp, _vp, _i64, _vp],

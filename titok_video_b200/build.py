@@ -1,6 +1,6 @@
 """Builds libtitok_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
 
-    python -m titok_video_b200.build [--force]
+    python titok_video_b200/build.py [--force]      (run as a script: importing the package needs the built library)
 
 nvcc cross-compiles without a GPU. The .so is git-ignored but travels to the GPU box with the repo snapshot.
 """

@@ -3,10 +3,12 @@
 //   C[M,N] = A[M,K] * W[N,K]^T      A, W bf16 (K contiguous), fp32 accumulation in TMEM
 //
 // One persistent CTA per SM. Warp roles:
-//   warp 0      TMA producer  (A tile 128x64, W tile BNx64 per stage, SWIZZLE_128B)
+//   warp 0      TMA producer  (A tile 128x64, W tile BNx64 per stage, SWIZZLE_128B; EPI_RESID: + residual tile)
 //   warp 1      MMA issuer    (one elected thread, tcgen05.mma cta_group::1, M=128, N=BN, K=16)
 //   warp 2      TMEM allocator
-//   warps 4..   epilogue      (tcgen05.ld 32x32b: thread == output row), double-buffered accumulators
+//   warps 4-11  epilogue      (tcgen05.ld 32x32b: thread == output row; two warps per TMEM lane quarter split the
+//                              columns), double-buffered accumulators; results leave through swizzled shared-memory
+//                              boxes [32 rows x 64 cols] and TMA stores, so every global write is a full 128-byte line
 //
 // Epilogues (all round to bf16 exactly where the reference's op boundaries do):
 //   EPI_STORE  out = bf16(acc + bias)                    nn.Linear         (blocks.py:93,103,165,173; transformer.py:104,55)
@@ -22,6 +24,10 @@ enum { EPI_STORE = 0, EPI_QKV = 1, EPI_GEGLU = 2, EPI_RESID = 3 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;
+// epilogue warps per kind: 8 (two per TMEM lane quarter) for the store-only epilogues, 16 (four per quarter) for the
+// arithmetic-heavy ones (GELU, residual + norms) so that each scheduler has four warps to hide latencies with
+__host__ __device__ constexpr int epi_warps(int epi) { return (epi == 2 || epi == 3) ? 16 : 8; }
+constexpr int BOX_BYTES = 32 * 128;  // one [32 rows x 64 bf16] staging box
 
 struct GemmParams {
   int M, N, K;
@@ -30,53 +36,116 @@ struct GemmParams {
   __nv_bfloat16* out;
   int64_t ldo;
   const __nv_bfloat16* bias;   // [N] or null
-  const int32_t* out_row_map;  // [M] or null; negative entries are skipped
+  const int32_t* out_row_map;  // [M] or null; negative entries are skipped (direct-store path only)
+  int direct;                  // EPI_STORE: 1 = per-thread global stores (row map / unaligned N), 0 = TMA stores
   // EPI_QKV
   const float* rope;  // [M, 60] (cos,sin) pairs for the first 30 complex lanes of every head
   int width;          // q width (= gate width)
   int gqa;            // k width (= v width)
   // EPI_GEGLU
   int inner;
-  // EPI_RESID  (N == BN == width)
-  const __nv_bfloat16* resid;  // x [M, ldr]
-  int64_t ldr;
-  __nv_bfloat16* x_out;  // x' [M, ldo]
-  __nv_bfloat16* xn_out; // RMSNorm(x') * w_next [M, ldo] (may be null)
-  const float* w_post;   // post-norm weight (mode 1)
-  const float* w_next;   // next pre-norm weight
+  // EPI_RESID  (N == BN == 256)
+  const float* w_post;  // post-norm weight (mode 1)
+  const float* w_next;  // next pre-norm weight (null: no xn output)
   float alpha;
   int mode;  // 0: x + y ; 1: RMSNorm(alpha*x + y)*w_post
+  long long* trace;  // optional [gridDim][64] clock64 stamps (ttk_debug_set_trace), null in production
 };
 
-template <int BN, bool B_MN>
+// development aid: per-CTA timeline of the three pipelines (slot = 1 + 8 * local tile + event)
+__device__ __forceinline__ void trace_stamp(const GemmParams& p, int slot) {
+  if (p.trace && slot < 64) p.trace[blockIdx.x * 64 + slot] = clock64();
+}
+
+template <int BN, int EPI>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
+  // EPI_RESID: the [128 x 256] residual tile (4 swizzled boxes of 128 rows x 64 cols), updated in place and stored
+  // from there. Other epilogues: two staging boxes per epilogue warp.
+  static constexpr int OUT_BYTES = (EPI == EPI_RESID) ? BM * 256 * 2 : 8 * 2 * BOX_BYTES;
+  static constexpr int AUX_BYTES = 2 * 256 * 4 + 2 * 4 * 128 * 4;  // EPI_RESID: norm weights + partial sums of squares
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+  static constexpr int BUDGET = 227 * 1024 - 1024 - OUT_BYTES - AUX_BYTES - BAR_BYTES;
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + AUX_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// 0.5 * g * (1 + erf(g / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, two MUFU ops).
+// Against the exact function rounded to bf16 it differs on 117 of the 65280 finite bf16 inputs, all of them
+// g < -3 with |gelu| < 3e-3 (torch's own CPU bf16 kernel differs on 765); see tests/test_gpu_kernels.py.
+__device__ __forceinline__ float gelu_erf(float g) {
+  const float x = g * 0.70710678118654752440f;
+  const float ax = fabsf(x);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-ax * ax * 1.4426950408889634f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float y = fmaf(-p * t, e, 1.0f);  // erf(|x|)
+  return 0.5f * g * (1.0f + copysignf(y, x));
+}
 
-template <int BN, int EPI, int EPI_WARPS, bool B_MN>
-__global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using S = GemmSmem<BN, B_MN>;
+// Per-warp staging of [32 rows x 64 cols] bf16 boxes for TMA stores (double-buffered).
+struct BoxStager {
+  uint8_t* base;  // 2 * BOX_BYTES, 1024-byte aligned
+  int buf;
+  __device__ __forceinline__ uint8_t* acquire(int lane) {
+    if (lane == 0) tma_store_wait_read<1>();  // the store issued two boxes ago has finished reading this buffer
+    __syncwarp();
+    return base + buf * BOX_BYTES;
+  }
+  // all lanes have written their rows
+  __device__ __forceinline__ void flush(const CUtensorMap* tm, int lane, int col0, int row0) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tm, base + buf * BOX_BYTES, col0, row0);
+      tma_store_commit();
+    }
+    buf ^= 1;
+  }
+};
+
+// thread == row: write 64 bf16 (32 packed words) of this lane's row into a swizzled box
+__device__ __forceinline__ void box_write_row(uint8_t* box, int lane, const uint32_t (&pk)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<uint4*>(box + sw128_offset(lane, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+}
+
+template <int BN, int EPI, bool B_MN>
+__global__ void __launch_bounds__(128 + 32 * epi_warps(EPI), 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmO,   // out / x_out: box [32 rows x 64 cols]
+            const __grid_constant__ CUtensorMap tmO2,  // EPI_RESID: xn_out, same box
+            const __grid_constant__ CUtensorMap tmR,   // EPI_RESID: residual x, box [128 rows x 64 cols]
+            const GemmParams p) {
+  using S = GemmSmem<BN, EPI>;
   constexpr int STAGES = S::STAGES;
+  constexpr int EPI_WARPS = epi_warps(EPI);
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
-  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
+  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of the 64-column store box");
+  static_assert(EPI != EPI_RESID || BN == 256, "row epilogue owns complete 256-wide rows");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint8_t* smem_out = smem + STAGES * S::STAGE_BYTES;
+  float* wsm = reinterpret_cast<float*>(smem_out + S::OUT_BYTES);  // [2][256]
+  float* ssm = wsm + 512;                                          // [2 exchanges][4 column parts][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + S::OUT_BYTES + S::AUX_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* resid_full = bars + 2 * STAGES + 4;
+  uint64_t* resid_empty = bars + 2 * STAGES + 5;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,6 +154,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    if constexpr (EPI == EPI_RESID) {
+      tma_prefetch_desc(&tmO2);
+      tma_prefetch_desc(&tmR);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -95,6 +169,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], EPI_WARPS);
     }
+    mbar_init(resid_full, 1);
+    mbar_init(resid_empty, EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -102,17 +178,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) trace_stamp(p, 0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int m_blk = tile / p.num_n_tiles;
         const int n_blk = tile % p.num_n_tiles;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (kb == 0) trace_stamp(p, 1 + 8 * it + 0);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
@@ -133,6 +212,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             stage = 0;
             phase ^= 1;
           }
+          if constexpr (EPI == EPI_RESID) {
+            // residual tile of this M block: issued once the operand pipeline of the tile is primed (so the MMAs of
+            // this tile overlap the previous tile's epilogue); waits until that epilogue has stored its rows
+            if (kb == (p.num_k_blocks < STAGES ? p.num_k_blocks : STAGES) - 1) {
+              mbar_wait(resid_empty, (it & 1) ^ 1);
+              mbar_arrive_expect_tx(resid_full, BM * 256 * 2);
+#pragma unroll
+              for (int b = 0; b < 4; ++b) tma_load_2d(smem_out + b * (BM * 128), &tmR, resid_full, b * 64, m_blk * BM);
+            }
+          }
         }
       }
     }
@@ -145,13 +234,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int itm = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++itm) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
+        trace_stamp(p, 1 + 8 * itm + 1);
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kb == 0) trace_stamp(p, 1 + 8 * itm + 2);
+          if (kb == p.num_k_blocks - 1) trace_stamp(p, 1 + 8 * itm + 3);
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
           const uint32_t sb = sa + S::A_BYTES;
 #pragma unroll
@@ -178,51 +271,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int ew = warp - 4;
-    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int chalf = ew >> 2;               // column split when EPI_WARPS == 8
-    constexpr int CSPLIT = EPI_WARPS / 4;    // 1 or 2
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int cpart = ew >> 2;     // column part of this warp (0..EPI_WARPS/4-1)
     const int row_in_tile = quarter * 32 + lane;
+    // store-only epilogues: a private double-buffered staging box per warp. GEGLU: warps (cpart 2b, 2b+1) of a lane
+    // quarter fill the two halves of one shared 64-column box.
+    BoxStager stg{smem_out + (EPI == EPI_GEGLU ? (quarter * 2 + (cpart >> 1)) : ew) * 2 * BOX_BYTES, 0};
+    if constexpr (EPI == EPI_RESID) {
+      for (int te = threadIdx.x - 128; te < 256; te += 32 * EPI_WARPS) {
+        wsm[te] = (p.mode == 1) ? p.w_post[te] : 1.0f;
+        wsm[256 + te] = p.w_next ? p.w_next[te] : 1.0f;
+      }
+      named_bar_sync(1, 32 * EPI_WARPS);
+    }
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / p.num_n_tiles;
       const int n_blk = tile % p.num_n_tiles;
-      const int row = m_blk * BM + row_in_tile;
+      const int row0 = m_blk * BM + quarter * 32;  // first row of this warp's 32-row slice
+      const int row = row0 + lane;
       const bool row_ok = row < p.M;
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
 
       if constexpr (EPI == EPI_STORE) {
-        int orow = row;
-        if (row_ok && p.out_row_map) orow = p.out_row_map[row];
-        const bool st_ok = row_ok && orow >= 0;
-        constexpr int CPW = BN / CSPLIT;  // columns per warp
+        constexpr int CPW = BN / 2;  // columns per warp
+        if (p.direct) {
+          if (threadIdx.x == 128) trace_stamp(p, 1 + 8 * it + 4);
+          mbar_wait(&tmem_full[as], aphase);
+          tc_fence_after();
+          if (threadIdx.x == 128) trace_stamp(p, 1 + 8 * it + 5);
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+          int orow = row;
+          if (row_ok && p.out_row_map) orow = p.out_row_map[row];
+          const bool st_ok = row_ok && orow >= 0;
 #pragma unroll 1
-        for (int c0 = chalf * CPW; c0 < (chalf + 1) * CPW; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + c0, v);
-          tmem_ld_wait();
-          const int col0 = n_blk * BN + c0;
-          if (st_ok && col0 < p.N) {
-            __nv_bfloat16* dst = p.out + static_cast<int64_t>(orow) * p.ldo + col0;
-            if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint32_t w[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float a = __uint_as_float(v[j * 8 + e * 2]);
-                  float b = __uint_as_float(v[j * 8 + e * 2 + 1]);
-                  if (p.bias) {
-                    a += __bfloat162float(p.bias[col0 + j * 8 + e * 2]);
-                    b += __bfloat162float(p.bias[col0 + j * 8 + e * 2 + 1]);
-                  }
-                  w[e] = pack_bf16x2(a, b);
-                }
-                stg16(dst + j * 8, make_uint4(w[0], w[1], w[2], w[3]));
-              }
-            } else {
+          for (int c0 = cpart * CPW; c0 < (cpart + 1) * CPW; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_row + c0, v);
+            tmem_ld_wait();
+            const int col0 = n_blk * BN + c0;
+            if (st_ok && col0 < p.N) {
+              __nv_bfloat16* dst = p.out + static_cast<int64_t>(orow) * p.ldo + col0;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 if (col0 + j < p.N) {
@@ -233,146 +323,252 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
           }
+        } else {
+          // bias of this warp's first box is fetched before the accumulator is ready (off the critical path)
+          uint32_t bb[32];
+          auto load_bias = [&](int col0) {
+            const uint32_t* b2 = reinterpret_cast<const uint32_t*>(p.bias + col0);  // col0 % 64 == 0: 4-byte aligned
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bb[j] = (p.bias && col0 + 2 * j < p.N) ? __ldg(b2 + j) : 0u;
+          };
+          load_bias(n_blk * BN + cpart * CPW);
+          if (threadIdx.x == 128) trace_stamp(p, 1 + 8 * it + 4);
+          mbar_wait(&tmem_full[as], aphase);
+          tc_fence_after();
+          if (threadIdx.x == 128) trace_stamp(p, 1 + 8 * it + 5);
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+#pragma unroll 1
+          for (int cb = cpart * CPW; cb < (cpart + 1) * CPW; cb += 64) {
+            const int col0 = n_blk * BN + cb;
+            if (col0 >= p.N) break;  // warp-uniform
+            uint32_t v0[32], v1[32], pk[32];
+            tmem_ld_32x32b_x32(t_row + cb, v0);
+            tmem_ld_32x32b_x32(t_row + cb + 32, v1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              pk[j] = pack_bf16x2(__uint_as_float(v0[2 * j]) + bf16_lo(bb[j]), __uint_as_float(v0[2 * j + 1]) + bf16_hi(bb[j]));
+              pk[16 + j] = pack_bf16x2(__uint_as_float(v1[2 * j]) + bf16_lo(bb[16 + j]),
+                                       __uint_as_float(v1[2 * j + 1]) + bf16_hi(bb[16 + j]));
+            }
+            if (cb + 64 < (cpart + 1) * CPW) load_bias(col0 + 64);
+            uint8_t* box = stg.acquire(lane);
+            box_write_row(box, lane, pk);
+            stg.flush(&tmO, lane, col0, row0);
+          }
         }
       } else if constexpr (EPI == EPI_QKV) {
-        // column classes: [0,w) q (RoPE) | [w,2w) gate | [2w,2w+g) k (RoPE) | [2w+g,2w+2g) v
-        constexpr int CPW = BN / CSPLIT;
+        // column classes: [0,w) q (RoPE) | [w,2w) gate | [2w,2w+g) k (RoPE) | [2w+g,2w+2g) v; one 64-col box == one head
+        constexpr int CPW = BN / 2;
+        // RoPE second pass runs with lane == complex pair over the staged box; the (cos, sin) of the 32 rows of this
+        // warp's slice are fetched up front (one contiguous 240-byte run per row), before the accumulator is ready.
+        // Complex lanes 30, 31 (head dims 60..63) are not rotated (rope.py:22-24).
+        const int colw0 = n_blk * BN + cpart * CPW;
+        const bool any_rope = (colw0 < p.width) || (colw0 + CPW > 2 * p.width && colw0 < 2 * p.width + p.gqa);
+        float2 cs[32];
+        if (any_rope && lane < 30) {
+          const float2* src = reinterpret_cast<const float2*>(p.rope) + static_cast<int64_t>(row0) * 30 + lane;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) cs[rr] = (row0 + rr < p.M) ? __ldg(src + rr * 30) : make_float2(1.f, 0.f);
+        }
+        if (threadIdx.x == 128) trace_stamp(p, 1 + 8 * it + 4);
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        if (threadIdx.x == 128) trace_stamp(p, 1 + 8 * it + 5);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
-        for (int c0 = chalf * CPW; c0 < (chalf + 1) * CPW; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + c0, v);
+        for (int cb = cpart * CPW; cb < (cpart + 1) * CPW; cb += 64) {
+          const int col0 = n_blk * BN + cb;
+          if (col0 >= p.N) break;
+          uint32_t v0[32], v1[32], pk[32];
+          tmem_ld_32x32b_x32(t_row + cb, v0);
+          tmem_ld_32x32b_x32(t_row + cb + 32, v1);
           tmem_ld_wait();
-          const int col0 = n_blk * BN + c0;
-          if (row_ok && col0 < p.N) {
-            const bool is_rope = (col0 < p.width) || (col0 >= 2 * p.width && col0 < 2 * p.width + p.gqa);
-            float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = bf16r(__uint_as_float(v[j]));  // Linear output is bf16
-            if (is_rope) {
-              const int d0 = col0 & 63;  // 0 or 32: first head dim of this chunk
-              const float* cs = p.rope + static_cast<int64_t>(row) * 60 + d0;
+          for (int j = 0; j < 16; ++j) {  // Linear output is bf16
+            pk[j] = pack_bf16x2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+            pk[16 + j] = pack_bf16x2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
+          }
+          uint8_t* box = stg.acquire(lane);
+          box_write_row(box, lane, pk);
+          const bool is_rope = (col0 < p.width) || (col0 >= 2 * p.width && col0 < 2 * p.width + p.gqa);
+          if (is_rope) {
+            __syncwarp();
+            if (lane < 30) {
+              uint32_t x[32];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if (d0 + 2 * j < 60) {  // complex lanes 30,31 (dims 60..63) are not rotated
-                  const float2 t = *reinterpret_cast<const float2*>(cs + 2 * j);
-                  const float x0 = f[2 * j], x1 = f[2 * j + 1];
-                  f[2 * j] = x0 * t.x - x1 * t.y;
-                  f[2 * j + 1] = x0 * t.y + x1 * t.x;
-                }
+              for (int rr = 0; rr < 32; ++rr)
+                x[rr] = *reinterpret_cast<const uint32_t*>(box + sw128_offset(rr, lane >> 2) + (lane & 3) * 4);
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) {
+                const float x0 = bf16_lo(x[rr]), x1 = bf16_hi(x[rr]);
+                *reinterpret_cast<uint32_t*>(box + sw128_offset(rr, lane >> 2) + (lane & 3) * 4) =
+                    pack_bf16x2(x0 * cs[rr].x - x1 * cs[rr].y, x0 * cs[rr].y + x1 * cs[rr].x);
               }
             }
-            __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + col0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              stg16(dst + j * 8, make_uint4(pack_bf16x2(f[j * 8], f[j * 8 + 1]), pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]),
-                                            pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]),
-                                            pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7])));
-            }
           }
+          stg.flush(&tmO, lane, col0, row0);
         }
       } else if constexpr (EPI == EPI_GEGLU) {
-        constexpr int HALF = BN / 2;         // value columns [0,HALF), gate columns [HALF,BN)
-        constexpr int CPW = HALF / CSPLIT;
-#pragma unroll 1
-        for (int c0 = chalf * CPW; c0 < (chalf + 1) * CPW; c0 += 32) {
-          uint32_t xv[32], gv[32];
-          tmem_ld_32x32b_x32(t_row + c0, xv);
-          tmem_ld_32x32b_x32(t_row + HALF + c0, gv);
-          tmem_ld_wait();
-          const int col0 = n_blk * HALF + c0;
-          if (row_ok && col0 < p.inner) {
-            __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + col0;
-            float h[32];
+        constexpr int HALF = BN / 2;  // value columns [0,HALF), gate columns [HALF,BN) of the accumulator
+        static_assert(HALF == 128, "four column parts of 32 output columns");
+        if (threadIdx.x == 128) trace_stamp(p, 1 + 8 * it + 4);
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        if (threadIdx.x == 128) trace_stamp(p, 1 + 8 * it + 5);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+        const int cb = cpart * 32;
+        const int colbox = n_blk * HALF + (cpart >> 1) * 64;  // first output column of the pair's shared box
+        const uint32_t pair_bar = 2 + quarter * 2 + (cpart >> 1);
+        if (colbox < p.inner) {  // uniform over the pair
+          uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float x = bf16r(__uint_as_float(xv[j]));
-              const float g = bf16r(__uint_as_float(gv[j]));
-              h[j] = bf16r(gelu_erf(g)) * x;
-            }
-            if (col0 + 32 <= p.inner) {
+          for (int hh = 0; hh < 2; ++hh) {  // 16 columns at a time: 640 threads leave 96 registers per thread
+            uint32_t xv[16], gv[16];
+            tmem_ld_32x32b_x16(t_row + cb + hh * 16, xv);
+            tmem_ld_32x32b_x16(t_row + HALF + cb + hh * 16, gv);
+            tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                stg16(dst + j * 8,
-                      make_uint4(pack_bf16x2(h[j * 8], h[j * 8 + 1]), pack_bf16x2(h[j * 8 + 2], h[j * 8 + 3]),
-                                 pack_bf16x2(h[j * 8 + 4], h[j * 8 + 5]), pack_bf16x2(h[j * 8 + 6], h[j * 8 + 7])));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.inner) dst[j] = __float2bfloat16_rn(h[j]);
+            for (int j = 0; j < 8; ++j) {
+              const float x0 = bf16r(__uint_as_float(xv[2 * j])), x1 = bf16r(__uint_as_float(xv[2 * j + 1]));
+              const float g0 = bf16r(__uint_as_float(gv[2 * j])), g1 = bf16r(__uint_as_float(gv[2 * j + 1]));
+              pk[hh * 8 + j] = pack_bf16x2(bf16r(gelu_erf(g0)) * x0, bf16r(gelu_erf(g1)) * x1);
             }
           }
+          if ((cpart & 1) == 0 && lane == 0) tma_store_wait_read<1>();  // the pair's buffer of two tiles ago is free
+          named_bar_sync(pair_bar, 64);
+          uint8_t* box = stg.base + stg.buf * BOX_BYTES;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(box + sw128_offset(lane, (cpart & 1) * 4 + c)) =
+                make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          fence_proxy_async_smem();
+          named_bar_sync(pair_bar, 64);
+          if ((cpart & 1) == 0 && lane == 0) {
+            tma_store_2d(&tmO, box, colbox, row0);
+            tma_store_commit();
+          }
+          stg.buf ^= 1;
         }
       } else if constexpr (EPI == EPI_RESID) {
-        // full output row in this tile (N == BN); thread == row. Values kept as packed bf16 in registers.
-        static_assert(EPI != EPI_RESID || EPI_WARPS == 4, "row epilogue uses one thread per row");
-        uint32_t xs[BN / 2];
+        // thread == (row, column part): 64 columns as packed bf16 in registers; the four parts of a row exchange their
+        // partial sums of squares through shared memory. bf16 adds / multiplies run on the packed bf16x2 pipe: one
+        // rounding of the exact result, which is what the reference's bf16 ops (fp32 op-math, then round) produce.
+        uint32_t xs[32];
         float ss = 0.f;
-        const __nv_bfloat16* xr = p.resid + static_cast<int64_t>(row_ok ? row : 0) * p.ldr;
+        uint8_t* rbox = smem_out + cpart * (BM * 128) + quarter * BOX_BYTES;  // this warp's 32 rows of 64-col box `cpart`
+        const __nv_bfloat162 alpha2 = __float2bfloat162_rn(p.alpha);
+        mbar_wait(resid_full, it & 1);
+        if (threadIdx.x == 128) trace_stamp(p, 1 + 8 * it + 4);
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        if (threadIdx.x == 128) trace_stamp(p, 1 + 8 * it + 5);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int hh = 0; hh < 2; ++hh) {  // 32 columns at a time (register footprint)
           uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + c0, v);
+          tmem_ld_32x32b_x32(t_row + cpart * 64 + hh * 32, v);
           tmem_ld_wait();
+          if (hh == 1) {
+            // accumulator in registers: hand the TMEM stage back before the norm / store phase
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 r = ldg16(xr + c0 + j * 8);
+          for (int c = 0; c < 4; ++c) {
+            const uint4 r = *reinterpret_cast<const uint4*>(rbox + sw128_offset(lane, hh * 4 + c));
             const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float y0 = bf16r(__uint_as_float(v[j * 8 + e * 2]));
-              const float y1 = bf16r(__uint_as_float(v[j * 8 + e * 2 + 1]));
-              float a0 = bf16_lo(rr[e]), a1 = bf16_hi(rr[e]);
-              if (p.mode == 1) {
-                a0 = bf16r(a0 * p.alpha);
-                a1 = bf16r(a1 * p.alpha);
-              }
-              const float s0 = bf16r(a0 + y0), s1 = bf16r(a1 + y1);
-              ss += s0 * s0 + s1 * s1;
-              xs[(c0 + j * 8 + e * 2) / 2] = pack_bf16x2(s0, s1);
+              const int i = c * 4 + e;  // packed pair index within this 32-column half
+              const uint32_t y = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+              __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&rr[e]);
+              if (p.mode == 1) a = __hmul2(a, alpha2);
+              const __nv_bfloat162 sv = __hadd2(a, *reinterpret_cast<const __nv_bfloat162*>(&y));
+              const uint32_t su = *reinterpret_cast<const uint32_t*>(&sv);
+              const float s0 = bf16_lo(su), s1 = bf16_hi(su);
+              ss = fmaf(s0, s0, ss);
+              ss = fmaf(s1, s1, ss);
+              xs[hh * 16 + i] = su;
             }
           }
         }
+        // exchange slot: mode 1 uses slots 0 and 1 within a tile; mode 0 alternates them between tiles, so a slot is
+        // never rewritten before the partners' reads of its previous value are ordered by a barrier
+        float* ex0 = ssm + ((p.mode == 1) ? 0 : static_cast<int>(it & 1)) * 512;
+        ex0[cpart * 128 + row_in_tile] = ss;
+        named_bar_sync(1, 32 * EPI_WARPS);
+        ss = (ex0[row_in_tile] + ex0[128 + row_in_tile]) + (ex0[256 + row_in_tile] + ex0[384 + row_in_tile]);
         if (p.mode == 1) {
-          const float rstd = 1.0f / sqrtf(ss * (1.0f / BN) + 1e-5f);
-          ss = 0.f;
+          const float rstd = 1.0f / sqrtf(ss * (1.0f / 256) + 1e-5f);
+          float part = 0.f;
+          const float* wp = wsm + cpart * 64;
 #pragma unroll
-          for (int i = 0; i < BN / 2; ++i) {
-            const float2 w = *reinterpret_cast<const float2*>(p.w_post + 2 * i);
-            const float s0 = bf16r(bf16_lo(xs[i]) * rstd * w.x);
-            const float s1 = bf16r(bf16_hi(xs[i]) * rstd * w.y);
-            ss += s0 * s0 + s1 * s1;
-            xs[i] = pack_bf16x2(s0, s1);
+          for (int i = 0; i < 32; ++i) {
+            const float2 w = *reinterpret_cast<const float2*>(wp + 2 * i);
+            const uint32_t o = pack_bf16x2(bf16_lo(xs[i]) * rstd * w.x, bf16_hi(xs[i]) * rstd * w.y);
+            const float s0 = bf16_lo(o), s1 = bf16_hi(o);
+            part = fmaf(s0, s0, part);
+            part = fmaf(s1, s1, part);
+            xs[i] = o;
+          }
+          float* ex1 = ssm + 512;
+          ex1[cpart * 128 + row_in_tile] = part;
+          named_bar_sync(1, 32 * EPI_WARPS);
+          ss = (ex1[row_in_tile] + ex1[128 + row_in_tile]) + (ex1[256 + row_in_tile] + ex1[384 + row_in_tile]);
+        }
+        // x' in place over the residual rows, then out through TMA (rows >= M are clipped)
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(rbox + sw128_offset(lane, c)) = make_uint4(xs[4 * c], xs[4 * c + 1], xs[4 * c + 2], xs[4 * c + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmO, rbox, cpart * 64, row0);
+          tma_store_commit();
+        }
+        if (p.w_next) {
+          const float rstd = 1.0f / sqrtf(ss * (1.0f / 256) + 1e-5f);
+          const float* wn = wsm + 256 + cpart * 64;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float2 w = *reinterpret_cast<const float2*>(wn + 2 * i);
+            xs[i] = pack_bf16x2(bf16_lo(xs[i]) * rstd * w.x, bf16_hi(xs[i]) * rstd * w.y);
+          }
+          if (lane == 0) tma_store_wait_read<0>();  // x' has left shared memory
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(rbox + sw128_offset(lane, c)) = make_uint4(xs[4 * c], xs[4 * c + 1], xs[4 * c + 2], xs[4 * c + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmO2, rbox, cpart * 64, row0);
+            tma_store_commit();
           }
         }
-        if (row_ok) {
-          __nv_bfloat16* xo = p.x_out + static_cast<int64_t>(row) * p.ldo;
-#pragma unroll
-          for (int i = 0; i < BN / 8; ++i) stg16(xo + i * 8, make_uint4(xs[4 * i], xs[4 * i + 1], xs[4 * i + 2], xs[4 * i + 3]));
-          if (p.xn_out) {
-            const float rstd = 1.0f / sqrtf(ss * (1.0f / BN) + 1e-5f);
-            __nv_bfloat16* no = p.xn_out + static_cast<int64_t>(row) * p.ldo;
-#pragma unroll
-            for (int i = 0; i < BN / 8; ++i) {
-              uint32_t w4[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 w = *reinterpret_cast<const float2*>(p.w_next + 8 * i + 2 * e);
-                w4[e] = pack_bf16x2(bf16_lo(xs[4 * i + e]) * rstd * w.x, bf16_hi(xs[4 * i + e]) * rstd * w.y);
-              }
-              stg16(no + i * 8, make_uint4(w4[0], w4[1], w4[2], w4[3]));
-            }
-          }
+        if (lane == 0) {
+          tma_store_wait_read<0>();
+          mbar_arrive(resid_empty);  // the producer may overwrite this warp's rows with the next residual tile
         }
+        __syncwarp();
       }
 
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if constexpr (EPI != EPI_RESID) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      }
+      if (threadIdx.x == 128) trace_stamp(p, 1 + 8 * it + 6);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
       }
     }
+    if (lane == 0) tma_store_wait<0>();  // shared memory must outlive the bulk stores that read it
+    if (threadIdx.x == 128) trace_stamp(p, 63);
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -383,29 +579,55 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
-template <int BN, int EPI, int EPI_WARPS, bool B_MN>
-static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, GemmParams& p, cudaStream_t stream) {
-  using S = GemmSmem<BN, B_MN>;
+struct GemmIo {
+  const void* A;
+  int64_t lda;
+  const void* W;
+  int64_t ldw;
+  void* out2 = nullptr;         // EPI_RESID: xn_out
+  const void* resid = nullptr;  // EPI_RESID: x
+  int64_t ldr = 0;
+};
+
+static long long* g_trace = nullptr;
+
+template <int BN, int EPI, bool B_MN>
+static int launch_gemm(const GemmIo& io, GemmParams& p, cudaStream_t stream) {
+  using S = GemmSmem<BN, EPI>;
+  p.trace = g_trace;
   if (int e = check_device_sm100()) return e;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return TTK_ERR_BAD_SHAPE;
-  CUtensorMap tmA, tmB;
-  if (int e = make_tmap_bf16_2d(&tmA, A, p.M, p.K, lda, BM)) return e;
+  CUtensorMap tmA, tmB, tmO, tmO2, tmR;
+  if (int e = make_tmap_bf16_2d(&tmA, io.A, p.M, p.K, io.lda, BM)) return e;
   int e2;
   if (B_MN) {
-    e2 = make_tmap_bf16_2d(&tmB, W, p.K, p.N, ldw, BK);  // [K, N] row-major, box [64 k][64 n]
+    e2 = make_tmap_bf16_2d(&tmB, io.W, p.K, p.N, io.ldw, BK);  // [K, N] row-major, box [64 k][64 n]
   } else if (EPI == EPI_GEGLU) {
-    e2 = make_tmap_bf16_2d(&tmB, W, 2 * static_cast<uint64_t>(p.inner), p.K, ldw, BN / 2);
+    e2 = make_tmap_bf16_2d(&tmB, io.W, 2 * static_cast<uint64_t>(p.inner), p.K, io.ldw, BN / 2);
   } else {
-    e2 = make_tmap_bf16_2d(&tmB, W, p.N, p.K, ldw, BN);
+    e2 = make_tmap_bf16_2d(&tmB, io.W, p.N, p.K, io.ldw, BN);
   }
   if (e2) return e2;
+  const int out_cols = (EPI == EPI_GEGLU) ? p.inner : p.N;
+  if (p.direct) {
+    tmO = tmA;  // unused
+  } else if (int e = make_tmap_bf16_2d(&tmO, p.out, p.M, out_cols, p.ldo, 32)) {
+    return e;
+  }
+  tmO2 = tmO;
+  tmR = tmO;
+  if (EPI == EPI_RESID) {
+    if (io.out2)
+      if (int e = make_tmap_bf16_2d(&tmO2, io.out2, p.M, 256, p.ldo, 32)) return e;
+    if (int e = make_tmap_bf16_2d(&tmR, io.resid, p.M, 256, io.ldr, BM)) return e;
+  }
   p.num_m_tiles = (p.M + BM - 1) / BM;
   if (EPI == EPI_GEGLU)
     p.num_n_tiles = (p.inner + BN / 2 - 1) / (BN / 2);
   else
     p.num_n_tiles = (p.N + BN - 1) / BN;
   p.num_k_blocks = (p.K + BK - 1) / BK;
-  auto kern = gemm_kernel<BN, EPI, EPI_WARPS, B_MN>;
+  auto kern = gemm_kernel<BN, EPI, B_MN>;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
@@ -414,7 +636,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, G
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 128 + 32 * EPI_WARPS, S::TOTAL, stream>>>(tmA, tmB, p);
+  kern<<<grid, 128 + 32 * epi_warps(EPI), S::TOTAL, stream>>>(tmA, tmB, tmO, tmO2, tmR, p);
   return launch_status();
 }
 
@@ -423,6 +645,13 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, G
 using namespace ttk;
 
 extern "C" {
+
+// Development aid: buf = device int64 [148][64] (zeroed by the caller) or NULL to switch tracing off. Every GEMM launch
+// after this call records clock64 stamps of its pipelines for the first local tiles of each CTA (see trace_stamp).
+int ttk_debug_set_trace(void* buf) {
+  g_trace = static_cast<long long*>(buf);
+  return TTK_OK;
+}
 
 // nn.Linear: out[M,N] = A[M,K] @ W[N,K]^T + bias. w_is_kn != 0: W is given as [K,N] (N contiguous).
 int ttk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, const void* bias,
@@ -436,12 +665,18 @@ int ttk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M,
   p.ldo = ldo;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.out_row_map = out_row_map;
+  // TMA stores need 16-byte aligned rows; a row map scatters rows, which a tiled store cannot express
+  p.direct = (out_row_map != nullptr || (ldo % 8) != 0 || (N % 2) != 0 || (reinterpret_cast<uintptr_t>(out) & 15u) != 0 ||
+              (bias && (reinterpret_cast<uintptr_t>(bias) & 3u) != 0))
+                 ? 1
+                 : 0;
+  GemmIo io{A, lda, W, ldw};
   if (w_is_kn) {
     if (N % 8 != 0) return TTK_ERR_ALIGNMENT;
-    return launch_gemm<128, EPI_STORE, 4, true>(A, lda, W, ldw, p, stream);
+    return launch_gemm<128, EPI_STORE, true>(io, p, stream);
   }
-  if (N > 128) return launch_gemm<256, EPI_STORE, 8, false>(A, lda, W, ldw, p, stream);
-  return launch_gemm<128, EPI_STORE, 4, false>(A, lda, W, ldw, p, stream);
+  if (N > 128) return launch_gemm<256, EPI_STORE, false>(io, p, stream);
+  return launch_gemm<128, EPI_STORE, false>(io, p, stream);
 }
 
 // Attn.to_qkv + split + RoPE(q), RoPE(k): out[M, 2w+2g] = [rope(q) | gate | rope(k) | v]
@@ -449,6 +684,7 @@ int ttk_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldw, in
                       const float* rope, void* out, int64_t ldo, cudaStream_t stream) {
   if (!A || !W || !out || !rope) return TTK_ERR_BAD_ARG;
   if (width % 64 != 0 || gqa % 64 != 0 || ldo % 8 != 0) return TTK_ERR_BAD_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(rope) & 7u) != 0) return TTK_ERR_ALIGNMENT;
   GemmParams p{};
   p.M = M;
   p.N = 2 * width + 2 * gqa;
@@ -458,7 +694,8 @@ int ttk_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldw, in
   p.rope = rope;
   p.width = width;
   p.gqa = gqa;
-  return launch_gemm<256, EPI_QKV, 8, false>(A, lda, W, ldw, p, stream);
+  GemmIo io{A, lda, W, ldw};
+  return launch_gemm<256, EPI_QKV, false>(io, p, stream);
 }
 
 // GEGLU.w12 + chunk + gelu(gate)*value: out[M, inner]; W12 is [2*inner, K] (value rows first).
@@ -473,7 +710,8 @@ int ttk_gemm_geglu(const void* A, int64_t lda, const void* W12, int64_t ldw, int
   p.inner = inner;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
-  return launch_gemm<128, EPI_GEGLU, 8, false>(A, lda, W12, ldw, p, stream);
+  GemmIo io{A, lda, W12, ldw};
+  return launch_gemm<256, EPI_GEGLU, false>(io, p, stream);
 }
 
 // Linear(K -> 256, no bias) fused with the residual / KEEL post-norm and the next pre-norm (width 256 only):
@@ -490,16 +728,17 @@ int ttk_gemm_resid_norm256(const void* A, int64_t lda, const void* W, int64_t ld
   p.M = M;
   p.N = 256;
   p.K = K;
-  p.resid = static_cast<const __nv_bfloat16*>(x);
-  p.ldr = ldx;
   p.mode = mode;
   p.alpha = alpha;
   p.w_post = w_post;
-  p.w_next = w_next;
-  p.x_out = static_cast<__nv_bfloat16*>(x_out);
-  p.xn_out = static_cast<__nv_bfloat16*>(xn_out);
+  p.w_next = xn_out ? w_next : nullptr;
+  p.out = static_cast<__nv_bfloat16*>(x_out);
   p.ldo = ldo;
-  return launch_gemm<256, EPI_RESID, 4, false>(A, lda, W, ldw, p, stream);
+  GemmIo io{A, lda, W, ldw};
+  io.out2 = xn_out;
+  io.resid = x;
+  io.ldr = ldx;
+  return launch_gemm<256, EPI_RESID, false>(io, p, stream);
 }
 
 }  // extern "C"

@@ -112,11 +112,12 @@ class FSQ(nn.Module):
         return (self._scale_and_shift(zhat) * self._basis).sum(dim=-1).to(torch.int32)
 
     def indices_to_codes(self, indices: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
-        """Inverse of codes_to_indices (fsq.py:111-121). CUDA tensors use the fused kernel."""
+        """Inverse of codes_to_indices (fsq.py:111-121) on the fused CUDA kernel. CPU tensors are rejected: the only
+        host-side evaluation is the one-off construction of the `implicit_codebook` buffer in __init__."""
         assert indices is not None
-        if indices.device.type != "cuda":
-            return self._indices_to_codes(indices).to(out_dtype)
         from ... import _lib, engine
+
+        engine.require_cuda(indices.device)
 
         if indices.dtype not in (torch.int32, torch.int64):
             indices = indices.to(torch.int64)
