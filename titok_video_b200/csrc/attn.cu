@@ -10,14 +10,17 @@
 //
 // Work item (one CTA): TWO 128-row query tiles that share one K/V stream (two query heads of the
 // same kv group, or two consecutive row tiles of one head). Warp roles:
-//   warp 0        TMA producer: Q tiles once, K and V tiles through 3-stage rings
-//   warp 1        MMA issuer:   S_t = Q_t K^T (M128 N128 K64), PV_t = P_t V (M128 N64 K128, V is MN-major)
-//   warp 2        TMEM allocator (512 columns: S0 S1 PV0 PV1)
+//   warp 0        TMA producer: Q tiles once, K and V tiles through 4-stage rings
+//   warp 1        MMA issuer:   S_t = Q_t K^T  (SS: M128 N128 K64)
+//                               O_t += P_t V    (TS: P read from tensor memory, V MN-major in smem, M128 N64 K128)
+//   warp 2        TMEM allocator (512 columns: S0 S1 | O0 O1 | P0 P1)
 //   warps 4-7     softmax for query tile 0 (thread == query row)
 //   warps 8-11    softmax for query tile 1
-// While one softmax group exponentiates, the tensor core works on the other tile (ping-pong).
-// Online softmax keeps the running max / sum and the fp32 output row in registers; each P V product
-// lands in a fresh TMEM buffer and is folded in one iteration later, off the critical path.
+// Pipeline: S_t(j+1) is issued as soon as the softmax warps have pulled S_t(j) into registers, so the next score
+// tile is ready before the exponentials of the current one are done; P_t(j) goes back to tensor memory as bf16
+// (tcgen05.st) and the P V product accumulates into O_t in tensor memory. The running maximum is updated lazily:
+// O_t / l are rescaled (by the softmax warps themselves) only when the row maximum grew by more than 2^8, which
+// after the first one or two kv tiles practically never happens; the final division by l makes the result exact.
 #include "common.cuh"
 #include "host_util.cuh"
 
@@ -46,11 +49,15 @@ struct AttnParams {
 constexpr int AT_BM = 128;  // query rows per tile
 constexpr int AT_BN = 128;  // keys per kv tile
 constexpr int AT_D = 64;
-constexpr int AT_KST = 3;  // K / V ring depth
+constexpr int AT_KST = 4;  // K / V ring depth
 constexpr int AT_Q_BYTES = AT_BM * AT_D * 2;   // 16 KB
 constexpr int AT_KV_BYTES = AT_BN * AT_D * 2;  // 16 KB
-constexpr int AT_P_BYTES = AT_BM * AT_BN * 2;  // 32 KB (two 64-key swizzle atoms)
-constexpr int AT_SMEM = 2 * AT_Q_BYTES + 2 * AT_KST * AT_KV_BYTES + 2 * AT_P_BYTES + 512 + 1024;
+constexpr int AT_SMEM = 2 * AT_Q_BYTES + 2 * AT_KST * AT_KV_BYTES + 512 + 1024;
+// TMEM columns
+constexpr uint32_t AT_TM_S = 0;    // S0 [0,128)   S1 [128,256)
+constexpr uint32_t AT_TM_O = 256;  // O0 [256,320) O1 [320,384)
+constexpr uint32_t AT_TM_P = 384;  // P0 [384,448) P1 [448,512)   (128 keys x bf16 = 64 columns)
+constexpr float AT_RESCALE_LOG2 = 8.0f;  // rescale O only when the row maximum grew by more than 2^8
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
@@ -60,7 +67,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
@@ -69,23 +76,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                  // [2][128][64]
-  uint8_t* sK = sQ + 2 * AT_Q_BYTES;                   // [KST][128][64]
-  uint8_t* sV = sK + AT_KST * AT_KV_BYTES;             // [KST][128][64]
-  uint8_t* sP = sV + AT_KST * AT_KV_BYTES;             // [2][2 atoms][128][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_P_BYTES);
-  uint64_t* q_full = bars;                 // [1]
-  uint64_t* k_full = bars + 1;             // [KST]
-  uint64_t* k_empty = k_full + AT_KST;     // [KST]
-  uint64_t* v_full = k_empty + AT_KST;     // [KST]
-  uint64_t* v_empty = v_full + AT_KST;     // [KST]
-  uint64_t* s_full = v_empty + AT_KST;     // [2]
-  uint64_t* s_empty = s_full + 2;          // [2]
-  uint64_t* p_full = s_empty + 2;          // [2]
-  uint64_t* p_empty = p_full + 2;          // [2]
-  uint64_t* pv_full = p_empty + 2;         // [2]
-  uint64_t* pv_empty = pv_full + 2;        // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_empty + 2);
+  uint8_t* sQ = smem;                       // [2][128][64]
+  uint8_t* sK = sQ + 2 * AT_Q_BYTES;        // [KST][128][64]
+  uint8_t* sV = sK + AT_KST * AT_KV_BYTES;  // [KST][128][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AT_KST * AT_KV_BYTES);
+  uint64_t* q_full = bars;              // [1]
+  uint64_t* k_full = bars + 1;          // [KST]
+  uint64_t* k_empty = k_full + AT_KST;  // [KST]
+  uint64_t* v_full = k_empty + AT_KST;  // [KST]
+  uint64_t* v_empty = v_full + AT_KST;  // [KST]
+  uint64_t* s_full = v_empty + AT_KST;  // [2]  S_t(j) is in tensor memory
+  uint64_t* s_empty = s_full + 2;       // [2]  the softmax warps hold S_t(j) in registers
+  uint64_t* p_full = s_empty + 2;       // [2]  P_t(j) is in tensor memory (and O_t has been rescaled if needed)
+  uint64_t* pv_done = p_full + 2;       // [2]  O_t += P_t(j) V(j) has retired
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,9 +114,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&s_full[t], 1);
       mbar_init(&s_empty[t], 4);
       mbar_init(&p_full[t], 4);
-      mbar_init(&p_empty[t], 1);
-      mbar_init(&pv_full[t], 1);
-      mbar_init(&pv_empty[t], 4);
+      mbar_init(&pv_done[t], 1);
     }
     fence_barrier_init();
   }
@@ -121,12 +123,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  // TMEM columns: S0 [0,128) S1 [128,256) PV0 [256,320) PV1 [320,384)
 
-  // Register re-distribution: the producer / MMA / allocator warpgroup needs few registers; each softmax
-  // thread keeps a 128-key score row plus its 64-wide fp32 output row live (12 warps x 168 = 4 x 40 + 8 x 232).
-  // (setmaxnreg sits at the top of each role branch so that ptxas allocates registers per role.)
-
+  // Register re-distribution: the control warpgroup needs few registers; each softmax thread keeps a 128-key score
+  // row live (12 warps x 168 = 4 x 40 + 8 x 232). setmaxnreg sits at the top of each role branch.
   if (warp == 0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (elect_one()) {
@@ -150,24 +149,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_D, 0, 1);   // P (K-major) x V (MN-major)
+      constexpr uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_D, 0, 1);   // P (tmem, K-major) x V (MN-major)
       const bool act[2] = {act0, act1};
       auto issue_s = [&](int t, int st) {
         const uint32_t sa = smem_u32(sQ + t * AT_Q_BYTES);
         const uint32_t sb = smem_u32(sK + st * AT_KV_BYTES);
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16_ss(tmem_base + t * AT_BN, umma_smem_desc_sw128(sa + k * 32, 1024, 0),
+          umma_bf16_ss(tmem_base + AT_TM_S + t * AT_BN, umma_smem_desc_sw128(sa + k * 32, 1024, 0),
                        umma_smem_desc_sw128(sb + k * 32, 1024, 0), idesc_s, k != 0 ? 1u : 0u);
       };
-      auto issue_pv = [&](int t, int st) {
-        const uint32_t sa = smem_u32(sP + t * AT_P_BYTES);
+      auto issue_pv = [&](int t, int st, bool accumulate) {
         const uint32_t sb = smem_u32(sV + st * AT_KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < AT_BN / 16; ++k)
-          umma_bf16_ss(tmem_base + 2 * AT_BN + t * AT_D,
-                       umma_smem_desc_sw128(sa + (k >> 2) * (AT_BM * 128) + (k & 3) * 32, 1024, 0),
-                       umma_smem_desc_sw128(sb + k * 2048, 1024, 0), idesc_o, k != 0 ? 1u : 0u);
+        for (int k = 0; k < AT_BN / 16; ++k)  // 16 keys == 8 packed columns of P
+          umma_bf16_ts(tmem_base + AT_TM_O + t * AT_D, tmem_base + AT_TM_P + t * (AT_BN / 2) + k * 8,
+                       umma_smem_desc_sw128(sb + k * 2048, 1024, 0), idesc_o, (accumulate || k != 0) ? 1u : 0u);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
@@ -177,41 +174,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         issue_s(t, 0);
         umma_commit(&s_full[t]);
       }
-      umma_commit(&k_empty[0]);  // K stage 0 is released once the S MMAs of kv tile 0 retire
+      umma_commit(&k_empty[0]);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % AT_KST;
         const uint32_t ph = (j / AT_KST) & 1;
-        const int st1 = (j + 1) % AT_KST;
-        const uint32_t ph1 = ((j + 1) / AT_KST) & 1;
         const uint32_t par = j & 1;
-        bool v_ready = false, k_ready = false;
-        for (int t = 0; t < 2; ++t) {
-          if (!act[t]) continue;
-          // ---- PV_t(j) = P_t(j) V(j)
-          mbar_wait(&p_full[t], par);
-          if (!v_ready) {
-            mbar_wait(&v_full[st], ph);
-            v_ready = true;
-          }
-          if (j > 0) mbar_wait(&pv_empty[t], (j - 1) & 1);
-          tc_fence_after();
-          issue_pv(t, st);
-          umma_commit(&pv_full[t]);
-          umma_commit(&p_empty[t]);
-          // ---- S_t(j+1) = Q_t K(j+1)^T
-          if (j + 1 < n_kv) {
-            if (!k_ready) {
-              mbar_wait(&k_full[st1], ph1);
-              k_ready = true;
-            }
+        if (j + 1 < n_kv) {
+          // ---- S_t(j+1) = Q_t K(j+1)^T as soon as S_t(j) has been read out of tensor memory
+          const int st1 = (j + 1) % AT_KST;
+          mbar_wait(&k_full[st1], ((j + 1) / AT_KST) & 1);
+          for (int t = 0; t < 2; ++t) {
+            if (!act[t]) continue;
             mbar_wait(&s_empty[t], par);
             tc_fence_after();
             issue_s(t, st1);
             umma_commit(&s_full[t]);
           }
+          umma_commit(&k_empty[st1]);
+        }
+        // ---- O_t += P_t(j) V(j)
+        mbar_wait(&v_full[st], ph);
+        for (int t = 0; t < 2; ++t) {
+          if (!act[t]) continue;
+          mbar_wait(&p_full[t], par);
+          tc_fence_after();
+          issue_pv(t, st, j > 0);
+          umma_commit(&pv_done[t]);
         }
         umma_commit(&v_empty[st]);
-        if (j + 1 < n_kv) umma_commit(&k_empty[st1]);
       }
     }
     __syncwarp();
@@ -224,14 +214,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = quarter * 32 + lane;  // row within the tile == TMEM lane
     const bool active = t == 0 ? act0 : act1;
     if (active) {
-      const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * AT_BN;
-      const uint32_t t_pv = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 2 * AT_BN + t * AT_D;
-      uint8_t* myP = sP + t * AT_P_BYTES;
-      float o[AT_D];
-#pragma unroll
-      for (int i = 0; i < AT_D; ++i) o[i] = 0.f;
-      float m_run = -INFINITY, l_run = 0.f;
+      const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+      const uint32_t t_s = tmem_base + lane_off + AT_TM_S + t * AT_BN;
+      const uint32_t t_o = tmem_base + lane_off + AT_TM_O + t * AT_D;
+      const uint32_t t_p = tmem_base + lane_off + AT_TM_P + t * (AT_BN / 2);
       const float c = p.scale_log2;
+      const uint64_t c2 = f32x2_pack(c, c);
+      float m_ref = 0.f, l_run = 0.f;
 
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t par = j & 1;
@@ -245,7 +234,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[t]);  // S(j+1) = Q K(j+1)^T may now overwrite the accumulator
+        if (lane == 0) mbar_arrive(&s_empty[t]);  // S_t(j+1) may now overwrite the accumulator
 
         const int kv_valid = w.kv_len - j * AT_BN;  // >= 1; < 128 only for the clip's last kv tile
         if (kv_valid < AT_BN) {
@@ -253,64 +242,84 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int i = 0; i < AT_BN; ++i)
             if (i >= kv_valid) sv[i] = 0xff800000u;  // -inf: exp2 -> 0, never the max
         }
-        float m_tile = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
+        float m0 = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
+        float m1 = fmaxf(__uint_as_float(sv[2]), __uint_as_float(sv[3]));
 #pragma unroll
-        for (int i = 2; i < AT_BN; i += 2)
-          m_tile = fmax3(m_tile, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
-        const float m_new = fmaxf(m_run, m_tile);
-        const float alpha = ex2_approx((m_run - m_new) * c);  // 0 on the first tile
-        const float mc = m_new * c;
+        for (int i = 4; i < AT_BN; i += 4) {
+          m0 = fmax3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+          m1 = fmax3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+        }
+        const float m_tile = fmaxf(m0, m1);
 
-        // ---- fold in P V of the previous kv tile (its MMA ran while the other query tile was busy)
-        if (j > 0) {
-          mbar_wait(&pv_full[t], (j - 1) & 1);
+        // ---- lazy maximum: keep the old reference unless some row of this warp outgrew it by 2^8
+        if (j == 0) {
+          m_ref = m_tile;
+        } else if (__any_sync(0xffffffffu, (m_tile - m_ref) * c > AT_RESCALE_LOG2)) {
+          const float m_new = fmaxf(m_ref, m_tile);
+          const float alpha = ex2_approx((m_ref - m_new) * c);
+          mbar_wait(&pv_done[t], (j - 1) & 1);  // O_t holds every product up to kv tile j-1
           tc_fence_after();
-          uint32_t v[AT_D];
-          tmem_ld_32x32b_x32(t_pv, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tmem_ld_32x32b_x32(t_pv + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&pv_empty[t]);
 #pragma unroll
-          for (int i = 0; i < AT_D; ++i) o[i] = (o[i] + __uint_as_float(v[i])) * alpha;
+          for (int h = 0; h < 2; ++h) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(t_o + h * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(t_o + h * 32, o);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          m_ref = m_new;
         }
 
-        // ---- P(j) = 2^(s*c - m*c) as bf16 into swizzled smem (A operand of P V); row sum in fp32
-        float l0 = 0.f, l1 = 0.f;
+        // ---- P(j) = 2^(s*c - m*c): packed FMA, MUFU ex2, packed row-sum, bf16 pairs (in place, sv[0..63])
+        const float nmc = -m_ref * c;
+        const uint64_t nmc2 = f32x2_pack(nmc, nmc);
+        uint64_t la = f32x2_pack(0.f, 0.f), lb = la;
 #pragma unroll
-        for (int i = 0; i < AT_BN; i += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), c, -mc));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), c, -mc));
-          l0 += p0;
-          l1 += p1;
-          sv[i >> 1] = pack_bf16x2(p0, p1);
+        for (int i = 0; i < AT_BN; i += 4) {
+          const uint64_t ta = f32x2_fma(f32x2_pack(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), c2, nmc2);
+          const uint64_t tb = f32x2_fma(f32x2_pack(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), c2, nmc2);
+          float a0, a1, b0, b1;
+          f32x2_unpack(ta, a0, a1);
+          f32x2_unpack(tb, b0, b1);
+          a0 = ex2_approx(a0);
+          a1 = ex2_approx(a1);
+          b0 = ex2_approx(b0);
+          b1 = ex2_approx(b1);
+          la = f32x2_add(la, f32x2_pack(a0, a1));
+          lb = f32x2_add(lb, f32x2_pack(b0, b1));
+          sv[i >> 1] = pack_bf16x2(a0, a1);
+          sv[(i >> 1) + 1] = pack_bf16x2(b0, b1);
         }
-        if (j > 0) mbar_wait(&p_empty[t], (j - 1) & 1);  // P V(j-1) has consumed the P buffer
-#pragma unroll
-        for (int q = 0; q < AT_BN / 8; ++q) {
-          uint8_t* atom = myP + (q >> 3) * (AT_BM * 128);
-          *reinterpret_cast<uint4*>(atom + sw128_offset(r, q & 7)) =
-              make_uint4(sv[4 * q], sv[4 * q + 1], sv[4 * q + 2], sv[4 * q + 3]);
+        {
+          float x0, x1, y0, y1;
+          f32x2_unpack(f32x2_add(la, lb), x0, x1);
+          (void)y0;
+          (void)y1;
+          l_run += x0 + x1;
         }
-        fence_proxy_async_smem();
+        // ---- P(j) -> tensor memory once P V(j-1) no longer reads the buffer
+        if (j > 0) {
+          mbar_wait(&pv_done[t], (j - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st_32x32b_x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        tmem_st_32x32b_x32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
-        l_run = l_run * alpha + (l0 + l1);
-        m_run = m_new;
       }
-      // last P V
-      {
-        mbar_wait(&pv_full[t], (n_kv - 1) & 1);
-        tc_fence_after();
-        uint32_t v[AT_D];
-        tmem_ld_32x32b_x32(t_pv, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        tmem_ld_32x32b_x32(t_pv + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < AT_D; ++i) o[i] += __uint_as_float(v[i]);
-      }
-      // epilogue: out = bf16(O / l) * bf16(sigmoid(gate))
+
+      // ---- epilogue: out = bf16(O / l) * bf16(sigmoid(gate))
+      mbar_wait(&pv_done[t], (n_kv - 1) & 1);
+      tc_fence_after();
+      uint32_t o[AT_D];
+      tmem_ld_32x32b_x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+      tmem_ld_32x32b_x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+      tmem_ld_wait();
       const int qv = w.q_valid[t];
       if (r < qv) {
         const int row = w.q_row0[t] + r;
@@ -328,8 +337,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const float g0 = bf16_lo(gg[e]), g1 = bf16_hi(gg[e]);
             const float s0 = bf16r(1.0f / (1.0f + __expf(-g0)));
             const float s1 = bf16r(1.0f / (1.0f + __expf(-g1)));
-            const float a0 = bf16r(o[q * 8 + 2 * e] * inv_l);
-            const float a1 = bf16r(o[q * 8 + 2 * e + 1] * inv_l);
+            const float a0 = bf16r(__uint_as_float(o[q * 8 + 2 * e]) * inv_l);
+            const float a1 = bf16r(__uint_as_float(o[q * 8 + 2 * e + 1]) * inv_l);
             ov[e] = pack_bf16x2(a0 * s0, a1 * s1);
           }
           stg16(dst + q * 8, make_uint4(ov[0], ov[1], ov[2], ov[3]));
