@@ -14,8 +14,8 @@
 //   warp 1        MMA issuer:   S_t = Q_t K^T  (SS: M128 N128 K64)
 //                               O_t += P_t V    (TS: P read from tensor memory, V MN-major in smem, M128 N64 K128)
 //   warp 2        TMEM allocator (512 columns: S0 S1 | O0 O1 | P0 P1)
-//   warps 4-7     softmax for query tile 0 (thread == query row)
-//   warps 8-11    softmax for query tile 1
+//   warps 4-11    softmax for query tile 0: thread == (query row, half of the 128 keys of a kv tile); the two
+//   warps 12-19   softmax for query tile 1   half-row threads agree on the row maximum through shared memory
 // Pipeline: S_t(j+1) is issued as soon as the softmax warps have pulled S_t(j) into registers, so the next score
 // tile is ready before the exponentials of the current one are done; P_t(j) goes back to tensor memory as bf16
 // (tcgen05.st) and the P V product accumulates into O_t in tensor memory. The running maximum is updated lazily:
@@ -52,7 +52,9 @@ constexpr int AT_D = 64;
 constexpr int AT_KST = 4;  // K / V ring depth
 constexpr int AT_Q_BYTES = AT_BM * AT_D * 2;   // 16 KB
 constexpr int AT_KV_BYTES = AT_BN * AT_D * 2;  // 16 KB
-constexpr int AT_SMEM = 2 * AT_Q_BYTES + 2 * AT_KST * AT_KV_BYTES + 512 + 1024;
+constexpr int AT_XCH_BYTES = 3 * 2 * 2 * 128 * 4;  // half-row exchange: row max (two parities) and row sum
+constexpr int AT_SMEM = 2 * AT_Q_BYTES + 2 * AT_KST * AT_KV_BYTES + 512 + AT_XCH_BYTES + 1024;
+constexpr int AT_THREADS = 128 + 16 * 32;
 // TMEM columns
 constexpr uint32_t AT_TM_S = 0;    // S0 [0,128)   S1 [128,256)
 constexpr uint32_t AT_TM_O = 256;  // O0 [256,320) O1 [320,384)
@@ -71,7 +73,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -90,6 +92,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* p_full = s_empty + 2;       // [2]  P_t(j) is in tensor memory (and O_t has been rescaled if needed)
   uint64_t* pv_done = p_full + 2;       // [2]  O_t += P_t(j) V(j) has retired
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // [3][tile][half][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -112,8 +115,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&s_empty[t], 4);
-      mbar_init(&p_full[t], 4);
+      mbar_init(&s_empty[t], 8);
+      mbar_init(&p_full[t], 8);
       mbar_init(&pv_done[t], 1);
     }
     fence_barrier_init();
@@ -124,8 +127,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // Register re-distribution: the control warpgroup needs few registers; each softmax thread keeps a 128-key score
-  // row live (12 warps x 168 = 4 x 40 + 8 x 232). setmaxnreg sits at the top of each role branch.
+  // Register re-distribution: 640 threads start with 96 registers; the control warpgroup drops to 40 and the 16
+  // softmax warps (64 scores per thread live) grow to 104 (4 x 32 x 56 freed >= 16 x 32 x 8 taken).
+  // setmaxnreg sits at the top of each role branch.
   if (warp == 0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (elect_one()) {
@@ -208,48 +212,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int t = (warp - 4) >> 2;  // query tile of this softmax group
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int sw = warp - 4;        // 0..15
+    const int t = sw >> 3;          // query tile of this softmax group
+    const int half = (sw >> 2) & 1; // key half [64*half, +64) of every kv tile
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row within the tile == TMEM lane
     const bool active = t == 0 ? act0 : act1;
     if (active) {
       const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-      const uint32_t t_s = tmem_base + lane_off + AT_TM_S + t * AT_BN;
-      const uint32_t t_o = tmem_base + lane_off + AT_TM_O + t * AT_D;
-      const uint32_t t_p = tmem_base + lane_off + AT_TM_P + t * (AT_BN / 2);
+      const uint32_t t_s = tmem_base + lane_off + AT_TM_S + t * AT_BN + half * 64;
+      const uint32_t t_o = tmem_base + lane_off + AT_TM_O + t * AT_D + half * 32;
+      const uint32_t t_p = tmem_base + lane_off + AT_TM_P + t * (AT_BN / 2) + half * 32;
+      const uint32_t pair_bar = 1 + t;  // named barrier of this tile's 8 softmax warps
+      float* x_mine = xch + (t * 2 + half) * 128 + r;        // + parity * 512 (max) / + 1024 (sum)
+      float* x_other = xch + (t * 2 + (half ^ 1)) * 128 + r;
       const float c = p.scale_log2;
       const uint64_t c2 = f32x2_pack(c, c);
-      float m_ref = 0.f, l_run = 0.f;
+      float m_ref = 0.f, l_run = 0.f;  // l_run: this half's share of the row sum
 
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t par = j & 1;
-        // ---- S(j): the whole 128-key row into registers with one wait, then hand S back to the tensor core
+        // ---- S(j): this thread's 64 scores into registers with one wait, then hand S back to the tensor core
         mbar_wait(&s_full[t], par);
         tc_fence_after();
-        uint32_t sv[AT_BN];
-#pragma unroll
-        for (int c0 = 0; c0 < AT_BN; c0 += 32)
-          tmem_ld_32x32b_x32(t_s + c0, *reinterpret_cast<uint32_t(*)[32]>(&sv[c0]));
+        uint32_t sv[64];
+        tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        tmem_ld_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[t]);  // S_t(j+1) may now overwrite the accumulator
+        if (lane == 0) mbar_arrive(&s_empty[t]);  // S_t(j+1) may overwrite the accumulator once all 8 warps arrived
 
-        const int kv_valid = w.kv_len - j * AT_BN;  // >= 1; < 128 only for the clip's last kv tile
-        if (kv_valid < AT_BN) {
+        const int kv_valid = w.kv_len - j * AT_BN - half * 64;  // valid keys of this half; < 64 only in the last kv tile
+        if (kv_valid < 64) {
 #pragma unroll
-          for (int i = 0; i < AT_BN; ++i)
+          for (int i = 0; i < 64; ++i)
             if (i >= kv_valid) sv[i] = 0xff800000u;  // -inf: exp2 -> 0, never the max
         }
         float m0 = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
         float m1 = fmaxf(__uint_as_float(sv[2]), __uint_as_float(sv[3]));
 #pragma unroll
-        for (int i = 4; i < AT_BN; i += 4) {
+        for (int i = 4; i < 64; i += 4) {
           m0 = fmax3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
           m1 = fmax3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
         }
-        const float m_tile = fmaxf(m0, m1);
+        // both halves of a row take the same decisions: exchange the half maxima (parity-alternating slots)
+        x_mine[par * 512] = fmaxf(m0, m1);
+        named_bar_sync(pair_bar, 256);
+        const float m_tile = fmaxf(fmaxf(m0, m1), x_other[par * 512]);  // the first half always holds >= 1 valid key
 
         // ---- lazy maximum: keep the old reference unless some row of this warp outgrew it by 2^8
         if (j == 0) {
@@ -259,26 +270,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float alpha = ex2_approx((m_ref - m_new) * c);
           mbar_wait(&pv_done[t], (j - 1) & 1);  // O_t holds every product up to kv tile j-1
           tc_fence_after();
+          uint32_t o[32];  // this half rescales 32 of the 64 output columns
+          tmem_ld_32x32b_x32(t_o, o);
+          tmem_ld_wait();
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(t_o + h * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32b_x32(t_o + h * 32, o);
-          }
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32b_x32(t_o, o);
           tmem_st_wait();
           l_run *= alpha;
           m_ref = m_new;
         }
 
-        // ---- P(j) = 2^(s*c - m*c): packed FMA, MUFU ex2, packed row-sum, bf16 pairs (in place, sv[0..63])
+        // ---- P(j) = 2^(s*c - m*c): packed FMA, MUFU ex2, packed row-sum, bf16 pairs (in place, sv[0..31])
         const float nmc = -m_ref * c;
         const uint64_t nmc2 = f32x2_pack(nmc, nmc);
         uint64_t la = f32x2_pack(0.f, 0.f), lb = la;
 #pragma unroll
-        for (int i = 0; i < AT_BN; i += 4) {
+        for (int i = 0; i < 64; i += 4) {
           const uint64_t ta = f32x2_fma(f32x2_pack(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), c2, nmc2);
           const uint64_t tb = f32x2_fma(f32x2_pack(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), c2, nmc2);
           float a0, a1, b0, b1;
@@ -294,10 +302,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           sv[(i >> 1) + 1] = pack_bf16x2(b0, b1);
         }
         {
-          float x0, x1, y0, y1;
+          float x0, x1;
           f32x2_unpack(f32x2_add(la, lb), x0, x1);
-          (void)y0;
-          (void)y1;
           l_run += x0 + x1;
         }
         // ---- P(j) -> tensor memory once P V(j-1) no longer reads the buffer
@@ -306,29 +312,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tc_fence_after();
         }
         tmem_st_32x32b_x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-        tmem_st_32x32b_x32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
       }
 
-      // ---- epilogue: out = bf16(O / l) * bf16(sigmoid(gate))
+      // ---- epilogue: out = bf16(O / l) * bf16(sigmoid(gate)); this half writes 32 of the 64 head dims
+      x_mine[1024] = l_run;
+      named_bar_sync(pair_bar, 256);
+      const float inv_l = 1.0f / (l_run + x_other[1024]);
       mbar_wait(&pv_done[t], (n_kv - 1) & 1);
       tc_fence_after();
-      uint32_t o[AT_D];
-      tmem_ld_32x32b_x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
-      tmem_ld_32x32b_x32(t_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(t_o, o);
       tmem_ld_wait();
       const int qv = w.q_valid[t];
       if (r < qv) {
         const int row = w.q_row0[t] + r;
-        const int head = w.q_head[t];
-        const float inv_l = 1.0f / l_run;
-        const __nv_bfloat16* g = p.gate + static_cast<int64_t>(row) * p.ld + head * AT_D;
-        __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + head * AT_D;
+        const int col = w.q_head[t] * AT_D + half * 32;
+        const __nv_bfloat16* g = p.gate + static_cast<int64_t>(row) * p.ld + col;
+        __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + col;
 #pragma unroll
-        for (int q = 0; q < AT_D / 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
           const uint4 gv = ldg16(g + q * 8);
           const uint32_t gg[4] = {gv.x, gv.y, gv.z, gv.w};
           uint32_t ov[4];
@@ -384,7 +390,7 @@ int ttk_attn_varlen_fwd(const void* qkv, int64_t ld, int M, int width, int gqa, 
       return TTK_ERR_CUDA;
     attr_done = true;
   }
-  attn_fwd_kernel<<<n_work, 384, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  attn_fwd_kernel<<<n_work, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
   return launch_status();
 }
 

@@ -53,13 +53,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// round-to-nearest-even fp32 -> bf16 -> fp32 (the reference rounds at every op boundary)
-__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits), .y = hi
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t r;  // cvt.rn.bf16x2.f32 d, a, b: a -> upper half, b -> lower half (F2FP, full-rate pipe)
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
+// round-to-nearest-even fp32 -> bf16 -> fp32 (the reference rounds at every op boundary). Goes through the packed
+// convert: the scalar cvt.rn.bf16.f32 is an F2F on the quarter-rate conversion (XU) pipe, which it shares with MUFU.
+__device__ __forceinline__ float bf16r(float x) { return __uint_as_float(pack_bf16x2(0.f, x) & 0xffff0000u); }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
