@@ -49,6 +49,22 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic(kernel, batch):
+    """dram bytes (read + write) per launch of `kernel` from the committed ncu --set full summary of this same bench
+    command (profiles/r1_traffic.json, written by scripts/summarize_profiles.py); None when no capture matches."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        d = json.load(open(p))
+        e = d.get(kernel)
+        if e and int(e.get("batch", -1)) == int(batch):
+            return float(e["dram_bytes_per_launch"])
+    except Exception:
+        return None
+    return None
+
+
 def clip_flops(shape=CLIP_A, t=TOKENS_A):
     """Forward FLOPs of one clip through encoder + decoder."""
     g = (shape[0] // PATCH[0]) * (shape[1] // PATCH[1]) * (shape[2] // PATCH[2])
@@ -200,8 +216,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="clips per GPU per step")
+    ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vq", action="store_true", help="skip the quantizer microbench (BASELINE configs[1]) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -231,6 +248,9 @@ def main():
         torch.cuda.synchronize()
 
     B = args.batch
+    global INPUT_SETS
+    if B * 3 * CLIP_A[0] * CLIP_A[1] * CLIP_A[2] * 2 > 126e6:
+        INPUT_SETS = 2  # one step's clips already exceed the 126 MB L2
     torch.manual_seed(42)
     model = T.TiTok(tiny_config(LEVELS, PATCH)).to(dev).eval()
     tcs = [TOKENS_A] * B
@@ -362,9 +382,16 @@ def main():
         peak = pk["bf16_tflops_sustained"]
         ach = fl / (avg_ms * 1e-3) / 1e12 if fl else None
         roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
+                    "frac": (ach / peak) if ach else None, "traffic": ncu_traffic(top, B), "peak_source": pk["source"] + " (sustained bf16)",
                     "avg_launch_ms": avg_ms, "share_of_step": ksum[top][0] / tot_k}
     whole = {"tflops": value * flops_clip / 1e12, "frac_of_tensor_peak": value * flops_clip / 1e12 / pk["bf16_tflops_sustained"]}
+
+    vq = None
+    if rank == 0 and world == 1 and not args.no_vq:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import vq_bench
+
+        vq = vq_bench.main(quick=True, quiet=True)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -388,7 +415,7 @@ def main():
                     "wall_ms_per_step": float(ms[1].item()) / args.steps,
                     "api": "TiTok.tokenize_reconstruct_(clips, token_counts) from pinned host clips, 2-slot pipeline"},
             "gpu_launches": launches, "roofline": roofline, "whole_step": whole, "kernels": kernels, "clocks": clocks,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "quantizer_microbench": vq,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -67,3 +67,6 @@ for name in names:
                 break
             line.append("t%d[P %d | M %d %d %d | E %d %d %d]" % ((it,) + tuple(e - t0 if e else -1 for e in ev)))
         print(f" cta {cta}: end {int(r[63]) - t0}  " + "  ".join(line))
+        if int(r[48]):
+            print("    resid epilogue tile0 phases (after accum+resid | after norm1 | x' store issued | x' read done | before final wait):",
+                  [int(r[k]) - t0 for k in range(48, 53)])

@@ -6,10 +6,10 @@ OUT=gpurun_out
 mkdir -p $OUT
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $CMD > $OUT/plain_$TAG.log 2> $OUT/plain_$TAG.err || { echo "plain run failed"; tail -n 20 $OUT/plain_$TAG.err; exit 1; }
-ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 80 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 120 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 17 -c 2 -f -o $OUT/attn_$TAG $CMD > $OUT/ncu_attn_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 17 -c 1 -f -o $OUT/attn_$TAG $CMD > $OUT/ncu_attn_$TAG.log 2>&1
 echo "attn capture rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 70 -c 5 -f -o $OUT/gemm_$TAG $CMD > $OUT/ncu_gemm_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 70 -c 6 -f -o $OUT/gemm_$TAG $CMD > $OUT/ncu_gemm_$TAG.log 2>&1
 echo "gemm capture rc=$?"
 ls -la $OUT

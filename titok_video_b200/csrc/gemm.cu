@@ -213,9 +213,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             phase ^= 1;
           }
           if constexpr (EPI == EPI_RESID) {
-            // residual tile of this M block: issued once the operand pipeline of the tile is primed (so the MMAs of
-            // this tile overlap the previous tile's epilogue); waits until that epilogue has stored its rows
-            if (kb == (p.num_k_blocks < STAGES ? p.num_k_blocks : STAGES) - 1) {
+            // residual tile of this M block. First tile: right behind the first operand stage (nothing to wait for).
+            // Later tiles: behind the LAST operand stage, because the load has to wait until the previous tile's
+            // epilogue has stored its rows and must not hold back the operands that let this tile's MMAs overlap it.
+            if (kb == (it == 0 ? 0 : p.num_k_blocks - 1)) {
               mbar_wait(resid_empty, (it & 1) ^ 1);
               mbar_arrive_expect_tx(resid_full, BM * 256 * 2);
 #pragma unroll
@@ -494,6 +495,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
+        if (threadIdx.x == 128 && it == 0) trace_stamp(p, 48);
         // exchange slot: mode 1 uses slots 0 and 1 within a tile; mode 0 alternates them between tiles, so a slot is
         // never rewritten before the partners' reads of its previous value are ordered by a barrier
         float* ex0 = ssm + ((p.mode == 1) ? 0 : static_cast<int>(it & 1)) * 512;
@@ -518,6 +520,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           named_bar_sync(1, 32 * EPI_WARPS);
           ss = (ex1[row_in_tile] + ex1[128 + row_in_tile]) + (ex1[256 + row_in_tile] + ex1[384 + row_in_tile]);
         }
+        if (threadIdx.x == 128 && it == 0) trace_stamp(p, 49);
         // x' in place over the residual rows, then out through TMA (rows >= M are clipped)
 #pragma unroll
         for (int c = 0; c < 8; ++c)
@@ -528,6 +531,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tma_store_2d(&tmO, rbox, cpart * 64, row0);
           tma_store_commit();
         }
+        if (threadIdx.x == 128 && it == 0) trace_stamp(p, 50);
         if (p.w_next) {
           const float rstd = 1.0f / sqrtf(ss * (1.0f / 256) + 1e-5f);
           const float* wn = wsm + 256 + cpart * 64;
@@ -538,6 +542,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (lane == 0) tma_store_wait_read<0>();  // x' has left shared memory
           __syncwarp();
+        if (threadIdx.x == 128 && it == 0) trace_stamp(p, 51);
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             *reinterpret_cast<uint4*>(rbox + sw128_offset(lane, c)) = make_uint4(xs[4 * c], xs[4 * c + 1], xs[4 * c + 2], xs[4 * c + 3]);
@@ -548,6 +553,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_store_commit();
           }
         }
+        if (threadIdx.x == 128 && it == 0) trace_stamp(p, 52);
         if (lane == 0) {
           tma_store_wait_read<0>();
           mbar_arrive(resid_empty);  // the producer may overwrite this warp's rows with the next residual tile
