@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtitok_b200.so")
+LIB_PATH = os.environ.get("TTK_LIB_PATH") or os.path.join(_HERE, "lib", "libtitok_b200.so")  # override: kernel experiments
 
 
 class TitokB200Error(RuntimeError):

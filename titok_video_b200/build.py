@@ -40,7 +40,13 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, tag: str = "", defines: tuple = ()) -> str:
+    """tag / defines: experimental variants (lib/libtitok_b200_<tag>.so built with -D<define>, selected at run time
+    with TTK_LIB_PATH); the product library is the untagged one."""
+    global OBJDIR, LIB
+    if tag:
+        OBJDIR = os.path.join(ROOT, "build", "variant_" + tag)
+        LIB = os.path.join(LIBDIR, f"libtitok_b200_{tag}.so")
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     nvcc = _nvcc()
@@ -52,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            jobs.append([nvcc, *NVCC_FLAGS, "-c", s, "-o", o])
+            jobs.append([nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -69,5 +75,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose=True)
+    _tag = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--tag=")), "")
+    _defs = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
+    path = build(force="--force" in sys.argv, verbose=True, tag=_tag, defines=_defs)
     print(path)

@@ -44,7 +44,17 @@ struct AttnParams {
   __nv_bfloat16* out;         // [M, ldo]
   int64_t ldo;
   float scale_log2;  // softmax_scale * log2(e)
+  long long* trace;  // development aid (ttk_debug_set_trace): [CTA][64] clock64 stamps of kv iterations 3..7
 };
+
+// slot = (j - 3) * 12 + event for kv iterations 3..7; events 0-5 softmax warp 4 (tile 0), 6-7 softmax warp 12 (tile 1),
+// 8-11 MMA issuer
+// (compiled in only with -DAT_TRACE: the stamps cost ~15 % in the softmax loop)
+__device__ __forceinline__ void at_stamp(const AttnParams& p, int j, int ev) {
+#ifdef AT_TRACE
+  if (p.trace && j >= 3 && j < 8) p.trace[blockIdx.x * 64 + (j - 3) * 12 + ev] = clock64();
+#endif
+}
 
 constexpr int AT_BM = 128;  // query rows per tile
 constexpr int AT_BN = 128;  // keys per kv tile
@@ -59,6 +69,9 @@ constexpr int AT_THREADS = 128 + 16 * 32;
 constexpr uint32_t AT_TM_S = 0;    // S0 [0,128)   S1 [128,256)
 constexpr uint32_t AT_TM_O = 256;  // O0 [256,320) O1 [320,384)
 constexpr uint32_t AT_TM_P = 384;  // P0 [384,448) P1 [448,512)   (128 keys x bf16 = 64 columns)
+#ifndef AT_STAGGER_NS
+#define AT_STAGGER_NS 600
+#endif
 constexpr float AT_RESCALE_LOG2 = 8.0f;  // rescale O only when the row maximum grew by more than 2^8
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -68,9 +81,13 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
+#ifdef AT_EXP_NOMUFU  // timing experiment only (scripts/attn_bench.py): how much of the kernel is MUFU time?
+  return fmaf(x, 1e-3f, 1e-2f);
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
@@ -175,6 +192,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
       for (int t = 0; t < 2; ++t) {
         if (!act[t]) continue;
+        // Stagger the two query tiles by roughly half a kv iteration: their softmax groups share the four MUFU
+        // pipes, and nothing else would ever move them out of phase (measured: in phase, every exponential phase
+        // runs at half speed while the pipes idle during the load / max / store phases of both tiles).
+        if (t == 1 && act[0]) __nanosleep(AT_STAGGER_NS);
         issue_s(t, 0);
         umma_commit(&s_full[t]);
       }
@@ -191,6 +212,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (!act[t]) continue;
             mbar_wait(&s_empty[t], par);
             tc_fence_after();
+            at_stamp(p, j, 8 + t);
             issue_s(t, st1);
             umma_commit(&s_full[t]);
           }
@@ -202,6 +224,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (!act[t]) continue;
           mbar_wait(&p_full[t], par);
           tc_fence_after();
+          at_stamp(p, j, 10 + t);
           issue_pv(t, st, j > 0);
           umma_commit(&pv_done[t]);
         }
@@ -236,6 +259,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // ---- S(j): this thread's 64 scores into registers with one wait, then hand S back to the tensor core
         mbar_wait(&s_full[t], par);
         tc_fence_after();
+        if (threadIdx.x == 128) at_stamp(p, j, 0);
+        if (threadIdx.x == 384) at_stamp(p, j, 6);
         uint32_t sv[64];
         tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
         tmem_ld_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
@@ -243,6 +268,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[t]);  // S_t(j+1) may overwrite the accumulator once all 8 warps arrived
+        if (threadIdx.x == 128) at_stamp(p, j, 1);
 
         const int kv_valid = w.kv_len - j * AT_BN - half * 64;  // valid keys of this half; < 64 only in the last kv tile
         if (kv_valid < 64) {
@@ -258,10 +284,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           m1 = fmax3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
         }
         // both halves of a row take the same decisions: exchange the half maxima (parity-alternating slots)
+#ifdef AT_EXP_NOBAR  // timing experiment only: cost of the half-row exchange
+        const float m_tile = fmaxf(m0, m1);
+#else
         x_mine[par * 512] = fmaxf(m0, m1);
         named_bar_sync(pair_bar, 256);
         const float m_tile = fmaxf(fmaxf(m0, m1), x_other[par * 512]);  // the first half always holds >= 1 valid key
+#endif
 
+        if (threadIdx.x == 128) at_stamp(p, j, 2);
         // ---- lazy maximum: keep the old reference unless some row of this warp outgrew it by 2^8
         if (j == 0) {
           m_ref = m_tile;
@@ -307,15 +338,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           l_run += x0 + x1;
         }
         // ---- P(j) -> tensor memory once P V(j-1) no longer reads the buffer
+        if (threadIdx.x == 128) at_stamp(p, j, 3);
         if (j > 0) {
           mbar_wait(&pv_done[t], (j - 1) & 1);
           tc_fence_after();
         }
+        if (threadIdx.x == 128) at_stamp(p, j, 4);
         tmem_st_32x32b_x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+        if (threadIdx.x == 128) at_stamp(p, j, 5);
+        if (threadIdx.x == 384) at_stamp(p, j, 7);
       }
 
       // ---- epilogue: out = bf16(O / l) * bf16(sigmoid(gate)); this half writes 32 of the 64 head dims
@@ -384,6 +419,7 @@ int ttk_attn_varlen_fwd(const void* qkv, int64_t ld, int M, int width, int gqa, 
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.trace = g_trace;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess)

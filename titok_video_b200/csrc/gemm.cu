@@ -595,8 +595,6 @@ struct GemmIo {
   int64_t ldr = 0;
 };
 
-static long long* g_trace = nullptr;
-
 template <int BN, int EPI, bool B_MN>
 static int launch_gemm(const GemmIo& io, GemmParams& p, cudaStream_t stream) {
   using S = GemmSmem<BN, EPI>;

@@ -36,6 +36,8 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return r == CUDA_SUCCESS ? TTK_OK : TTK_ERR_DRIVER;
 }
 
+long long* g_trace = nullptr;
+
 static int g_sm_major = -1, g_sm_minor = -1, g_num_sms = 0;
 static std::once_flag g_dev_once;
 static void query_dev() {

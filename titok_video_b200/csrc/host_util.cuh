@@ -22,6 +22,9 @@ PFN_tensorMapEncodeTiled get_encode_fn();
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols = 64);
 
+// development aid: device buffer for clock64 pipeline stamps (ttk_debug_set_trace), null in production
+extern long long* g_trace;
+
 int check_device_sm100();
 int num_sms();
 
