@@ -217,3 +217,28 @@ def test_state_dict_roundtrip_with_reference_layout(golden_default):
     m2 = build_model(True)
     m2.load_state_dict(sd, strict=True)
     assert checksum_matches(m2.state_dict(), golden_default["weight_checksum"])
+
+
+def test_cuda_graph_replay_equals_eager_launches(golden_stress):
+    """The throughput path replays one captured CUDA graph per shape signature; results must be bit-identical to the
+    kernel-by-kernel launches, for new inputs and after an in-place weight update (the graph must not go stale)."""
+    shapes, tcs, clips = _case(golden_stress)
+    model = build_model(True).cuda().eval()
+    cl = [c.cuda() for c in clips]
+    with torch.no_grad():
+        ref, dref = model(cl, tcs)
+        ref = [r.clone() for r in ref]
+        for _ in range(2):  # first call captures, second replays
+            rec, d = model.tokenize_reconstruct_(cl, tcs, use_graph=True)
+            assert torch.equal(d["indices"], dref["indices"])
+            assert all(torch.equal(a, b) for a, b in zip(rec, ref))
+        cl2 = [torch.flip(c, dims=(-1,)).contiguous() for c in cl]
+        ref2, dref2 = model(cl2, tcs)
+        ref2 = [r.clone() for r in ref2]
+        rec2, d2 = model.tokenize_reconstruct_(cl2, tcs, use_graph=True)
+        assert torch.equal(d2["indices"], dref2["indices"]) and all(torch.equal(a, b) for a, b in zip(rec2, ref2))
+        model.decoder.proj_out.bias.add_(0.25)
+        ref3, _ = model(cl2, tcs)
+        ref3 = [r.clone() for r in ref3]
+        rec3, _ = model.tokenize_reconstruct_(cl2, tcs, use_graph=True)
+        assert all(torch.equal(a, b) for a, b in zip(rec3, ref3)) and not torch.equal(ref3[0], ref2[0])

@@ -3,6 +3,7 @@
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -64,10 +65,48 @@ class TiTok(nn.Module):
 
     # ---- throughput path: no defensive copies, results live in the plan's workspace ---------------
     @torch.no_grad()
-    def tokenize_reconstruct_(self, x: Sequence[torch.Tensor], token_counts):
+    def tokenize_reconstruct_(self, x: Sequence[torch.Tensor], token_counts, use_graph: Optional[bool] = None):
         """forward() without the output clones: the returned clips / indices alias workspace buffers that the next
-        call with the same shapes overwrites. Used by bench.py and batch jobs that consume results immediately."""
+        call with the same shapes overwrites. Used by bench.py and batch jobs that consume results immediately.
+
+        The 47 kernel launches of encoder + FSQ + decoder are captured once per (shapes, token_counts) signature into
+        a CUDA graph and replayed (`use_graph=False` or TTK_CUDA_GRAPH=0 launches them one by one). Inputs are copied
+        into the plan's static clip buffer first; weights are refreshed in place, so a captured graph stays valid
+        across optimizer steps."""
+        dev = x[0].device
+        engine.require_cuda(dev)
         grids = [tuple(v.shape[1:]) for v in x]
-        _, codes, idx, dp = self.encoder.forward_impl(x, token_counts, grids, fsq=self.quantize)
-        out, _ = self.decoder.forward_impl(codes, token_counts, grids)
+        tcs = engine.to_host_ints(token_counts)
+        if len(tcs) != len(x):
+            raise ValueError("len(token_counts) must equal the number of clips")
+        enc, dec = self.encoder, self.decoder
+        dp = enc._plan(grids, tcs, dev)
+        flat = engine.flatten_clips(x, dp)
+        consts = self.quantize._consts(dev)
+        engine.prepared(enc, "enc")
+        engine.prepared(dec, "dec")
+        out = dp.buf("clips_out", (dp.plan.total_numel,))
+
+        def launch():
+            _, codes, idx = engine.encoder_launch(enc, dp, flat, consts)
+            engine.decoder_launch(dec, dp, codes, out)
+            return idx
+
+        if use_graph is None:
+            use_graph = os.environ.get("TTK_CUDA_GRAPH", "1") != "0"
+        if not use_graph:
+            idx = launch()
+        else:
+            key = ("tokenize_reconstruct", id(self), flat.data_ptr())
+            entry = dp.graphs.get(key)
+            if entry is None:
+                idx = launch()  # eager warm-up: workspace allocation, one-time function attributes
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    idx = launch()
+                entry = (g, idx)
+                dp.graphs[key] = entry
+            entry[0].replay()
+            idx = entry[1]
         return engine.split_clips(out, dp.plan), {"indices": idx}
