@@ -247,45 +247,59 @@ enc_head_fsq_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const int32
 
 // ------------------------------------------------------------------------------------------------
 // patchify: clips (flat bf16 buffer, each clip [3,T,H,W]) -> patches [G, 3*P0*P1*P2] with feature order
-// (c, p0, p1, p2). geom[g] = {element offset of (c=0,t0,h0,w0), W, H*W, T*H*W}. One thread per 8-element
-// run along W (P2 == 8).
+// (c, p0, p1, p2). geom[g] = {element offset of (c=0,t0,h0,w0), W, H*W, T*H*W}; P2 == 8, so a patch is
+// C*P0*P1 runs of 16 bytes along W.
+// One CTA moves PATCH_CHUNK consecutive patches through shared memory so that BOTH sides are coalesced: on the
+// clip side consecutive lanes take the same run of consecutive patches (neighbours along W: one contiguous
+// segment), on the patch side a warp streams whole 1.5 KB patch rows.
 // ------------------------------------------------------------------------------------------------
+constexpr int PATCH_CHUNK = 16;
+
+__device__ __forceinline__ int64_t patch_run_offset(const int64_t* ge, int rr, int P0, int P1) {
+  const int c = rr / (P0 * P1);
+  const int p0 = (rr / P1) % P0;
+  const int p1 = rr % P1;
+  return ge[0] + c * ge[3] + p0 * ge[2] + p1 * ge[1];
+}
+
 __global__ void __launch_bounds__(256) patchify_kernel(const __nv_bfloat16* __restrict__ clips,
                                                        const int64_t* __restrict__ geom, int C, int P0, int P1,
                                                        __nv_bfloat16* __restrict__ patches, int64_t ldp, int64_t G) {
-  const int runs = C * P0 * P1;  // 16-byte runs per patch
-  const int64_t total = G * runs;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t g = i / runs;
-    const int rr = static_cast<int>(i - g * runs);
-    const int c = rr / (P0 * P1);
-    const int p0 = (rr / P1) % P0;
-    const int p1 = rr % P1;
-    const int64_t* ge = geom + g * 4;
-    const int64_t src = ge[0] + c * ge[3] + p0 * ge[2] + p1 * ge[1];
-    stg16(patches + g * ldp + rr * 8, ldg16_stream(clips + src));
+  extern __shared__ uint4 patch_smem[];  // [PATCH_CHUNK][runs + 1] 16-byte cells (+1: bank-conflict padding)
+  const int runs = C * P0 * P1;
+  const int pitch = runs + 1;
+  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * PATCH_CHUNK;
+  const int np = static_cast<int>(min(static_cast<int64_t>(PATCH_CHUNK), G - g0));
+  for (int i = threadIdx.x; i < PATCH_CHUNK * runs; i += blockDim.x) {
+    const int pi = i % PATCH_CHUNK, rr = i / PATCH_CHUNK;
+    if (pi < np) patch_smem[pi * pitch + rr] = ldg16_stream(clips + patch_run_offset(geom + (g0 + pi) * 4, rr, P0, P1));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < np * runs; i += blockDim.x) {
+    const int pi = i / runs, rr = i - pi * runs;
+    stg16(patches + (g0 + pi) * ldp + rr * 8, patch_smem[pi * pitch + rr]);
   }
 }
 
 // unpatchify: rows of `proj` ([*, ldp], feature order (c,p0,p1,p2)) for the patch rows -> clips.
-// patch_row[g] = row of proj holding patch g.
+// patch_row[g] = row of proj holding patch g. Same staging, opposite direction.
 __global__ void __launch_bounds__(256) unpatchify_kernel(const __nv_bfloat16* __restrict__ proj, int64_t ldp,
                                                          const int32_t* __restrict__ patch_row,
                                                          const int64_t* __restrict__ geom, int C, int P0, int P1,
                                                          __nv_bfloat16* __restrict__ clips, int64_t G) {
+  extern __shared__ uint4 patch_smem[];
   const int runs = C * P0 * P1;
-  const int64_t total = G * runs;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t g = i / runs;
-    const int rr = static_cast<int>(i - g * runs);
-    const int c = rr / (P0 * P1);
-    const int p0 = (rr / P1) % P0;
-    const int p1 = rr % P1;
-    const int64_t* ge = geom + g * 4;
-    const int64_t dst = ge[0] + c * ge[3] + p0 * ge[2] + p1 * ge[1];
-    stg16(clips + dst, ldg16_stream(proj + static_cast<int64_t>(patch_row[g]) * ldp + rr * 8));
+  const int pitch = runs + 1;
+  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * PATCH_CHUNK;
+  const int np = static_cast<int>(min(static_cast<int64_t>(PATCH_CHUNK), G - g0));
+  for (int i = threadIdx.x; i < np * runs; i += blockDim.x) {
+    const int pi = i / runs, rr = i - pi * runs;
+    patch_smem[pi * pitch + rr] = ldg16_stream(proj + static_cast<int64_t>(patch_row[g0 + pi]) * ldp + rr * 8);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PATCH_CHUNK * runs; i += blockDim.x) {
+    const int pi = i % PATCH_CHUNK, rr = i / PATCH_CHUNK;
+    if (pi < np) stg16(clips + patch_run_offset(geom + (g0 + pi) * 4, rr, P0, P1), patch_smem[pi * pitch + rr]);
   }
 }
 
@@ -391,10 +405,11 @@ int ttk_patchify(const void* clips, const int64_t* geom, int C, int P0, int P1, 
   if (int e = check_device_sm100()) return e;
   if (P2 != 8 || C < 1 || P0 < 1 || P1 < 1 || ldp % 8) return TTK_ERR_BAD_SHAPE;
   if (G <= 0) return TTK_OK;
-  const int64_t total = G * C * P0 * P1;
-  const int64_t blocks = (total + 255) / 256;
-  const int grid = static_cast<int>(blocks < 32LL * num_sms() ? blocks : 32LL * num_sms());
-  patchify_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(clips), geom, C, P0, P1,
+  const size_t smem = static_cast<size_t>(PATCH_CHUNK) * (C * P0 * P1 + 1) * 16;
+  if (smem > 48 * 1024) return TTK_ERR_BAD_SHAPE;
+  const int64_t blocks = (G + PATCH_CHUNK - 1) / PATCH_CHUNK;
+  if (blocks > 0x7fffffffLL) return TTK_ERR_BAD_SHAPE;
+  patchify_kernel<<<static_cast<int>(blocks), 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(clips), geom, C, P0, P1,
                                             static_cast<__nv_bfloat16*>(patches), ldp, G);
   return launch_status();
 }
@@ -405,10 +420,11 @@ int ttk_unpatchify(const void* proj, int64_t ldp, const int32_t* patch_row, cons
   if (int e = check_device_sm100()) return e;
   if (P2 != 8 || C < 1 || P0 < 1 || P1 < 1 || ldp % 8) return TTK_ERR_BAD_SHAPE;
   if (G <= 0) return TTK_OK;
-  const int64_t total = G * C * P0 * P1;
-  const int64_t blocks = (total + 255) / 256;
-  const int grid = static_cast<int>(blocks < 32LL * num_sms() ? blocks : 32LL * num_sms());
-  unpatchify_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(proj), ldp, patch_row, geom, C, P0,
+  const size_t smem = static_cast<size_t>(PATCH_CHUNK) * (C * P0 * P1 + 1) * 16;
+  if (smem > 48 * 1024) return TTK_ERR_BAD_SHAPE;
+  const int64_t blocks = (G + PATCH_CHUNK - 1) / PATCH_CHUNK;
+  if (blocks > 0x7fffffffLL) return TTK_ERR_BAD_SHAPE;
+  unpatchify_kernel<<<static_cast<int>(blocks), 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(proj), ldp, patch_row, geom, C, P0,
                                               P1, static_cast<__nv_bfloat16*>(clips), G);
   return launch_status();
 }
