@@ -36,10 +36,21 @@ if "--trace" in sys.argv:
     _lib.check(_lib.fn("ttk_debug_set_trace")(_vp(0)))
     t = tr.cpu()
     names = ["S ready", "S in regs", "max+xchg", "exps done", "pv_done ok", "P stored", "t1 S ready", "t1 P stored", "MMA S0 issue", "MMA S1 issue", "MMA PV0 issue", "MMA PV1 issue"]
+    # whole-CTA phases and back-to-back CTAs on one SM (globaltimer-free: clock64 is per SM, so compare CTAs on the same SM)
+    by_sm = {}
+    for cta in range(work.shape[0]):
+        r = t[cta]
+        if int(r[63]):
+            by_sm.setdefault(int(r[59]), []).append((int(r[60]), int(r[58]), int(r[61]), int(r[62]), int(r[63]), cta))
+    for sm in (0, 77):
+        seq = sorted(by_sm.get(sm, []))
+        print(f"SM {sm}: per CTA [setup->firstS | kv loop | epilogue | teardown] and gap to the next CTA's setup stamp")
+        for a, b in zip(seq[:6], seq[1:7]):
+            print(f"   cta {a[5]}: {a[1]-a[0]} | {a[2]-a[1]} | {a[3]-a[2]} | {a[4]-a[3]} | gap {b[0]-a[4]}")
     for cta in (0, 500):
         r = t[cta]
         t0 = int(r[0])
         print(f"cta {cta}: cycles relative to 'S ready' of kv iteration 3 (tile 0)")
-        for jj in range(5):
+        for jj in range(4):
             ev = [int(r[jj * 12 + k]) - t0 for k in range(12)]
             print(f"  j={jj + 3}: " + "  ".join(f"{n}={v}" for n, v in zip(names, ev)))

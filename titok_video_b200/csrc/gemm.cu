@@ -73,21 +73,31 @@ struct GemmSmem {
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
 
-// 0.5 * g * (1 + erf(g / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, two MUFU ops).
+// gelu(g) = 0.5 g (1 + erf(g / sqrt 2)) for two values at once, erf from Abramowitz-Stegun 7.1.26
+// (|abs err| <= 1.5e-7; two MUFU ops per value: rcp and ex2), evaluated with packed FFMA2 / FMUL2:
+//   t = 1 / (1 + p |g| / sqrt 2),  erf(|x|) = 1 - (a1 t + .. + a5 t^5) exp(-g^2 / 2),  gelu = 0.5 g + 0.5 |g| erf(|x|)
 // Against the exact function rounded to bf16 it differs on 117 of the 65280 finite bf16 inputs, all of them
 // g < -3 with |gelu| < 3e-3 (torch's own CPU bf16 kernel differs on 765); see tests/test_gpu_kernels.py.
-__device__ __forceinline__ float gelu_erf(float g) {
-  const float x = g * 0.70710678118654752440f;
-  const float ax = fabsf(x);
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-ax * ax * 1.4426950408889634f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float y = fmaf(-p * t, e, 1.0f);  // erf(|x|)
-  return 0.5f * g * (1.0f + copysignf(y, x));
+__device__ __forceinline__ void gelu_erf_x2(float g0, float g1, float& o0, float& o1) {
+  const uint64_t g = f32x2_pack(g0, g1);
+  const uint64_t ag = f32x2_pack(fabsf(g0), fabsf(g1));
+  float d0, d1, a0, a1, t0, t1, e0, e1;
+  f32x2_unpack(f32x2_fma(ag, f32x2_pack(0.23164189f, 0.23164189f), f32x2_pack(1.0f, 1.0f)), d0, d1);  // p / sqrt 2
+  f32x2_unpack(f32x2_mul(f32x2_mul(g, g), f32x2_pack(-0.72134752f, -0.72134752f)), a0, a1);           // -log2(e) / 2
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const uint64_t t = f32x2_pack(t0, t1), e = f32x2_pack(e0, e1);
+  // negated coefficients: q = -(a1 t + ... + a5 t^5)
+  uint64_t q = f32x2_fma(f32x2_pack(-1.061405429f, -1.061405429f), t, f32x2_pack(1.453152027f, 1.453152027f));
+  q = f32x2_fma(q, t, f32x2_pack(-1.421413741f, -1.421413741f));
+  q = f32x2_fma(q, t, f32x2_pack(0.284496736f, 0.284496736f));
+  q = f32x2_fma(q, t, f32x2_pack(-0.254829592f, -0.254829592f));
+  q = f32x2_mul(q, t);
+  const uint64_t y = f32x2_fma(q, e, f32x2_pack(1.0f, 1.0f));  // erf(|x|)
+  const uint64_t half = f32x2_pack(0.5f, 0.5f);
+  f32x2_unpack(f32x2_fma(f32x2_mul(ag, half), y, f32x2_mul(g, half)), o0, o1);
 }
 
 // Per-warp staging of [32 rows x 64 cols] bf16 boxes for TMA stores (double-buffered).
@@ -431,9 +441,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float x0 = bf16r(__uint_as_float(xv[2 * j])), x1 = bf16r(__uint_as_float(xv[2 * j + 1]));
-              const float g0 = bf16r(__uint_as_float(gv[2 * j])), g1 = bf16r(__uint_as_float(gv[2 * j + 1]));
-              pk[hh * 8 + j] = pack_bf16x2(bf16r(gelu_erf(g0)) * x0, bf16r(gelu_erf(g1)) * x1);
+              // Linear output is bf16: round value and gate pairs with one packed convert each; the product
+              // bf16(gelu) * value is one packed bf16 multiply (exact product, one rounding, like the reference's op)
+              const uint32_t x2 = pack_bf16x2(__uint_as_float(xv[2 * j]), __uint_as_float(xv[2 * j + 1]));
+              const uint32_t g2 = pack_bf16x2(__uint_as_float(gv[2 * j]), __uint_as_float(gv[2 * j + 1]));
+              float a0, a1;
+              gelu_erf_x2(bf16_lo(g2), bf16_hi(g2), a0, a1);
+              const uint32_t a2 = pack_bf16x2(a0, a1);
+              const __nv_bfloat162 h2 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&a2), *reinterpret_cast<const __nv_bfloat162*>(&x2));
+              pk[hh * 8 + j] = *reinterpret_cast<const uint32_t*>(&h2);
             }
           }
           if ((cpart & 1) == 0 && lane == 0) tma_store_wait_read<1>();  // the pair's buffer of two tiles ago is free
