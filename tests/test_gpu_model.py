@@ -242,3 +242,46 @@ def test_cuda_graph_replay_equals_eager_launches(golden_stress):
         ref3 = [r.clone() for r in ref3]
         rec3, _ = model.tokenize_reconstruct_(cl2, tcs, use_graph=True)
         assert all(torch.equal(a, b) for a, b in zip(rec3, ref3)) and not torch.equal(ref3[0], ref2[0])
+
+
+def test_ragged_batch_from_config_ranges_and_long_clip():
+    """Packed ragged batch drawn from the sampling ranges of configs/tiny.yaml (tiny.yaml:56-66: T 8..16, H/W 128..168,
+    1..128 latent tokens, multiples of the patch size) plus one long clip (8x256x256, 256 tokens, s = 2304) of the
+    scaled configuration (BASELINE configs[4]); includes token_count == 1 and sequence lengths that are not multiples
+    of the 128-row attention tile."""
+    import random
+
+    rnd = random.Random(0)
+    shapes = [(rnd.choice([8, 12, 16]), rnd.choice([128, 136, 152, 168]), rnd.choice([128, 144, 160, 168])) for _ in range(4)]
+    tcs = [1, rnd.randint(2, 128), rnd.randint(2, 128), 128]
+    shapes.append((8, 256, 256))
+    tcs.append(256)
+    clips = O.make_clips(shapes, 5)
+    model = build_model(True)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda().eval()
+    with torch.no_grad():
+        z = model.encoder([c.cuda() for c in clips], tcs)
+        x_q, d = model.encode([c.cuda() for c in clips], tcs)
+        rec = model.decode(x_q, tcs, shapes)
+    z_o = O.encoder_forward(sd, "tiny", PATCH, clips, tcs)
+    _check(z, z_o, True, "ragged z")
+    _, idx_o, _ = O.fsq_forward(z_o, LEVELS)
+    _check_indices(d["indices"], idx_o, z, z_o, "ragged indices")
+    rec_o = O.decoder_forward(sd, "tiny", PATCH, x_q.float().cpu(), tcs, shapes)
+    for i, (a, b) in enumerate(zip(rec, rec_o)):
+        assert tuple(a.shape) == (3, *shapes[i])
+        _check(a, b, True, f"ragged recon clip {i}")
+
+
+def test_base_size_odd_gqa_ratio():
+    """'base' (width 768, 12 layers, heads 12/4: three query heads per kv head) takes the other attention work-list
+    branch (two consecutive row tiles of one head share a K/V stream, last tile of a head possibly alone)."""
+    shapes, tcs = [(8, 48, 40), (4, 16, 16)], [7, 2]  # s = 67 and 6 -> one 128-row tile each; odd tile counts
+    clips = O.make_clips(shapes, 9)
+    model = build_model(False, enc="base", dec="base")
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda().eval()
+    with torch.no_grad():
+        z = model.encoder([c.cuda() for c in clips], tcs)
+    _check(z, O.encoder_forward(sd, "base", PATCH, clips, tcs), False, "base z")
