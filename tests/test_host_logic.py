@@ -147,3 +147,21 @@ def test_shard_clips_balances_cost():
     loads = [sum(costs[i] for i in p) for p in parts]
     assert max(loads) / min(loads) < 1.15
     assert P.shard_clips([1.0], 2) == [[0], []]
+
+
+def test_fsq_division_free_arithmetic_is_exact():
+    """csrc/fsq.cuh replaces q / half_width by q*RN(1/hw) plus one FMA correction, and rintf by the 1.5*2^23 magic
+    constant; both must reproduce fp32 division / round-half-even bit for bit on every value FSQ can produce."""
+    import numpy as np
+
+    f = np.float32
+    for hw in range(1, 17):
+        r = f(1) / f(hw)
+        for q in range(-hw - 2, hw + 3):
+            r0 = f(f(q) * r)
+            e = f(np.float64(f(q)) - np.float64(f(hw)) * np.float64(r0))      # fma(-hw, r0, q)
+            r1 = f(np.float64(r0) + np.float64(e) * np.float64(r))            # fma(e, rcp, r0)
+            assert r1 == f(q) / f(hw), (q, hw)
+    x = np.concatenate([(np.random.default_rng(0).standard_normal(200000) * 4).astype(f), np.arange(-9, 9.5, 0.5, dtype=f)])
+    m = f(12582912.0)
+    assert np.array_equal((x + m) - m, np.rint(x))

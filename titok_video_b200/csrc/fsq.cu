@@ -22,7 +22,9 @@ __device__ __forceinline__ T from_f32(float v);
 template <>
 __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <>
-__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+  return __ushort_as_bfloat16(static_cast<unsigned short>(pack_bf16x2(v, 0.f) & 0xffffu));  // F2FP, not the XU-pipe F2F
+}
 
 // coalesced copy of `n` elements global <-> shared using 16-byte accesses where alignment allows
 template <typename T>
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(FSQ_THREADS) fsq_i2c_kernel(const TI* __restri
           long long m = q % c.levels[d];
           if (m < 0) m += c.levels[d];
           const float lv = static_cast<float>(m);
-          s[v * D + d] = from_f32<TO>(__fdiv_rn(__fsub_rn(lv, c.half_width[d]), c.half_width[d]));
+          s[v * D + d] = from_f32<TO>(fsq_div_hw(__fsub_rn(lv, c.half_width[d]), c.half_width[d], c.rcp_half_width[d]));
         }
       }
     }
@@ -214,6 +216,7 @@ static int fill_consts(FsqConsts& c, int D, const float* half_l, const float* of
     c.offset[d] = ok ? offset[d] : 0.f;
     c.shift[d] = ok ? shift[d] : 0.f;
     c.half_width[d] = ok ? half_width[d] : 1.f;
+    c.rcp_half_width[d] = 1.0f / c.half_width[d];
     c.basis[d] = ok ? static_cast<float>(basis[d]) : 0.f;
     c.ibasis[d] = ok ? basis[d] : 1;
     c.levels[d] = ok ? levels[d] : 1;
