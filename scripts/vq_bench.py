@@ -14,8 +14,8 @@ def peaks():
     p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d["hbm_gbs"], d["bf16_tflops"], "measured"
-    return 6650.0, 1590.0, "fallback"
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
 
 
 def time_ms(fn, iters=10, warm=3):
@@ -50,7 +50,7 @@ def vq_case(N, K, D, dev, cb=None):
 
 def main(quick=False, quiet=False):
     dev = torch.device("cuda:0")
-    hbm, tf, src = peaks()
+    hbm, tf, tf_sus, src = peaks()
     N = 1 << 20
     out = []
     fsq_cb = T.FSQ([7, 5, 5, 5, 5]).implicit_codebook
@@ -66,6 +66,7 @@ def main(quick=False, quiet=False):
         rec["mma_frac_of_tensor_peak"] = rec["tflops_mma_issued"] / tf
         rec["peak"] = tf
         rec["peak_source"] = src + " (burst bf16: kernel timed alone)"
+        rec["frac_of_sustained_tensor_peak"] = rec["tflops_algorithmic"] / tf_sus  # the 10-launch loop of a >= 10 ms kernel runs under the power cap
         out.append(rec)
         if not quiet:
             print(json.dumps(rec), flush=True)

@@ -463,7 +463,9 @@ def _vq_run(z, cb):
 
 
 @pytest.mark.parametrize("N,K,D", [(1000, 256, 16), (4096, 1024, 64), (3000, 4096, 128), (2048, 1000, 5),
-                                   (5000, 4375, 5), (1500, 777, 256), (300, 16384, 32)])
+                                   (5000, 4375, 5), (1500, 777, 256), (300, 16384, 32),
+                                   # > 148 row tiles and D <= 189: the two-tiles-per-CTA kernel (odd tile count, ragged K)
+                                   (19072 + 77, 1000, 64), (40000, 4375, 5), (25000, 777, 128), (20000, 300, 189)])
 def test_vq_argmin(N, K, D):
     g = torch.Generator().manual_seed(N + K + D)
     z = (torch.randn((N, D), generator=g) * 2).to(BF)

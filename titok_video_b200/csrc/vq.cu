@@ -273,6 +273,180 @@ vq_argmin_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant_
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// Variant for feature dims up to 189 (num_kb <= 3): the CTA owns TWO 128-row z tiles (256 rows) and every codebook
+// tile that streams through shared memory feeds both, which halves the L2 -> SM traffic per MMA -- at D <= 128 the
+// single-tile kernel is bound by streaming the codebook (96 KB per 1152 MMA cycles), not by the tensor core.
+// TMEM holds one accumulator per z tile; while the tensor core works on one, four epilogue warps drain the other
+// (thread == row, all 256 columns of the tile: no cross-warp merge).
+//   warp 0      B producer      warp 1   MMA issuer      warp 2   TMEM allocator      warp 3   A producer + ones patch
+//   warps 4-7   argmin epilogue of z tile 0            warps 8-11   argmin epilogue of z tile 1
+__global__ void __launch_bounds__(384, 1)
+vq_argmin2_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmC, const VqParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                     // [2 tiles][num_kb][128 x 64]
+  uint8_t* sB = sA + 2 * p.num_kb * VQ_A_KB_BYTES;        // [b_stages][256 x 64]
+  uint8_t* tail = sB + p.b_stages * VQ_B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* a_full = bars;          // [1]
+  uint64_t* a_ready = bars + 1;     // [1]
+  uint64_t* a_empty = bars + 2;     // [1]
+  uint64_t* t_full = bars + 3;      // [2]
+  uint64_t* t_empty = bars + 5;     // [2]
+  uint64_t* b_full = bars + 7;      // [b_stages <= 8]
+  uint64_t* b_empty = bars + 15;    // [b_stages <= 8]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 23);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_blocks = (p.num_m_tiles + 1) / 2;  // 256-row blocks
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmZ);
+    tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(a_full, 1);
+    mbar_init(a_ready, 1);
+    mbar_init(a_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&t_full[s], 1);
+      mbar_init(&t_empty[s], 4);
+    }
+    for (int s = 0; s < p.b_stages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== codebook (B) producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
+        for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&b_full[stage], VQ_B_BYTES);
+            tma_load_2d(sB + stage * VQ_B_BYTES, &tmC, &b_full[stage], kb * VQ_BK, nt * VQ_BN);
+            if (++stage == p.b_stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ===================== z (A) producer + ones patch: both tiles of the block =====================
+    uint32_t it = 0;
+    for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
+      if (lane == 0) {
+        mbar_wait(a_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(a_full, 2 * p.num_kb * VQ_A_KB_BYTES);
+        for (int a = 0; a < 2; ++a)
+          for (int kb = 0; kb < p.num_kb; ++kb)
+            tma_load_2d(sA + (a * p.num_kb + kb) * VQ_A_KB_BYTES, &tmZ, a_full, kb * VQ_BK, (blk * 2 + a) * VQ_BM);
+      }
+      __syncwarp();
+      mbar_wait(a_full, it & 1);
+      // columns D, D+1, D+2 of every row := 1.0 (they multiply the hi/mid/lo norm terms of c')
+      for (int e = lane; e < 2 * VQ_BM * 3; e += 32) {
+        const int a = e / (VQ_BM * 3);
+        const int r = (e / 3) % VQ_BM;
+        const int col = p.D + (e % 3);
+        const int kb = col >> 6;
+        const int cc = col & 63;
+        uint8_t* dst = sA + (a * p.num_kb + kb) * VQ_A_KB_BYTES + sw128_offset(r, cc >> 3) + (cc & 7) * 2;
+        *reinterpret_cast<unsigned short*>(dst) = 0x3f80;  // bf16(1.0)
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(VQ_BM, VQ_BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0, tcount = 0;  // tcount: codebook tiles processed so far (parity of the accumulator barriers)
+      for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
+        mbar_wait(a_ready, it & 1);
+        for (int nt = 0; nt < p.num_n_tiles; ++nt, ++tcount) {
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&b_full[stage], phase);
+            const uint32_t sb = smem_u32(sB + stage * VQ_B_BYTES);
+            const int rem = p.DA - kb * VQ_BK;
+            const int ksteps = rem >= VQ_BK ? 4 : (rem + 15) / 16;
+            for (int a = 0; a < 2; ++a) {
+              if (kb == 0) mbar_wait(&t_empty[a], (tcount & 1) ^ 1);  // the epilogue has drained this accumulator
+              tc_fence_after();
+              const uint32_t sa = smem_u32(sA + (a * p.num_kb + kb) * VQ_A_KB_BYTES);
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16_ss(tmem_base + a * VQ_BN, umma_smem_desc_sw128(sa + k * 32, 1024, 0),
+                             umma_smem_desc_sw128(sb + k * 32, 1024, 0), idesc, (kb | k) != 0 ? 1u : 0u);
+              if (kb == p.num_kb - 1) umma_commit(&t_full[a]);
+            }
+            umma_commit(&b_empty[stage]);
+            if (++stage == p.b_stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        umma_commit(a_empty);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue: running argmin, one accumulator per warpgroup =====================
+    const int quarter = warp & 3;
+    const int a = (warp - 4) >> 2;  // z tile / accumulator of this warpgroup
+    const int r = quarter * 32 + lane;
+    uint32_t tcount = 0;
+    for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
+      float best = INFINITY;
+      int best_i = 0;
+      for (int nt = 0; nt < p.num_n_tiles; ++nt, ++tcount) {
+        mbar_wait(&t_full[a], tcount & 1);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + a * VQ_BN;
+        const int colbase = nt * VQ_BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < VQ_BN; c0 += 64) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32b_x32(t_row + c0, v0);
+          tmem_ld_32x32b_x32(t_row + c0 + 32, v1);
+          tmem_ld_wait();
+          if (colbase + c0 < p.K) vq_chunk_update(v0, colbase + c0, p.K, best, best_i);
+          if (colbase + c0 + 32 < p.K) vq_chunk_update(v1, colbase + c0 + 32, p.K, best, best_i);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[a]);
+      }
+      const int64_t row = (static_cast<int64_t>(blk) * 2 + a) * VQ_BM + r;
+      if (row < p.N) {
+        p.idx[row] = best_i;
+        if (p.best) p.best[row] = best;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 // c'_k = [-2 c_k | hi, mid, lo of |c_k|^2 | 0..]; one warp per code.
 __global__ void __launch_bounds__(256) vq_prepare_kernel(const __nv_bfloat16* __restrict__ cb, int64_t ldc, int K,
                                                          int D, __nv_bfloat16* __restrict__ out, int64_t lda,
@@ -388,14 +562,26 @@ int ttk_vq_argmin(const void* z, int64_t ldz, const void* cb_aug, int64_t lda, i
   // inner extent = true D for z (columns >= D read as zero, then patched with ones), DA for the codebook
   if (int e = make_tmap_bf16_2d(&tmZ, z, static_cast<uint64_t>(N), D, ldz, VQ_BM)) return e;
   if (int e = make_tmap_bf16_2d(&tmC, cb_aug, K, DA, lda, VQ_BN)) return e;
-  const int smem = p.a_bufs * a_one + p.b_stages * VQ_B_BYTES + 1024 + 256 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(vq_argmin2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return TTK_ERR_CUDA;
     attr_done = true;
   }
+  if (num_kb <= 3 && p.num_m_tiles > num_sms()) {
+    // two z tiles per CTA share every codebook tile (vq_argmin2_kernel)
+    int bs2 = (VQ_SMEM_BUDGET - 2 * a_one) / VQ_B_BYTES;
+    if (bs2 > 6) bs2 = 6;
+    p.b_stages = bs2;
+    p.a_bufs = 1;
+    const int num_blocks = (p.num_m_tiles + 1) / 2;
+    const int smem2 = 2 * a_one + p.b_stages * VQ_B_BYTES + 256 + 1024;
+    const int grid2 = num_blocks < num_sms() ? num_blocks : num_sms();
+    vq_argmin2_kernel<<<grid2, 384, smem2, stream>>>(tmZ, tmC, p);
+    return launch_status();
+  }
+  const int smem = p.a_bufs * a_one + p.b_stages * VQ_B_BYTES + 1024 + 256 + 1024;
   const int grid = p.num_m_tiles < num_sms() ? p.num_m_tiles : num_sms();
   vq_argmin_kernel<<<grid, 384, smem, stream>>>(tmZ, tmC, p);
   return launch_status();
