@@ -81,7 +81,9 @@ def close_bf16(out, ref, ulps=2.0, atol=None, what=""):
 # --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K,bias", [(128, 128, 64, False), (300, 256, 256, True), (1000, 768, 256, True),
                                         (517, 256, 704, False), (256, 768, 768, True), (77, 40, 128, True),
-                                        (5676, 256, 768, True)])
+                                        (5676, 256, 768, True),
+                                        # >= 2 x 148 tiles with K <= 256: the weight-stationary kernel (ragged M and N)
+                                        (12800 + 77, 768, 256, True), (20000, 600, 192, False)])
 def test_gemm_store(M, N, K, bias):
     A, W = randn(M, K, seed=1), randn(N, K, seed=2, scale=0.1)
     b = randn(N, seed=3) if bias else None
@@ -125,7 +127,8 @@ def test_gemm_weight_given_as_kn(M, N, K):
     close_bf16(out, ref, what="gemm kn")
 
 
-@pytest.mark.parametrize("M,width,gqa", [(300, 256, 128), (1892, 256, 128), (200, 768, 256)])
+@pytest.mark.parametrize("M,width,gqa", [(300, 256, 128), (1892, 256, 128), (200, 768, 256),
+                                         (13000 + 5, 256, 128)])  # last: many tiles per CTA
 def test_gemm_qkv_rope(M, width, gqa):
     K = width
     A, W = randn(M, K, seed=8), randn(2 * width + 2 * gqa, K, seed=9, scale=0.08)
@@ -148,7 +151,8 @@ def test_gemm_qkv_rope(M, width, gqa):
     close_bf16(out, ref, ulps=3.0, atol=2.0 ** -8 * ref.abs().max().item() * 0.5, what="qkv+rope")
 
 
-@pytest.mark.parametrize("M,inner,K", [(300, 704, 256), (1000, 1376, 512), (64, 704, 256)])
+@pytest.mark.parametrize("M,inner,K", [(300, 704, 256), (1000, 1376, 512), (64, 704, 256),
+                                       (6400 + 33, 704, 256)])  # last: weight-stationary kernel
 def test_gemm_geglu(M, inner, K):
     A, W = randn(M, K, seed=10), randn(2 * inner, K, seed=11, scale=0.1)
     h = O.linear(A.float(), W)

@@ -57,20 +57,56 @@ __device__ __forceinline__ void trace_stamp(const GemmParams& p, int slot) {
   if (p.trace && slot < 64) p.trace[blockIdx.x * 64 + slot] = clock64();
 }
 
-template <int BN, int EPI>
+// WS ("weight-stationary", K <= 256): the CTA keeps the whole [BN x K] weight tile of ONE n block resident in shared
+// memory and streams only A tiles. At K = 256 a streamed 128x256 tile needs 192 KB of operands for 2048 MMA cycles,
+// more than the L2 can feed every SM (~50 B/clk/SM measured); with the weights resident it is 64 KB per tile.
+template <int BN, int EPI, bool WS>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int RES_KB = 4;  // resident k blocks (K <= 256)
+  static constexpr int RES_BYTES = WS ? RES_KB * B_BYTES : 0;
+  static constexpr int STAGE_BYTES = WS ? A_BYTES : A_BYTES + B_BYTES;
   // EPI_RESID: the [128 x 256] residual tile (4 swizzled boxes of 128 rows x 64 cols), updated in place and stored
-  // from there. Other epilogues: two staging boxes per epilogue warp.
-  static constexpr int OUT_BYTES = (EPI == EPI_RESID) ? BM * 256 * 2 : 8 * 2 * BOX_BYTES;
-  static constexpr int AUX_BYTES = 2 * 256 * 4 + 2 * 4 * 128 * 4;  // EPI_RESID: norm weights + partial sums of squares
+  // from there. Other epilogues: staging boxes per epilogue warp (double-buffered unless the weights are resident).
+  static constexpr int OUT_BUFS = WS ? 1 : 2;
+  static constexpr int OUT_BYTES = (EPI == EPI_RESID) ? BM * 256 * 2 : 8 * OUT_BUFS * BOX_BYTES;
+  static constexpr int AUX_BYTES = (EPI == EPI_RESID) ? 2 * 256 * 4 + 2 * 4 * 128 * 4 : 0;  // norm weights + partial sums
   static constexpr int BAR_BYTES = 256;
-  static constexpr int BUDGET = 227 * 1024 - 1024 - OUT_BYTES - AUX_BYTES - BAR_BYTES;
-  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + AUX_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+  static constexpr int BUDGET = 227 * 1024 - 1024 - RES_BYTES - OUT_BYTES - AUX_BYTES - BAR_BYTES;
+  static constexpr int STAGES = WS ? 4 : ((BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES));
+  static constexpr int TOTAL = RES_BYTES + STAGES * STAGE_BYTES + OUT_BYTES + AUX_BYTES + BAR_BYTES + 1024;  // +1024: alignment
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+};
+
+// Which tiles a CTA walks. Streaming kernels: tile = blockIdx.x + i * gridDim.x over the (m, n) grid. Weight-stationary
+// kernels: n block = blockIdx.x % num_n_tiles for the CTA's lifetime, m blocks strided over the CTAs of that n block.
+template <bool WS>
+struct TileWalk {
+  int m_blk, n_blk, step, num_m, num_n, tile;
+  __device__ __forceinline__ TileWalk(int num_m_tiles, int num_n_tiles) : num_m(num_m_tiles), num_n(num_n_tiles) {
+    if (WS) {
+      n_blk = blockIdx.x % num_n;
+      m_blk = blockIdx.x / num_n;
+      step = (gridDim.x - n_blk + num_n - 1) / num_n;  // CTAs that share this n block
+    } else {
+      tile = blockIdx.x;
+      step = gridDim.x;
+      m_blk = tile / num_n;
+      n_blk = tile % num_n;
+    }
+  }
+  __device__ __forceinline__ bool valid() const { return WS ? (m_blk < num_m) : (tile < num_m * num_n); }
+  __device__ __forceinline__ void next() {
+    if (WS) {
+      m_blk += step;
+    } else {
+      tile += step;
+      m_blk = tile / num_n;
+      n_blk = tile % num_n;
+    }
+  }
 };
 
 // gelu(g) = 0.5 g (1 + erf(g / sqrt 2)) for two values at once, erf from Abramowitz-Stegun 7.1.26
@@ -101,11 +137,12 @@ __device__ __forceinline__ void gelu_erf_x2(float g0, float g1, float& o0, float
 }
 
 // Per-warp staging of [32 rows x 64 cols] bf16 boxes for TMA stores (double-buffered).
+template <int NBUF>
 struct BoxStager {
-  uint8_t* base;  // 2 * BOX_BYTES, 1024-byte aligned
+  uint8_t* base;  // NBUF * BOX_BYTES, 1024-byte aligned
   int buf;
   __device__ __forceinline__ uint8_t* acquire(int lane) {
-    if (lane == 0) tma_store_wait_read<1>();  // the store issued two boxes ago has finished reading this buffer
+    if (lane == 0) tma_store_wait_read<NBUF - 1>();  // the store that last read this buffer has finished
     __syncwarp();
     return base + buf * BOX_BYTES;
   }
@@ -117,7 +154,7 @@ struct BoxStager {
       tma_store_2d(tm, base + buf * BOX_BYTES, col0, row0);
       tma_store_commit();
     }
-    buf ^= 1;
+    if (NBUF > 1) buf ^= 1;
   }
 };
 
@@ -128,23 +165,25 @@ __device__ __forceinline__ void box_write_row(uint8_t* box, int lane, const uint
     *reinterpret_cast<uint4*>(box + sw128_offset(lane, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
 }
 
-template <int BN, int EPI, bool B_MN>
+template <int BN, int EPI, bool B_MN, bool WS>
 __global__ void __launch_bounds__(128 + 32 * epi_warps(EPI), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO,   // out / x_out: box [32 rows x 64 cols]
             const __grid_constant__ CUtensorMap tmO2,  // EPI_RESID: xn_out, same box
             const __grid_constant__ CUtensorMap tmR,   // EPI_RESID: residual x, box [128 rows x 64 cols]
             const GemmParams p) {
-  using S = GemmSmem<BN, EPI>;
+  using S = GemmSmem<BN, EPI, WS>;
   constexpr int STAGES = S::STAGES;
   constexpr int EPI_WARPS = epi_warps(EPI);
+  static_assert(!WS || (!B_MN && EPI != EPI_RESID), "weight-stationary mode: K-major weights, store-type epilogues");
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of the 64-column store box");
   static_assert(EPI != EPI_RESID || BN == 256, "row epilogue owns complete 256-wide rows");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sres = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = sres + S::RES_BYTES;  // operand stage ring (behind the resident weight tile, if any)
   uint8_t* smem_out = smem + STAGES * S::STAGE_BYTES;
   float* wsm = reinterpret_cast<float*>(smem_out + S::OUT_BYTES);  // [2][256]
   float* ssm = wsm + 512;                                          // [2 exchanges][4 column parts][128]
@@ -155,11 +194,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint64_t* resid_full = bars + 2 * STAGES + 4;
   uint64_t* resid_empty = bars + 2 * STAGES + 5;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+  uint64_t* res_full = bars + 2 * STAGES + 6;  // WS: the resident weight tile has landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 7);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -181,6 +220,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     mbar_init(resid_full, 1);
     mbar_init(resid_empty, EPI_WARPS);
+    mbar_init(res_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -196,9 +236,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int m_blk = tile / p.num_n_tiles;
-        const int n_blk = tile % p.num_n_tiles;
+      TileWalk<WS> tw(p.num_m_tiles, p.num_n_tiles);
+      if constexpr (WS) {
+        // the CTA's weight tile: all k blocks of its n block, once
+        if (tw.valid()) {
+          mbar_arrive_expect_tx(res_full, p.num_k_blocks * S::B_BYTES);
+          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            uint8_t* sb = sres + kb * S::B_BYTES;
+            if constexpr (EPI == EPI_GEGLU) {
+              tma_load_2d(sb, &tmB, res_full, kb * BK, tw.n_blk * (BN / 2));
+              tma_load_2d(sb + (BN / 2) * 128, &tmB, res_full, kb * BK, p.inner + tw.n_blk * (BN / 2));
+            } else {
+              tma_load_2d(sb, &tmB, res_full, kb * BK, tw.n_blk * BN);
+            }
+          }
+        }
+      }
+      for (; tw.valid(); tw.next(), ++it) {
+        const int m_blk = tw.m_blk;
+        const int n_blk = tw.n_blk;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (kb == 0) trace_stamp(p, 1 + 8 * it + 0);
@@ -206,6 +262,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint8_t* sb = sa + S::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          if constexpr (WS) {
+            (void)sb;
+            (void)n_blk;
+          } else
           if constexpr (B_MN) {
             // W given as [K, N] (N contiguous): one [64 k][64 n] box per 64-wide N block
 #pragma unroll
@@ -246,7 +306,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int as = 0;
       uint32_t aphase = 0;
       int itm = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++itm) {
+      TileWalk<WS> tw(p.num_m_tiles, p.num_n_tiles);
+      if constexpr (WS) {
+        if (tw.valid()) mbar_wait(res_full, 0);
+      }
+      for (; tw.valid(); tw.next(), ++itm) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         trace_stamp(p, 1 + 8 * itm + 1);
@@ -257,7 +321,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (kb == 0) trace_stamp(p, 1 + 8 * itm + 2);
           if (kb == p.num_k_blocks - 1) trace_stamp(p, 1 + 8 * itm + 3);
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint32_t sb = sa + S::A_BYTES;
+          const uint32_t sb = WS ? smem_u32(sres + kb * S::B_BYTES) : sa + S::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = umma_smem_desc_sw128(sa + k * 32, 1024, 0);
@@ -287,7 +351,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int row_in_tile = quarter * 32 + lane;
     // store-only epilogues: a private double-buffered staging box per warp. GEGLU: warps (cpart 2b, 2b+1) of a lane
     // quarter fill the two halves of one shared 64-column box.
-    BoxStager stg{smem_out + (EPI == EPI_GEGLU ? (quarter * 2 + (cpart >> 1)) : ew) * 2 * BOX_BYTES, 0};
+    BoxStager<S::OUT_BUFS> stg{smem_out + (EPI == EPI_GEGLU ? (quarter * 2 + (cpart >> 1)) : ew) * S::OUT_BUFS * BOX_BYTES, 0};
     if constexpr (EPI == EPI_RESID) {
       for (int te = threadIdx.x - 128; te < 256; te += 32 * EPI_WARPS) {
         wsm[te] = (p.mode == 1) ? p.w_post[te] : 1.0f;
@@ -298,9 +362,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int as = 0;
     uint32_t aphase = 0;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / p.num_n_tiles;
-      const int n_blk = tile % p.num_n_tiles;
+    for (TileWalk<WS> tw(p.num_m_tiles, p.num_n_tiles); tw.valid(); tw.next(), ++it) {
+      const int m_blk = tw.m_blk;
+      const int n_blk = tw.n_blk;
       const int row0 = m_blk * BM + quarter * 32;  // first row of this warp's 32-row slice
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
@@ -452,7 +516,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               pk[hh * 8 + j] = *reinterpret_cast<const uint32_t*>(&h2);
             }
           }
-          if ((cpart & 1) == 0 && lane == 0) tma_store_wait_read<1>();  // the pair's buffer of two tiles ago is free
+          if ((cpart & 1) == 0 && lane == 0) tma_store_wait_read<S::OUT_BUFS - 1>();  // the pair's buffer is free again
           named_bar_sync(pair_bar, 64);
           uint8_t* box = stg.base + stg.buf * BOX_BYTES;
 #pragma unroll
@@ -465,7 +529,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_store_2d(&tmO, box, colbox, row0);
             tma_store_commit();
           }
-          stg.buf ^= 1;
+          if (S::OUT_BUFS > 1) stg.buf ^= 1;
         }
       } else if constexpr (EPI == EPI_RESID) {
         // thread == (row, column part): 64 columns as packed bf16 in registers; the four parts of a row exchange their
@@ -611,9 +675,9 @@ struct GemmIo {
   int64_t ldr = 0;
 };
 
-template <int BN, int EPI, bool B_MN>
+template <int BN, int EPI, bool B_MN, bool WS = false>
 static int launch_gemm(const GemmIo& io, GemmParams& p, cudaStream_t stream) {
-  using S = GemmSmem<BN, EPI>;
+  using S = GemmSmem<BN, EPI, WS>;
   p.trace = g_trace;
   if (int e = check_device_sm100()) return e;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return TTK_ERR_BAD_SHAPE;
@@ -647,7 +711,7 @@ static int launch_gemm(const GemmIo& io, GemmParams& p, cudaStream_t stream) {
   else
     p.num_n_tiles = (p.N + BN - 1) / BN;
   p.num_k_blocks = (p.K + BK - 1) / BK;
-  auto kern = gemm_kernel<BN, EPI, B_MN>;
+  auto kern = gemm_kernel<BN, EPI, B_MN, WS>;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
@@ -658,6 +722,12 @@ static int launch_gemm(const GemmIo& io, GemmParams& p, cudaStream_t stream) {
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, 128 + 32 * epi_warps(EPI), S::TOTAL, stream>>>(tmA, tmB, tmO, tmO2, tmR, p);
   return launch_status();
+}
+
+// weight-stationary mode pays off when K fits the resident tile and every n group gets a few m tiles per CTA
+static bool use_ws(int M, int N_tiles_of_256, int K) {
+  const int m_tiles = (M + BM - 1) / BM;
+  return K <= 4 * BK && m_tiles * N_tiles_of_256 >= 2 * num_sms();
 }
 
 }  // namespace ttk
@@ -695,7 +765,10 @@ int ttk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M,
     if (N % 8 != 0) return TTK_ERR_ALIGNMENT;
     return launch_gemm<128, EPI_STORE, true>(io, p, stream);
   }
-  if (N > 128) return launch_gemm<256, EPI_STORE, false>(io, p, stream);
+  if (N > 128) {
+    if (!p.direct && use_ws(M, (N + 255) / 256, K)) return launch_gemm<256, EPI_STORE, false, true>(io, p, stream);
+    return launch_gemm<256, EPI_STORE, false>(io, p, stream);
+  }
   return launch_gemm<128, EPI_STORE, false>(io, p, stream);
 }
 
@@ -715,6 +788,7 @@ int ttk_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldw, in
   p.width = width;
   p.gqa = gqa;
   GemmIo io{A, lda, W, ldw};
+  // (weight-stationary mode measured slower here: its single staging box per warp serialises the RoPE pass and the store)
   return launch_gemm<256, EPI_QKV, false>(io, p, stream);
 }
 
@@ -731,6 +805,7 @@ int ttk_gemm_geglu(const void* A, int64_t lda, const void* W12, int64_t ldw, int
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   GemmIo io{A, lda, W12, ldw};
+  if (use_ws(M, (inner + 127) / 128, K)) return launch_gemm<256, EPI_GEGLU, false, true>(io, p, stream);
   return launch_gemm<256, EPI_GEGLU, false>(io, p, stream);
 }
 
