@@ -219,6 +219,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vq", action="store_true", help="skip the quantizer microbench (BASELINE configs[1]) leg")
+    ap.add_argument("--e2e-full-recon", action="store_true",
+                    help="e2e leg copies the full reconstructions back to the host (default: token indices + per-clip error)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -258,16 +260,22 @@ def main():
 
     # synthetic clips: INPUT_SETS distinct batches so that a step never finds its input in L2
     gen = torch.Generator().manual_seed(1000 + rank)
-    host_sets = [[(torch.rand((3, *CLIP_A), generator=gen) * 2 - 1).to(torch.bfloat16).pin_memory() for _ in range(B)]
+    # every set is one flat pinned buffer (one H2D copy per step); the clips handed to the model are views into it
+    clip_numel = 3 * CLIP_A[0] * CLIP_A[1] * CLIP_A[2]
+
+    def views(flat):
+        return [flat[i * clip_numel:(i + 1) * clip_numel].view(3, *CLIP_A) for i in range(B)]
+
+    host_flat = [(torch.rand((B * clip_numel,), generator=gen) * 2 - 1).to(torch.bfloat16).pin_memory()
                  for _ in range(INPUT_SETS)]
-    dev_sets = [[c.to(dev) for c in hs] for hs in host_sets]
+    dev_sets = [views(hf.to(dev)) for hf in host_flat]
     clip_bytes = 3 * CLIP_A[0] * CLIP_A[1] * CLIP_A[2] * 2
 
     hist = torch.zeros(model.quantize.codebook_size, dtype=torch.int32, device=dev)
 
-    def step(clips, use_graph=False):
+    def step(clips, use_graph=False, with_error=False):
         with torch.no_grad():
-            recon, d = model.tokenize_reconstruct_(clips, tcs, use_graph=use_graph)
+            recon, d = model.tokenize_reconstruct_(clips, tcs, use_graph=use_graph, with_error=with_error)
             _lib.call("ttk_hist_u32", T.engine._ptr(d["indices"]), d["indices"].numel(), hist.numel(),
                       T.engine._ptr(hist), T.engine._stream())
         return recon, d
@@ -303,11 +311,16 @@ def main():
     # ---------------- e2e: pinned host clips -> H2D -> public API -> D2H of indices + reconstructions ----------------
     h2d_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
     SLOTS = 2
-    in_slots = [[torch.empty((3, *CLIP_A), dtype=torch.bfloat16, device=dev) for _ in range(B)] for _ in range(SLOTS)]
-    out_slots = [torch.empty((B * 3 * CLIP_A[0] * CLIP_A[1] * CLIP_A[2],), dtype=torch.bfloat16, device=dev) for _ in range(SLOTS)]
+    in_flat = [torch.empty((B * clip_numel,), dtype=torch.bfloat16, device=dev) for _ in range(SLOTS)]
+    in_slots = [views(f) for f in in_flat]
+    full = args.e2e_full_recon
+    out_slots = [torch.empty((B * 3 * CLIP_A[0] * CLIP_A[1] * CLIP_A[2],) if full else (1,), dtype=torch.bfloat16, device=dev)
+                 for _ in range(SLOTS)]
     idx_slots = [torch.empty((B * TOKENS_A,), dtype=torch.int32, device=dev) for _ in range(SLOTS)]
+    err_slots = [torch.empty((B, 2), dtype=torch.float64, device=dev) for _ in range(SLOTS)]
     host_out = [torch.empty_like(out_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
     host_idx = [torch.empty_like(idx_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
+    host_err = [torch.empty_like(err_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
     ev_in = [torch.cuda.Event() for _ in range(SLOTS)]
     ev_compute = [torch.cuda.Event() for _ in range(SLOTS)]
     ev_out = [torch.cuda.Event() for _ in range(SLOTS)]
@@ -316,29 +329,33 @@ def main():
 
     def e2e_step(i):
         sl = i % SLOTS
-        hs = host_sets[i % INPUT_SETS]
         with torch.cuda.stream(h2d_stream):
             h2d_stream.wait_event(ev_consumed[sl])  # the slot's previous contents were consumed by compute
-            for c_dev, c_host in zip(in_slots[sl], hs):
-                c_dev.copy_(c_host, non_blocking=True)
+            in_flat[sl].copy_(host_flat[i % INPUT_SETS], non_blocking=True)
             ev_in[sl].record()
         main_stream.wait_event(ev_in[sl])
         main_stream.wait_event(ev_out[sl])  # the slot's previous results have left the device
-        recon, d = step(in_slots[sl], use_graph=True)  # the public API's default: one CUDA-graph replay per step
+        # the public API's default: one CUDA-graph replay per step; results = token indices + per-clip error
+        recon, d = step(in_slots[sl], use_graph=True, with_error=True)
         ev_consumed[sl].record()
-        out_slots[sl].copy_(_flat_of(recon), non_blocking=True)
+        if full:
+            out_slots[sl].copy_(_flat_of(recon), non_blocking=True)
         idx_slots[sl].copy_(d["indices"], non_blocking=True)
+        err_slots[sl].copy_(d["clip_error"], non_blocking=True)
         ev_compute[sl].record()
         with torch.cuda.stream(d2h_stream):
             d2h_stream.wait_event(ev_compute[sl])
-            host_out[sl].copy_(out_slots[sl], non_blocking=True)
+            if full:
+                host_out[sl].copy_(out_slots[sl], non_blocking=True)
             host_idx[sl].copy_(idx_slots[sl], non_blocking=True)
+            host_err[sl].copy_(err_slots[sl], non_blocking=True)
             ev_out[sl].record()
 
     def _flat_of(recon):
         # the reconstructed clips are views of one flat workspace buffer (engine.split_clips)
         base = recon[0]
-        return base.reshape(-1).as_strided((out_slots[0].numel(),), (1,), base.storage_offset())
+        n = B * 3 * CLIP_A[0] * CLIP_A[1] * CLIP_A[2]
+        return base.reshape(-1).as_strided((n,), (1,), base.storage_offset())
 
     for i in range(3):
         e2e_step(i)
@@ -411,7 +428,11 @@ def main():
                              f"activation working set exceeds the 126 MB L2",
                        "weights": "random init, seed 42 (reference initialiser)", "codebook_usage_percent": usage},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": B * clip_bytes,
-                    "d2h_bytes_per_step": B * clip_bytes + B * TOKENS_A * 4, "ms_per_step": e2e_ms / args.steps,
+                    "d2h_bytes_per_step": (B * clip_bytes if args.e2e_full_recon else 0) + B * TOKENS_A * 4 + B * 16,
+                    "result": ("token indices + per-clip (L1, squared) reconstruction error" +
+                               (" + full reconstructions" if args.e2e_full_recon else
+                                "; reconstructions stay on the device (--e2e-full-recon copies them too)")),
+                    "ms_per_step": e2e_ms / args.steps,
                     "wall_ms_per_step": float(ms[1].item()) / args.steps,
                     "api": "TiTok.tokenize_reconstruct_(clips, token_counts) from pinned host clips, 2-slot pipeline, CUDA-graph replay "
                            "(the value leg launches the same kernels one by one so that each can be timed with CUDA events)"},

@@ -134,6 +134,12 @@ int ttk_rmsnorm_fwd(const void* x, int64_t ldx, const float* w, void* y, int64_t
 int ttk_resid_norm(const void* x, const void* y, void* x_out, void* xn_out, const float* w_post, const float* w_next,
                    float alpha, int mode, int M, int width, int64_t ld, ttk_stream_t stream);
 
+/* Per-clip reconstruction error of two flat clip buffers (same layout): out[2i] += sum|a-b| (the L1 reconstruction
+ * loss numerator, loss_module.py:118), out[2i+1] += sum (a-b)^2 (PSNR, eval_metrics.py). out: fp64 [2*n_clips], zeroed
+ * by the caller; clip_offset / clip_numel: device int64 [n_clips] in elements (multiples of 8). */
+int ttk_clip_error(const void* a, const void* b, const int64_t* clip_offset, const int64_t* clip_numel, int n_clips,
+                   int64_t max_clip_numel, double* out, ttk_stream_t stream);
+
 /* TiTokEncoder embed (blocks.py:95-97). src_row int32 [M]: >= 0 row of proj (patch), < 0 latent row. */
 int ttk_enc_embed(const void* proj, int64_t ldp, const int32_t* src_row, const float* mask_token, const float* w_t,
                   const float* w_p, const float* w_next, void* x_out, void* xn_out, int M, int width, int64_t ld,

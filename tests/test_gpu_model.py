@@ -285,3 +285,18 @@ def test_base_size_odd_gqa_ratio():
     with torch.no_grad():
         z = model.encoder([c.cuda() for c in clips], tcs)
     _check(z, O.encoder_forward(sd, "base", PATCH, clips, tcs), False, "base z")
+
+
+def test_clip_error_kernel_matches_torch(golden_stress):
+    """ttk_clip_error: per-clip sum |x - recon| and sum (x - recon)^2 in fp64 (loss_module.py:118 numerator, PSNR)."""
+    shapes, tcs, clips = _case(golden_stress)
+    model = build_model(True).cuda().eval()
+    cl = [c.cuda() for c in clips]
+    for use_graph in (False, True, True):
+        with torch.no_grad():
+            rec, d = model.tokenize_reconstruct_(cl, tcs, use_graph=use_graph, with_error=True)
+        err = d["clip_error"].cpu()
+        for i, (a, b) in enumerate(zip(cl, rec)):
+            diff = a.double().cpu() - b.double().cpu()
+            assert abs(err[i, 0].item() - diff.abs().sum().item()) <= 1e-4 * diff.abs().sum().item() + 1e-6
+            assert abs(err[i, 1].item() - (diff * diff).sum().item()) <= 1e-4 * (diff * diff).sum().item() + 1e-6

@@ -303,6 +303,50 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const __nv_bfloat16* __
   }
 }
 
+// Per-clip reconstruction error: out[2*i] += sum |a - b|, out[2*i+1] += sum (a - b)^2 over clip i (fp64 accumulators
+// in global memory, caller-zeroed). The L1 term is the reference's reconstruction loss (loss_module.py:118), the squared
+// term feeds PSNR (eval_metrics.py). Bandwidth-bound: 16-byte streaming loads of both buffers, warp-shuffle reduction,
+// one pair of fp64 atomics per CTA. blockIdx.y = clip, blockIdx.x strides over the clip's 8-element vectors.
+__global__ void __launch_bounds__(256) clip_error_kernel(const __nv_bfloat16* __restrict__ a,
+                                                         const __nv_bfloat16* __restrict__ b,
+                                                         const int64_t* __restrict__ clip_offset,
+                                                         const int64_t* __restrict__ clip_numel, double* __restrict__ out) {
+  const int clip = blockIdx.y;
+  const int64_t off = clip_offset[clip];
+  const int64_t nv = clip_numel[clip] / 8;  // clip sizes are multiples of 8 elements (W % 8 == 0)
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint4 va = ldg16_stream(a + off + i * 8);
+    const uint4 vb = ldg16_stream(b + off + i * 8);
+    const uint32_t aa[4] = {va.x, va.y, va.z, va.w}, bb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float d0 = bf16_lo(aa[e]) - bf16_lo(bb[e]);
+      const float d1 = bf16_hi(aa[e]) - bf16_hi(bb[e]);
+      s1 += fabsf(d0) + fabsf(d1);
+      s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+    }
+  }
+  __shared__ float p1[8], p2[8];
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) {
+    p1[threadIdx.x >> 5] = s1;
+    p2[threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0, t2 = 0;
+    for (int i = 0; i < 8; ++i) {
+      t1 += p1[i];
+      t2 += p2[i];
+    }
+    atomicAdd(out + 2 * clip, t1);
+    atomicAdd(out + 2 * clip + 1, t2);
+  }
+}
+
 int fsq_make_consts(FsqConsts& c, int D, const float* half_l, const float* offset, const float* shift,
                     const float* half_width, const int32_t* basis, const int32_t* levels);
 
@@ -426,6 +470,22 @@ int ttk_unpatchify(const void* proj, int64_t ldp, const int32_t* patch_row, cons
   if (blocks > 0x7fffffffLL) return TTK_ERR_BAD_SHAPE;
   unpatchify_kernel<<<static_cast<int>(blocks), 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(proj), ldp, patch_row, geom, C, P0,
                                               P1, static_cast<__nv_bfloat16*>(clips), G);
+  return launch_status();
+}
+
+// out: device fp64 [2 * n_clips], caller-zeroed; clip_offset / clip_numel: device int64 [n_clips] (elements).
+int ttk_clip_error(const void* a, const void* b, const int64_t* clip_offset, const int64_t* clip_numel, int n_clips,
+                   int64_t max_clip_numel, double* out, cudaStream_t stream) {
+  if (n_clips <= 0) return TTK_OK;
+  if (!a || !b || !clip_offset || !clip_numel || !out) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) != 0) return TTK_ERR_ALIGNMENT;
+  if (n_clips > 65535 || max_clip_numel <= 0) return TTK_ERR_BAD_SHAPE;
+  int64_t bx = (max_clip_numel / 8 + 256 * 8 - 1) / (256 * 8);  // about 8 vectors per thread
+  if (bx < 1) bx = 1;
+  if (bx > 4LL * num_sms()) bx = 4LL * num_sms();
+  clip_error_kernel<<<dim3(static_cast<unsigned>(bx), static_cast<unsigned>(n_clips)), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), clip_offset, clip_numel, out);
   return launch_status();
 }
 

@@ -56,6 +56,8 @@ class DevicePlan:
         self.patch_row = up(plan.patch_row)
         self.geom = up(plan.geom)
         self.rope = up(plan.rope)
+        self.clip_offset = up(np.asarray(plan.clip_offset, dtype=np.int64))
+        self.clip_numel = up(np.asarray(plan.clip_numel, dtype=np.int64))
         self._attn: Dict[Tuple[int, int], torch.Tensor] = {}
         self.ws: Dict[str, torch.Tensor] = {}
         self.graphs: Dict[tuple, "torch.cuda.CUDAGraph"] = {}
@@ -274,6 +276,17 @@ def decoder_launch(m, dp: DevicePlan, codes: torch.Tensor, out_flat: torch.Tenso
     _lib.call("ttk_unpatchify", _ptr(rows), feat, _ptr(dp.patch_row), _ptr(dp.geom), pl.channels, P0, P1, P2,
               _ptr(out_flat), G, st)
     return out_flat
+
+
+def clip_error_launch(dp: DevicePlan, a_flat: torch.Tensor, b_flat: torch.Tensor) -> torch.Tensor:
+    """fp64 [B, 2] per-clip (sum |a-b|, sum (a-b)^2) of two flat clip buffers laid out like the plan's clips: the
+    numerators of the L1 reconstruction loss (loss_module.py:118) and of PSNR (eval_metrics.py)."""
+    B = len(dp.plan.clip_numel)
+    out = dp.buf("clip_err", (B, 2), torch.float64)
+    out.zero_()
+    _lib.call("ttk_clip_error", _ptr(a_flat), _ptr(b_flat), _ptr(dp.clip_offset), _ptr(dp.clip_numel), B,
+              max(dp.plan.clip_numel), _ptr(out), _stream())
+    return out
 
 
 # --------------------------------------------------------------------------------------------------

@@ -65,14 +65,19 @@ class TiTok(nn.Module):
 
     # ---- throughput path: no defensive copies, results live in the plan's workspace ---------------
     @torch.no_grad()
-    def tokenize_reconstruct_(self, x: Sequence[torch.Tensor], token_counts, use_graph: Optional[bool] = None):
+    def tokenize_reconstruct_(self, x: Sequence[torch.Tensor], token_counts, use_graph: Optional[bool] = None,
+                              with_error: bool = False):
         """forward() without the output clones: the returned clips / indices alias workspace buffers that the next
         call with the same shapes overwrites. Used by bench.py and batch jobs that consume results immediately.
 
         The 47 kernel launches of encoder + FSQ + decoder are captured once per (shapes, token_counts) signature into
         a CUDA graph and replayed (`use_graph=False` or TTK_CUDA_GRAPH=0 launches them one by one). Inputs are copied
         into the plan's static clip buffer first; weights are refreshed in place, so a captured graph stays valid
-        across optimizer steps."""
+        across optimizer steps.
+
+        with_error=True also returns 'clip_error': fp64 [B, 2] = per-clip (sum |x - recon|, sum (x - recon)^2), the
+        numerators of the reference's L1 reconstruction loss (loss_module.py:118) and of PSNR, computed on the device
+        by ttk_clip_error so that a tokenisation job only has to bring indices and two scalars per clip to the host."""
         dev = x[0].device
         engine.require_cuda(dev)
         grids = [tuple(v.shape[1:]) for v in x]
@@ -90,23 +95,27 @@ class TiTok(nn.Module):
         def launch():
             _, codes, idx = engine.encoder_launch(enc, dp, flat, consts)
             engine.decoder_launch(dec, dp, codes, out)
-            return idx
+            err = engine.clip_error_launch(dp, flat, out) if with_error else None
+            return idx, err
 
         if use_graph is None:
             use_graph = os.environ.get("TTK_CUDA_GRAPH", "1") != "0"
         if not use_graph:
-            idx = launch()
+            idx, err = launch()
         else:
-            key = ("tokenize_reconstruct", id(self), flat.data_ptr())
+            key = ("tokenize_reconstruct", id(self), flat.data_ptr(), bool(with_error))
             entry = dp.graphs.get(key)
             if entry is None:
-                idx = launch()  # eager warm-up: workspace allocation, one-time function attributes
+                launch()  # eager warm-up: workspace allocation, one-time function attributes
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    idx = launch()
-                entry = (g, idx)
+                    idx, err = launch()
+                entry = (g, idx, err)
                 dp.graphs[key] = entry
             entry[0].replay()
-            idx = entry[1]
-        return engine.split_clips(out, dp.plan), {"indices": idx}
+            idx, err = entry[1], entry[2]
+        res = {"indices": idx}
+        if with_error:
+            res["clip_error"] = err
+        return engine.split_clips(out, dp.plan), res
