@@ -130,7 +130,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                          str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                          str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                                          text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -158,9 +158,25 @@ class ClockSampler:
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        note = None
+        if not sm and self.lines:
+            # the timed region was shorter than the sampling period: use the sample closest to it and say so
+            ts, line = min(self.lines, key=lambda tl: min(abs(tl[0] - t0), abs(tl[0] - t1)))
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm, mx = [float(f[1])], float(f[2])
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+                note = "no sample fell inside the timed region; nearest sample (%.0f ms away) reported" % (
+                    1e3 * min(abs(ts - t0), abs(ts - t1)))
+            except (ValueError, IndexError):
+                sm = []
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -281,13 +297,13 @@ def main():
         return recon, d
 
     # ---------------- value: inputs resident in HBM ----------------
+    sampler = ClockSampler(local_rank)  # started ahead of the warm-up: nvidia-smi needs ~0.3 s to deliver its first sample
+    sampler.start()
     for i in range(args.warmup):
         step(dev_sets[i % INPUT_SETS])
     barrier()
     timer = KernelTimer()
     _lib.set_profiler(timer)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = _lib.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
