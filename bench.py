@@ -235,6 +235,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vq", action="store_true", help="skip the quantizer microbench (BASELINE configs[1]) leg")
+    ap.add_argument("--ragged-stream", type=int, default=8,
+                    help="steps of the ragged-stream leg (new batch composition every step; 0 = skip)")
     ap.add_argument("--e2e-full-recon", action="store_true",
                     help="e2e leg copies the full reconstructions back to the host (default: token indices + per-clip error)")
     args = ap.parse_args()
@@ -394,6 +396,39 @@ def main():
     e2e_ms = float(ms[0].item())
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
 
+    # ---------------- ragged stream: a NEW batch composition every step (what train.py / a tokenisation job feeds) ------
+    # shapes and token counts drawn from the sampling ranges of configs/tiny.yaml (tiny.yaml:56-66); every step pays the
+    # host planner, the metadata upload and kernel-by-kernel launches (no plan cache hit, no graph replay).
+    ragged = None
+    if args.ragged_stream > 0 and rank == 0:
+        import random
+
+        from titok_video_b200 import engine as _eng
+
+        rnd = random.Random(0)
+        n_clips = min(B, 16)
+        batches = []
+        for _ in range(args.ragged_stream + 2):
+            shp = [(rnd.choice([8, 12, 16]), rnd.choice([128, 136, 144, 152, 160, 168]), rnd.choice([128, 136, 144, 152, 160, 168]))
+                   for _ in range(n_clips)]
+            tc = [rnd.randint(1, 128) for _ in range(n_clips)]
+            batches.append(([(torch.rand((3, *sh), device=dev) * 2 - 1).to(torch.bfloat16) for sh in shp], tc))
+        _eng.clear_caches()
+        for clips_r, tc_r in batches[:2]:
+            with torch.no_grad():
+                model.tokenize_reconstruct_(clips_r, tc_r, use_graph=False)
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for clips_r, tc_r in batches[2:]:
+            with torch.no_grad():
+                model.tokenize_reconstruct_(clips_r, tc_r, use_graph=False)
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        ragged = {"clips_per_s": n_clips * args.ragged_stream / (w1 - w0), "clips_per_step": n_clips, "steps": args.ragged_stream,
+                  "ms_per_step_wall": 1e3 * (w1 - w0) / args.ragged_stream,
+                  "note": "new shapes / token counts every step (tiny.yaml sampling ranges): includes host planning, metadata "
+                          "upload and eager launches; wall clock around a synchronised loop"}
+
     # ---------------- codebook usage over the whole job (the only data-path collective) ----------------
     if world > 1:
         dist.all_reduce(hist)
@@ -453,7 +488,7 @@ def main():
                     "api": "TiTok.tokenize_reconstruct_(clips, token_counts) from pinned host clips, 2-slot pipeline, CUDA-graph replay "
                            "(the value leg launches the same kernels one by one so that each can be timed with CUDA events)"},
             "gpu_launches": launches, "roofline": roofline, "whole_step": whole, "kernels": kernels, "clocks": clocks,
-            "cpu_baseline": cpu, "quantizer_microbench": vq,
+            "cpu_baseline": cpu, "quantizer_microbench": vq, "ragged_stream": ragged,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -134,6 +134,21 @@ int ttk_rmsnorm_fwd(const void* x, int64_t ldx, const float* w, void* y, int64_t
 int ttk_resid_norm(const void* x, const void* y, void* x_out, void* xn_out, const float* w_post, const float* w_next,
                    float alpha, int mode, int M, int width, int64_t ld, ttk_stream_t stream);
 
+/* Packing metadata of a batch (TiTokEncoder.forward, blocks.py:72-89; RoPE ids, rope.py:57-71; patch geometry,
+ * utils.py:26-51) expanded on the device from per-clip descriptors desc int64 [n_clips,12] =
+ * {row_start, tok_start, pat_start, token_count, n_patches, g1, g2, clip_offset, W, H*W, T*H*W, 0}.
+ * Outputs: enc_src_row / dec_src_row int32 [M], latent_row int32 [T], patch_row int32 [G], geom int64 [G,4],
+ * rope_pos int32 [M,3]. */
+int ttk_build_plan(const int64_t* desc, int n_clips, int64_t M, int P0, int P1, int P2, int32_t* enc_src_row,
+                   int32_t* dec_src_row, int32_t* latent_row, int32_t* patch_row, int64_t* geom, int32_t* rope_pos,
+                   ttk_stream_t stream);
+
+/* RoPE table of a packed batch (RoPE.forward + _get_freqs_cis, rope.py:48-71): rope [M,60] fp32 (cos, sin) pairs,
+ * complex lane = freq*3 + axis, gathered from cs_table [n_ids,10,2] fp32 = (cos, sin)(inv_freq[f] * id), evaluated once
+ * in float64 by the host planner, by the integer position ids pos [M,3] int32. */
+int ttk_rope_table_gather(const int32_t* pos, const float* cs_table, int n_ids, float* rope, int64_t M,
+                          ttk_stream_t stream);
+
 /* Per-clip reconstruction error of two flat clip buffers (same layout): out[2i] += sum|a-b| (the L1 reconstruction
  * loss numerator, loss_module.py:118), out[2i+1] += sum (a-b)^2 (PSNR, eval_metrics.py). out: fp64 [2*n_clips], zeroed
  * by the caller; clip_offset / clip_numel: device int64 [n_clips] in elements (multiples of 8). */

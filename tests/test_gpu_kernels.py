@@ -530,3 +530,24 @@ def test_bad_arguments_return_errors_not_crashes():
     assert L.fn("ttk_gemm_bf16")(P(x), 255, P(x), 256, 8, 8, 256, P(None), P(x), 256, P(None), 0, ST()) == -3
     with pytest.raises(L.TitokB200Error):
         L.call("ttk_patchify", P(x), P(x), 3, 4, 8, 4, P(x), 768, 1, ST())
+
+
+def test_device_built_plan_equals_host_planner():
+    """engine.DevicePlan expands the packing metadata on the device (ttk_build_plan) from per-clip descriptors and gathers
+    the [M,60] RoPE table (ttk_rope_table_gather); every array must equal the host planner's (plan.make_plan, which
+    tests/test_host_logic.py and tests/test_oracle_golden.py pin to the reference's packing and RoPE.forward)."""
+    from titok_video_b200 import engine
+    from titok_video_b200.plan import make_plan
+
+    shapes, tcs = [(16, 168, 168), (8, 128, 136), (4, 16, 24), (12, 160, 152)], [128, 1, 0, 77]
+    engine.clear_caches()
+    dp = engine.get_device_plan(shapes, tcs, (4, 8, 8), 3, torch.device(DEV))
+    torch.cuda.synchronize()
+    hp = make_plan(shapes, tcs, (4, 8, 8), 3)
+    assert (dp.plan.M, dp.plan.T, dp.plan.G) == (hp.M, hp.T, hp.G)
+    for name in ("enc_src_row", "dec_src_row", "latent_row", "patch_row", "geom", "rope_pos"):
+        want = torch.from_numpy(getattr(hp, name))
+        got = getattr(dp, name).cpu()[:want.shape[0]]
+        assert torch.equal(got, want), name
+    assert torch.equal(dp.rope.cpu()[:hp.M], torch.from_numpy(hp.rope))
+    assert torch.equal(dp.clip_offset.cpu(), torch.tensor(hp.clip_offset)) and torch.equal(dp.clip_numel.cpu(), torch.tensor(hp.clip_numel))

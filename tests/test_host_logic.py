@@ -165,3 +165,12 @@ def test_fsq_division_free_arithmetic_is_exact():
     x = np.concatenate([(np.random.default_rng(0).standard_normal(200000) * 4).astype(f), np.arange(-9, 9.5, 0.5, dtype=f)])
     m = f(12582912.0)
     assert np.array_equal((x + m) - m, np.rint(x))
+
+
+def test_rope_table_gather_is_bit_identical_to_direct_evaluation():
+    from titok_video_b200.plan import rope_ids, rope_inv_freqs, rope_table, rope_table_from_int_ids
+
+    inv = rope_inv_freqs()
+    for grid, tc in (((4, 21, 21), 128), ((2, 16, 16), 1), ((8, 32, 32), 256), ((3, 17, 20), 0)):
+        ids = rope_ids(grid, tc)
+        assert np.array_equal(rope_table(ids, inv), rope_table_from_int_ids(ids, inv))

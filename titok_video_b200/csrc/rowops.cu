@@ -303,6 +303,68 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const __nv_bfloat16* __
   }
 }
 
+// Expands the per-clip descriptors of a packed batch into the per-row metadata every other kernel consumes
+// (TiTokEncoder.forward metadata, blocks.py:72-89; RoPE.forward position ids, rope.py:57-71; patch geometry of
+// utils.py:26-51). desc[b] = {row_start, tok_start, pat_start, token_count, n_patches, g1, g2, clip_offset, W, H*W, T*H*W}.
+// One thread per packed row; the clip of a row is found by binary search over row_start.
+__global__ void __launch_bounds__(256) build_plan_kernel(const int64_t* __restrict__ desc, int B, int64_t M,
+                                                         int P0, int P1, int P2, int32_t* __restrict__ enc_src,
+                                                         int32_t* __restrict__ dec_src, int32_t* __restrict__ latent_row,
+                                                         int32_t* __restrict__ patch_row, int64_t* __restrict__ geom,
+                                                         int32_t* __restrict__ rope_pos) {
+  for (int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; row < M;
+       row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int lo = 0, hi = B - 1;
+    while (lo < hi) {  // last clip whose row_start <= row
+      const int mid = (lo + hi + 1) >> 1;
+      if (desc[mid * 12] <= row) lo = mid; else hi = mid - 1;
+    }
+    const int64_t* d = desc + lo * 12;
+    const int64_t local = row - d[0];
+    const int64_t tc = d[3];
+    if (local < tc) {
+      const int64_t tok = d[1] + local;
+      enc_src[row] = -1;
+      dec_src[row] = static_cast<int32_t>(tok);
+      latent_row[tok] = static_cast<int32_t>(row);
+      rope_pos[row * 3 + 0] = rope_pos[row * 3 + 1] = rope_pos[row * 3 + 2] = static_cast<int32_t>(local);
+    } else {
+      const int64_t pl = local - tc;
+      const int64_t pat = d[2] + pl;
+      const int64_t g1 = d[5], g2 = d[6];
+      const int64_t d0 = pl / (g1 * g2), rem = pl - d0 * g1 * g2, d1 = rem / g2, d2 = rem - d1 * g2;
+      enc_src[row] = static_cast<int32_t>(pat);
+      dec_src[row] = -1;
+      patch_row[pat] = static_cast<int32_t>(row);
+      rope_pos[row * 3 + 0] = static_cast<int32_t>(d0 + tc);
+      rope_pos[row * 3 + 1] = static_cast<int32_t>(d1 + tc);
+      rope_pos[row * 3 + 2] = static_cast<int32_t>(d2 + tc);
+      geom[pat * 4 + 0] = d[7] + (d0 * P0) * d[9] + (d1 * P1) * d[8] + d2 * P2;
+      geom[pat * 4 + 1] = d[8];
+      geom[pat * 4 + 2] = d[9];
+      geom[pat * 4 + 3] = d[10];
+    }
+  }
+}
+
+// RoPE table of a packed batch: rope[row, (f*3 + a)*2 + {0,1}] = cs_table[pos[row, a], f, {cos, sin}].
+// pos: int32 [M,3] integer position ids (RoPE.forward, rope.py:57-71); cs_table: fp32 [n_ids, 10, 2] evaluated once on
+// the host in float64 exactly as rope.py:40-54 does. The [M,60] table never crosses PCIe. One thread per complex lane.
+__global__ void __launch_bounds__(256) rope_table_gather_kernel(const int32_t* __restrict__ pos,
+                                                                const float2* __restrict__ cs_table, int n_ids,
+                                                                float2* __restrict__ rope, int64_t M) {
+  const int64_t total = M * 30;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / 30;
+    const int l = static_cast<int>(i - row * 30);
+    const int f = l / 3, a = l - f * 3;
+    int id = pos[row * 3 + a];
+    id = id < 0 ? 0 : (id >= n_ids ? n_ids - 1 : id);
+    rope[i] = __ldg(cs_table + id * 10 + f);
+  }
+}
+
 // Per-clip reconstruction error: out[2*i] += sum |a - b|, out[2*i+1] += sum (a - b)^2 over clip i (fp64 accumulators
 // in global memory, caller-zeroed). The L1 term is the reference's reconstruction loss (loss_module.py:118), the squared
 // term feeds PSNR (eval_metrics.py). Bandwidth-bound: 16-byte streaming loads of both buffers, warp-shuffle reduction,
@@ -486,6 +548,34 @@ int ttk_clip_error(const void* a, const void* b, const int64_t* clip_offset, con
   if (bx > 4LL * num_sms()) bx = 4LL * num_sms();
   clip_error_kernel<<<dim3(static_cast<unsigned>(bx), static_cast<unsigned>(n_clips)), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), clip_offset, clip_numel, out);
+  return launch_status();
+}
+
+// rope [M,60] fp32 <- gather of cs_table [n_ids,10,2] fp32 by pos [M,3] int32 (see rope_table_gather_kernel).
+int ttk_rope_table_gather(const int32_t* pos, const float* cs_table, int n_ids, float* rope, int64_t M,
+                          cudaStream_t stream) {
+  if (M <= 0) return TTK_OK;
+  if (!pos || !cs_table || !rope || n_ids <= 0) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (((reinterpret_cast<uintptr_t>(cs_table) | reinterpret_cast<uintptr_t>(rope)) & 7u) != 0) return TTK_ERR_ALIGNMENT;
+  const int64_t blocks = (M * 30 + 255) / 256;
+  const int grid = static_cast<int>(blocks < 16LL * num_sms() ? blocks : 16LL * num_sms());
+  rope_table_gather_kernel<<<grid, 256, 0, stream>>>(pos, reinterpret_cast<const float2*>(cs_table), n_ids,
+                                                     reinterpret_cast<float2*>(rope), M);
+  return launch_status();
+}
+
+// Per-row metadata of a packed batch from per-clip descriptors (see build_plan_kernel). All pointers are device memory.
+int ttk_build_plan(const int64_t* desc, int n_clips, int64_t M, int P0, int P1, int P2, int32_t* enc_src_row,
+                   int32_t* dec_src_row, int32_t* latent_row, int32_t* patch_row, int64_t* geom, int32_t* rope_pos,
+                   cudaStream_t stream) {
+  if (M <= 0 || n_clips <= 0) return TTK_OK;
+  if (!desc || !enc_src_row || !dec_src_row || !latent_row || !patch_row || !geom || !rope_pos) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  const int64_t blocks = (M + 255) / 256;
+  const int grid = static_cast<int>(blocks < 16LL * num_sms() ? blocks : 16LL * num_sms());
+  build_plan_kernel<<<grid, 256, 0, stream>>>(desc, n_clips, M, P0, P1, P2, enc_src_row, dec_src_row, latent_row, patch_row,
+                                              geom, rope_pos);
   return launch_status();
 }
 

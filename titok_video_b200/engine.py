@@ -46,18 +46,48 @@ def require_cuda(device: torch.device) -> None:
 # device-resident plan (metadata uploaded once) + workspace
 # --------------------------------------------------------------------------------------------------
 class DevicePlan:
+    """Device copy of a PackedPlan. All integer metadata travels in ONE pinned staging buffer and one asynchronous
+    H2D copy (a ragged stream builds a new plan every step); the fp32 RoPE table is gathered on the device."""
+
     def __init__(self, plan: PackedPlan, device: torch.device):
         self.plan = plan
         self.device = device
-        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
-        self.enc_src_row = up(plan.enc_src_row)
-        self.dec_src_row = up(plan.dec_src_row)
-        self.latent_row = up(plan.latent_row)
-        self.patch_row = up(plan.patch_row)
-        self.geom = up(plan.geom)
-        self.rope = up(plan.rope)
-        self.clip_offset = up(np.asarray(plan.clip_offset, dtype=np.int64))
-        self.clip_numel = up(np.asarray(plan.clip_numel, dtype=np.int64))
+        pieces = {
+            "clip_desc": plan.clip_desc,
+            "clip_offset": np.asarray(plan.clip_offset, dtype=np.int64),
+            "clip_numel": np.asarray(plan.clip_numel, dtype=np.int64),
+        }
+        offs, total = {}, 0
+        for k, a in pieces.items():
+            offs[k] = total
+            total += (a.nbytes + 255) // 256 * 256
+        total = max(total, 256)
+        host, done = _staging(total)
+        hv = host.numpy()
+        for k, a in pieces.items():
+            hv[offs[k]:offs[k] + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        self._meta = torch.empty(total, dtype=torch.uint8, device=device)
+        self._meta.copy_(host[:total], non_blocking=True)
+        done.record()
+        for k, a in pieces.items():
+            setattr(self, k, self._meta[offs[k]:offs[k] + a.nbytes].view(torch.int64).view(a.shape))
+        # per-row metadata: expanded on the device from the per-clip descriptors (the host only did O(B) work)
+        M, T, G = plan.M, plan.T, plan.G
+        i32 = dict(dtype=torch.int32, device=device)
+        self.enc_src_row = torch.empty(max(M, 1), **i32)
+        self.dec_src_row = torch.empty(max(M, 1), **i32)
+        self.latent_row = torch.empty(max(T, 1), **i32)
+        self.patch_row = torch.empty(max(G, 1), **i32)
+        self.geom = torch.empty((max(G, 1), 4), dtype=torch.int64, device=device)
+        self.rope_pos = torch.empty((max(M, 1), 3), **i32)
+        P0, P1, P2 = plan.patch_size
+        _lib.call("ttk_build_plan", _ptr(self.clip_desc), len(plan.token_counts), M, P0, P1, P2, _ptr(self.enc_src_row),
+                  _ptr(self.dec_src_row), _ptr(self.latent_row), _ptr(self.patch_row), _ptr(self.geom), _ptr(self.rope_pos),
+                  _stream())
+        # RoPE table: gathered on the device from the integer position ids and the shared per-id cos / sin table
+        cs, n_ids = _cs_table(device, plan.max_pos + 1)
+        self.rope = torch.empty((max(M, 1), 60), dtype=torch.float32, device=device)
+        _lib.call("ttk_rope_table_gather", _ptr(self.rope_pos), _ptr(cs), n_ids, _ptr(self.rope), M, _stream())
         self._attn: Dict[Tuple[int, int], torch.Tensor] = {}
         self.ws: Dict[str, torch.Tensor] = {}
         self.graphs: Dict[tuple, "torch.cuda.CUDAGraph"] = {}
@@ -65,16 +95,85 @@ class DevicePlan:
     def attn_work(self, hq: int, hkv: int) -> torch.Tensor:
         k = (hq, hkv)
         if k not in self._attn:
-            w = get_attn_work(self.plan, hq, hkv)
-            self._attn[k] = torch.from_numpy(np.ascontiguousarray(w)).to(self.device)
+            w = np.ascontiguousarray(get_attn_work(self.plan, hq, hkv))
+            host, done = _staging(max(w.nbytes, 256))
+            host.numpy()[:w.nbytes] = w.view(np.uint8).reshape(-1)
+            dev = torch.empty(max(w.nbytes, 256), dtype=torch.uint8, device=self.device)
+            dev.copy_(host[:dev.numel()], non_blocking=True)
+            done.record()
+            self._attn[k] = dev[:w.nbytes].view(torch.int32).view(w.shape)
         return self._attn[k]
 
     def buf(self, name: str, shape: Sequence[int], dtype=torch.bfloat16) -> torch.Tensor:
-        t = self.ws.get(name)
-        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
-            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
-            self.ws[name] = t
+        """Named workspace tensor: a typed view of the device-wide arena of that name (see _arena). Plans of different
+        batch compositions share the arenas, so a ragged stream does not allocate device memory per step; results that
+        live in workspace buffers are therefore only valid until the next launch sequence on the device."""
+        shape = tuple(int(v) for v in shape)
+        key = (name, shape, dtype)
+        hit = self.ws.get(key)
+        if hit is not None and hit[0] == _ARENA_GEN:
+            return hit[1]
+        nbytes = max(1, math.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        base = _arena(self.device, name, nbytes)
+        t = base[:nbytes].view(dtype)[:math.prod(shape)].view(shape)
+        self.ws[key] = (_ARENA_GEN, t)
         return t
+
+
+_ARENA: Dict[Tuple[str, str], torch.Tensor] = {}
+_ARENA_GEN = 0  # bumped whenever an arena is re-allocated: cached views and captured CUDA graphs of older generations are stale
+
+
+def _arena(device: torch.device, name: str, nbytes: int) -> torch.Tensor:
+    global _ARENA_GEN
+    k = (str(device), name)
+    t = _ARENA.get(k)
+    if t is None or t.numel() < nbytes:
+        cap = max(nbytes, int(1.5 * t.numel()) if t is not None else 0)
+        cap = (cap + (1 << 20) - 1) >> 20 << 20
+        t = torch.empty(cap, dtype=torch.uint8, device=device)
+        _ARENA[k] = t
+        _ARENA_GEN += 1
+    return t
+
+
+def arena_generation() -> int:
+    return _ARENA_GEN
+
+
+# Ring of pinned staging buffers for plan metadata (pinning memory costs milliseconds, so it is done once): a slot is
+# reused only after the copy that last read it has finished.
+_STAGING: List[list] = []
+_STAGING_NEXT = 0
+_STAGING_SLOTS = 8
+
+
+def _staging(nbytes: int):
+    global _STAGING_NEXT
+    if not _STAGING:
+        for _ in range(_STAGING_SLOTS):
+            _STAGING.append([torch.empty(1 << 22, dtype=torch.uint8).pin_memory(), torch.cuda.Event()])
+    slot = _STAGING[_STAGING_NEXT]
+    _STAGING_NEXT = (_STAGING_NEXT + 1) % _STAGING_SLOTS
+    slot[1].synchronize()
+    if slot[0].numel() < nbytes:
+        slot[0] = torch.empty(1 << max(22, (nbytes - 1).bit_length()), dtype=torch.uint8).pin_memory()
+    return slot[0], slot[1]
+
+
+_CS_TABLES: Dict[str, Tuple[torch.Tensor, int]] = {}
+
+
+def _cs_table(device: torch.device, n_ids: int) -> Tuple[torch.Tensor, int]:
+    """Device copy of plan.cos_sin_id_table (fp32 [n,10,2]), shared by every plan on that device."""
+    from .plan import cos_sin_id_table
+
+    cur = _CS_TABLES.get(str(device))
+    if cur is None or cur[1] < n_ids:
+        t = cos_sin_id_table(n_ids)
+        cur = (torch.from_numpy(np.ascontiguousarray(t)).to(device), int(t.shape[0]))
+        _CS_TABLES[str(device)] = cur
+    return cur
 
 
 _PLAN_CACHE: Dict[tuple, DevicePlan] = {}
@@ -88,13 +187,13 @@ def get_device_plan(grids_px, token_counts, patch_size, channels, device) -> Dev
     if dp is None:
         if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
             _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
-        dp = DevicePlan(make_plan(key[0], key[1], key[2], key[3]), device)
+        dp = DevicePlan(make_plan(key[0], key[1], key[2], key[3], arrays=False), device)
         _PLAN_CACHE[key] = dp
     return dp
 
 
 def clear_caches() -> None:
-    _PLAN_CACHE.clear()
+    _PLAN_CACHE.clear()  # (the workspace arenas stay: they are sized by the largest batch seen, not per plan)
 
 
 # --------------------------------------------------------------------------------------------------

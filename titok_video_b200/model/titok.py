@@ -105,13 +105,15 @@ class TiTok(nn.Module):
         else:
             key = ("tokenize_reconstruct", id(self), flat.data_ptr(), bool(with_error))
             entry = dp.graphs.get(key)
+            if entry is not None and entry[3] != engine.arena_generation():
+                entry = None  # a workspace arena was re-allocated since the capture: the graph's pointers are stale
             if entry is None:
                 launch()  # eager warm-up: workspace allocation, one-time function attributes
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     idx, err = launch()
-                entry = (g, idx, err)
+                entry = (g, idx, err, engine.arena_generation())
                 dp.graphs[key] = entry
             entry[0].replay()
             idx, err = entry[1], entry[2]

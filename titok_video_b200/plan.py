@@ -46,8 +46,19 @@ class PackedPlan:
     latent_row: np.ndarray = None  # int32 [T]
     patch_row: np.ndarray = None  # int32 [G]
     geom: np.ndarray = None  # int64 [G,4]: offset, W, H*W, T*H*W
-    rope: np.ndarray = None  # float32 [M,60]
+    clip_desc: np.ndarray = None  # int64 [B,12]: per-clip descriptor for the device-side expansion (ttk_build_plan)
+    max_pos: int = 0
+    rope_pos: np.ndarray = None  # int32 [M,3]: integer (T,H,W) position ids of every packed row (rope.py:57-71)
+    _rope: np.ndarray = None  # float32 [M,60], built on demand (tests / oracle); the engine builds it on the device
     attn_work: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)  # (hq,hkv) -> int32 [n,12]
+
+    @property
+    def rope(self) -> np.ndarray:
+        """float32 [M,60] (cos, sin) table on the host (the device copy is gathered by ttk_rope_table_gather from
+        `rope_pos` and the per-id cos / sin table, see engine.DevicePlan)."""
+        if self._rope is None:
+            self._rope = rope_table_from_int_ids(self.rope_pos, rope_inv_freqs())
+        return self._rope
 
     @property
     def key(self):
@@ -85,6 +96,32 @@ def rope_table(ids: np.ndarray, inv_freqs: np.ndarray) -> np.ndarray:
     return out.reshape(ids.shape[0], -1)
 
 
+_CS_CACHE = {"n": 0, "table": None}
+
+
+def _cos_sin_by_id(n_ids: int, inv_freqs: np.ndarray) -> np.ndarray:
+    """float32 [n_ids, F, 2]: (cos, sin) of inv_freqs[f] * id for the integer position ids 0..n_ids-1. Position ids are
+    small integers (latent index, or patch coordinate + token count), so every table entry of rope_table is one of
+    these values: same float64 product, same float64 cos / sin, same rounding. Grown on demand, computed once."""
+    if _CS_CACHE["n"] < n_ids:
+        n = max(1024, 2 * n_ids)
+        ang = np.arange(n, dtype=np.float64)[:, None] * inv_freqs[None, :]
+        t = np.empty((n, inv_freqs.shape[0], 2), dtype=np.float32)
+        t[..., 0] = np.cos(ang)
+        t[..., 1] = np.sin(ang)
+        _CS_CACHE["n"], _CS_CACHE["table"] = n, t
+    return _CS_CACHE["table"]
+
+
+def rope_table_from_int_ids(ids: np.ndarray, inv_freqs: np.ndarray) -> np.ndarray:
+    """rope_table for integer-valued ids [L, A] through the per-id cache: a gather instead of L*F*A cos/sin pairs
+    (bit-identical to rope_table, checked in tests/test_host_logic.py)."""
+    ii = ids.astype(np.int64)
+    t = _cos_sin_by_id(int(ii.max()) + 1 if ii.size else 1, inv_freqs)  # [n, F, 2]
+    out = t[ii]  # [L, A, F, 2]
+    return np.ascontiguousarray(out.transpose(0, 2, 1, 3)).reshape(ids.shape[0], -1)
+
+
 def attn_work_list(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: int, hkv: int) -> np.ndarray:
     """int32 [n, 12] records {q_row0[2], q_valid[2], q_head[2], kv_head, kv_row0, kv_len, pad[3]} (csrc/attn.cu).
     Two query tiles per record share one kv head: two heads of the same group when the group size is even,
@@ -115,7 +152,9 @@ def attn_work_list(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: int, 
 
 
 def make_plan(grids_px: Sequence[Sequence[int]], token_counts: Sequence[int], patch_size: Sequence[int],
-              channels: int = 3) -> PackedPlan:
+              channels: int = 3, arrays: bool = True) -> PackedPlan:
+    """arrays=False computes only the O(B) part (sizes, prefix sums, `clip_desc`); the engine then expands the per-row
+    metadata on the device (ttk_build_plan). arrays=True also fills the numpy arrays on the host (tests, tools)."""
     patch_size = tuple(int(p) for p in patch_size)
     grids_px = tuple(tuple(int(v) for v in g) for g in grids_px)
     token_counts = tuple(int(t) for t in token_counts)
@@ -133,7 +172,6 @@ def make_plan(grids_px: Sequence[Sequence[int]], token_counts: Sequence[int], pa
     plan = PackedPlan(grids_px=grids_px, grids=tuple(grids), token_counts=token_counts, patch_size=patch_size,
                       channels=channels)
 
-    inv = rope_inv_freqs()
     gsz = [int(np.prod(g)) for g in grids]
     seq = [g + t for g, t in zip(gsz, token_counts)]
     plan.seq_lens = tuple(seq)
@@ -144,34 +182,72 @@ def make_plan(grids_px: Sequence[Sequence[int]], token_counts: Sequence[int], pa
     plan.clip_offset = tuple(int(v) for v in np.concatenate([[0], np.cumsum(numel)[:-1]]))
     plan.total_numel = int(sum(numel))
 
+    B = len(grids)
+    g_arr = np.asarray(grids, dtype=np.int64).reshape(B, 3)
+    px = np.asarray(grids_px, dtype=np.int64).reshape(B, 3)
+    tc_arr = np.asarray(token_counts, dtype=np.int64)
+    ng_arr = np.asarray(gsz, dtype=np.int64)
+    row_start = np.concatenate([[0], np.cumsum(tc_arr + ng_arr)[:-1]]).astype(np.int64)  # first packed row of a clip
+    tok_start = np.concatenate([[0], np.cumsum(tc_arr)[:-1]]).astype(np.int64)
+    pat_start = np.concatenate([[0], np.cumsum(ng_arr)[:-1]]).astype(np.int64)
+    clip_off = np.asarray(plan.clip_offset, dtype=np.int64)
+    # per-clip descriptor consumed by ttk_build_plan (csrc/rowops.cu): int64 [B, 12]
+    desc = np.zeros((B, 12), dtype=np.int64)
+    desc[:, 0], desc[:, 1], desc[:, 2], desc[:, 3] = row_start, tok_start, pat_start, tc_arr
+    desc[:, 4], desc[:, 5], desc[:, 6] = ng_arr, g_arr[:, 1], g_arr[:, 2]
+    desc[:, 7], desc[:, 8], desc[:, 9], desc[:, 10] = clip_off, px[:, 2], px[:, 1] * px[:, 2], px[:, 0] * px[:, 1] * px[:, 2]
+    plan.clip_desc = desc
+    plan.max_pos = int((tc_arr + g_arr.max(axis=1)).max()) if B else 0  # upper bound of every position id (+1)
+    if not arrays:
+        return plan
+
+    # Everything below is vectorised over the whole batch (no per-clip numpy calls): a stream of ragged batches pays
+    # this planner on every step (train.py / tokenisation jobs never repeat a batch composition).
+    # np.repeat of per-clip values is much cheaper than fancy indexing; 32-bit arithmetic wherever the range allows
+    rep_t = lambda v: np.repeat(v, tc_arr)
+    rep_p = lambda v: np.repeat(v, ng_arr)
+    i32 = np.int32
+    # latent tokens: index within the clip and packed row
+    t_loc = np.arange(plan.T, dtype=i32) - rep_t(tok_start.astype(i32))
+    latent_row = rep_t(row_start.astype(i32)) + t_loc
+    # patches: index within the clip, (d0, d1, d2) with the last axis fastest (torch.cartesian_prod order)
+    p_loc = np.arange(plan.G, dtype=i32) - rep_p(pat_start.astype(i32))
+    g2 = rep_p(g_arr[:, 2].astype(i32))
+    g12 = rep_p((g_arr[:, 1] * g_arr[:, 2]).astype(i32))
+    d0 = p_loc // g12
+    rem = p_loc - d0 * g12
+    d1 = rem // g2
+    d2 = rem - d1 * g2
+    tcp = rep_p(tc_arr.astype(i32))
+    patch_row = rep_p(row_start.astype(i32)) + tcp + p_loc
+
     enc_src = np.full(plan.M, -1, dtype=np.int32)
     dec_src = np.full(plan.M, -1, dtype=np.int32)
-    latent_row = np.empty(plan.T, dtype=np.int32)
-    patch_row = np.empty(plan.G, dtype=np.int32)
-    geom = np.empty((plan.G, 4), dtype=np.int64)
-    rope = np.empty((plan.M, 2 * 3 * ROPE_LANES_PER_AXIS), dtype=np.float32)
-    row = tok = pat = 0
+    enc_src[patch_row] = np.arange(plan.G, dtype=np.int32)
+    dec_src[latent_row] = np.arange(plan.T, dtype=np.int32)
+
     p0, p1, p2 = patch_size
-    for b, (g, tc) in enumerate(zip(grids, token_counts)):
-        T_, H_, W_ = grids_px[b]
-        ng = gsz[b]
-        latent_row[tok:tok + tc] = np.arange(row, row + tc)
-        dec_src[row:row + tc] = np.arange(tok, tok + tc)
-        patch_row[pat:pat + ng] = np.arange(row + tc, row + tc + ng)
-        enc_src[row + tc:row + tc + ng] = np.arange(pat, pat + ng)
-        d0, d1, d2 = np.meshgrid(np.arange(g[0]), np.arange(g[1]), np.arange(g[2]), indexing="ij")
-        off = plan.clip_offset[b] + (d0.reshape(-1) * p0) * (H_ * W_) + (d1.reshape(-1) * p1) * W_ + d2.reshape(-1) * p2
-        geom[pat:pat + ng, 0] = off
-        geom[pat:pat + ng, 1] = W_
-        geom[pat:pat + ng, 2] = H_ * W_
-        geom[pat:pat + ng, 3] = T_ * H_ * W_
-        rope[row:row + tc + ng] = rope_table(rope_ids(g, tc), inv)
-        row += tc + ng
-        tok += tc
-        pat += ng
+    W_ = rep_p(px[:, 2])
+    HW_ = rep_p(px[:, 1] * px[:, 2])
+    geom = np.empty((plan.G, 4), dtype=np.int64)
+    geom[:, 0] = rep_p(clip_off) + (d0 * p0) * HW_ + (d1 * p1) * W_ + d2 * p2
+    geom[:, 1] = W_
+    geom[:, 2] = HW_
+    geom[:, 3] = rep_p(px[:, 0] * px[:, 1] * px[:, 2])
+
+    rope_pos = np.empty((plan.M, 3), dtype=np.int32)
+    rope_pos[latent_row] = t_loc[:, None]                 # latent j -> (j, j, j)
+    rope_pos[patch_row, 0] = d0 + tcp                      # patch (a, b, c) -> (a, b, c) + token_count
+    rope_pos[patch_row, 1] = d1 + tcp
+    rope_pos[patch_row, 2] = d2 + tcp
     plan.enc_src_row, plan.dec_src_row = enc_src, dec_src
-    plan.latent_row, plan.patch_row, plan.geom, plan.rope = latent_row, patch_row, geom, rope
+    plan.latent_row, plan.patch_row, plan.geom, plan.rope_pos = latent_row, patch_row, geom, rope_pos
     return plan
+
+
+def cos_sin_id_table(n_ids: int) -> np.ndarray:
+    """float32 [n, F, 2] (cos, sin) of inv_freq[f] * id for id < n (n >= n_ids): the only trigonometry of a plan."""
+    return _cos_sin_by_id(n_ids, rope_inv_freqs())
 
 
 def get_attn_work(plan: PackedPlan, hq: int, hkv: int) -> np.ndarray:
