@@ -127,6 +127,25 @@ def attn_work_list(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: int, 
     Two query tiles per record share one kv head: two heads of the same group when the group size is even,
     otherwise two consecutive row tiles of one head. Longest sequences first (LPT) to shorten the tail."""
     ratio = hq // hkv
+    if ratio % 2 == 0 and len(seq_starts):
+        # vectorised: one record per (clip, row tile, pair of query heads of one kv group)
+        st = np.asarray(seq_starts, dtype=np.int64)
+        sl = np.asarray(seq_lens, dtype=np.int64)
+        nt = (sl + ATTN_TILE - 1) // ATTN_TILE
+        clip = np.repeat(np.arange(len(sl)), nt)
+        ti = np.arange(int(nt.sum()), dtype=np.int64) - np.repeat(np.concatenate([[0], np.cumsum(nt)[:-1]]), nt)
+        r0 = st[clip] + ti * ATTN_TILE
+        valid = np.minimum(ATTN_TILE, sl[clip] - ti * ATTN_TILE)
+        hp = hq // 2
+        rec = np.zeros((len(ti) * hp, 12), dtype=np.int32)
+        h = np.tile(np.arange(0, hq, 2), len(ti))
+        rep = lambda v: np.repeat(v, hp)
+        rec[:, 0] = rec[:, 1] = rep(r0)
+        rec[:, 2] = rec[:, 3] = rep(valid)
+        rec[:, 4], rec[:, 5], rec[:, 6] = h, h + 1, h // ratio
+        rec[:, 7], rec[:, 8] = rep(st[clip]), rep(sl[clip])
+        order = np.argsort(-rec[:, 8], kind="stable")  # longest sequences first (LPT), ties in generation order
+        return np.ascontiguousarray(rec[order])
     recs: List[List[int]] = []
     for start, slen in zip(seq_starts, seq_lens):
         n_tiles = (slen + ATTN_TILE - 1) // ATTN_TILE
