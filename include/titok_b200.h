@@ -180,6 +180,76 @@ int ttk_patchify(const void* clips, const int64_t* geom, int C, int P0, int P1, 
 int ttk_unpatchify(const void* proj, int64_t ldp, const int32_t* patch_row, const int64_t* geom, int C, int P0,
                    int P1, int P2, void* clips, int64_t G, ttk_stream_t stream);
 
+/* =============================================================================================
+ * Training path: backward kernels. The reference has no hand-written backward; each entry point replaces what
+ * torch.autograd runs for the cited forward lines under bf16 autocast (train.py:68-80: manual_backward of the
+ * reconstruction loss through TiTokDecoder -> FSQ (straight-through) -> TiTokEncoder). Activation gradients are
+ * bf16, parameter gradients fp32 and ACCUMULATED (+=) into caller-zeroed buffers.
+ * =========================================================================================== */
+
+/* ttk_attn_varlen_fwd that also saves what the backward needs: o_save [M, ldo] = attention output before the gate,
+ * lse fp32 [width/64][M] = log2-domain log-sum-exp of the scaled scores. */
+int ttk_attn_varlen_fwd_train(const void* qkv, int64_t ld, int M, int width, int gqa, const void* work, int n_work,
+                              float softmax_scale, void* out, int64_t ldo, void* o_save, float* lse,
+                              ttk_stream_t stream);
+
+/* Backward of `attn * sigmoid(gate)` (transformer.py:101-103) + the row sums flash-attn's backward needs:
+ * dO = d_out * sigmoid(gate) [M,width]; dqkv[:, width:2*width] = d gate; delta fp32 [width/64][M] = rowsum(dO o O). */
+int ttk_attn_bwd_prep(const void* d_out, int64_t ldd, const void* o, int64_t ldo, const void* qkv, int64_t ld, int M,
+                      int width, void* dO, int64_t lddo, void* dqkv, int64_t ldq, float* delta, ttk_stream_t stream);
+
+/* Backward of flash_attn_varlen_func (transformer.py:100) and of apply_rotary_emb on q, k (rope.py:19-27).
+ * work: int32 [n_work, 8] records {st_row0, st_valid, st_head, o_head0, n_heads, clip_row0, clip_len, 0} (plan.py:
+ * attn_bwd_work_lists). dkv writes dqkv[:, 2w:2w+g] (dk, rotated back) and dqkv[:, 2w+g:] (dv); dq writes dqkv[:, :w]. */
+int ttk_attn_bwd_dkv(const void* qkv, int64_t ld, const void* dO, int64_t lddo, int M, int width, int gqa,
+                     const void* work, int n_work, const float* lse, const float* delta, const float* rope,
+                     float softmax_scale, void* dqkv, int64_t ldq, ttk_stream_t stream);
+int ttk_attn_bwd_dq(const void* qkv, int64_t ld, const void* dO, int64_t lddo, int M, int width, int gqa,
+                    const void* work, int n_work, const float* lse, const float* delta, const float* rope,
+                    float softmax_scale, void* dqkv, int64_t ldq, ttk_stream_t stream);
+
+/* nn.Linear weight gradient: dW[n_out, k_in] (fp32, row pitch ldw) += dY[M, n_out]^T @ X[M, k_in] (split-K tcgen05
+ * GEMM over the token dimension). The input gradient dX = dY @ W is ttk_gemm_bf16(dY, W, w_is_kn = 1). */
+int ttk_gemm_wgrad(const void* dy, int64_t ldy, const void* x, int64_t ldx, int M, int n_out, int k_in, float* dw,
+                   int64_t ldw, ttk_stream_t stream);
+
+/* RMSNorm backward (fa:ops/triton/layer_norm.py:1093-1126), optionally through the KEEL pre-sum (transformer.py:141-145):
+ *   u = y ? bf16(bf16(alpha*x) + y) : x;  dx = d(RMSNorm(u)*w)/du . dy + add_scale * add;  dw += sum_rows dy * u * rstd.
+ * sel (optional int32 [M]): rows with sel < 0 use w2 / dw2 (the two pre-norms of the embed, blocks.py:95-97,164-167). */
+int ttk_rmsnorm_bwd(const void* x, const void* y, float alpha, const float* w, const float* w2, const int32_t* sel,
+                    const void* dy, const void* add, float add_scale, void* dx, float* dw, float* dw2, int M, int width,
+                    int64_t ld, ttk_stream_t stream);
+
+/* GEGLU on a stored w12 output h12 [M, 2*inner] = [value | gate] (transformer.py:50-52) and its backward. */
+int ttk_geglu_fwd(const void* h12, int64_t ld12, int inner, void* h, int64_t ldh, int64_t M, ttk_stream_t stream);
+int ttk_geglu_bwd(const void* h12, int64_t ld12, int inner, const void* dh, int64_t ldh, void* dh12, int64_t ldd,
+                  int64_t M, ttk_stream_t stream);
+
+/* dst[i] = src[idx[i]] / dst[idx[i]] = src[i] for n rows of `width` bf16 (latent / patch row maps, blocks.py:85-86). */
+int ttk_gather_rows(const void* src, int64_t lds, const int32_t* idx, void* dst, int64_t ldd, int64_t n, int width,
+                    ttk_stream_t stream);
+int ttk_scatter_rows(const void* src, int64_t lds, const int32_t* idx, void* dst, int64_t ldd, int64_t n, int width,
+                     ttk_stream_t stream);
+
+/* Bias / mask_token gradients: out[c] (optional) += sum_r x[r,c]; total[0] (optional) += sum of all of x. */
+int ttk_colsum(const void* x, int64_t ld, int64_t M, int N, float* out, float* total, ttk_stream_t stream);
+
+/* Backward of the encoder head Linear(width -> token_size) on the latent rows (blocks.py:101-103). */
+int ttk_head_bwd(const void* dz, int token_size, const void* xn, int64_t ld, const int32_t* latent_row, const void* w_out,
+                 void* dxn, float* dw, float* db, int T, int width, ttk_stream_t stream);
+
+/* Backward of the decoder's Linear(token_size -> width) on the latent rows (blocks.py:164-165). dcodes fp32 [T, TS]. */
+int ttk_dec_in_bwd(const void* de, int64_t ld, const int32_t* latent_row, const void* codes, int token_size,
+                   const void* w_in, float* dcodes, float* dw, float* db, int T, int width, ttk_stream_t stream);
+
+/* ttk_enc_embed / ttk_dec_embed that also store the rows before ln_pre_t / ln_pre_p (e0_out [M, ld]). */
+int ttk_enc_embed_train(const void* proj, int64_t ldp, const int32_t* src_row, const float* mask_token, const float* w_t,
+                        const float* w_p, const float* w_next, void* x_out, void* xn_out, void* e0_out, int M, int width,
+                        int64_t ld, ttk_stream_t stream);
+int ttk_dec_embed_train(const void* codes, int token_size, const int32_t* src_row, const void* w_in, const void* b_in,
+                        const float* mask_token, const float* w_t, const float* w_p, const float* w_next, void* x_out,
+                        void* xn_out, void* e0_out, int M, int width, int64_t ld, ttk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -252,6 +252,35 @@ def titok_forward(sd: Dict[str, torch.Tensor], levels: Sequence[int], patch: Seq
     return {"z": z, "bounded": bounded, "codes": codes, "indices": idx, "recon": recon}
 
 
+def fsq_forward_ste(z: torch.Tensor, levels: Sequence[int]) -> torch.Tensor:
+    """FSQ.quantize with the straight-through rounding of round_ste  [fsq.py:48-51,85-90]: differentiable codes."""
+    lv, basis, half_l, offset, shift, hw = fsq_constants(levels)
+    bounded = (z.float() + shift).tanh() * half_l - offset
+    q = bounded + (bounded.round() - bounded).detach()
+    return q / hw
+
+
+def recon_l1_loss(clips: List[torch.Tensor], recon: List[torch.Tensor]) -> torch.Tensor:
+    """Reconstruction term of ReconstructionLoss: mean over clips of the per-clip mean |x - recon|
+    [model/losses/loss_module.py:118,160]."""
+    return torch.stack([(r_.float() - c.float()).abs().mean() for c, r_ in zip(clips, recon)]).mean()
+
+
+def titok_train_grads(sd: Dict[str, torch.Tensor], levels: Sequence[int], patch: Sequence[int],
+                      clips: List[torch.Tensor], token_counts: Sequence[int], enc_size: str = "tiny",
+                      dec_size: str = "tiny"):
+    """One generator training step without the optimizer  [train.py:68-80: forward, L1 reconstruction loss, backward]:
+    returns (loss, {state-dict name: fp32 gradient}). torch.autograd differentiates the restated forward; every r()
+    rounds the gradient to bf16 on the way back exactly where bf16 autocast would hold a bf16 tensor."""
+    leaves = {k: v.detach().clone().float().requires_grad_(True) for k, v in sd.items()}
+    z = encoder_forward(leaves, enc_size, patch, clips, token_counts)
+    codes = r(fsq_forward_ste(z, levels))
+    recon = decoder_forward(leaves, dec_size, patch, codes, token_counts, [c.shape[1:] for c in clips])
+    loss = recon_l1_loss(clips, recon)
+    loss.backward()
+    return float(loss), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+
+
 # ------------------------------------------------------------------------------------------------
 # generic VQ oracle (north_star): torch.cdist(z, C).argmin(-1), chunked
 # ------------------------------------------------------------------------------------------------

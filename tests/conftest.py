@@ -34,6 +34,15 @@ def load_golden(name: str):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 
 
+GRAD_SAMPLES = 2048
+
+
+def grad_sample_index(numel: int) -> np.ndarray:
+    """Indices of the gradient entries the titok_grads_* fixtures keep per parameter (tests/golden/make_golden.py)."""
+    stride = max(1, -(-numel // GRAD_SAMPLES))
+    return np.arange(0, numel, stride)
+
+
 def param_checksum(sd) -> np.ndarray:
     return np.array([float(v.double().sum()) for _, v in sorted(sd.items())] +
                     [float(v.double().abs().sum()) for _, v in sorted(sd.items())])

@@ -117,7 +117,49 @@ def rope_case():
                         cos=f.real.numpy(), sin=f.imag.numpy(), x_bits=bits(x), y_bits=bits(y))
 
 
+GRAD_SHAPES = [(8, 32, 32), (4, 16, 24)]
+GRAD_TCS = [8, 3]
+GRAD_SAMPLES = 2048
+
+
+def grad_sample_index(numel: int) -> np.ndarray:
+    """Indices of the (at most GRAD_SAMPLES) gradient entries a fixture keeps per parameter."""
+    stride = max(1, -(-numel // GRAD_SAMPLES))
+    return np.arange(0, numel, stride)
+
+
+def grads_case(name: str, stress: bool):
+    """Parameter gradients of one generator step (L1 reconstruction loss, train.py:68-80; loss_module.py:118) from the
+    unmodified reference in bf16 on CPU. Per parameter: the gradient's norm and a strided sample of its entries."""
+    m = ref_shim.build_reference_titok(fsq_levels=LEVELS, patch_size=PATCH, seed=42)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    if stress:
+        O.stress_init_(sd, 1)
+        m.load_state_dict(sd)
+    mb = m.to(torch.bfloat16).train()
+    clips = O.make_clips(GRAD_SHAPES, 0)
+    tc = torch.tensor(GRAD_TCS, dtype=torch.int32)
+    recon, d = mb(clips, tc)
+    loss = torch.stack([(r_.float() - c.float()).abs().mean() for c, r_ in zip(clips, recon)]).mean()
+    loss.backward()
+    arrays = {"shapes": np.array(GRAD_SHAPES), "token_counts": np.array(GRAD_TCS), "stress": np.array(int(stress)),
+              "loss": np.array(float(loss)), "indices": d["indices"].numpy().astype(np.int32),
+              "weight_checksum": checksum(sd)}
+    for k, p in mb.named_parameters():
+        g = (p.grad if p.grad is not None else torch.zeros_like(p)).float().reshape(-1)
+        arrays[f"norm/{k}"] = np.array(float(g.double().norm()))
+        arrays[f"sample/{k}"] = g[torch.from_numpy(grad_sample_index(g.numel()))].numpy()
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **arrays)
+    print(name, "loss", float(loss))
+
+
 if __name__ == "__main__":
+    if "--grads-only" in sys.argv:
+        grads_case("titok_grads_default", stress=False)
+        grads_case("titok_grads_stress", stress=True)
+        sys.exit(0)
+    grads_case("titok_grads_default", stress=False)
+    grads_case("titok_grads_stress", stress=True)
     titok_case("titok_default", stress=False)
     titok_case("titok_stress", stress=True)
     fsq_case()

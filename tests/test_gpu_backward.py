@@ -1,0 +1,408 @@
+"""Training path on the B200: every backward entry point of libtitok_b200.so against torch.autograd of the same op in
+fp32 on the CPU (the ops are floating point: tolerances are written in each test), and the whole generator step
+(encoder -> FSQ straight-through -> decoder -> L1 loss -> backward, train.py:68-80) against (a) the CPU oracle's
+autograd and (b) fixtures produced by the unmodified reference (tests/golden/titok_grads_*.npz).
+"""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import build_model, grad_sample_index, load_golden
+from oracle import titok_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+DEV = "cuda"
+
+
+def lib():
+    from titok_video_b200 import _lib
+
+    return _lib
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def ST():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def randn(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(BF)
+
+
+def rel_err(out, ref):
+    o = out.float().cpu().double()
+    r = ref.double()
+    assert torch.isfinite(o).all(), "non-finite output"
+    return float((o - r).norm() / (r.norm() + 1e-30))
+
+
+def cos_sim(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+# --------------------------------------------------------------------------------------------------
+# weight-gradient GEMM (both operands MN-major, split-K, fp32 atomics)
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,n_out,k_in", [(64, 128, 128), (200, 128, 256), (1000, 768, 256), (2468, 256, 704),
+                                          (5676, 1408, 256), (777, 256, 768), (3000, 768, 256), (130, 256, 64)])
+def test_gemm_wgrad(M, n_out, k_in):
+    dy = randn(M, n_out, seed=1)
+    x = randn(M, k_in, seed=2)
+    ref = dy.double().t() @ x.double()
+    dyd, xd = dy.to(DEV), x.to(DEV)
+    dw = torch.zeros((n_out, k_in), dtype=torch.float32, device=DEV)
+    lib().call("ttk_gemm_wgrad", P(dyd), n_out, P(xd), k_in, M, n_out, k_in, P(dw), k_in, ST())
+    torch.cuda.synchronize()
+    # bf16 products are exact in fp32; only the summation order differs
+    assert rel_err(dw, ref) < 1e-5
+    d = (dw.cpu().double() - ref).abs().max().item()
+    assert d < 1e-3 * ref.abs().max().item() + 1e-3
+    # accumulates (+=)
+    lib().call("ttk_gemm_wgrad", P(dyd), n_out, P(xd), k_in, M, n_out, k_in, P(dw), k_in, ST())
+    torch.cuda.synchronize()
+    assert rel_err(dw, 2 * ref) < 1e-5
+
+
+def test_gemm_dgrad_is_the_kn_gemm():
+    """dX = dY @ W with the ORIGINAL [out, in] weight: ttk_gemm_bf16(w_is_kn=1), shapes of the training path."""
+    for M, n_out, k_in in [(777, 256, 704), (500, 1408, 256), (300, 768, 256), (257, 256, 256)]:
+        dy = randn(M, n_out, seed=3)
+        w = randn(n_out, k_in, seed=4, scale=0.05)
+        ref = O.r(dy.float() @ w.float())
+        dyd, wd = dy.to(DEV), w.to(DEV)
+        out = torch.empty((M, k_in), dtype=BF, device=DEV)
+        lib().call("ttk_gemm_bf16", P(dyd), n_out, P(wd), k_in, M, k_in, n_out, P(None), P(out), k_in, P(None), 1, ST())
+        torch.cuda.synchronize()
+        assert rel_err(out, ref) < 4e-3
+
+
+# --------------------------------------------------------------------------------------------------
+# attention backward
+# --------------------------------------------------------------------------------------------------
+def _attn_ref(qkv, d_out, seq_lens, hq, hkv, cos_sin):
+    """fp32 autograd of rope(q), rope(k) -> softmax attention -> * sigmoid(gate) on the PRE-rope q, k. Returns
+    (out, d q_pre, d gate, d k_pre, d v)."""
+    width, gqa = hq * 64, hkv * 64
+    leaf = qkv.float().clone().requires_grad_(True)
+    q, gate, k, v = leaf.split([width, width, gqa, gqa], dim=-1)
+    outs, s0 = [], 0
+    for sl, (cos, sin) in zip(seq_lens, cos_sin):
+        def rope(x):
+            n = cos.shape[-1]
+            xe, xo = x[..., 0:2 * n:2], x[..., 1:2 * n:2]
+            c, s = cos.unsqueeze(1), sin.unsqueeze(1)
+            rot = torch.stack([xe * c - xo * s, xe * s + xo * c], dim=-1).flatten(-2)
+            return torch.cat([rot, x[..., 2 * n:]], dim=-1)
+        qq = rope(q[s0:s0 + sl].reshape(sl, hq, 64))
+        kk = rope(k[s0:s0 + sl].reshape(sl, hkv, 64)).repeat_interleave(hq // hkv, dim=1)
+        vv = v[s0:s0 + sl].reshape(sl, hkv, 64).repeat_interleave(hq // hkv, dim=1)
+        s = torch.einsum("qhd,khd->hqk", qq, kk) * 0.125
+        o = torch.einsum("hqk,khd->qhd", torch.softmax(s, -1), vv).reshape(sl, width)
+        outs.append(o * torch.sigmoid(gate[s0:s0 + sl]))
+        s0 += sl
+    out = torch.cat(outs, 0)
+    out.backward(d_out.float())
+    return out.detach(), leaf.grad
+
+
+@pytest.mark.parametrize("seq_lens,hq,hkv", [([128], 4, 2), ([200, 64, 513], 4, 2), ([1892, 576], 4, 2),
+                                               ([300, 129], 12, 4), ([257], 8, 2)])
+def test_attn_backward(seq_lens, hq, hkv):
+    from titok_video_b200.plan import attn_bwd_work_lists, attn_work_list
+
+    width, gqa = hq * 64, hkv * 64
+    M = sum(seq_lens)
+    ld = 2 * width + 2 * gqa
+    qkv_pre = randn(M, ld, seed=20)
+    d_out = randn(M, width, seed=21)
+    starts = np.concatenate([[0], np.cumsum(seq_lens)[:-1]]).tolist()
+    # a RoPE table with real structure: clip i = grid (1, 1, sl - 3) with 3 latent tokens
+    cos_sin = [O.rope_cos_sin([1, 1, sl - 3], 3) for sl in seq_lens]
+    rope = torch.cat([torch.stack([c, s], dim=-1).reshape(c.shape[0], 60) for c, s in cos_sin], 0).contiguous()
+    out_ref, g_ref = _attn_ref(qkv_pre, d_out, seq_lens, hq, hkv, cos_sin)
+
+    # forward on the device from the rope'd buffer (what ttk_gemm_qkv_rope leaves behind)
+    q, gate, k, v = qkv_pre.float().split([width, width, gqa, gqa], dim=-1)
+    qr = torch.cat([O.apply_rope(q[s0:s0 + sl].reshape(sl, hq, 64), *cs).reshape(sl, width)
+                    for s0, sl, cs in zip(starts, seq_lens, cos_sin)], 0)
+    kr = torch.cat([O.apply_rope(k[s0:s0 + sl].reshape(sl, hkv, 64), *cs).reshape(sl, gqa)
+                    for s0, sl, cs in zip(starts, seq_lens, cos_sin)], 0)
+    qkv = torch.cat([qr, gate, kr, v], dim=-1).to(BF).to(DEV).contiguous()
+    work = torch.from_numpy(attn_work_list(starts, seq_lens, hq, hkv)).to(DEV)
+    out = torch.empty((M, width), dtype=BF, device=DEV)
+    o_save = torch.empty((M, width), dtype=BF, device=DEV)
+    lse = torch.full((hq, M), float("nan"), dtype=torch.float32, device=DEV)
+    lib().call("ttk_attn_varlen_fwd_train", P(qkv), ld, M, width, gqa, P(work), work.shape[0], 0.125, P(out), width,
+               P(o_save), P(lse), ST())
+    torch.cuda.synchronize()
+    assert rel_err(out, out_ref) < 2e-2
+    assert torch.isfinite(lse).all()
+    # lse against the exact log-sum-exp (log2 domain)
+    s0 = 0
+    for sl in seq_lens:
+        qq = qkv[s0:s0 + sl, :width].float().cpu().reshape(sl, hq, 64)
+        kk = qkv[s0:s0 + sl, 2 * width:2 * width + gqa].float().cpu().reshape(sl, hkv, 64).repeat_interleave(hq // hkv, 1)
+        s = torch.einsum("qhd,khd->hqk", qq, kk) * 0.125
+        want = torch.logsumexp(s, -1) / math.log(2.0)
+        assert (lse[:, s0:s0 + sl].cpu() - want).abs().max().item() < 2e-3
+        s0 += sl
+
+    d_out_d = d_out.to(DEV)
+    dO = torch.empty((M, width), dtype=BF, device=DEV)
+    dqkv = torch.full((M, ld), float("nan"), dtype=BF, device=DEV)
+    delta = torch.empty((hq, M), dtype=torch.float32, device=DEV)
+    lib().call("ttk_attn_bwd_prep", P(d_out_d), width, P(o_save), width, P(qkv), ld, M, width, P(dO), width, P(dqkv), ld,
+               P(delta), ST())
+    wk_dkv, wk_dq = [torch.from_numpy(a).to(DEV) for a in attn_bwd_work_lists(starts, seq_lens, hq, hkv)]
+    rope_d = rope.to(DEV)
+    for name, wk in (("ttk_attn_bwd_dkv", wk_dkv), ("ttk_attn_bwd_dq", wk_dq)):
+        lib().call(name, P(qkv), ld, P(dO), width, M, width, gqa, P(wk), wk.shape[0], P(lse), P(delta), P(rope_d), 0.125,
+                   P(dqkv), ld, ST())
+    torch.cuda.synchronize()
+    got = dqkv.float().cpu()
+    assert torch.isfinite(got).all()
+    names = ["dq", "dgate", "dk", "dv"]
+    for nm, a, b in zip(names, got.split([width, width, gqa, gqa], -1), g_ref.split([width, width, gqa, gqa], -1)):
+        e = float((a.double() - b.double()).norm() / b.double().norm())
+        # bf16 P / dS / dO operands and bf16 outputs: ~1e-2 relative in the Frobenius norm
+        assert e < 2.5e-2, f"{nm}: rel fro {e:.4g}"
+        assert cos_sim(a, b) > 0.9995, nm
+
+
+# --------------------------------------------------------------------------------------------------
+# row kernels
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("width", [256, 768])
+@pytest.mark.parametrize("keel", [False, True])
+def test_rmsnorm_bwd(width, keel):
+    M = 1237
+    alpha = 8.0
+    x, y, dy, add = randn(M, width, seed=1), randn(M, width, seed=2), randn(M, width, seed=3), randn(M, width, seed=4)
+    w = torch.rand(width, generator=torch.Generator().manual_seed(5)) + 0.5
+    u_in = O.r(O.r(x.float() * alpha) + y.float()) if keel else x.float()
+    u = u_in.clone().requires_grad_(True)
+    wl = w.clone().requires_grad_(True)
+    out = u * torch.rsqrt(u.pow(2).mean(-1, keepdim=True) + 1e-5) * wl
+    out.backward(dy.float())
+    ref_dx = u.grad + 0.5 * add.float()
+    dx = torch.empty((M, width), dtype=BF, device=DEV)
+    dw = torch.zeros(width, dtype=torch.float32, device=DEV)
+    xd, yd, dyd, addd, wd = x.to(DEV), y.to(DEV), dy.to(DEV), add.to(DEV), w.to(DEV)
+    lib().call("ttk_rmsnorm_bwd", P(xd), P(yd if keel else None), alpha, P(wd), P(None), P(None), P(dyd), P(addd), 0.5,
+               P(dx), P(dw), P(None), M, width, width, ST())
+    torch.cuda.synchronize()
+    assert rel_err(dx, ref_dx) < 4e-3  # bf16 output rounding
+    assert rel_err(dw, wl.grad) < 1e-4
+
+
+def test_rmsnorm_bwd_two_weights():
+    M, width = 515, 256
+    x, dy = randn(M, width, seed=1), randn(M, width, seed=3)
+    g = torch.Generator().manual_seed(7)
+    w1, w2 = torch.rand(width, generator=g) + 0.5, torch.rand(width, generator=g) + 0.5
+    sel = torch.where(torch.rand(M, generator=g) < 0.3, -1, 5).to(torch.int32)
+    u = x.float().clone().requires_grad_(True)
+    a, b = w1.clone().requires_grad_(True), w2.clone().requires_grad_(True)
+    wrow = torch.where((sel < 0).unsqueeze(-1), b, a)
+    (u * torch.rsqrt(u.pow(2).mean(-1, keepdim=True) + 1e-5) * wrow).backward(dy.float())
+    dx = torch.empty((M, width), dtype=BF, device=DEV)
+    dw1 = torch.zeros(width, dtype=torch.float32, device=DEV)
+    dw2 = torch.zeros(width, dtype=torch.float32, device=DEV)
+    xd, dyd, w1d, w2d, seld = x.to(DEV), dy.to(DEV), w1.to(DEV), w2.to(DEV), sel.to(DEV)
+    lib().call("ttk_rmsnorm_bwd", P(xd), P(None), 1.0, P(w1d), P(w2d), P(seld), P(dyd), P(None), 0.0, P(dx), P(dw1), P(dw2),
+               M, width, width, ST())
+    torch.cuda.synchronize()
+    assert rel_err(dx, u.grad) < 4e-3
+    assert rel_err(dw1, a.grad) < 1e-4 and rel_err(dw2, b.grad) < 1e-4
+
+
+def test_geglu_fwd_bwd():
+    M, inner = 700, 704
+    h12, dh = randn(M, 2 * inner, seed=1, scale=1.5), randn(M, inner, seed=2)
+    leaf = h12.float().clone().requires_grad_(True)
+    val, gate = leaf.chunk(2, -1)
+    h = O.gelu_erf(gate) * val
+    h.backward(dh.float())
+    h12d, dhd = h12.to(DEV), dh.to(DEV)
+    out = torch.empty((M, inner), dtype=BF, device=DEV)
+    dh12 = torch.empty((M, 2 * inner), dtype=BF, device=DEV)
+    lib().call("ttk_geglu_fwd", P(h12d), 2 * inner, inner, P(out), inner, M, ST())
+    lib().call("ttk_geglu_bwd", P(h12d), 2 * inner, inner, P(dhd), inner, P(dh12), 2 * inner, M, ST())
+    torch.cuda.synchronize()
+    ref_h = O.r(O.r(O.gelu_erf(h12.float()[:, inner:])) * h12.float()[:, :inner])
+    assert rel_err(out, ref_h) < 1e-3
+    assert rel_err(dh12, leaf.grad) < 6e-3  # two bf16 roundings per element
+
+
+def test_gather_scatter_colsum():
+    M, n, width = 900, 333, 768
+    src = randn(M, width, seed=1)
+    idx = torch.randperm(M, generator=torch.Generator().manual_seed(2))[:n].to(torch.int32)
+    sd, idd = src.to(DEV), idx.to(DEV)
+    out = torch.empty((n, width), dtype=BF, device=DEV)
+    lib().call("ttk_gather_rows", P(sd), width, P(idd), P(out), width, n, width, ST())
+    back = torch.zeros((M, width), dtype=BF, device=DEV)
+    lib().call("ttk_scatter_rows", P(out), width, P(idd), P(back), width, n, width, ST())
+    cs = torch.zeros(width, dtype=torch.float32, device=DEV)
+    tot = torch.zeros(1, dtype=torch.float32, device=DEV)
+    lib().call("ttk_colsum", P(sd), width, M, width, P(cs), P(tot), ST())
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), src[idx.long()])
+    want = torch.zeros_like(src)
+    want[idx.long()] = src[idx.long()]
+    assert torch.equal(back.cpu(), want)
+    assert rel_err(cs, src.double().sum(0)) < 1e-5
+    assert abs(tot.item() - src.double().sum().item()) < 1e-3 * src.double().abs().sum().item() ** 0.5 + 1e-2
+
+
+def test_head_and_dec_in_backward():
+    M, T, width, ts = 700, 97, 256, 5
+    g = torch.Generator().manual_seed(3)
+    latent_row = torch.randperm(M, generator=g)[:T].to(torch.int32)
+    xn, dz = randn(M, width, seed=1), randn(T, ts, seed=2)
+    w_out = randn(ts, width, seed=4, scale=0.1)
+    # encoder head: z = xn[rows] @ w_out^T + b
+    a = xn.float()[latent_row.long()].clone().requires_grad_(True)
+    wl = w_out.float().clone().requires_grad_(True)
+    (a @ wl.t()).backward(dz.float())
+    dxn = torch.zeros((M, width), dtype=BF, device=DEV)
+    dw = torch.zeros((ts, width), dtype=torch.float32, device=DEV)
+    db = torch.zeros(ts, dtype=torch.float32, device=DEV)
+    dzd, xnd, lrd, wod = dz.to(DEV), xn.to(DEV), latent_row.to(DEV), w_out.to(DEV)
+    lib().call("ttk_head_bwd", P(dzd), ts, P(xnd), width, P(lrd), P(wod), P(dxn), P(dw), P(db), T, width, ST())
+    torch.cuda.synchronize()
+    assert rel_err(dxn[latent_row.long().to(DEV)], a.grad) < 4e-3
+    mask = torch.ones(M, dtype=torch.bool)
+    mask[latent_row.long()] = False
+    assert (dxn.cpu()[mask] == 0).all()
+    assert rel_err(dw, wl.grad) < 1e-5
+    assert rel_err(db, dz.float().sum(0)) < 1e-5
+    # decoder proj_in: e[rows] = codes @ w_in^T + b
+    de, codes = randn(M, width, seed=5), randn(T, ts, seed=6)
+    w_in = randn(width, ts, seed=7, scale=0.1)
+    c = codes.float().clone().requires_grad_(True)
+    wi = w_in.float().clone().requires_grad_(True)
+    (c @ wi.t()).backward(de.float()[latent_row.long()])
+    dcodes = torch.zeros((T, ts), dtype=torch.float32, device=DEV)
+    dwi = torch.zeros((width, ts), dtype=torch.float32, device=DEV)
+    dbi = torch.zeros(width, dtype=torch.float32, device=DEV)
+    ded, cd, wid = de.to(DEV), codes.to(DEV), w_in.to(DEV)
+    lib().call("ttk_dec_in_bwd", P(ded), width, P(lrd), P(cd), ts, P(wid), P(dcodes), P(dwi), P(dbi), T, width, ST())
+    torch.cuda.synchronize()
+    assert rel_err(dcodes, c.grad) < 1e-5
+    assert rel_err(dwi, wi.grad) < 1e-5
+    assert rel_err(dbi, de.float()[latent_row.long()].sum(0)) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------------
+# whole generator step
+# --------------------------------------------------------------------------------------------------
+def _train_step_grads(model, clips, tcs):
+    model.zero_grad(set_to_none=True)
+    recon, d = model([c.to(DEV) for c in clips], tcs)
+    loss = torch.stack([(r_.float() - c.to(DEV).float()).abs().mean() for c, r_ in zip(clips, recon)]).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    return float(loss), d["indices"].cpu(), {k: p.grad.detach().float().cpu() for k, p in model.named_parameters()}
+
+
+@pytest.mark.parametrize("stress", [False, True])
+def test_generator_step_matches_reference_fixture(stress):
+    """train.py:68-80 on the drop-in modules vs gradients of the UNMODIFIED reference (tests/golden/make_golden.py).
+    Reference initialiser: cosine >= 0.995 per parameter and norms within 3 % (the CPU oracle itself reaches 0.9998).
+    Stress initialiser (weights ~ N(0, 4/fan_in)): the bf16 network is chaotic -- the CPU oracle agrees with the
+    reference only to cosine 0.79..0.99 there -- so the bar is cosine >= 0.7 on the weight matrices."""
+    f = load_golden("titok_grads_stress" if stress else "titok_grads_default")
+    model = build_model(stress).to(DEV).train()
+    clips = O.make_clips([tuple(s) for s in f["shapes"]], 0)
+    loss, idx, grads = _train_step_grads(model, clips, f["token_counts"].tolist())
+    assert abs(loss - float(f["loss"])) < (2e-2 if stress else 2e-3) * float(f["loss"])
+    worst = (1.0, "")
+    for k, g in grads.items():
+        assert torch.isfinite(g).all(), k
+        ref_norm = float(f["norm/" + k])
+        want = torch.from_numpy(f["sample/" + k]).double()
+        got = g.reshape(-1)[torch.from_numpy(grad_sample_index(g.numel()))].double()
+        if g.numel() == 1:
+            if not stress:
+                # mask_token: a sum over every row and column with heavy cancellation
+                assert abs(float(got) - float(want)) < 0.5 * abs(float(want)) + 2e-3, k
+            continue
+        c = cos_sim(got, want)
+        worst = min(worst, (c, k))
+        if stress:
+            if g.dim() == 2:
+                assert c > 0.7, f"{k}: cos {c:.4f}"
+        else:
+            assert c > 0.995, f"{k}: cos {c:.4f}"
+            assert abs(float(g.double().norm()) / ref_norm - 1.0) < 0.03, f"{k}: norm {float(g.norm()):.4g} vs {ref_norm:.4g}"
+    print("worst cosine", worst)
+
+
+def test_generator_step_matches_oracle_autograd_ragged():
+    """Three ragged clips (partial tiles on both sides of the attention) against the CPU oracle's autograd."""
+    model = build_model(False).to(DEV).train()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    shapes, tcs = [(8, 64, 48), (4, 16, 24), (8, 32, 40)], [16, 3, 40]
+    clips = O.make_clips(shapes, 3)
+    loss, _, grads = _train_step_grads(model, clips, tcs)
+    loss_o, grads_o = O.titok_train_grads(sd, [7, 5, 5, 5, 5], [4, 8, 8], clips, tcs)
+    assert abs(loss - loss_o) < 2e-3 * loss_o
+    for k, g in grads.items():
+        if g.numel() == 1:
+            continue
+        c = cos_sim(g, grads_o[k])
+        assert c > 0.995, f"{k}: cos {c:.4f}"
+        assert abs(float(g.double().norm()) / float(grads_o[k].double().norm()) - 1.0) < 0.03, k
+
+
+def test_encoder_input_gradient_and_frozen_parameters():
+    """The discriminator differentiates the encoder w.r.t. its pixels (loss_module.py:149-152); parameters with
+    requires_grad=False get no gradient."""
+    import titok_video_b200 as T
+
+    torch.manual_seed(0)
+    enc = T.TiTokEncoder("tiny", (4, 8, 8), 3, 1).to(DEV)
+    from titok_video_b200.model.base.utils import init_weights
+    enc.apply(init_weights)
+    for p in enc.parameters():
+        p.requires_grad_(False)
+    clips = [c.to(DEV).float().requires_grad_(True) for c in O.make_clips([(4, 32, 32), (8, 16, 24)], 5)]
+    tcs = [4, 4]
+    out = enc(clips, tcs)
+    assert out.shape == (8, 1)
+    w = torch.linspace(-1, 1, 8, device=DEV).view(8, 1)
+    (out.float() * w).sum().backward()
+    assert all(p.grad is None for p in enc.parameters())
+    # oracle: autograd w.r.t. the pixels
+    sd = {"encoder." + k: v.detach().cpu() for k, v in enc.state_dict().items()}
+    leaves = [c.detach().cpu().float().requires_grad_(True) for c in clips]
+    z = O.encoder_forward(sd, "tiny", [4, 8, 8], leaves, tcs)
+    (z * w.cpu()).sum().backward()
+    for a, b in zip(clips, leaves):
+        assert a.grad is not None and torch.isfinite(a.grad).all()
+        assert cos_sim(a.grad.cpu(), b.grad) > 0.99
+
+
+def test_training_forward_equals_inference_forward():
+    """The recorded (unfused) forward and the fused inference forward produce the same tokens."""
+    model = build_model(True).to(DEV)
+    clips = [c.to(DEV) for c in O.make_clips([(8, 64, 48), (4, 16, 24)], 0)]
+    tcs = [16, 3]
+    with torch.no_grad():
+        rec_i, d_i = model(clips, tcs)
+    rec_t, d_t = model(clips, tcs)
+    same = (d_i["indices"] == d_t["indices"]).float().mean().item()
+    assert same >= 0.8  # GELU: exact erf (training) vs the fused kernel's A&S polynomial can flip a boundary token
+    for a, b in zip(rec_i, rec_t):
+        assert rel_err(b.detach(), a.float().cpu()) < 3e-2 or same < 1.0

@@ -174,3 +174,32 @@ def test_rope_table_gather_is_bit_identical_to_direct_evaluation():
     for grid, tc in (((4, 21, 21), 128), ((2, 16, 16), 1), ((8, 32, 32), 256), ((3, 17, 20), 0)):
         ids = rope_ids(grid, tc)
         assert np.array_equal(rope_table(ids, inv), rope_table_from_int_ids(ids, inv))
+
+
+@pytest.mark.parametrize("hq,hkv", [(4, 2), (12, 4)])
+def test_attention_backward_work_lists_cover_every_tile_once(hq, hkv):
+    """dkv: every (128-key tile, kv head) once, streaming all grouped query heads; dq: every (query tile, query head)."""
+    from titok_video_b200.plan import attn_bwd_work_lists
+
+    seq_lens = [513, 128, 1892, 77]
+    starts = np.concatenate([[0], np.cumsum(seq_lens)[:-1]]).tolist()
+    dkv, dq = attn_bwd_work_lists(starts, seq_lens, hq, hkv)
+    assert dkv.dtype == np.int32 and dkv.shape[1] == 8 and dq.shape[1] == 8
+    n_tiles = sum((s + 127) // 128 for s in seq_lens)
+    assert len(dkv) == n_tiles * hkv and len(dq) == n_tiles * hq
+    grp = hq // hkv
+    seen = set()
+    for st_row0, st_valid, st_head, o_head0, n_heads, clip_row0, clip_len, _ in dkv.tolist():
+        assert (st_row0, st_head) not in seen
+        seen.add((st_row0, st_head))
+        assert o_head0 == st_head * grp and n_heads == grp
+        assert clip_row0 in starts and clip_len == seq_lens[starts.index(clip_row0)]
+        assert 0 < st_valid <= 128 and st_row0 + st_valid <= clip_row0 + clip_len and (st_row0 - clip_row0) % 128 == 0
+    rows = np.zeros((sum(seq_lens), hq), dtype=np.int32)
+    for st_row0, st_valid, st_head, o_head0, n_heads, clip_row0, clip_len, _ in dq.tolist():
+        rows[st_row0:st_row0 + st_valid, st_head] += 1
+        assert o_head0 == st_head // grp and n_heads == 1
+    assert (rows == 1).all()
+    # longest work first
+    cost = dkv[:, 4].astype(np.int64) * ((dkv[:, 6] + 127) // 128)
+    assert (np.diff(cost) <= 0).all()

@@ -61,6 +61,22 @@ SIGNATURES = {
     "ttk_clip_error": [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp],
     "ttk_patchify": [_vp, _vp, _i, _i, _i, _i, _vp, _i64, _i64, _vp],
     "ttk_unpatchify": [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp, _i64, _vp],
+    # ---- training path (backward kernels)
+    "ttk_attn_varlen_fwd_train": [_vp, _i64, _i, _i, _i, _vp, _i, _f, _vp, _i64, _vp, _vp, _vp],
+    "ttk_attn_bwd_prep": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp],
+    "ttk_attn_bwd_dkv": [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _f, _vp, _i64, _vp],
+    "ttk_attn_bwd_dq": [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _f, _vp, _i64, _vp],
+    "ttk_gemm_wgrad": [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i64, _vp],
+    "ttk_rmsnorm_bwd": [_vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i64, _vp],
+    "ttk_geglu_fwd": [_vp, _i64, _i, _vp, _i64, _i64, _vp],
+    "ttk_geglu_bwd": [_vp, _i64, _i, _vp, _i64, _vp, _i64, _i64, _vp],
+    "ttk_gather_rows": [_vp, _i64, _vp, _vp, _i64, _i64, _i, _vp],
+    "ttk_scatter_rows": [_vp, _i64, _vp, _vp, _i64, _i64, _i, _vp],
+    "ttk_colsum": [_vp, _i64, _i64, _i, _vp, _vp, _vp],
+    "ttk_head_bwd": [_vp, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "ttk_dec_in_bwd": [_vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "ttk_enc_embed_train": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp],
+    "ttk_dec_embed_train": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp],
 }
 _RESTYPES = {"ttk_strerror": c_char_p}
 

@@ -1,0 +1,389 @@
+"""Training path: launch sequences that record what the backward needs, the backward launch sequences, and the
+torch.autograd.Function wrappers that plug them into autograd (so `train.py:68-80` -- forward under bf16 autocast,
+`manual_backward(loss)`, `grad_norm(self.model)`, AdamW on `model.parameters()` -- works on the drop-in modules).
+
+What the reference gets from torch.autograd for model/base/blocks.py:71-104,148-177 and
+model/base/transformer.py:47-56,85-104,126-146 is computed here by the sm_100a kernels of csrc/attn_bwd.cu (attention),
+csrc/wgrad.cu (weight gradients), csrc/gemm.cu (input gradients: `ttk_gemm_bf16(..., w_is_kn=1)`) and
+csrc/bwd_rows.cu (RMSNorm / GEGLU / gathers / small projections). Activation gradients are bf16 (as under the
+reference's autocast), parameter gradients fp32 in the reference's parameter layout.
+
+Saved activations live in ordinary torch tensors (not in the shared workspace arenas), so several forwards may be
+in flight before their backwards (generator + discriminator passes, gradient accumulation).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .engine import DevicePlan, PreparedStack, _ptr, _stream, _vp, patch_feature_perm, prepared
+
+bf16 = torch.bfloat16
+
+
+def _new(shape, device, dtype=bf16) -> torch.Tensor:
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+class Tape:
+    """Activations of one stack forward, kept for its backward."""
+
+    def __init__(self):
+        self.layers: List[Dict[str, torch.Tensor]] = []
+        self.t: Dict[str, torch.Tensor] = {}
+
+
+# --------------------------------------------------------------------------------------------------
+# forward (unfused where the backward needs the intermediate)
+# --------------------------------------------------------------------------------------------------
+def _gemm(a: torch.Tensor, wmat: torch.Tensor, out: torch.Tensor, N: int, K: int, bias=None, kn: int = 0) -> None:
+    _lib.call("ttk_gemm_bf16", _ptr(a), a.stride(0), _ptr(wmat), wmat.stride(0), a.shape[0], N, K, _ptr(bias), _ptr(out),
+              out.stride(0), _vp(0), kn, _stream())
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor) -> None:
+    """dw [n_out, k_in] fp32 += dy^T x."""
+    _lib.call("ttk_gemm_wgrad", _ptr(dy), dy.stride(0), _ptr(x), x.stride(0), dy.shape[0], dw.shape[0], dw.shape[1],
+              _ptr(dw), dw.stride(0), _stream())
+
+
+def _rmsnorm_bwd(x, w, dy, dx, dw, *, y=None, alpha=1.0, add=None, add_scale=1.0, sel=None, w2=None, dw2=None) -> None:
+    M, width = x.shape
+    _lib.call("ttk_rmsnorm_bwd", _ptr(x), _ptr(y), float(alpha), _ptr(w), _ptr(w2), _ptr(sel), _ptr(dy), _ptr(add),
+              float(add_scale), _ptr(dx), _ptr(dw), _ptr(dw2), M, width, x.stride(0), _stream())
+
+
+def _layers_train(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tensor, tape: Tape):
+    """ResidualAttentionBlock.forward (transformer.py:126-146), recording per-layer activations."""
+    M, w = x.shape
+    dev = x.device
+    hq, hkv = m.heads
+    gqa = hkv * 64
+    inner = m.inner_dim
+    L = m.num_layers
+    alpha = float(2 * L)
+    st = _stream()
+    work = dp.attn_work(hq, hkv)
+    scale = 1.0 / math.sqrt(64.0)
+    T = W.t
+    for i in range(L):
+        mode = 0 if i == 0 else 1
+        qkv = _new((M, 2 * w + 2 * gqa), dev)
+        att, o = _new((M, w), dev), _new((M, w), dev)
+        lse = _new((hq, M), dev, torch.float32)
+        _lib.call("ttk_gemm_qkv_rope", _ptr(xn), xn.stride(0), _ptr(T[f"to_qkv{i}"]), w, M, w, w, gqa, _ptr(dp.rope),
+                  _ptr(qkv), qkv.stride(0), st)
+        _lib.call("ttk_attn_varlen_fwd_train", _ptr(qkv), qkv.stride(0), M, w, gqa, _ptr(work), work.shape[0], scale,
+                  _ptr(att), att.stride(0), _ptr(o), _ptr(lse), st)
+        y_a = _new((M, w), dev)
+        _gemm(att, T[f"out_proj{i}"], y_a, w, w)
+        x_f, xn_f = _new((M, w), dev), _new((M, w), dev)
+        _lib.call("ttk_resid_norm", _ptr(x), _ptr(y_a), _ptr(x_f), _ptr(xn_f), _ptr(T.get(f"attn_post_ln{i}")),
+                  _ptr(T[f"ffn_norm{i}"]), alpha, mode, M, w, w, st)
+        h12 = _new((M, 2 * inner), dev)
+        _gemm(xn_f, T[f"w12_{i}"], h12, 2 * inner, w)
+        h = _new((M, inner), dev)
+        _lib.call("ttk_geglu_fwd", _ptr(h12), h12.stride(0), inner, _ptr(h), h.stride(0), M, st)
+        y_f = _new((M, w), dev)
+        _gemm(h, T[f"w3_{i}"], y_f, w, inner)
+        x_n, xn_n = _new((M, w), dev), _new((M, w), dev)
+        w_next = T[f"pre_ln{i + 1}"] if i + 1 < L else T["ln_post"]
+        _lib.call("ttk_resid_norm", _ptr(x_f), _ptr(y_f), _ptr(x_n), _ptr(xn_n), _ptr(T.get(f"ffd_post_ln{i}")),
+                  _ptr(w_next), alpha, mode, M, w, w, st)
+        tape.layers.append(dict(x_a=x, xn_a=xn, qkv=qkv, att=att, o=o, lse=lse, y_a=y_a, x_f=x_f, xn_f=xn_f, h12=h12,
+                                h=h, y_f=y_f))
+        x, xn = x_n, xn_n
+    return x, xn
+
+
+def encoder_forward_train(m, dp: DevicePlan, clips_flat: torch.Tensor, fsq_consts):
+    """TiTokEncoder.forward recording a tape. Returns (z, codes, idx, tape); z/codes bf16 [T, ts]."""
+    W = prepared(m, "enc")
+    pl = dp.plan
+    M, G, Tn, w = pl.M, pl.G, pl.T, m.width
+    P0, P1, P2 = pl.patch_size
+    feat = pl.channels * P0 * P1 * P2
+    dev = clips_flat.device
+    st = _stream()
+    tape = Tape()
+    T = W.t
+    patches = _new((G, feat), dev)
+    proj = _new((G, w), dev)
+    x, xn, e0 = _new((M, w), dev), _new((M, w), dev), _new((M, w), dev)
+    _lib.call("ttk_patchify", _ptr(clips_flat), _ptr(dp.geom), pl.channels, P0, P1, P2, _ptr(patches), feat, G, st)
+    _gemm(patches, T["proj_in_w"], proj, w, feat, bias=T["proj_in_b"])
+    _lib.call("ttk_enc_embed_train", _ptr(proj), w, _ptr(dp.enc_src_row), _ptr(T["mask_token"]), _ptr(T["ln_pre_t"]),
+              _ptr(T["ln_pre_p"]), _ptr(T["pre_ln0"]), _ptr(x), _ptr(xn), _ptr(e0), M, w, w, st)
+    x_fin, xn_fin = _layers_train(m, W, dp, x, xn, tape)
+    ts = m.token_size
+    z = _new((max(Tn, 1), ts), dev)
+    codes = _new((max(Tn, 1), ts), dev)
+    idx = _new((max(Tn, 1),), dev, torch.int32)
+    half_l, offset, shift, half_width, basis, levels = fsq_consts
+    _lib.call("ttk_enc_head_fsq", _ptr(xn_fin), w, _ptr(dp.latent_row), _ptr(T["ln_post"]), 1, _ptr(T["proj_out_w"]),
+              _ptr(T["proj_out_b"]), ts, _ptr(z), _ptr(codes), _ptr(idx), Tn, w, half_l, offset, shift, half_width,
+              basis, levels, st)
+    tape.t.update(patches=patches, e0=e0, x_fin=x_fin, xn_fin=xn_fin)
+    return z[:Tn], codes[:Tn], idx[:Tn], tape
+
+
+def decoder_forward_train(m, dp: DevicePlan, codes: torch.Tensor):
+    """TiTokDecoder.forward recording a tape. Returns (out_flat bf16 [sum 3*T*H*W], tape)."""
+    W = prepared(m, "dec")
+    pl = dp.plan
+    M, G, w = pl.M, pl.G, m.width
+    P0, P1, P2 = pl.patch_size
+    feat = pl.channels * P0 * P1 * P2
+    dev = codes.device
+    st = _stream()
+    tape = Tape()
+    T = W.t
+    x, xn, e0 = _new((M, w), dev), _new((M, w), dev), _new((M, w), dev)
+    _lib.call("ttk_dec_embed_train", _ptr(codes), m.token_size, _ptr(dp.dec_src_row), _ptr(T["proj_in_w"]),
+              _ptr(T["proj_in_b"]), _ptr(T["mask_token"]), _ptr(T["ln_pre_t"]), _ptr(T["ln_pre_p"]), _ptr(T["pre_ln0"]),
+              _ptr(x), _ptr(xn), _ptr(e0), M, w, w, st)
+    x_fin, xn_fin = _layers_train(m, W, dp, x, xn, tape)
+    rows = _new((M, feat), dev)
+    _gemm(xn_fin, T["proj_out_w"], rows, feat, w, bias=T["proj_out_b"])
+    out = _new((pl.total_numel,), dev)
+    _lib.call("ttk_unpatchify", _ptr(rows), feat, _ptr(dp.patch_row), _ptr(dp.geom), pl.channels, P0, P1, P2, _ptr(out),
+              G, st)
+    tape.t.update(codes=codes, e0=e0, x_fin=x_fin, xn_fin=xn_fin)
+    return out, tape
+
+
+# --------------------------------------------------------------------------------------------------
+# backward
+# --------------------------------------------------------------------------------------------------
+def _zero_grads(W: PreparedStack) -> Dict[str, torch.Tensor]:
+    """fp32 zero buffers with the shapes of the prepared (kernel-layout) parameters."""
+    return {k: torch.zeros(v.shape, dtype=torch.float32, device=v.device) for k, v in W.t.items()}
+
+
+def _layers_backward(m, W: PreparedStack, dp: DevicePlan, tape: Tape, g: torch.Tensor, grads) -> torch.Tensor:
+    """g = dL/dx at the output of the last layer -> dL/dx at the input of layer 0."""
+    M, w = g.shape
+    dev = g.device
+    hq, hkv = m.heads
+    gqa = hkv * 64
+    inner = m.inner_dim
+    L = m.num_layers
+    alpha = float(2 * L)
+    st = _stream()
+    scale = 1.0 / math.sqrt(64.0)
+    T = W.t
+    wk_dkv, wk_dq = dp.attn_bwd_work(hq, hkv)
+    for i in reversed(range(L)):
+        t = tape.layers[i]
+        mode = 0 if i == 0 else 1
+        c = alpha if mode == 1 else 1.0
+        # ---- GEGLU block: x_out = x_f + y_f | RMSNorm(alpha x_f + y_f)
+        if mode == 1:
+            du = _new((M, w), dev)
+            _rmsnorm_bwd(t["x_f"], T[f"ffd_post_ln{i}"], g, du, grads[f"ffd_post_ln{i}"], y=t["y_f"], alpha=alpha)
+        else:
+            du = g
+        dh = _new((M, inner), dev)
+        _gemm(du, T[f"w3_{i}"], dh, inner, w, kn=1)
+        _wgrad(du, t["h"], grads[f"w3_{i}"])
+        dh12 = _new((M, 2 * inner), dev)
+        _lib.call("ttk_geglu_bwd", _ptr(t["h12"]), 2 * inner, inner, _ptr(dh), inner, _ptr(dh12), 2 * inner, M, st)
+        dxn = _new((M, w), dev)
+        _gemm(dh12, T[f"w12_{i}"], dxn, w, 2 * inner, kn=1)
+        _wgrad(dh12, t["xn_f"], grads[f"w12_{i}"])
+        g_f = _new((M, w), dev)
+        _rmsnorm_bwd(t["x_f"], T[f"ffn_norm{i}"], dxn, g_f, grads[f"ffn_norm{i}"], add=du, add_scale=c)
+        # ---- attention block: x_f = x_a + y_a | RMSNorm(alpha x_a + y_a)
+        if mode == 1:
+            du = _new((M, w), dev)
+            _rmsnorm_bwd(t["x_a"], T[f"attn_post_ln{i}"], g_f, du, grads[f"attn_post_ln{i}"], y=t["y_a"], alpha=alpha)
+        else:
+            du = g_f
+        d_att = _new((M, w), dev)
+        _gemm(du, T[f"out_proj{i}"], d_att, w, w, kn=1)
+        _wgrad(du, t["att"], grads[f"out_proj{i}"])
+        qkv = t["qkv"]
+        dqkv = _new(qkv.shape, dev)
+        dO = _new((M, w), dev)
+        delta = _new((hq, M), dev, torch.float32)
+        _lib.call("ttk_attn_bwd_prep", _ptr(d_att), w, _ptr(t["o"]), w, _ptr(qkv), qkv.stride(0), M, w, _ptr(dO), w,
+                  _ptr(dqkv), dqkv.stride(0), _ptr(delta), st)
+        for name, wk in (("ttk_attn_bwd_dkv", wk_dkv), ("ttk_attn_bwd_dq", wk_dq)):
+            _lib.call(name, _ptr(qkv), qkv.stride(0), _ptr(dO), w, M, w, gqa, _ptr(wk), wk.shape[0], _ptr(t["lse"]),
+                      _ptr(delta), _ptr(dp.rope), scale, _ptr(dqkv), dqkv.stride(0), st)
+        _gemm(dqkv, T[f"to_qkv{i}"], dxn, w, 2 * w + 2 * gqa, kn=1)
+        _wgrad(dqkv, t["xn_a"], grads[f"to_qkv{i}"])
+        g = _new((M, w), dev)
+        _rmsnorm_bwd(t["x_a"], T[f"pre_ln{i}"], dxn, g, grads[f"pre_ln{i}"], add=du, add_scale=c)
+    return g
+
+
+def encoder_backward(m, dp: DevicePlan, tape: Tape, dz: torch.Tensor, need_input_grad: bool = False):
+    """dz bf16 [T, ts] -> (grads in kernel layout, d clips_flat or None)."""
+    W = prepared(m, "enc")
+    pl = dp.plan
+    M, G, Tn, w = pl.M, pl.G, pl.T, m.width
+    P0, P1, P2 = pl.patch_size
+    feat = pl.channels * P0 * P1 * P2
+    dev = dz.device
+    st = _stream()
+    T = W.t
+    grads = _zero_grads(W)
+    dxn = torch.zeros((M, w), dtype=bf16, device=dev)
+    _lib.call("ttk_head_bwd", _ptr(dz), m.token_size, _ptr(tape.t["xn_fin"]), w, _ptr(dp.latent_row), _ptr(T["proj_out_w"]),
+              _ptr(dxn), _ptr(grads["proj_out_w"]), _ptr(grads["proj_out_b"]), Tn, w, st)
+    g = _new((M, w), dev)
+    _rmsnorm_bwd(tape.t["x_fin"], T["ln_post"], dxn, g, grads["ln_post"])
+    g0 = _layers_backward(m, W, dp, tape, g, grads)
+    # embed: latent rows (enc_src_row < 0) went through ln_pre_t, patch rows through ln_pre_p (blocks.py:95-97)
+    d_e0 = _new((M, w), dev)
+    _rmsnorm_bwd(tape.t["e0"], T["ln_pre_p"], g0, d_e0, grads["ln_pre_p"], sel=dp.enc_src_row, w2=T["ln_pre_t"],
+                 dw2=grads["ln_pre_t"])
+    _lib.call("ttk_colsum", _ptr(d_e0), w, M, w, _vp(0), _ptr(grads["mask_token"]), st)
+    dproj = _new((G, w), dev)
+    _lib.call("ttk_gather_rows", _ptr(d_e0), w, _ptr(dp.patch_row), _ptr(dproj), w, G, w, st)
+    _lib.call("ttk_colsum", _ptr(dproj), w, G, w, _ptr(grads["proj_in_b"]), _vp(0), st)
+    _wgrad(dproj, tape.t["patches"], grads["proj_in_w"])
+    dflat = None
+    if need_input_grad:
+        dpatches = _new((G, feat), dev)
+        _gemm(dproj, T["proj_in_w"], dpatches, feat, w, kn=1)
+        ident = torch.arange(G, dtype=torch.int32, device=dev)
+        dflat = _new((pl.total_numel,), dev)
+        _lib.call("ttk_unpatchify", _ptr(dpatches), feat, _ptr(ident), _ptr(dp.geom), pl.channels, P0, P1, P2,
+                  _ptr(dflat), G, st)
+    return grads, dflat
+
+
+def decoder_backward(m, dp: DevicePlan, tape: Tape, dout: torch.Tensor):
+    """dout bf16 flat [sum 3*T*H*W] -> (grads in kernel layout, dcodes fp32 [T, ts])."""
+    W = prepared(m, "dec")
+    pl = dp.plan
+    M, G, Tn, w = pl.M, pl.G, pl.T, m.width
+    P0, P1, P2 = pl.patch_size
+    feat = pl.channels * P0 * P1 * P2
+    dev = dout.device
+    st = _stream()
+    T = W.t
+    grads = _zero_grads(W)
+    d_rows = _new((G, feat), dev)
+    _lib.call("ttk_patchify", _ptr(dout), _ptr(dp.geom), pl.channels, P0, P1, P2, _ptr(d_rows), feat, G, st)
+    xn_patch = _new((G, w), dev)
+    _lib.call("ttk_gather_rows", _ptr(tape.t["xn_fin"]), w, _ptr(dp.patch_row), _ptr(xn_patch), w, G, w, st)
+    _wgrad(d_rows, xn_patch, grads["proj_out_w"])
+    _lib.call("ttk_colsum", _ptr(d_rows), feat, G, feat, _ptr(grads["proj_out_b"]), _vp(0), st)
+    dxn_patch = _new((G, w), dev)
+    _gemm(d_rows, T["proj_out_w"], dxn_patch, w, feat, kn=1)
+    dxn = torch.zeros((M, w), dtype=bf16, device=dev)
+    _lib.call("ttk_scatter_rows", _ptr(dxn_patch), w, _ptr(dp.patch_row), _ptr(dxn), w, G, w, st)
+    g = _new((M, w), dev)
+    _rmsnorm_bwd(tape.t["x_fin"], T["ln_post"], dxn, g, grads["ln_post"])
+    g0 = _layers_backward(m, W, dp, tape, g, grads)
+    # embed: latent rows (dec_src_row >= 0) went through ln_pre_t, patch rows through ln_pre_p (blocks.py:164-167)
+    d_e0 = _new((M, w), dev)
+    _rmsnorm_bwd(tape.t["e0"], T["ln_pre_t"], g0, d_e0, grads["ln_pre_t"], sel=dp.dec_src_row, w2=T["ln_pre_p"],
+                 dw2=grads["ln_pre_p"])
+    _lib.call("ttk_colsum", _ptr(d_e0), w, M, w, _vp(0), _ptr(grads["mask_token"]), st)
+    dcodes = torch.zeros((max(Tn, 1), m.token_size), dtype=torch.float32, device=dev)
+    _lib.call("ttk_dec_in_bwd", _ptr(d_e0), w, _ptr(dp.latent_row), _ptr(tape.t["codes"]), m.token_size,
+              _ptr(T["proj_in_w"]), _ptr(dcodes), _ptr(grads["proj_in_w"]), _ptr(grads["proj_in_b"]), Tn, w, st)
+    return grads, dcodes[:Tn]
+
+
+# --------------------------------------------------------------------------------------------------
+# kernel-layout gradients -> the module's parameters (reference layout, blocks.py state-dict names)
+# --------------------------------------------------------------------------------------------------
+def _param_grads(m, kind: str, grads: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    out: Dict[str, torch.Tensor] = {}
+    perm = patch_feature_perm(m.patch_size_tuple, m.patch_channels).to(grads["mask_token"].device)
+    out["mask_token"] = grads["mask_token"].view(1, 1)
+    out["ln_pre_t.weight"] = grads["ln_pre_t"]
+    out["ln_pre_p.weight"] = grads["ln_pre_p"]
+    out["ln_post.weight"] = grads["ln_post"]
+    if kind == "enc":
+        gw = torch.empty_like(grads["proj_in_w"])
+        gw[:, perm] = grads["proj_in_w"]  # kernel layout is weight[:, perm]
+        out["proj_in.weight"] = gw
+        out["proj_in.bias"] = grads["proj_in_b"]
+        out["proj_out.weight"] = grads["proj_out_w"]
+        out["proj_out.bias"] = grads["proj_out_b"]
+    else:
+        out["proj_in.weight"] = grads["proj_in_w"]
+        out["proj_in.bias"] = grads["proj_in_b"]
+        gw = torch.empty_like(grads["proj_out_w"])
+        gw[perm, :] = grads["proj_out_w"]
+        gb = torch.empty_like(grads["proj_out_b"])
+        gb[perm] = grads["proj_out_b"]
+        out["proj_out.weight"] = gw
+        out["proj_out.bias"] = gb
+    for i in range(m.num_layers):
+        out[f"model_layers.attn_layer.{i}.pre_ln.weight"] = grads[f"pre_ln{i}"]
+        out[f"model_layers.attn_layer.{i}.to_qkv.weight"] = grads[f"to_qkv{i}"]
+        out[f"model_layers.attn_layer.{i}.out_proj.weight"] = grads[f"out_proj{i}"]
+        out[f"model_layers.ffd_layer.{i}.norm.weight"] = grads[f"ffn_norm{i}"]
+        out[f"model_layers.ffd_layer.{i}.w12.weight"] = grads[f"w12_{i}"]
+        out[f"model_layers.ffd_layer.{i}.w3.weight"] = grads[f"w3_{i}"]
+        if i > 0:
+            out[f"model_layers.attn_post_ln.{i - 1}.weight"] = grads[f"attn_post_ln{i}"]
+            out[f"model_layers.ffd_post_ln.{i - 1}.weight"] = grads[f"ffd_post_ln{i}"]
+    return out
+
+
+def _ordered(m, kind: str, grads, params_meta) -> Tuple[Optional[torch.Tensor], ...]:
+    pg = _param_grads(m, kind, grads)
+    res = []
+    for name, shape, dtype, req in params_meta:
+        if not req:
+            res.append(None)
+            continue
+        g = pg[name].reshape(shape)
+        res.append(g if g.dtype == dtype else g.to(dtype))
+    return tuple(res)
+
+
+def _meta(m):
+    return [(n, p.shape, p.dtype, p.requires_grad) for n, p in m.named_parameters()]
+
+
+class EncoderFn(torch.autograd.Function):
+    """z = TiTokEncoder(clips) recorded for autograd. Inputs after `flat` are the module's parameters (graph edges only;
+    the kernels read the prepared bf16 copies)."""
+
+    @staticmethod
+    def forward(ctx, m, dp, fsq_consts, flat, *params):
+        z, codes, idx, tape = encoder_forward_train(m, dp, flat, fsq_consts)
+        ctx.m, ctx.dp, ctx.tape, ctx.meta = m, dp, tape, _meta(m)
+        ctx.need_input = flat.requires_grad
+        ctx.mark_non_differentiable(idx, codes)
+        return z, codes, idx
+
+    @staticmethod
+    def backward(ctx, dz, _dcodes, _didx):
+        dz = dz.to(bf16).contiguous()
+        grads, dflat = encoder_backward(ctx.m, ctx.dp, ctx.tape, dz, ctx.need_input)
+        ctx.tape = None
+        return (None, None, None, dflat) + _ordered(ctx.m, "enc", grads, ctx.meta)
+
+
+class DecoderFn(torch.autograd.Function):
+    """flat reconstruction = TiTokDecoder(codes) recorded for autograd."""
+
+    @staticmethod
+    def forward(ctx, m, dp, codes, *params):
+        codes_b = codes.detach().to(bf16).contiguous()
+        out, tape = decoder_forward_train(m, dp, codes_b)
+        ctx.m, ctx.dp, ctx.tape, ctx.meta = m, dp, tape, _meta(m)
+        ctx.codes_dtype = codes.dtype
+        ctx.need_codes = codes.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.to(bf16).contiguous()
+        grads, dcodes = decoder_backward(ctx.m, ctx.dp, ctx.tape, dout)
+        ctx.tape = None
+        dc = dcodes.to(ctx.codes_dtype) if ctx.need_codes else None
+        return (None, None, dc) + _ordered(ctx.m, "dec", grads, ctx.meta)

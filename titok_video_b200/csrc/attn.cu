@@ -44,6 +44,9 @@ struct AttnParams {
   __nv_bfloat16* out;         // [M, ldo]
   int64_t ldo;
   float scale_log2;  // softmax_scale * log2(e)
+  __nv_bfloat16* o_save;  // training: un-gated attention output [M, ldo] (null in inference)
+  float* lse;             // training: [heads][M] log2-domain log-sum-exp of the scaled scores (null in inference)
+  int M;
   long long* trace;  // development aid (ttk_debug_set_trace): [CTA][64] clock64 stamps of kv iterations 3..7
 };
 
@@ -363,7 +366,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // ---- epilogue: out = bf16(O / l) * bf16(sigmoid(gate)); this half writes 32 of the 64 head dims
       x_mine[1024] = l_run;
       named_bar_sync(pair_bar, 256);
-      const float inv_l = __fdividef(1.0f, l_run + x_other[1024]);
+      const float l_tot = l_run + x_other[1024];
+      const float inv_l = __fdividef(1.0f, l_tot);
+      if (p.lse && half == 0 && r < w.q_valid[t])  // the backward kernels recompute P = 2^(s*c - lse)
+        p.lse[static_cast<int64_t>(w.q_head[t]) * p.M + w.q_row0[t] + r] = fmaf(m_ref, c, __log2f(l_tot));
       mbar_wait(&pv_done[t], (n_kv - 1) & 1);
       tc_fence_after();
       uint32_t o[32];
@@ -375,11 +381,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int col = w.q_head[t] * AT_D + half * 32;
         const __nv_bfloat16* g = p.gate + static_cast<int64_t>(row) * p.ld + col;
         __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + col;
+        __nv_bfloat16* osv = p.o_save ? p.o_save + static_cast<int64_t>(row) * p.ldo + col : nullptr;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint4 gv = ldg16(g + q * 8);
           const uint32_t gg[4] = {gv.x, gv.y, gv.z, gv.w};
-          uint32_t ov[4];
+          uint32_t ov[4], av[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float g0 = bf16_lo(gg[e]), g1 = bf16_hi(gg[e]);
@@ -388,8 +395,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const float a0 = bf16r(__uint_as_float(o[q * 8 + 2 * e]) * inv_l);
             const float a1 = bf16r(__uint_as_float(o[q * 8 + 2 * e + 1]) * inv_l);
             ov[e] = pack_bf16x2(a0 * s0, a1 * s1);
+            av[e] = pack_bf16x2(a0, a1);
           }
           stg16(dst + q * 8, make_uint4(ov[0], ov[1], ov[2], ov[3]));
+          if (osv) stg16(osv + q * 8, make_uint4(av[0], av[1], av[2], av[3]));
         }
       }
     }
@@ -408,8 +417,8 @@ extern "C" {
 
 // qkv: packed [M, ld] bf16 (see header). work: device array of n_work AttnWork records (built by the
 // host planner). out: [M, ldo] bf16 = attention(q,k,v) * sigmoid(gate).
-int ttk_attn_varlen_fwd(const void* qkv, int64_t ld, int M, int width, int gqa, const void* work, int n_work,
-                        float softmax_scale, void* out, int64_t ldo, cudaStream_t stream) {
+static int attn_fwd_launch(const void* qkv, int64_t ld, int M, int width, int gqa, const void* work, int n_work,
+                           float softmax_scale, void* out, int64_t ldo, void* o_save, float* lse, cudaStream_t stream) {
   if (!qkv || !work || !out) return TTK_ERR_BAD_ARG;
   if (int e = check_device_sm100()) return e;
   if (width % 64 != 0 || gqa % 64 != 0 || ld % 8 != 0 || ldo % 8 != 0) return TTK_ERR_BAD_SHAPE;
@@ -427,6 +436,9 @@ int ttk_attn_varlen_fwd(const void* qkv, int64_t ld, int M, int width, int gqa, 
   p.ldo = ldo;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.trace = g_trace;
+  p.o_save = static_cast<__nv_bfloat16*>(o_save);
+  p.lse = lse;
+  p.M = M;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess)
@@ -435,6 +447,20 @@ int ttk_attn_varlen_fwd(const void* qkv, int64_t ld, int M, int width, int gqa, 
   }
   attn_fwd_kernel<<<n_work, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
   return launch_status();
+}
+
+int ttk_attn_varlen_fwd(const void* qkv, int64_t ld, int M, int width, int gqa, const void* work, int n_work,
+                        float softmax_scale, void* out, int64_t ldo, cudaStream_t stream) {
+  return attn_fwd_launch(qkv, ld, M, width, gqa, work, n_work, softmax_scale, out, ldo, nullptr, nullptr, stream);
+}
+
+// Training forward: additionally saves what the backward kernels (attn_bwd.cu) need: o_save [M, ldo] = the attention
+// output before the gate, lse fp32 [width/64][M] = log2-domain log-sum-exp of the scaled scores.
+int ttk_attn_varlen_fwd_train(const void* qkv, int64_t ld, int M, int width, int gqa, const void* work, int n_work,
+                              float softmax_scale, void* out, int64_t ldo, void* o_save, float* lse,
+                              cudaStream_t stream) {
+  if (!o_save || !lse) return TTK_ERR_BAD_ARG;
+  return attn_fwd_launch(qkv, ld, M, width, gqa, work, n_work, softmax_scale, out, ldo, o_save, lse, stream);
 }
 
 }  // extern "C"

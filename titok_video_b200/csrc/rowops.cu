@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 enc_embed_kernel(const __nv_bfloat16* __restrict__ proj, int64_t ldp, const int32_t* __restrict__ src_row,
                  const float* __restrict__ mask_token, const float* __restrict__ w_t, const float* __restrict__ w_p,
                  const float* __restrict__ w_next, __nv_bfloat16* __restrict__ x_out,
-                 __nv_bfloat16* __restrict__ xn_out, int M, int64_t ld) {
+                 __nv_bfloat16* __restrict__ xn_out, __nv_bfloat16* __restrict__ e0_out, int M, int64_t ld) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -131,10 +131,12 @@ enc_embed_kernel(const __nv_bfloat16* __restrict__ proj, int64_t ldp, const int3
     a.load(proj + src * ldp, lane);
 #pragma unroll
     for (int i = 0; i < NV * 8; ++i) a.v[i] = bf16r(a.v[i] + mt);
+    if (e0_out) a.store(e0_out + row * ld, lane);  // training: the pre-norm row (input of rmsnorm_bwd)
     a.norm(w_p, lane, rstd_of(a.sumsq(), NV * 256));
   } else {
 #pragma unroll
     for (int i = 0; i < NV * 8; ++i) a.v[i] = mt;
+    if (e0_out) a.store(e0_out + row * ld, lane);
     a.norm(w_t, lane, rstd_of(a.sumsq(), NV * 256));
   }
   a.store(x_out + row * ld, lane);
@@ -155,7 +157,7 @@ dec_embed_kernel(const __nv_bfloat16* __restrict__ codes, int TS, const int32_t*
                  const __nv_bfloat16* __restrict__ w_in, const __nv_bfloat16* __restrict__ b_in,
                  const float* __restrict__ mask_token, const float* __restrict__ w_t, const float* __restrict__ w_p,
                  const float* __restrict__ w_next, __nv_bfloat16* __restrict__ x_out,
-                 __nv_bfloat16* __restrict__ xn_out, int M, int64_t ld) {
+                 __nv_bfloat16* __restrict__ xn_out, __nv_bfloat16* __restrict__ e0_out, int M, int64_t ld) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -179,10 +181,12 @@ dec_embed_kernel(const __nv_bfloat16* __restrict__ codes, int TS, const int32_t*
         a.v[i * 8 + e] = bf16r(bf16r(acc) + mt);
       }
     }
+    if (e0_out) a.store(e0_out + row * ld, lane);
     a.norm(w_t, lane, rstd_of(a.sumsq(), NV * 256));
   } else {
 #pragma unroll
     for (int i = 0; i < NV * 8; ++i) a.v[i] = mt;
+    if (e0_out) a.store(e0_out + row * ld, lane);
     a.norm(w_p, lane, rstd_of(a.sumsq(), NV * 256));
   }
   a.store(x_out + row * ld, lane);
@@ -455,9 +459,9 @@ int ttk_resid_norm(const void* x, const void* y, void* x_out, void* xn_out, cons
   return launch_status();
 }
 
-int ttk_enc_embed(const void* proj, int64_t ldp, const int32_t* src_row, const float* mask_token, const float* w_t,
-                  const float* w_p, const float* w_next, void* x_out, void* xn_out, int M, int width, int64_t ld,
-                  cudaStream_t stream) {
+static int enc_embed_launch(const void* proj, int64_t ldp, const int32_t* src_row, const float* mask_token,
+                            const float* w_t, const float* w_p, const float* w_next, void* x_out, void* xn_out,
+                            void* e0_out, int M, int width, int64_t ld, cudaStream_t stream) {
   if (!proj || !src_row || !mask_token || !w_t || !w_p || !x_out) return TTK_ERR_BAD_ARG;
   if (xn_out && !w_next) return TTK_ERR_BAD_ARG;
   if (int e = check_device_sm100()) return e;
@@ -465,13 +469,28 @@ int ttk_enc_embed(const void* proj, int64_t ldp, const int32_t* src_row, const f
   if (M <= 0) return TTK_OK;
   TTK_DISPATCH_NV(width, enc_embed_kernel<NV><<<row_grid(M), ROW_WARPS * 32, 0, stream>>>(
                              static_cast<const __nv_bfloat16*>(proj), ldp, src_row, mask_token, w_t, w_p, w_next,
-                             static_cast<__nv_bfloat16*>(x_out), static_cast<__nv_bfloat16*>(xn_out), M, ld));
+                             static_cast<__nv_bfloat16*>(x_out), static_cast<__nv_bfloat16*>(xn_out),
+                             static_cast<__nv_bfloat16*>(e0_out), M, ld));
   return launch_status();
 }
 
-int ttk_dec_embed(const void* codes, int token_size, const int32_t* src_row, const void* w_in, const void* b_in,
-                  const float* mask_token, const float* w_t, const float* w_p, const float* w_next, void* x_out,
-                  void* xn_out, int M, int width, int64_t ld, cudaStream_t stream) {
+int ttk_enc_embed(const void* proj, int64_t ldp, const int32_t* src_row, const float* mask_token, const float* w_t,
+                  const float* w_p, const float* w_next, void* x_out, void* xn_out, int M, int width, int64_t ld,
+                  cudaStream_t stream) {
+  return enc_embed_launch(proj, ldp, src_row, mask_token, w_t, w_p, w_next, x_out, xn_out, nullptr, M, width, ld, stream);
+}
+
+// training variant: e0_out [M, ld] additionally receives the rows BEFORE ln_pre_t / ln_pre_p
+int ttk_enc_embed_train(const void* proj, int64_t ldp, const int32_t* src_row, const float* mask_token, const float* w_t,
+                        const float* w_p, const float* w_next, void* x_out, void* xn_out, void* e0_out, int M, int width,
+                        int64_t ld, cudaStream_t stream) {
+  if (!e0_out) return TTK_ERR_BAD_ARG;
+  return enc_embed_launch(proj, ldp, src_row, mask_token, w_t, w_p, w_next, x_out, xn_out, e0_out, M, width, ld, stream);
+}
+
+static int dec_embed_launch(const void* codes, int token_size, const int32_t* src_row, const void* w_in, const void* b_in,
+                            const float* mask_token, const float* w_t, const float* w_p, const float* w_next,
+                            void* x_out, void* xn_out, void* e0_out, int M, int width, int64_t ld, cudaStream_t stream) {
   if (!codes || !src_row || !w_in || !b_in || !mask_token || !w_t || !w_p || !x_out) return TTK_ERR_BAD_ARG;
   if (xn_out && !w_next) return TTK_ERR_BAD_ARG;
   if (int e = check_device_sm100()) return e;
@@ -481,8 +500,23 @@ int ttk_dec_embed(const void* codes, int token_size, const int32_t* src_row, con
                              static_cast<const __nv_bfloat16*>(codes), token_size, src_row,
                              static_cast<const __nv_bfloat16*>(w_in), static_cast<const __nv_bfloat16*>(b_in),
                              mask_token, w_t, w_p, w_next, static_cast<__nv_bfloat16*>(x_out),
-                             static_cast<__nv_bfloat16*>(xn_out), M, ld));
+                             static_cast<__nv_bfloat16*>(xn_out), static_cast<__nv_bfloat16*>(e0_out), M, ld));
   return launch_status();
+}
+
+int ttk_dec_embed(const void* codes, int token_size, const int32_t* src_row, const void* w_in, const void* b_in,
+                  const float* mask_token, const float* w_t, const float* w_p, const float* w_next, void* x_out,
+                  void* xn_out, int M, int width, int64_t ld, cudaStream_t stream) {
+  return dec_embed_launch(codes, token_size, src_row, w_in, b_in, mask_token, w_t, w_p, w_next, x_out, xn_out, nullptr, M,
+                          width, ld, stream);
+}
+
+int ttk_dec_embed_train(const void* codes, int token_size, const int32_t* src_row, const void* w_in, const void* b_in,
+                        const float* mask_token, const float* w_t, const float* w_p, const float* w_next, void* x_out,
+                        void* xn_out, void* e0_out, int M, int width, int64_t ld, cudaStream_t stream) {
+  if (!e0_out) return TTK_ERR_BAD_ARG;
+  return dec_embed_launch(codes, token_size, src_row, w_in, b_in, mask_token, w_t, w_p, w_next, x_out, xn_out, e0_out, M,
+                          width, ld, stream);
 }
 
 int ttk_enc_head_fsq(const void* x, int64_t ld, const int32_t* latent_row, const float* w_post, int pre_normed,

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .plan import PackedPlan, get_attn_work, make_plan
+from .plan import PackedPlan, get_attn_bwd_work, get_attn_work, make_plan
 
 _vp = ctypes.c_void_p
 
@@ -102,6 +102,23 @@ class DevicePlan:
             dev.copy_(host[:dev.numel()], non_blocking=True)
             done.record()
             self._attn[k] = dev[:w.nbytes].view(torch.int32).view(w.shape)
+        return self._attn[k]
+
+    def _upload_i32(self, w: np.ndarray) -> torch.Tensor:
+        w = np.ascontiguousarray(w)
+        host, done = _staging(max(w.nbytes, 256))
+        host.numpy()[:w.nbytes] = w.view(np.uint8).reshape(-1)
+        dev = torch.empty(max(w.nbytes, 256), dtype=torch.uint8, device=self.device)
+        dev.copy_(host[:dev.numel()], non_blocking=True)
+        done.record()
+        return dev[:w.nbytes].view(torch.int32).view(w.shape)
+
+    def attn_bwd_work(self, hq: int, hkv: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(dkv, dq) work lists of the attention backward kernels (plan.attn_bwd_work_lists)."""
+        k = ("bwd", hq, hkv)
+        if k not in self._attn:
+            a, b = get_attn_bwd_work(self.plan, hq, hkv)
+            self._attn[k] = (self._upload_i32(a), self._upload_i32(b))
         return self._attn[k]
 
     def buf(self, name: str, shape: Sequence[int], dtype=torch.bfloat16) -> torch.Tensor:

@@ -9,7 +9,6 @@ patch rows (blocks.py:85-86). All packing metadata is derived on the host (plan.
 from __future__ import annotations
 
 import math
-import warnings
 from typing import List, Optional, Sequence
 
 import torch
@@ -19,17 +18,14 @@ from ... import engine
 from .transformer import ResidualAttentionBlock
 from .utils import RMSNorm, geglu_inner_dim, get_model_dims
 
-_warned_grad = False
-
-
-def _warn_no_backward(params_require_grad: bool) -> None:
-    global _warned_grad
-    if torch.is_grad_enabled() and params_require_grad and not _warned_grad:
-        _warned_grad = True
-        warnings.warn(
-            "titok_video_b200: the CUDA forward is not recorded by autograd yet (backward kernels are the next "
-            "milestone); outputs are returned detached. Wrap inference in torch.no_grad() to silence this.",
-            RuntimeWarning, stacklevel=3)
+def _wants_grad(module: nn.Module, *inputs) -> bool:
+    """True when autograd has to see this forward: grad mode on and a parameter (or a tensor input) requires grad.
+    The training path (titok_video_b200/backward.py) then records the activations the backward kernels need."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(isinstance(t, torch.Tensor) and t.requires_grad for t in inputs):
+        return True
+    return any(p.requires_grad for p in module.parameters())
 
 
 class _Stack(nn.Module):
@@ -68,7 +64,6 @@ class TiTokEncoder(_Stack):
         """Returns (z, codes, indices, device_plan). z: [sum(token_counts), token_size] pre-quantisation tokens."""
         device = videos[0].device
         engine.require_cuda(device)
-        _warn_no_backward(self.mask_token.requires_grad)
         tcs = engine.to_host_ints(token_counts)
         if len(tcs) != len(videos):
             raise ValueError("len(token_counts) must equal the number of clips")
@@ -83,14 +78,28 @@ class TiTokEncoder(_Stack):
             if v.shape[0] != self.in_channels:
                 raise ValueError(f"expected {self.in_channels} channels, got {tuple(v.shape)}")
         dp = self._plan(gpx, tcs, device)
+        consts = (fsq if fsq is not None else _dummy_fsq(self.token_size))._consts(device)
+        if _wants_grad(self, *videos):
+            # training path: recorded by autograd (backward.EncoderFn); pixels get a gradient if they ask for one
+            # (the discriminator's gradient penalties differentiate w.r.t. the input, loss_module.py:149-152)
+            from ... import backward
+
+            if any(v.requires_grad for v in videos):
+                flat = torch.cat([v.reshape(-1).to(torch.bfloat16) for v in videos])
+            else:
+                with torch.no_grad():
+                    flat = engine.flatten_clips(videos, dp)
+            z, codes, idx = backward.EncoderFn.apply(self, dp, consts, flat, *self.parameters())
+            return z, codes, idx, dp
         with torch.no_grad():
             flat = engine.flatten_clips(videos, dp)
-            consts = (fsq if fsq is not None else _dummy_fsq(self.token_size))._consts(device)
             z, codes, idx = engine.encoder_launch(self, dp, flat, consts)
         return z, codes, idx, dp
 
     def forward(self, videos, token_counts, grids=None):
         z, _, _, _ = self.forward_impl(videos, token_counts, grids)
+        if z.requires_grad:
+            return z.to(videos[0].dtype)
         return z.clone().to(videos[0].dtype)
 
 
@@ -107,12 +116,15 @@ class TiTokDecoder(_Stack):
     def forward_impl(self, tokens: torch.Tensor, token_counts, grids) -> (torch.Tensor, engine.DevicePlan):
         device = tokens.device
         engine.require_cuda(device)
-        _warn_no_backward(self.mask_token.requires_grad)
         tcs = engine.to_host_ints(token_counts)
         gpx = [tuple(g) for g in engine.to_host_ints(grids)]
         if tokens.shape[0] != sum(tcs) or tokens.shape[-1] != self.token_size:
             raise ValueError(f"tokens {tuple(tokens.shape)} do not match token_counts (sum {sum(tcs)})")
         dp = self._plan(gpx, tcs, device)
+        if _wants_grad(self, tokens):
+            from ... import backward
+
+            return backward.DecoderFn.apply(self, dp, tokens, *self.parameters()), dp
         with torch.no_grad():
             codes = tokens.detach().to(torch.bfloat16).contiguous()
             out = dp.buf("clips_out", (dp.plan.total_numel,))
@@ -121,6 +133,8 @@ class TiTokDecoder(_Stack):
 
     def forward(self, tokens, token_counts, grids) -> List[torch.Tensor]:
         out, dp = self.forward_impl(tokens, token_counts, grids)
+        if out.requires_grad:
+            return engine.split_clips(out.to(tokens.dtype if tokens.is_floating_point() else torch.bfloat16), dp.plan)
         return engine.split_clips(out.clone().to(tokens.dtype if tokens.is_floating_point() else torch.bfloat16), dp.plan)
 
 

@@ -33,9 +33,13 @@ class TiTok(nn.Module):
         """x_q [sum(token_counts), token_size] in the clips' dtype, {'indices': int32 [sum(token_counts)]}.
         split_indices=True returns a tuple of per-clip index tensors (the reference's intent; its own
         torch.split call fails for tensor token_counts)."""
-        _, codes, idx, _ = self.encoder.forward_impl(x, token_counts, grids, fsq=self.quantize)
-        x_q = codes.clone().to(x[0].dtype)
-        indices = idx.clone()
+        z, codes, idx, _ = self.encoder.forward_impl(x, token_counts, grids, fsq=self.quantize)
+        if z.requires_grad:  # training: FSQ with its straight-through gradient (fsq.py:48-51)
+            x_q, d = self.quantize(z)
+            x_q, indices = x_q.to(x[0].dtype), d["indices"]
+        else:
+            x_q = codes.clone().to(x[0].dtype)
+            indices = idx.clone()
         if split_indices:
             indices = torch.split(indices, engine.to_host_ints(token_counts), dim=0)
         return x_q, {"indices": indices}
@@ -58,7 +62,11 @@ class TiTok(nn.Module):
         """list of reconstructed clips [3,T,H,W] (input dtype) and {'indices': int32}."""
         grids = [tuple(v.shape[1:]) for v in x]
         tcs = engine.to_host_ints(token_counts)
-        _, codes, idx, dp = self.encoder.forward_impl(x, tcs, grids, fsq=self.quantize)
+        z, codes, idx, dp = self.encoder.forward_impl(x, tcs, grids, fsq=self.quantize)
+        if z.requires_grad:  # training: encoder -> FSQ (straight-through) -> decoder, all recorded by autograd
+            codes, d = self.quantize(z)
+            out, _ = self.decoder.forward_impl(codes, tcs, grids)
+            return engine.split_clips(out.to(x[0].dtype), dp.plan), {"indices": d["indices"]}
         out, _ = self.decoder.forward_impl(codes, tcs, grids)
         recon = engine.split_clips(out.clone().to(x[0].dtype), dp.plan)
         return recon, {"indices": idx.clone()}

@@ -276,6 +276,37 @@ def get_attn_work(plan: PackedPlan, hq: int, hkv: int) -> np.ndarray:
     return plan.attn_work[k]
 
 
+def attn_bwd_work_lists(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: int, hkv: int):
+    """Work lists of the attention backward kernels (csrc/attn_bwd.cu), int32 [n, 8] records
+    {st_row0, st_valid, st_head, o_head0, n_heads, clip_row0, clip_len, 0}, longest work first:
+      dkv: one record per (128-key tile, kv head); streams the clip's query tiles of the `hq // hkv` grouped query heads
+      dq : one record per (128-row query tile, query head); streams the clip's key tiles of kv head `h // (hq // hkv)`."""
+    grp = hq // hkv
+    dkv, dq = [], []
+    for start, n in zip(seq_starts, seq_lens):
+        start, n = int(start), int(n)
+        for t0 in range(0, n, 128):
+            valid = min(128, n - t0)
+            for kh in range(hkv):
+                dkv.append((start + t0, valid, kh, kh * grp, grp, start, n, 0))
+            for qh in range(hq):
+                dq.append((start + t0, valid, qh, qh // grp, 1, start, n, 0))
+    a = np.asarray(dkv, dtype=np.int32).reshape(-1, 8)
+    b = np.asarray(dq, dtype=np.int32).reshape(-1, 8)
+    if len(a):
+        a = a[np.argsort(-(a[:, 4].astype(np.int64) * ((a[:, 6] + 127) // 128)), kind="stable")]
+    if len(b):
+        b = b[np.argsort(-((b[:, 6] + 127) // 128), kind="stable")]
+    return np.ascontiguousarray(a), np.ascontiguousarray(b)
+
+
+def get_attn_bwd_work(plan: PackedPlan, hq: int, hkv: int):
+    k = ("bwd", hq, hkv)
+    if k not in plan.attn_work:
+        plan.attn_work[k] = attn_bwd_work_lists(plan.cu_seqlens[:-1].tolist(), plan.seq_lens, hq, hkv)
+    return plan.attn_work[k]
+
+
 def shard_clips(costs: Sequence[float], world_size: int) -> List[List[int]]:
     """Greedy longest-processing-time partition of clip indices over ranks (balance by cost).
     Returns, per rank, the sorted list of clip indices it owns."""
