@@ -206,6 +206,88 @@ def cpu_reference_run(steps, warmup, sample_clips=1):
             "sample": f"{sample_clips} clip(s) 3x16x168x168 / 128 tokens per step, {len(times)} timed steps, torch CPU oracle port"}
 
 
+# ----------------------------------------------------------------------------------------------------
+# training step (BASELINE configs[3]): forward + L1 loss + backward + gradient all-reduce + AdamW
+# ----------------------------------------------------------------------------------------------------
+def train_flops(B):
+    """Algorithmic FLOPs of one training step on B clips A: forward + backward (2x forward: dgrad + wgrad; the attention
+    backward's recomputation of S and dP is NOT counted)."""
+    f, _, _ = clip_flops()
+    return 3.0 * B * f
+
+
+def train_leg(T, _lib, dev, world, rank, dist, batch, steps, warmup):
+    """One generator training step per iteration through the public module API (train.py:68-80): bf16 autocast forward of
+    TiTok (fp32 master parameters), L1 reconstruction loss (loss_module.py:118, plain torch: the loss module is not on
+    the path), backward through the CUDA backward kernels, gradient all-reduce over NCCL (N > 1, decoder bucket
+    overlapped with the encoder backward), fused AdamW with tiny.yaml's betas / weight decay, codebook histogram of the
+    step's indices. Device-timed with CUDA events, max over ranks."""
+    from titok_video_b200.config import tiny_config
+    from titok_video_b200.dist import GradientAllReducer
+
+    torch.manual_seed(42)
+    model = T.TiTok(tiny_config(LEVELS, PATCH)).to(dev).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.5, 0.96), weight_decay=1e-4, fused=True)
+    red = GradientAllReducer(model)
+    hist = torch.zeros(model.quantize.codebook_size, dtype=torch.int32, device=dev)
+    gen = torch.Generator().manual_seed(2000 + rank)
+    sets = [[(torch.rand((3, *CLIP_A), generator=gen) * 2 - 1).to(torch.bfloat16).to(dev) for _ in range(batch)]
+            for _ in range(2)]
+    tcs = [TOKENS_A] * batch
+
+    def step(clips):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            recon, d = model(clips, tcs)
+        loss = torch.stack([(r_.float() - c.float()).abs().mean() for c, r_ in zip(clips, recon)]).mean()
+        loss.backward()
+        red.finish()
+        opt.step()
+        idx = d["indices"]
+        _lib.call("ttk_hist_u32", T.engine._ptr(idx), idx.numel(), hist.numel(), T.engine._ptr(hist), T.engine._stream())
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(warmup, 3)):
+        step(sets[i % 2])
+    barrier()
+    timer = KernelTimer()
+    _lib.set_profiler(timer)
+    l0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(steps):
+        loss = step(sets[i % 2])
+    e1.record()
+    barrier()
+    _lib.set_profiler(None)
+    launches = _lib.LAUNCHES - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(hist)
+    ms_step = float(ms.item()) / steps
+    ks = timer.summary()
+    tot = sum(v[0] for v in ks.values()) or 1.0
+    kernels = {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps, "share_of_kernel_time": v[0] / tot}
+               for k, v in sorted(ks.items(), key=lambda kv: -kv[1][0])}
+    pk = peaks()
+    tf = train_flops(batch) / (ms_step * 1e-3) / 1e12
+    red.remove()
+    return {"clips_per_s": world * batch / (ms_step * 1e-3), "ms_per_step": ms_step, "clips_per_gpu_per_step": batch,
+            "packed_rows_per_gpu": batch * clip_flops()[1], "loss": float(loss), "gpu_launches_per_step": launches / steps,
+            "tflops_algorithmic": tf, "frac_of_tensor_peak": tf / pk["bf16_tflops_sustained"],
+            "kernel_ms_per_step": sum(v[0] for v in ks.values()) / steps, "kernels": kernels,
+            "what": "TiTok.forward under bf16 autocast + L1 loss + backward (CUDA backward kernels) + "
+                    + ("NCCL gradient all-reduce (per-stack buckets, overlapped) + " if world > 1 else "")
+                    + "fused AdamW + codebook histogram; synthetic clips 3x16x168x168 / 128 tokens, random-init weights"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -237,6 +319,9 @@ def main():
     ap.add_argument("--no-vq", action="store_true", help="skip the quantizer microbench (BASELINE configs[1]) leg")
     ap.add_argument("--ragged-stream", type=int, default=8,
                     help="steps of the ragged-stream leg (new batch composition every step; 0 = skip)")
+    ap.add_argument("--train-batch", default="3,16",
+                    help="clips per GPU per step of the training-step leg(s) (BASELINE configs[3]; 3 clips A = tiny.yaml's "
+                         "6144-token budget); empty = skip")
     ap.add_argument("--e2e-full-recon", action="store_true",
                     help="e2e leg copies the full reconstructions back to the host (default: token indices + per-clip error)")
     args = ap.parse_args()
@@ -429,6 +514,13 @@ def main():
                   "note": "new shapes / token counts every step (tiny.yaml sampling ranges): includes host planning, metadata "
                           "upload and eager launches; wall clock around a synchronised loop"}
 
+    # ---------------- training step (BASELINE configs[3]) ----------------
+    train = None
+    if args.train_batch:
+        train = {}
+        for tb in [int(v) for v in args.train_batch.split(",") if v]:
+            train[f"batch{tb}"] = train_leg(T, _lib, dev, world, rank, dist, tb, max(4, args.steps // 2), args.warmup)
+
     # ---------------- codebook usage over the whole job (the only data-path collective) ----------------
     if world > 1:
         dist.all_reduce(hist)
@@ -488,7 +580,7 @@ def main():
                     "api": "TiTok.tokenize_reconstruct_(clips, token_counts) from pinned host clips, 2-slot pipeline, CUDA-graph replay "
                            "(the value leg launches the same kernels one by one so that each can be timed with CUDA events)"},
             "gpu_launches": launches, "roofline": roofline, "whole_step": whole, "kernels": kernels, "clocks": clocks,
-            "cpu_baseline": cpu, "quantizer_microbench": vq, "ragged_stream": ragged,
+            "cpu_baseline": cpu, "quantizer_microbench": vq, "ragged_stream": ragged, "train_step": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -89,3 +89,44 @@ def test_single_process_helpers_are_noops():
     assert D.allreduce_counts(c) is c
     out = D.gather_indices([torch.tensor([1, 2]), torch.tensor([3])], [1, 0], 2)
     assert out[0].tolist() == [3] and out[1].tolist() == [1, 2]
+
+
+def _grad_worker(rank, world, port, out_dir):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from titok_video_b200 import dist as D
+
+    torch.manual_seed(0)
+    net = torch.nn.ModuleDict({"encoder": torch.nn.Linear(6, 4), "decoder": torch.nn.Linear(4, 3)})
+    red = D.GradientAllReducer(net)
+    for step in range(2):  # hooks re-arm after finish()
+        net.zero_grad(set_to_none=True)
+        x = torch.full((5, 6), float(rank + 1 + step))
+        net["decoder"](net["encoder"](x)).square().sum().backward()
+        red.finish()
+    torch.save({k: p.grad.clone() for k, p in net.named_parameters()}, os.path.join(out_dir, f"g{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreducer_averages_per_stack_buckets(tmp_path):
+    """world_size 2, gloo: after finish() every rank holds the mean of the per-rank gradients (DDP semantics)."""
+    world = 2
+    mp.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = [torch.load(tmp_path / f"g{r}.pt") for r in range(world)]
+    torch.manual_seed(0)
+    net = torch.nn.ModuleDict({"encoder": torch.nn.Linear(6, 4), "decoder": torch.nn.Linear(4, 3)})
+    want = None
+    for r in range(world):
+        net.zero_grad(set_to_none=True)
+        x = torch.full((5, 6), float(r + 1 + 1))
+        net["decoder"](net["encoder"](x)).square().sum().backward()
+        g = {k: p.grad.clone() for k, p in net.named_parameters()}
+        want = g if want is None else {k: want[k] + g[k] for k in g}
+    for k in want:
+        for r in range(world):
+            assert torch.allclose(got[r][k], want[k] / world, rtol=1e-5, atol=1e-6), k

@@ -72,3 +72,75 @@ def gather_indices(local: Sequence[torch.Tensor], owned: Sequence[int], n_clips:
                 out[cid] = f[off:off + ln].clone()
                 off += ln
     return out
+
+
+class GradientAllReducer:
+    """DDP-equivalent gradient averaging for the drop-in TiTok (train.py runs Lightning DDP, train.py:172-181).
+
+    The backward of a stack (backward.EncoderFn / DecoderFn) produces ALL of that stack's parameter gradients at once,
+    decoder first, then (through the FSQ straight-through estimator) the encoder. Parameters are therefore bucketed per
+    top-level child module (`decoder`, `encoder`, ...): a post-accumulate-grad hook counts the bucket's parameters
+    down, and when the last one has its gradient the bucket is flattened and all-reduced asynchronously -- the
+    decoder bucket (13.7 MB fp32) crosses NVLink while the encoder backward is still computing. `finish()` waits,
+    divides by the world size and scatters the averages back into `.grad`. One NCCL call per bucket; no per-parameter
+    collectives. Single process: every method is a no-op.
+    """
+
+    def __init__(self, module: torch.nn.Module, group=None):
+        self.group = group
+        self.rank, self.world = _world(group)
+        self.buckets: List[List[torch.nn.Parameter]] = []
+        self._pending: List[int] = []
+        self._work: List[Optional[Tuple[object, torch.Tensor]]] = []
+        self._handles = []
+        if self.world == 1:
+            return
+        by_child = {}
+        for name, p in module.named_parameters():
+            if p.requires_grad:
+                by_child.setdefault(name.split(".")[0], []).append(p)
+        for b, params in enumerate(by_child.values()):
+            self.buckets.append(params)
+            self._pending.append(len(params))
+            self._work.append(None)
+            for p in params:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
+
+    def _make_hook(self, b: int):
+        def hook(_param):
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b: int) -> None:
+        flat = torch.cat([p.grad.reshape(-1).float() for p in self.buckets[b]])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._work[b] = (work, flat)
+
+    def finish(self) -> None:
+        """Call after loss.backward(): completes the outstanding all-reduces and writes the averaged gradients."""
+        if self.world == 1:
+            return
+        for b, params in enumerate(self.buckets):
+            if self._work[b] is None:
+                if all(p.grad is not None for p in params):
+                    self._launch(b)  # a bucket whose hooks did not all fire (gradient accumulation without zero_grad)
+                else:
+                    self._pending[b] = len(params)
+                    continue
+            work, flat = self._work[b]
+            work.wait()
+            flat.div_(self.world)
+            off = 0
+            for p in params:
+                n = p.numel()
+                p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                off += n
+            self._work[b] = None
+            self._pending[b] = len(params)
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
