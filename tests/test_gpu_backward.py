@@ -406,3 +406,23 @@ def test_training_forward_equals_inference_forward():
     assert same >= 0.8  # GELU: exact erf (training) vs the fused kernel's A&S polynomial can flip a boundary token
     for a, b in zip(rec_i, rec_t):
         assert rel_err(b.detach(), a.float().cpu()) < 3e-2 or same < 1.0
+
+
+def test_generator_step_base_size_matches_oracle_autograd():
+    """encoder 'base' (width 768, 12 layers, 12/4 heads: three 256-column vectors per row, group of 3 query heads per kv
+    head) + decoder 'small' (width 512): the wider row kernels and the 3-head kv groups of the attention backward."""
+    model = build_model(False, enc="base", dec="small").to(DEV).train()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    shapes, tcs = [(4, 32, 40), (8, 16, 24)], [9, 32]
+    clips = O.make_clips(shapes, 4)
+    loss, _, grads = _train_step_grads(model, clips, tcs)
+    loss_o, grads_o = O.titok_train_grads(sd, [7, 5, 5, 5, 5], [4, 8, 8], clips, tcs, enc_size="base", dec_size="small")
+    assert abs(loss - loss_o) < 2e-3 * loss_o
+    worst = (1.0, "")
+    for k, g in grads.items():
+        if g.numel() == 1:
+            continue
+        c = cos_sim(g, grads_o[k])
+        worst = min(worst, (c, k))
+        assert c > 0.99, f"{k}: cos {c:.4f}"
+    print("worst cosine", worst)

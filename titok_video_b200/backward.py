@@ -159,8 +159,15 @@ def decoder_forward_train(m, dp: DevicePlan, codes: torch.Tensor):
 # backward
 # --------------------------------------------------------------------------------------------------
 def _zero_grads(W: PreparedStack) -> Dict[str, torch.Tensor]:
-    """fp32 zero buffers with the shapes of the prepared (kernel-layout) parameters."""
-    return {k: torch.zeros(v.shape, dtype=torch.float32, device=v.device) for k, v in W.t.items()}
+    """fp32 zero buffers with the shapes of the prepared (kernel-layout) parameters: views of ONE flat buffer (one
+    memset per stack; every view starts on a 16-byte boundary for the vector reductions of ttk_gemm_wgrad)."""
+    offs, total = {}, 0
+    for k, v in W.t.items():
+        offs[k] = total
+        total += (v.numel() + 3) // 4 * 4
+    dev = next(iter(W.t.values())).device
+    flat = torch.zeros(total, dtype=torch.float32, device=dev)
+    return {k: flat[offs[k]:offs[k] + v.numel()].view(v.shape) for k, v in W.t.items()}
 
 
 def _layers_backward(m, W: PreparedStack, dp: DevicePlan, tape: Tape, g: torch.Tensor, grads) -> torch.Tensor:

@@ -27,6 +27,7 @@ struct WgradParams {
   int n_out, k_in;
   int tiles_m, tiles_n, splits;
   int num_k_blocks;  // ceil(M / 64)
+  int vec4;          // dw and ldw allow 16-byte vector reductions
 };
 
 template <int BN>
@@ -137,9 +138,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tmem_ld_wait();
         if (row < p.n_out) {
           float* dst = p.dw + static_cast<int64_t>(row) * p.ldw + col0;
+          if (p.vec4 && col0 + 32 <= p.k_in) {
+            // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the atomic instructions
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.k_in) atomicAdd(dst + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.k_in) atomicAdd(dst + j, __uint_as_float(v[j]));
+          }
         }
       }
     }
@@ -166,9 +176,14 @@ static int launch_wgrad(const void* dy, int64_t ldy, const void* x, int64_t ldx,
   p.tiles_n = (k_in + BN - 1) / BN;
   p.num_k_blocks = (M + WG_BK - 1) / WG_BK;
   const int tiles = p.tiles_m * p.tiles_n;
-  int splits = (2 * num_sms()) / tiles;  // about two waves of CTAs: the atomic epilogue of one overlaps the next
+  // splits: fill the SMs, but every CTA should contract at least 8 token blocks (512 rows) -- each split pays a full
+  // [128 x BN] atomic epilogue, which dominates when the token range per CTA is short
+  int splits = num_sms() / tiles;
   if (splits < 1) splits = 1;
-  if (splits > p.num_k_blocks) splits = p.num_k_blocks;
+  const int max_splits = (p.num_k_blocks + 7) / 8;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.vec4 = ((reinterpret_cast<uintptr_t>(dw) & 15u) == 0 && ldw % 4 == 0) ? 1 : 0;
   // no empty splits: every CTA gets at least one token block
   const int per = (p.num_k_blocks + splits - 1) / splits;
   splits = (p.num_k_blocks + per - 1) / per;
