@@ -48,13 +48,21 @@ struct AttnBwdParams {
 };
 
 constexpr int AB_T = 128;            // tile rows (both sides)
+constexpr int AB_H = 64;             // rows of the streamed tile per stream
 constexpr int AB_D = 64;
 constexpr int AB_TILE = AB_T * AB_D * 2;  // 16 KB
 constexpr int AB_STAGES = 3;
 constexpr int AB_SMEM = 2 * AB_TILE + AB_STAGES * 2 * AB_TILE + 2 * 2 * 128 * 4 + 256 + 1024;
 constexpr int AB_THREADS = 128 + 8 * 32;
-// TMEM columns
-constexpr uint32_t AB_TM_S = 0, AB_TM_DP = 128, AB_TM_P = 256, AB_TM_DS = 320, AB_TM_A0 = 384, AB_TM_A1 = 448;
+// TMEM columns. Two STREAMS per CTA: stream s owns rows [64 s, 64 s + 64) of every streamed tile, i.e. a [128 x 64] slice
+// of S and dP, its own P / dS buffers and its own barriers; both streams accumulate into the same acc0 / acc1. While the
+// math warps of one stream are busy, the tensor core works for the other: the serial latencies of a stream (mbarrier
+// round trips, tcgen05.ld / st, MMA issue) hide behind the other stream instead of adding up.
+constexpr uint32_t AB_TM_S = 0;     // S0 [0,64)    S1 [64,128)
+constexpr uint32_t AB_TM_DP = 128;  // dP0 [128,192) dP1 [192,256)
+constexpr uint32_t AB_TM_P = 256;   // P0 [256,288) P1 [288,320)   (64 bf16 = 32 columns)
+constexpr uint32_t AB_TM_DS = 320;  // dS0 [320,352) dS1 [352,384)
+constexpr uint32_t AB_TM_A0 = 384, AB_TM_A1 = 448;
 
 __device__ __forceinline__ float ab_ex2(float x) {
   float y;
@@ -72,16 +80,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sX1 = smem;                 // stationary: dkv K | dq Q
   uint8_t* sX2 = smem + AB_TILE;       //             dkv V | dq dO
   uint8_t* sY = smem + 2 * AB_TILE;    // ring of [Y1 | Y2]: dkv (Q, dO) | dq (K, V)
-  float* cols = reinterpret_cast<float*>(sY + AB_STAGES * 2 * AB_TILE);  // dkv: [2 parities][lse 128 | delta 128]
+  float* cols = reinterpret_cast<float*>(sY + AB_STAGES * 2 * AB_TILE);  // dkv: [2 parities][2 streams][lse 64 | delta 64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(cols) + 2 * 2 * 128 * 4);
   uint64_t* x_full = bars;
   uint64_t* y_full = bars + 1;
   uint64_t* y_empty = y_full + AB_STAGES;
-  uint64_t* sdp_full = y_empty + AB_STAGES;  // S and dP of iteration i are in tensor memory
-  uint64_t* sdp_empty = sdp_full + 1;        // ... and have been read into registers
-  uint64_t* pds_full = sdp_empty + 1;        // P and dS of iteration i are in tensor memory
-  uint64_t* pds_empty = pds_full + 1;        // ... and the MMAs reading them have retired
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pds_empty + 1);
+  uint64_t* sdp_full = y_empty + AB_STAGES;  // [2] S and dP of the stream's iteration i are in tensor memory
+  uint64_t* sdp_empty = sdp_full + 2;        // [2] ... and have been read into registers
+  uint64_t* pds_full = sdp_empty + 2;        // [2] P and dS of the stream's iteration i are in tensor memory
+  uint64_t* pds_empty = pds_full + 2;        // [2] ... and the MMAs reading them have retired
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pds_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,10 +109,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&y_full[s], 1);
       mbar_init(&y_empty[s], 1);
     }
-    mbar_init(sdp_full, 1);
-    mbar_init(sdp_empty, 8);
-    mbar_init(pds_full, 8);
-    mbar_init(pds_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sdp_full[s], 1);
+      mbar_init(&sdp_empty[s], 4);
+      mbar_init(&pds_full[s], 4);
+      mbar_init(&pds_empty[s], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, 512);
@@ -143,64 +153,72 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncwarp();
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(AB_T, AB_T, 0, 0);  // X (K-major) x Y (K-major)
-      constexpr uint32_t idesc_a = umma_idesc_bf16(AB_T, AB_D, 0, 1);  // P / dS (tmem) x Y (MN-major)
-      auto issue_sdp = [&](int st) {
-        const uint32_t y1 = smem_u32(sY + st * 2 * AB_TILE);
+      constexpr uint32_t idesc_s = umma_idesc_bf16(AB_T, AB_H, 0, 0);  // X (K-major) x Y rows of the stream (K-major)
+      constexpr uint32_t idesc_a = umma_idesc_bf16(AB_T, AB_D, 0, 1);  // P / dS (tmem) x Y rows of the stream (MN-major)
+      constexpr uint32_t HOFF = AB_H * 128;                            // byte offset of a stream's rows inside a tile
+      auto issue_sdp = [&](int s, int st) {
+        const uint32_t y1 = smem_u32(sY + st * 2 * AB_TILE) + s * HOFF;
         const uint32_t x1 = smem_u32(sX1), x2 = smem_u32(sX2);
 #pragma unroll
         for (int k = 0; k < AB_D / 16; ++k)
-          umma_bf16_ss(tmem_base + AB_TM_S, umma_smem_desc_sw128(x1 + k * 32, 1024, 0),
+          umma_bf16_ss(tmem_base + AB_TM_S + s * AB_H, umma_smem_desc_sw128(x1 + k * 32, 1024, 0),
                        umma_smem_desc_sw128(y1 + k * 32, 1024, 0), idesc_s, k != 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < AB_D / 16; ++k)
-          umma_bf16_ss(tmem_base + AB_TM_DP, umma_smem_desc_sw128(x2 + k * 32, 1024, 0),
+          umma_bf16_ss(tmem_base + AB_TM_DP + s * AB_H, umma_smem_desc_sw128(x2 + k * 32, 1024, 0),
                        umma_smem_desc_sw128(y1 + AB_TILE + k * 32, 1024, 0), idesc_s, k != 0 ? 1u : 0u);
       };
-      auto issue_acc = [&](int st, bool accumulate) {
-        const uint32_t y1 = smem_u32(sY + st * 2 * AB_TILE);
+      auto issue_acc = [&](int s, int st, bool accumulate) {
+        const uint32_t y1 = smem_u32(sY + st * 2 * AB_TILE) + s * HOFF;
         if (DKV) {
 #pragma unroll
-          for (int k = 0; k < AB_T / 16; ++k)  // acc0 (dV) += P^T dO
-            umma_bf16_ts(tmem_base + AB_TM_A0, tmem_base + AB_TM_P + k * 8,
+          for (int k = 0; k < AB_H / 16; ++k)  // acc0 (dV) += P^T dO
+            umma_bf16_ts(tmem_base + AB_TM_A0, tmem_base + AB_TM_P + s * (AB_H / 2) + k * 8,
                          umma_smem_desc_sw128(y1 + AB_TILE + k * 2048, 1024, 0), idesc_a, (accumulate || k != 0) ? 1u : 0u);
         }
 #pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k)  // acc1 += dS Y1   (dkv: dK += dS^T Q; dq: dQ += dS K)
-          umma_bf16_ts(tmem_base + AB_TM_A1, tmem_base + AB_TM_DS + k * 8, umma_smem_desc_sw128(y1 + k * 2048, 1024, 0),
-                       idesc_a, (accumulate || k != 0) ? 1u : 0u);
+        for (int k = 0; k < AB_H / 16; ++k)  // acc1 += dS Y1   (dkv: dK += dS^T Q; dq: dQ += dS K)
+          umma_bf16_ts(tmem_base + AB_TM_A1, tmem_base + AB_TM_DS + s * (AB_H / 2) + k * 8,
+                       umma_smem_desc_sw128(y1 + k * 2048, 1024, 0), idesc_a, (accumulate || k != 0) ? 1u : 0u);
       };
       mbar_wait(x_full, 0);
       mbar_wait(&y_full[0], 0);
       tc_fence_after();
-      issue_sdp(0);
-      umma_commit(sdp_full);
+      for (int s = 0; s < 2; ++s) {
+        issue_sdp(s, 0);
+        umma_commit(&sdp_full[s]);
+      }
       for (int it = 0; it < n_it; ++it) {
         const int st = it % AB_STAGES;
+        const uint32_t par = it & 1;
         if (it + 1 < n_it) {
+          // S / dP of the next tile as soon as the stream's math warps hold the current ones in registers
           const int st1 = (it + 1) % AB_STAGES;
           mbar_wait(&y_full[st1], ((it + 1) / AB_STAGES) & 1);
-          mbar_wait(sdp_empty, it & 1);
-          tc_fence_after();
-          issue_sdp(st1);
-          umma_commit(sdp_full);
+          for (int s = 0; s < 2; ++s) {
+            mbar_wait(&sdp_empty[s], par);
+            tc_fence_after();
+            issue_sdp(s, st1);
+            umma_commit(&sdp_full[s]);
+          }
         }
-        mbar_wait(pds_full, it & 1);
-        tc_fence_after();
-        issue_acc(st, it > 0);
-        umma_commit(pds_empty);
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(&pds_full[s], par);
+          tc_fence_after();
+          issue_acc(s, st, it > 0 || s > 0);
+          umma_commit(&pds_empty[s]);
+        }
         umma_commit(&y_empty[st]);
       }
     }
     __syncwarp();
   } else if (warp >= 4) {
-    const int cw = warp - 4;
-    const int half = cw >> 2;      // columns [64*half, +64) of S / dP
-    const int quarter = warp & 3;  // TMEM lane quarter
+    const int s = (warp - 4) >> 2;  // stream: rows [64 s, +64) of every streamed tile == columns of S / dP
+    const int quarter = warp & 3;   // TMEM lane quarter
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const float c = p.scale_log2;
-    const int ct = threadIdx.x - 128;  // 0..255
+    const int ct = (threadIdx.x - 128) & 127;  // index within the stream's 128 threads
     float lse_r = 0.f, delta_r = 0.f;
     if (!DKV && r < w.st_valid) {
       lse_r = p.lse[static_cast<int64_t>(w.st_head) * p.M + w.st_row0 + r];
@@ -209,72 +227,81 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int it = 0; it < n_it; ++it) {
       const uint32_t par = it & 1;
       const int tile = it % n_tiles;
-      const int y_valid = w.clip_len - tile * AB_T;  // valid rows of the streamed tile (>= 128: all)
-      float* cl = cols + par * 256;
+      const int y_valid = w.clip_len - tile * AB_T - s * AB_H;  // valid rows of the stream's slice (>= 64: all)
+      float* cl = cols + (par * 2 + s) * 128;                   // [lse 64 | delta 64]
       if (DKV) {
-        // per-column (query row) log-sum-exp and D of the streamed tile; +inf / 0 beyond the clip => P = dS = 0
+        // per-column (query row) log-sum-exp and D of the stream's slice; +inf / 0 beyond the clip => P = dS = 0
         const int head = w.o_head0 + it / n_tiles;
-        const int cc = ct & 127;
+        const int cc = ct & 63;
         const bool ok = cc < y_valid;
-        const int64_t gi = static_cast<int64_t>(head) * p.M + w.clip_row0 + tile * AB_T + cc;
+        const int64_t gi = static_cast<int64_t>(head) * p.M + w.clip_row0 + tile * AB_T + s * AB_H + cc;
         float v;
-        if (ct < 128) v = ok ? p.lse[gi] : __int_as_float(0x7f800000);
+        if (ct < 64) v = ok ? p.lse[gi] : __int_as_float(0x7f800000);
         else v = ok ? p.delta[gi] : 0.f;
         cl[ct] = v;
-        named_bar_sync(1, 256);
+        named_bar_sync(1 + s, 128);
       }
-      mbar_wait(sdp_full, par);
+      mbar_wait(&sdp_full[s], par);
       tc_fence_after();
 #pragma unroll 1
       for (int ch = 0; ch < 2; ++ch) {
-        const int c0 = half * 64 + ch * 32;
+        const int c0 = ch * 32;
         uint32_t sv[32], dv[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_off + AB_TM_S + c0, sv);
-        tmem_ld_32x32b_x32(tmem_base + lane_off + AB_TM_DP + c0, dv);
+        tmem_ld_32x32b_x32(tmem_base + lane_off + AB_TM_S + s * AB_H + c0, sv);
+        tmem_ld_32x32b_x32(tmem_base + lane_off + AB_TM_DP + s * AB_H + c0, dv);
         tmem_ld_wait();
         if (ch == 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(sdp_empty);  // S / dP of the next iteration may overwrite the accumulators
+          if (lane == 0) mbar_arrive(&sdp_empty[s]);  // S / dP of the next iteration may overwrite the accumulators
         }
         uint32_t pp[16], ds[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float l0, l1, d0, d1;
+        for (int i = 0; i < 32; i += 4) {
+          float l[4], d[4];
           if (DKV) {
-            l0 = cl[c0 + i];
-            l1 = cl[c0 + i + 1];
-            d0 = cl[128 + c0 + i];
-            d1 = cl[128 + c0 + i + 1];
+            const float4 lv = *reinterpret_cast<const float4*>(cl + c0 + i);
+            const float4 dl = *reinterpret_cast<const float4*>(cl + 64 + c0 + i);
+            l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
+            d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = dl.w;
           } else {
-            l0 = l1 = lse_r;
-            d0 = d1 = delta_r;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              l[e] = lse_r;
+              d[e] = delta_r;
+            }
           }
-          float p0 = ab_ex2(fmaf(__uint_as_float(sv[i]), c, -l0));
-          float p1 = ab_ex2(fmaf(__uint_as_float(sv[i + 1]), c, -l1));
-          if (!DKV) {
-            if (c0 + i >= y_valid) p0 = 0.f;
-            if (c0 + i + 1 >= y_valid) p1 = 0.f;
+          float pv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            pv[e] = ab_ex2(fmaf(__uint_as_float(sv[i + e]), c, -l[e]));
+            if (!DKV && c0 + i + e >= y_valid) pv[e] = 0.f;
           }
-          pp[i >> 1] = pack_bf16x2(p0, p1);
-          ds[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[i]) - d0), p1 * (__uint_as_float(dv[i + 1]) - d1));
+          pp[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+          pp[(i >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+          ds[i >> 1] = pack_bf16x2(pv[0] * (__uint_as_float(dv[i]) - d[0]), pv[1] * (__uint_as_float(dv[i + 1]) - d[1]));
+          ds[(i >> 1) + 1] = pack_bf16x2(pv[2] * (__uint_as_float(dv[i + 2]) - d[2]), pv[3] * (__uint_as_float(dv[i + 3]) - d[3]));
         }
         if (ch == 0 && it > 0) {
-          mbar_wait(pds_empty, (it - 1) & 1);  // the MMAs of the previous iteration no longer read P / dS
+          mbar_wait(&pds_empty[s], (it - 1) & 1);  // the MMAs of the previous iteration no longer read P / dS
           tc_fence_after();
         }
-        if (DKV) tmem_st_32x32b_x16(tmem_base + lane_off + AB_TM_P + (c0 >> 1), pp);
-        tmem_st_32x32b_x16(tmem_base + lane_off + AB_TM_DS + (c0 >> 1), ds);
+        if (DKV) tmem_st_32x32b_x16(tmem_base + lane_off + AB_TM_P + s * (AB_H / 2) + (c0 >> 1), pp);
+        tmem_st_32x32b_x16(tmem_base + lane_off + AB_TM_DS + s * (AB_H / 2) + (c0 >> 1), ds);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
+      if (lane == 0) mbar_arrive(&pds_full[s]);
     }
 
-    // ---- epilogue: accumulators -> bf16 (RoPE conjugate rotation for dQ / dK) -> dqkv
-    mbar_wait(pds_empty, (n_it - 1) & 1);
+    // ---- epilogue: accumulators -> bf16 (RoPE conjugate rotation for dQ / dK) -> dqkv; stream s takes 32 of the 64 dims
+    // own stream's barrier first (a barrier this thread has followed phase by phase), then stream 1's, whose last MMAs
+    // were issued after stream 0's: by then it is at most one phase behind, so the parity wait cannot alias
+    mbar_wait(&pds_empty[s], (n_it - 1) & 1);
+    mbar_wait(&pds_empty[1], (n_it - 1) & 1);
     tc_fence_after();
+    const int half = s;
     const int row = w.st_row0 + r;
     const bool row_ok = r < w.st_valid;
     auto store32 = [&](uint32_t tm_col, float mul, int col, bool rot) {
