@@ -426,3 +426,66 @@ def test_generator_step_base_size_matches_oracle_autograd():
         worst = min(worst, (c, k))
         assert c > 0.99, f"{k}: cos {c:.4f}"
     print("worst cosine", worst)
+
+
+def test_discriminator_step_like_loss_module():
+    """ReconstructionLoss._forward_discriminator (loss_module.py:166-214) on the drop-in TiTokEncoder(out_channels=1):
+    four forwards of the SAME module (real, fake, real + noise, fake + noise; 4 register tokens per clip, logits =
+    mean over them, loss_module.py:96-101) before one backward -- several tapes in flight -- and then the generator's
+    adversarial term (loss_module.py:140-153): frozen parameters, gradient w.r.t. the reconstruction's pixels."""
+    import torch.nn.functional as F
+
+    import titok_video_b200 as T
+    from titok_video_b200.model.base.utils import init_weights
+
+    torch.manual_seed(0)
+    disc = T.TiTokEncoder("tiny", (4, 8, 8), 3, 1).apply(init_weights).to(DEV)
+    sd = {"encoder." + k: v.detach().cpu().clone() for k, v in disc.state_dict().items()}
+    shapes = [(4, 32, 32), (8, 16, 24), (4, 24, 16)]
+    real = O.make_clips(shapes, 7)
+    fake = O.make_clips(shapes, 8)
+    noise = [torch.randn(c.shape, generator=torch.Generator().manual_seed(9 + i)).to(BF) * 0.05 for i, c in enumerate(real)]
+    B = len(shapes)
+    gp_w, gp_noise, cen_w = 5.0, 0.05, 0.01
+
+    def wrapper(fn, xs):
+        return fn(xs).view(B, -1).float().mean(-1)
+
+    def d_loss(fn, to):
+        lr, lf = wrapper(fn, [to(c) for c in real]), wrapper(fn, [to(c) for c in fake])
+        lrn = wrapper(fn, [to(c) + to(n) for c, n in zip(real, noise)])
+        lfn = wrapper(fn, [to(c) + to(n) for c, n in zip(fake, noise)])
+        gp = (lr - lrn) ** 2 + (lf - lfn) ** 2
+        return (F.softplus(-(lr - lf)) + gp_w / gp_noise ** 2 * gp + cen_w * ((lr + lf) ** 2) / 2).mean()
+
+    tcs = torch.tensor([4], dtype=torch.int32).repeat(B)
+    loss = d_loss(lambda xs: disc(xs, tcs), lambda c: c.to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    leaves = {k: v.clone().float().requires_grad_(True) for k, v in sd.items()}
+    loss_o = d_loss(lambda xs: O.encoder_forward(leaves, "tiny", [4, 8, 8], xs, [4] * B), lambda c: O.r(c.float()))
+    loss_o.backward()
+    assert abs(float(loss) - float(loss_o)) < 0.05 * abs(float(loss_o)) + 1e-3
+    checked = 0
+    for k, p in disc.named_parameters():
+        g, go = p.grad.float().cpu(), leaves["encoder." + k].grad
+        assert torch.isfinite(g).all(), k
+        if g.numel() > 1 and float(go.norm()) > 1e-6:
+            # differences of nearly equal logits: the bf16 noise floor is higher than in the reconstruction loss
+            assert cos_sim(g, go) > 0.9, f"{k}: cos {cos_sim(g, go):.4f}"
+            checked += 1
+    assert checked > 30
+    # generator side: parameters frozen, gradient flows to the fake pixels only
+    for p in disc.parameters():
+        p.requires_grad_(False)
+        p.grad = None
+    fk = [c.to(DEV).requires_grad_(True) for c in fake]
+    g_loss = F.softplus(-(wrapper(lambda xs: disc(xs, tcs), fk) - wrapper(lambda xs: disc(xs, tcs), [c.to(DEV) for c in real]).detach())).mean()
+    g_loss.backward()
+    fo = [O.r(c.float()).requires_grad_(True) for c in fake]
+    fn_o = lambda xs: O.encoder_forward(sd, "tiny", [4, 8, 8], xs, [4] * B)
+    g_loss_o = F.softplus(-(wrapper(fn_o, fo) - wrapper(fn_o, [O.r(c.float()) for c in real]).detach())).mean()
+    g_loss_o.backward()
+    assert all(p.grad is None for p in disc.parameters())
+    for a, b in zip(fk, fo):
+        assert cos_sim(a.grad.float().cpu(), b.grad) > 0.98

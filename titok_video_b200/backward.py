@@ -394,3 +394,34 @@ class DecoderFn(torch.autograd.Function):
         ctx.tape = None
         dc = dcodes.to(ctx.codes_dtype) if ctx.need_codes else None
         return (None, None, dc) + _ordered(ctx.m, "dec", grads, ctx.meta)
+
+
+class SplitClips(torch.autograd.Function):
+    """flat reconstruction buffer -> per-clip [C, T, H, W] views (engine.split_clips), with a backward that writes every
+    clip's gradient straight into ONE flat buffer. (autograd's own backward of B slices materialises B full-size zero
+    tensors and adds them up: O(B^2) traffic for a batch of B clips.)"""
+
+    @staticmethod
+    def forward(ctx, flat, plan):
+        ctx.plan = plan
+        ctx.flat_meta = (flat.shape, flat.dtype, flat.device)
+        outs = []
+        for off, n, g in zip(plan.clip_offset, plan.clip_numel, plan.grids_px):
+            outs.append(flat[off:off + n].view(plan.channels, *g))
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        shape, dtype, device = ctx.flat_meta
+        plan = ctx.plan
+        if all(g is not None for g in grads) and len(grads) > 0:
+            return torch.cat([g.reshape(-1).to(dtype) for g in grads]), None
+        out = torch.zeros(shape, dtype=dtype, device=device)
+        for g, off, n in zip(grads, plan.clip_offset, plan.clip_numel):
+            if g is not None:
+                out[off:off + n].copy_(g.reshape(-1))
+        return out, None
+
+
+def split_clips_autograd(flat: torch.Tensor, plan) -> List[torch.Tensor]:
+    return list(SplitClips.apply(flat, plan))

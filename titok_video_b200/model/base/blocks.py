@@ -134,7 +134,9 @@ class TiTokDecoder(_Stack):
     def forward(self, tokens, token_counts, grids) -> List[torch.Tensor]:
         out, dp = self.forward_impl(tokens, token_counts, grids)
         if out.requires_grad:
-            return engine.split_clips(out.to(tokens.dtype if tokens.is_floating_point() else torch.bfloat16), dp.plan)
+            from ... import backward
+
+            return backward.split_clips_autograd(out.to(tokens.dtype if tokens.is_floating_point() else torch.bfloat16), dp.plan)
         return engine.split_clips(out.clone().to(tokens.dtype if tokens.is_floating_point() else torch.bfloat16), dp.plan)
 
 

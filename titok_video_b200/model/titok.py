@@ -66,8 +66,14 @@ class TiTok(nn.Module):
         if z.requires_grad:  # training: encoder -> FSQ (straight-through) -> decoder, all recorded by autograd
             codes, d = self.quantize(z)
             out, _ = self.decoder.forward_impl(codes, tcs, grids)
-            return engine.split_clips(out.to(x[0].dtype), dp.plan), {"indices": d["indices"]}
+            from .. import backward
+
+            return backward.split_clips_autograd(out.to(x[0].dtype), dp.plan), {"indices": d["indices"]}
         out, _ = self.decoder.forward_impl(codes, tcs, grids)
+        if out.requires_grad:  # frozen encoder, trainable decoder
+            from .. import backward
+
+            return backward.split_clips_autograd(out.to(x[0].dtype), dp.plan), {"indices": idx.clone()}
         recon = engine.split_clips(out.clone().to(x[0].dtype), dp.plan)
         return recon, {"indices": idx.clone()}
 
