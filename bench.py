@@ -295,6 +295,48 @@ def train_leg(T, _lib, dev, world, rank, dist, batch, steps, warmup):
                     + "fused AdamW + codebook histogram; synthetic clips 3x16x168x168 / 128 tokens, random-init weights"}
 
 
+def scaled_leg(T, dev, world, rank, dist, steps, warmup, clips_per_gpu=4):
+    """BASELINE configs[4]: the scaled-up variant that stresses the attention sequence length -- clips of
+    32x256x256 with 256 latent tokens (8192 patches, 8448 packed rows per clip; attention is 84 % of the FLOPs), tiny
+    stacks, forward tokenise + reconstruct through TiTok.tokenize_reconstruct_ (CUDA-graph replay), device-timed."""
+    from titok_video_b200.config import tiny_config
+
+    shape, t = (32, 256, 256), 256
+    torch.manual_seed(42)
+    model = T.TiTok(tiny_config(LEVELS, PATCH)).to(dev).eval()
+    gen = torch.Generator().manual_seed(3000 + rank)
+    sets = [[(torch.rand((3, *shape), generator=gen) * 2 - 1).to(torch.bfloat16).to(dev) for _ in range(clips_per_gpu)]
+            for _ in range(2)]
+    tcs = [t] * clips_per_gpu
+    fl, s_rows, _ = clip_flops(shape, t)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(max(warmup, 3)):
+            model.tokenize_reconstruct_(sets[i % 2], tcs)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            model.tokenize_reconstruct_(sets[i % 2], tcs)
+        e1.record()
+        barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / steps
+    cps = world * clips_per_gpu / (ms_step * 1e-3)
+    tf = cps / world * fl / 1e12
+    return {"workload": f"per GPU {clips_per_gpu} clips 3x32x256x256 bf16, 256 latent tokens each ({s_rows} packed rows per clip), "
+                        "tiny encoder / decoder, forward tokenise + reconstruct",
+            "clips_per_s": cps, "latent_tokens_per_s": cps * t, "ms_per_step": ms_step, "gflop_per_clip": fl / 1e9,
+            "tflops_per_gpu": tf, "frac_of_tensor_peak": tf / peaks()["bf16_tflops_sustained"]}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -329,6 +371,7 @@ def main():
     ap.add_argument("--train-batch", default="3,16",
                     help="clips per GPU per step of the training-step leg(s) (BASELINE configs[3]; 3 clips A = tiny.yaml's "
                          "6144-token budget); empty = skip")
+    ap.add_argument("--no-scaled", action="store_true", help="skip the scaled-up (32x256x256) leg (BASELINE configs[4])")
     ap.add_argument("--e2e-full-recon", action="store_true",
                     help="e2e leg copies the full reconstructions back to the host (default: token indices + per-clip error)")
     args = ap.parse_args()
@@ -528,6 +571,11 @@ def main():
         for tb in [int(v) for v in args.train_batch.split(",") if v]:
             train[f"batch{tb}"] = train_leg(T, _lib, dev, world, rank, dist, tb, max(4, args.steps // 2), args.warmup)
 
+    # ---------------- scaled-up variant (BASELINE configs[4]) ----------------
+    scaled = None
+    if not args.no_scaled:
+        scaled = scaled_leg(T, dev, world, rank, dist, max(4, args.steps // 2), args.warmup)
+
     # ---------------- codebook usage over the whole job (the only data-path collective) ----------------
     if world > 1:
         dist.all_reduce(hist)
@@ -587,7 +635,7 @@ def main():
                     "api": "TiTok.tokenize_reconstruct_(clips, token_counts) from pinned host clips, 2-slot pipeline, CUDA-graph replay "
                            "(the value leg launches the same kernels one by one so that each can be timed with CUDA events)"},
             "gpu_launches": launches, "roofline": roofline, "whole_step": whole, "kernels": kernels, "clocks": clocks,
-            "cpu_baseline": cpu, "quantizer_microbench": vq, "ragged_stream": ragged, "train_step": train,
+            "cpu_baseline": cpu, "quantizer_microbench": vq, "ragged_stream": ragged, "train_step": train, "scaled_config": scaled,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -300,3 +300,47 @@ def test_clip_error_kernel_matches_torch(golden_stress):
             diff = a.double().cpu() - b.double().cpu()
             assert abs(err[i, 0].item() - diff.abs().sum().item()) <= 1e-4 * diff.abs().sum().item() + 1e-6
             assert abs(err[i, 1].item() - (diff * diff).sum().item()) <= 1e-4 * (diff * diff).sum().item() + 1e-6
+
+
+def test_torch_compile_wrapper_is_transparent():
+    """train.py:38-39 / loss_module.py:50-51 may wrap the modules in torch.compile: the drop-in modules opt out of Dynamo
+    tracing (their kernels are opaque ctypes calls) and produce the same tokens and gradients as the unwrapped module."""
+    model = build_model(True).cuda()
+    clips = [c.cuda() for c in O.make_clips([(8, 32, 32), (4, 16, 24)], 0)]
+    tcs = torch.tensor([8, 3], dtype=torch.int32)
+    with torch.no_grad():
+        rec, d = model(clips, tcs)
+    cm = torch.compile(model)
+    with torch.no_grad():
+        rec_c, d_c = cm(clips, tcs)
+    assert torch.equal(d["indices"], d_c["indices"])
+    for a, b in zip(rec, rec_c):
+        assert torch.equal(a, b)
+    rec_t, _ = cm(clips, tcs)
+    torch.stack([r.float().abs().mean() for r in rec_t]).mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+def test_scaled_config_long_sequences():
+    """BASELINE configs[4] / SURVEY C5: a 32x256x256 clip with 256 latent tokens (8448 packed rows: 66 attention tiles per
+    head). Size-independent properties at full size: results do not depend on the batch composition (bit-exact),
+    decode_indices(forward().indices) reproduces forward()'s reconstruction (bit-exact), and one training step on it
+    yields finite gradients for every parameter."""
+    model = build_model(True).cuda().eval()
+    big, small = O.make_clips([(32, 256, 256), (4, 16, 24)], 11)
+    big, small = big.cuda(), small.cuda()
+    with torch.no_grad():
+        rec_a, d_a = model([big], [256])
+        rec_b, d_b = model([small, big], [3, 256])
+        rec_c = model.decode_indices(d_a["indices"], [(32, 256, 256)], [256])
+    assert d_a["indices"].shape == (256,)
+    assert torch.equal(d_a["indices"], d_b["indices"][3:])
+    assert torch.equal(rec_a[0], rec_b[1])
+    assert torch.equal(rec_a[0], rec_c[0])
+    assert torch.isfinite(rec_a[0].float()).all()
+    model.train()
+    rec_t, _ = model([big], [256])
+    (rec_t[0].float() - big.float()).abs().mean().backward()
+    for k, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+    assert sum(float(p.grad.abs().sum()) for p in model.parameters()) > 0

@@ -60,6 +60,7 @@ class TiTokEncoder(_Stack):
             raise ValueError("token size must be in 1..8")
         self._build(model_size, patch_size, in_channels * math.prod(patch_size), out_channels)
 
+    @torch.compiler.disable()
     def forward_impl(self, videos: Sequence[torch.Tensor], token_counts, grids=None, fsq=None):
         """Returns (z, codes, indices, device_plan). z: [sum(token_counts), token_size] pre-quantisation tokens."""
         device = videos[0].device
@@ -96,6 +97,7 @@ class TiTokEncoder(_Stack):
             z, codes, idx = engine.encoder_launch(self, dp, flat, consts)
         return z, codes, idx, dp
 
+    @torch.compiler.disable()
     def forward(self, videos, token_counts, grids=None):
         z, _, _, _ = self.forward_impl(videos, token_counts, grids)
         if z.requires_grad:
@@ -113,6 +115,7 @@ class TiTokDecoder(_Stack):
             raise ValueError("token size must be in 1..8")
         self._build(model_size, patch_size, in_channels, out_channels * math.prod(patch_size))
 
+    @torch.compiler.disable()
     def forward_impl(self, tokens: torch.Tensor, token_counts, grids) -> (torch.Tensor, engine.DevicePlan):
         device = tokens.device
         engine.require_cuda(device)
@@ -131,6 +134,7 @@ class TiTokDecoder(_Stack):
             engine.decoder_launch(self, dp, codes, out)
         return out, dp
 
+    @torch.compiler.disable()
     def forward(self, tokens, token_counts, grids) -> List[torch.Tensor]:
         out, dp = self.forward_impl(tokens, token_counts, grids)
         if out.requires_grad:

@@ -29,6 +29,7 @@ class TiTok(nn.Module):
         self.apply(init_weights)
 
     # ---- titok.py:47-52 -------------------------------------------------------------------------
+    @torch.compiler.disable()  # train.py:38-39 may wrap the model in torch.compile: the kernels are opaque to Dynamo
     def encode(self, x: Sequence[torch.Tensor], token_counts, grids=None, split_indices: bool = False):
         """x_q [sum(token_counts), token_size] in the clips' dtype, {'indices': int32 [sum(token_counts)]}.
         split_indices=True returns a tuple of per-clip index tensors (the reference's intent; its own
@@ -45,6 +46,7 @@ class TiTok(nn.Module):
         return x_q, {"indices": indices}
 
     # ---- titok.py:54-62 -------------------------------------------------------------------------
+    @torch.compiler.disable()  # train.py:38-39 may wrap the model in torch.compile: the kernels are opaque to Dynamo
     def decode_indices(self, indices, grids, token_counts=None):
         if token_counts is None:
             assert type(indices) in [list, tuple]
@@ -54,10 +56,12 @@ class TiTok(nn.Module):
         return self.decoder(x_q, token_counts, grids)
 
     # ---- titok.py:64-66 -------------------------------------------------------------------------
+    @torch.compiler.disable()  # train.py:38-39 may wrap the model in torch.compile: the kernels are opaque to Dynamo
     def decode(self, x, token_counts, grids):
         return self.decoder(x, token_counts, grids)
 
     # ---- titok.py:68-74 -------------------------------------------------------------------------
+    @torch.compiler.disable()  # train.py:38-39 may wrap the model in torch.compile: the kernels are opaque to Dynamo
     def forward(self, x: Sequence[torch.Tensor], token_counts):
         """list of reconstructed clips [3,T,H,W] (input dtype) and {'indices': int32}."""
         grids = [tuple(v.shape[1:]) for v in x]
