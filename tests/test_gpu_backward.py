@@ -439,14 +439,19 @@ def test_discriminator_step_like_loss_module():
     from titok_video_b200.model.base.utils import init_weights
 
     torch.manual_seed(0)
-    disc = T.TiTokEncoder("tiny", (4, 8, 8), 3, 1).apply(init_weights).to(DEV)
+    disc = T.TiTokEncoder("tiny", (4, 8, 8), 3, 1).apply(init_weights)
+    with torch.no_grad():  # x3 on the matrices: logits with some signal (at std 0.02 the penalties are bf16 noise --
+        for p in disc.parameters():  # there the CPU oracle and the bf16 reference agree only to cosine 0.45..0.85 themselves)
+            if p.dim() == 2 and p.shape[0] > 1 and p.shape[1] > 1:
+                p.mul_(3.0)
+    disc = disc.to(DEV)
     sd = {"encoder." + k: v.detach().cpu().clone() for k, v in disc.state_dict().items()}
     shapes = [(4, 32, 32), (8, 16, 24), (4, 24, 16)]
     real = O.make_clips(shapes, 7)
     fake = O.make_clips(shapes, 8)
-    noise = [torch.randn(c.shape, generator=torch.Generator().manual_seed(9 + i)).to(BF) * 0.05 for i, c in enumerate(real)]
+    noise = [torch.randn(c.shape, generator=torch.Generator().manual_seed(9 + i)).to(BF) * 0.5 for i, c in enumerate(real)]
     B = len(shapes)
-    gp_w, gp_noise, cen_w = 5.0, 0.05, 0.01
+    gp_w, gp_noise, cen_w = 5.0, 0.5, 0.01
 
     def wrapper(fn, xs):
         return fn(xs).view(B, -1).float().mean(-1)
@@ -471,8 +476,8 @@ def test_discriminator_step_like_loss_module():
         g, go = p.grad.float().cpu(), leaves["encoder." + k].grad
         assert torch.isfinite(g).all(), k
         if g.numel() > 1 and float(go.norm()) > 1e-6:
-            # differences of nearly equal logits: the bf16 noise floor is higher than in the reconstruction loss
-            assert cos_sim(g, go) > 0.9, f"{k}: cos {cos_sim(g, go):.4f}"
+            # (oracle vs the unmodified bf16 reference on this loss: cosine >= 0.9987 on every parameter)
+            assert cos_sim(g, go) > 0.99, f"{k}: cos {cos_sim(g, go):.4f}"
             checked += 1
     assert checked > 30
     # generator side: parameters frozen, gradient flows to the fake pixels only

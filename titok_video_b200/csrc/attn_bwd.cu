@@ -18,7 +18,7 @@
 //   S = X1 Y1^T, dP = X2 Y2^T, [P, dS] = f(S, dP),  acc0 += P Y2 (dkv only),  acc1 += dS Y1.
 // P is recomputed from the log-sum-exp the forward kernel saved (no running maximum): two extra GEMMs instead of
 // atomics on dQ, and the results are deterministic.
-//   warp 0  TMA producer   warp 1  MMA issuer   warp 2  TMEM allocator   warps 4-11  P / dS math (thread = lane row x 64 columns)
+//   warp 0  TMA producer   warp 1  MMA issuer   warp 2  TMEM allocator   warps 4-19  P / dS math (thread = lane row x 32 columns)
 #include "common.cuh"
 #include "host_util.cuh"
 
@@ -53,7 +53,7 @@ constexpr int AB_D = 64;
 constexpr int AB_TILE = AB_T * AB_D * 2;  // 16 KB
 constexpr int AB_STAGES = 3;
 constexpr int AB_SMEM = 2 * AB_TILE + AB_STAGES * 2 * AB_TILE + 2 * 2 * 128 * 4 + 256 + 1024;
-constexpr int AB_THREADS = 128 + 8 * 32;
+constexpr int AB_THREADS = 128 + 16 * 32;  // 4 control warps + 16 math warps (four per scheduler: latency hiding)
 // TMEM columns. Two STREAMS per CTA: stream s owns rows [64 s, 64 s + 64) of every streamed tile, i.e. a [128 x 64] slice
 // of S and dP, its own P / dS buffers and its own barriers; both streams accumulate into the same acc0 / acc1. While the
 // math warps of one stream are busy, the tensor core works for the other: the serial latencies of a stream (mbarrier
@@ -111,8 +111,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sdp_full[s], 1);
-      mbar_init(&sdp_empty[s], 4);
-      mbar_init(&pds_full[s], 4);
+      mbar_init(&sdp_empty[s], 8);
+      mbar_init(&pds_full[s], 8);
       mbar_init(&pds_empty[s], 1);
     }
     fence_barrier_init();
@@ -123,7 +123,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // 640 threads start with 96 registers; the control warpgroup drops to 40, the math warps grow to 104
   if (warp == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (elect_one()) {
       mbar_arrive_expect_tx(x_full, 2 * AB_TILE);
       if (DKV) {
@@ -152,6 +154,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     __syncwarp();
   } else if (warp == 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(AB_T, AB_H, 0, 0);  // X (K-major) x Y rows of the stream (K-major)
       constexpr uint32_t idesc_a = umma_idesc_bf16(AB_T, AB_D, 0, 1);  // P / dS (tmem) x Y rows of the stream (MN-major)
@@ -212,13 +215,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    const int s = (warp - 4) >> 2;  // stream: rows [64 s, +64) of every streamed tile == columns of S / dP
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int cw = warp - 4;        // 0..15
+    const int s = cw >> 3;          // stream: rows [64 s, +64) of every streamed tile == 64 columns of S / dP
+    const int h = (cw >> 2) & 1;    // 32-column half of the stream's slice
     const int quarter = warp & 3;   // TMEM lane quarter
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const float c = p.scale_log2;
-    const int ct = (threadIdx.x - 128) & 127;  // index within the stream's 128 threads
+    const int ct = (threadIdx.x - 128) & 255;  // index within the stream's 256 threads
+    const int c0 = h * 32;                     // first column (within the stream's slice) of this thread
     float lse_r = 0.f, delta_r = 0.f;
     if (!DKV && r < w.st_valid) {
       lse_r = p.lse[static_cast<int64_t>(w.st_head) * p.M + w.st_row0 + r];
@@ -231,92 +240,90 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float* cl = cols + (par * 2 + s) * 128;                   // [lse 64 | delta 64]
       if (DKV) {
         // per-column (query row) log-sum-exp and D of the stream's slice; +inf / 0 beyond the clip => P = dS = 0
-        const int head = w.o_head0 + it / n_tiles;
-        const int cc = ct & 63;
-        const bool ok = cc < y_valid;
-        const int64_t gi = static_cast<int64_t>(head) * p.M + w.clip_row0 + tile * AB_T + s * AB_H + cc;
-        float v;
-        if (ct < 64) v = ok ? p.lse[gi] : __int_as_float(0x7f800000);
-        else v = ok ? p.delta[gi] : 0.f;
-        cl[ct] = v;
-        named_bar_sync(1 + s, 128);
+        if (ct < 128) {
+          const int head = w.o_head0 + it / n_tiles;
+          const int cc = ct & 63;
+          const bool ok = cc < y_valid;
+          const int64_t gi = static_cast<int64_t>(head) * p.M + w.clip_row0 + tile * AB_T + s * AB_H + cc;
+          float v;
+          if (ct < 64) v = ok ? p.lse[gi] : __int_as_float(0x7f800000);
+          else v = ok ? p.delta[gi] : 0.f;
+          cl[ct] = v;
+        }
+        named_bar_sync(1 + s, 256);
       }
       mbar_wait(&sdp_full[s], par);
       tc_fence_after();
-#pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        const int c0 = ch * 32;
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_off + AB_TM_S + s * AB_H + c0, sv);
-        tmem_ld_32x32b_x32(tmem_base + lane_off + AB_TM_DP + s * AB_H + c0, dv);
-        tmem_ld_wait();
-        if (ch == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sdp_empty[s]);  // S / dP of the next iteration may overwrite the accumulators
-        }
-        uint32_t pp[16], ds[16];
+      uint32_t sv[32], dv[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_off + AB_TM_S + s * AB_H + c0, sv);
+      tmem_ld_32x32b_x32(tmem_base + lane_off + AB_TM_DP + s * AB_H + c0, dv);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sdp_empty[s]);  // S / dP of the next iteration may overwrite the accumulators
+      // in place: sv[0..15] <- packed P, dv[0..15] <- packed dS
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float l[4], d[4];
-          if (DKV) {
-            const float4 lv = *reinterpret_cast<const float4*>(cl + c0 + i);
-            const float4 dl = *reinterpret_cast<const float4*>(cl + 64 + c0 + i);
-            l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
-            d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = dl.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              l[e] = lse_r;
-              d[e] = delta_r;
-            }
-          }
-          float pv[4];
+      for (int i = 0; i < 32; i += 4) {
+        float l[4], d[4];
+        if (DKV) {
+          const float4 lv = *reinterpret_cast<const float4*>(cl + c0 + i);
+          const float4 dl = *reinterpret_cast<const float4*>(cl + 64 + c0 + i);
+          l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
+          d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = dl.w;
+        } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            pv[e] = ab_ex2(fmaf(__uint_as_float(sv[i + e]), c, -l[e]));
-            if (!DKV && c0 + i + e >= y_valid) pv[e] = 0.f;
+            l[e] = lse_r;
+            d[e] = delta_r;
           }
-          pp[i >> 1] = pack_bf16x2(pv[0], pv[1]);
-          pp[(i >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
-          ds[i >> 1] = pack_bf16x2(pv[0] * (__uint_as_float(dv[i]) - d[0]), pv[1] * (__uint_as_float(dv[i + 1]) - d[1]));
-          ds[(i >> 1) + 1] = pack_bf16x2(pv[2] * (__uint_as_float(dv[i + 2]) - d[2]), pv[3] * (__uint_as_float(dv[i + 3]) - d[3]));
         }
-        if (ch == 0 && it > 0) {
-          mbar_wait(&pds_empty[s], (it - 1) & 1);  // the MMAs of the previous iteration no longer read P / dS
-          tc_fence_after();
+        float pv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          pv[e] = ab_ex2(fmaf(__uint_as_float(sv[i + e]), c, -l[e]));
+          if (!DKV && c0 + i + e >= y_valid) pv[e] = 0.f;
         }
-        if (DKV) tmem_st_32x32b_x16(tmem_base + lane_off + AB_TM_P + s * (AB_H / 2) + (c0 >> 1), pp);
-        tmem_st_32x32b_x16(tmem_base + lane_off + AB_TM_DS + s * (AB_H / 2) + (c0 >> 1), ds);
+        const uint32_t ds0 = pack_bf16x2(pv[0] * (__uint_as_float(dv[i]) - d[0]), pv[1] * (__uint_as_float(dv[i + 1]) - d[1]));
+        const uint32_t ds1 = pack_bf16x2(pv[2] * (__uint_as_float(dv[i + 2]) - d[2]), pv[3] * (__uint_as_float(dv[i + 3]) - d[3]));
+        sv[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+        sv[(i >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+        dv[i >> 1] = ds0;
+        dv[(i >> 1) + 1] = ds1;
       }
+      if (it > 0) {
+        mbar_wait(&pds_empty[s], (it - 1) & 1);  // the MMAs of the previous iteration no longer read P / dS
+        tc_fence_after();
+      }
+      if (DKV) tmem_st_32x32b_x16(tmem_base + lane_off + AB_TM_P + s * (AB_H / 2) + (c0 >> 1), *reinterpret_cast<uint32_t(*)[16]>(&sv[0]));
+      tmem_st_32x32b_x16(tmem_base + lane_off + AB_TM_DS + s * (AB_H / 2) + (c0 >> 1), *reinterpret_cast<uint32_t(*)[16]>(&dv[0]));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full[s]);
     }
 
-    // ---- epilogue: accumulators -> bf16 (RoPE conjugate rotation for dQ / dK) -> dqkv; stream s takes 32 of the 64 dims
-    // own stream's barrier first (a barrier this thread has followed phase by phase), then stream 1's, whose last MMAs
-    // were issued after stream 0's: by then it is at most one phase behind, so the parity wait cannot alias
+    // ---- epilogue: accumulators -> bf16 (RoPE conjugate rotation for dQ / dK) -> dqkv; warp group g = 2 s + h takes 16 of
+    // the 64 head dims. Own stream's barrier first (a barrier this thread has followed phase by phase), then stream 1's,
+    // whose last MMAs were issued after stream 0's: by then it is at most one phase behind, so the parity wait cannot alias.
     mbar_wait(&pds_empty[s], (n_it - 1) & 1);
     mbar_wait(&pds_empty[1], (n_it - 1) & 1);
     tc_fence_after();
-    const int half = s;
+    const int g16 = s * 2 + h;
     const int row = w.st_row0 + r;
     const bool row_ok = r < w.st_valid;
-    auto store32 = [&](uint32_t tm_col, float mul, int col, bool rot) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_off + tm_col + half * 32, v);
+    auto store16 = [&](uint32_t tm_col, float mul, int col, bool rot) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tmem_base + lane_off + tm_col + g16 * 16, v);
       tmem_ld_wait();
       if (!row_ok) return;
-      float f[32];
+      float f[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = bf16r(__uint_as_float(v[i]) * mul);
+      for (int i = 0; i < 16; ++i) f[i] = bf16r(__uint_as_float(v[i]) * mul);
       if (rot) {
-        const float2* cs = reinterpret_cast<const float2*>(p.rope) + static_cast<int64_t>(row) * 30 + half * 16;
+        const float2* cs = reinterpret_cast<const float2*>(p.rope) + static_cast<int64_t>(row) * 30 + g16 * 8;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (half * 16 + i < 30) {  // complex lanes 30, 31 (head dims 60..63) are not rotated (rope.py:22-24)
+        for (int i = 0; i < 8; ++i) {
+          if (g16 * 8 + i < 30) {  // complex lanes 30, 31 (head dims 60..63) are not rotated (rope.py:22-24)
             const float2 t = __ldg(cs + i);
             const float a = f[2 * i], b = f[2 * i + 1];
             f[2 * i] = a * t.x + b * t.y;
@@ -324,17 +331,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
-      __nv_bfloat16* dst = p.dqkv + static_cast<int64_t>(row) * p.ld + col + half * 32;
+      __nv_bfloat16* dst = p.dqkv + static_cast<int64_t>(row) * p.ld + col + g16 * 16;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < 2; ++q)
         stg16(dst + q * 8, make_uint4(pack_bf16x2(f[q * 8], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
                                       pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7])));
     };
     if (DKV) {
-      store32(AB_TM_A0, 1.0f, 2 * p.width + p.gqa + w.st_head * AB_D, false);  // dV
-      store32(AB_TM_A1, p.scale, 2 * p.width + w.st_head * AB_D, true);        // dK
+      store16(AB_TM_A0, 1.0f, 2 * p.width + p.gqa + w.st_head * AB_D, false);  // dV
+      store16(AB_TM_A1, p.scale, 2 * p.width + w.st_head * AB_D, true);        // dK
     } else {
-      store32(AB_TM_A1, p.scale, w.st_head * AB_D, true);  // dQ
+      store16(AB_TM_A1, p.scale, w.st_head * AB_D, true);  // dQ
     }
   }
 
