@@ -93,6 +93,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 #endif
 }
 
+template <bool TRAIN>  // TRAIN: also store the un-gated output and the log-sum-exp (compiled out of the inference kernel)
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -368,7 +369,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       named_bar_sync(pair_bar, 256);
       const float l_tot = l_run + x_other[1024];
       const float inv_l = __fdividef(1.0f, l_tot);
-      if (p.lse && half == 0 && r < w.q_valid[t])  // the backward kernels recompute P = 2^(s*c - lse)
+      if (TRAIN && half == 0 && r < w.q_valid[t])  // the backward kernels recompute P = 2^(s*c - lse)
         p.lse[static_cast<int64_t>(w.q_head[t]) * p.M + w.q_row0[t] + r] = fmaf(m_ref, c, __log2f(l_tot));
       mbar_wait(&pv_done[t], (n_kv - 1) & 1);
       tc_fence_after();
@@ -381,7 +382,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int col = w.q_head[t] * AT_D + half * 32;
         const __nv_bfloat16* g = p.gate + static_cast<int64_t>(row) * p.ld + col;
         __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + col;
-        __nv_bfloat16* osv = p.o_save ? p.o_save + static_cast<int64_t>(row) * p.ldo + col : nullptr;
+        __nv_bfloat16* osv = TRAIN ? p.o_save + static_cast<int64_t>(row) * p.ldo + col : nullptr;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint4 gv = ldg16(g + q * 8);
@@ -398,7 +399,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             av[e] = pack_bf16x2(a0, a1);
           }
           stg16(dst + q * 8, make_uint4(ov[0], ov[1], ov[2], ov[3]));
-          if (osv) stg16(osv + q * 8, make_uint4(av[0], av[1], av[2], av[3]));
+          if (TRAIN) stg16(osv + q * 8, make_uint4(av[0], av[1], av[2], av[3]));
         }
       }
     }
@@ -441,11 +442,15 @@ static int attn_fwd_launch(const void* qkv, int64_t ld, int M, int width, int gq
   p.M = M;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess)
       return TTK_ERR_CUDA;
     attr_done = true;
   }
-  attn_fwd_kernel<<<n_work, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  if (o_save)
+    attn_fwd_kernel<true><<<n_work, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  else
+    attn_fwd_kernel<false><<<n_work, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
   return launch_status();
 }
 

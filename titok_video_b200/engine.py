@@ -238,7 +238,11 @@ class PreparedStack:
         self.t: Dict[str, torch.Tensor] = {}
 
     def _signature(self):
-        return tuple((p.data_ptr(), p._version, p.dtype) for p in self.module.parameters())
+        ps = self.module.__dict__.get("_ttk_param_list")
+        if ps is None:  # cached: walking the module tree on every launch sequence costs ~50 us
+            ps = list(self.module.parameters())
+            self.module.__dict__["_ttk_param_list"] = ps
+        return tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
 
     def _set(self, name: str, value: torch.Tensor, dtype) -> None:
         cur = self.t.get(name)

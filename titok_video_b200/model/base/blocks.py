@@ -25,7 +25,9 @@ def _wants_grad(module: nn.Module, *inputs) -> bool:
         return False
     if any(isinstance(t, torch.Tensor) and t.requires_grad for t in inputs):
         return True
-    return any(p.requires_grad for p in module.parameters())
+    from ... import backward
+
+    return any(p.requires_grad for p in backward.stack_params(module))
 
 
 class _Stack(nn.Module):
@@ -90,7 +92,7 @@ class TiTokEncoder(_Stack):
             else:
                 with torch.no_grad():
                     flat = engine.flatten_clips(videos, dp)
-            z, codes, idx = backward.EncoderFn.apply(self, dp, consts, flat, *self.parameters())
+            z, codes, idx = backward.EncoderFn.apply(self, dp, consts, flat, *backward.stack_params(self))
             return z, codes, idx, dp
         with torch.no_grad():
             flat = engine.flatten_clips(videos, dp)
@@ -127,7 +129,7 @@ class TiTokDecoder(_Stack):
         if _wants_grad(self, tokens):
             from ... import backward
 
-            return backward.DecoderFn.apply(self, dp, tokens, *self.parameters()), dp
+            return backward.DecoderFn.apply(self, dp, tokens, *backward.stack_params(self)), dp
         with torch.no_grad():
             codes = tokens.detach().to(torch.bfloat16).contiguous()
             out = dp.buf("clips_out", (dp.plan.total_numel,))
