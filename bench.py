@@ -464,45 +464,8 @@ def main():
     # ---------------- e2e: pinned host clips -> H2D -> public API -> D2H of indices + reconstructions ----------------
     h2d_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
     SLOTS = 2
-    in_flat = [torch.empty((B * clip_numel,), dtype=torch.bfloat16, device=dev) for _ in range(SLOTS)]
-    in_slots = [views(f) for f in in_flat]
     full = args.e2e_full_recon
-    out_slots = [torch.empty((B * 3 * CLIP_A[0] * CLIP_A[1] * CLIP_A[2],) if full else (1,), dtype=torch.bfloat16, device=dev)
-                 for _ in range(SLOTS)]
-    idx_slots = [torch.empty((B * TOKENS_A,), dtype=torch.int32, device=dev) for _ in range(SLOTS)]
-    err_slots = [torch.empty((B, 2), dtype=torch.float64, device=dev) for _ in range(SLOTS)]
-    host_out = [torch.empty_like(out_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
-    host_idx = [torch.empty_like(idx_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
-    host_err = [torch.empty_like(err_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
-    ev_in = [torch.cuda.Event() for _ in range(SLOTS)]
-    ev_compute = [torch.cuda.Event() for _ in range(SLOTS)]
-    ev_out = [torch.cuda.Event() for _ in range(SLOTS)]
-    ev_consumed = [torch.cuda.Event() for _ in range(SLOTS)]
     main_stream = torch.cuda.current_stream()
-
-    def e2e_step(i):
-        sl = i % SLOTS
-        with torch.cuda.stream(h2d_stream):
-            h2d_stream.wait_event(ev_consumed[sl])  # the slot's previous contents were consumed by compute
-            in_flat[sl].copy_(host_flat[i % INPUT_SETS], non_blocking=True)
-            ev_in[sl].record()
-        main_stream.wait_event(ev_in[sl])
-        main_stream.wait_event(ev_out[sl])  # the slot's previous results have left the device
-        # the public API's default: one CUDA-graph replay per step; results = token indices + per-clip error
-        recon, d = step(in_slots[sl], use_graph=True, with_error=True)
-        ev_consumed[sl].record()
-        if full:
-            out_slots[sl].copy_(_flat_of(recon), non_blocking=True)
-        idx_slots[sl].copy_(d["indices"], non_blocking=True)
-        err_slots[sl].copy_(d["clip_error"], non_blocking=True)
-        ev_compute[sl].record()
-        with torch.cuda.stream(d2h_stream):
-            d2h_stream.wait_event(ev_compute[sl])
-            if full:
-                host_out[sl].copy_(out_slots[sl], non_blocking=True)
-            host_idx[sl].copy_(idx_slots[sl], non_blocking=True)
-            host_err[sl].copy_(err_slots[sl], non_blocking=True)
-            ev_out[sl].record()
 
     def _flat_of(recon):
         # the reconstructed clips are views of one flat workspace buffer (engine.split_clips)
@@ -510,26 +473,78 @@ def main():
         n = B * 3 * CLIP_A[0] * CLIP_A[1] * CLIP_A[2]
         return base.reshape(-1).as_strided((n,), (1,), base.storage_offset())
 
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    d2h_stream.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    w0 = time.perf_counter()
-    e0.record()
-    for i in range(args.steps):
-        e2e_step(i)
-    main_stream.wait_stream(d2h_stream)
-    e1.record()
-    barrier()
-    d2h_stream.synchronize()
-    w1 = time.perf_counter()
-    ms = torch.tensor([max(e0.elapsed_time(e1), 0.0), (w1 - w0) * 1e3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    e2e_ms = float(ms[0].item())
+    def e2e_leg(host_bufs, in_dtype):
+        """Timed region per step: H2D of the step's clips from pinned host memory (side stream), the public API call,
+        D2H of the results into pinned host memory (side stream). Returns (device ms, wall ms) per step, max over ranks."""
+        in_flat = [torch.empty((B * clip_numel,), dtype=in_dtype, device=dev) for _ in range(SLOTS)]
+        in_slots = [views(f) for f in in_flat]
+        out_slots = [torch.empty((B * clip_numel,) if full else (1,), dtype=torch.bfloat16, device=dev) for _ in range(SLOTS)]
+        idx_slots = [torch.empty((B * TOKENS_A,), dtype=torch.int32, device=dev) for _ in range(SLOTS)]
+        err_slots = [torch.empty((B, 2), dtype=torch.float64, device=dev) for _ in range(SLOTS)]
+        host_out = [torch.empty_like(out_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
+        host_idx = [torch.empty_like(idx_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
+        host_err = [torch.empty_like(err_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
+        ev_in = [torch.cuda.Event() for _ in range(SLOTS)]
+        ev_compute = [torch.cuda.Event() for _ in range(SLOTS)]
+        ev_out = [torch.cuda.Event() for _ in range(SLOTS)]
+        ev_consumed = [torch.cuda.Event() for _ in range(SLOTS)]
+
+        def e2e_step(i):
+            sl = i % SLOTS
+            with torch.cuda.stream(h2d_stream):
+                h2d_stream.wait_event(ev_consumed[sl])  # the slot's previous contents were consumed by compute
+                in_flat[sl].copy_(host_bufs[i % len(host_bufs)], non_blocking=True)
+                ev_in[sl].record()
+            main_stream.wait_event(ev_in[sl])
+            main_stream.wait_event(ev_out[sl])  # the slot's previous results have left the device
+            # the public API's default: one CUDA-graph replay per step; results = token indices + per-clip error
+            recon, d = step(in_slots[sl], use_graph=True, with_error=True)
+            ev_consumed[sl].record()
+            if full:
+                out_slots[sl].copy_(_flat_of(recon), non_blocking=True)
+            idx_slots[sl].copy_(d["indices"], non_blocking=True)
+            err_slots[sl].copy_(d["clip_error"], non_blocking=True)
+            ev_compute[sl].record()
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(ev_compute[sl])
+                if full:
+                    host_out[sl].copy_(out_slots[sl], non_blocking=True)
+                host_idx[sl].copy_(idx_slots[sl], non_blocking=True)
+                host_err[sl].copy_(err_slots[sl], non_blocking=True)
+                ev_out[sl].record()
+
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        d2h_stream.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        w0 = time.perf_counter()
+        ea.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        main_stream.wait_stream(d2h_stream)
+        eb.record()
+        barrier()
+        d2h_stream.synchronize()
+        w1 = time.perf_counter()
+        t = torch.tensor([max(ea.elapsed_time(eb), 0.0), (w1 - w0) * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0].item()), float(t[1].item())
+
+    e2e_ms, e2e_wall_ms = e2e_leg(host_flat, torch.bfloat16)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    # same leg fed with decoded uint8 frames (what the reference's dataset holds before `/255*2-1`, video_dataset.py:111-119):
+    # half the PCIe bytes, normalised on the device by ttk_normalize_u8 (bit-identical to the host expression)
+    host_u8 = [torch.randint(0, 256, (B * clip_numel,), generator=gen, dtype=torch.uint8).pin_memory() for _ in range(INPUT_SETS)]
+    u8_ms, u8_wall_ms = e2e_leg(host_u8, torch.uint8)
+    e2e_u8 = {"value": world * B * args.steps / (u8_ms * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": B * clip_numel,
+              "d2h_bytes_per_step": (B * clip_bytes if full else 0) + B * TOKENS_A * 4 + B * 16, "ms_per_step": u8_ms / args.steps,
+              "wall_ms_per_step": u8_wall_ms / args.steps,
+              "input": "uint8 frames [3,T,H,W] from pinned host memory (the reference's dataset output before normalisation), "
+                       "normalised on the device; everything else as `e2e`"}
+    del host_u8
 
     # ---------------- ragged stream: a NEW batch composition every step (what train.py / a tokenisation job feeds) ------
     # shapes and token counts drawn from the sampling ranges of configs/tiny.yaml (tiny.yaml:56-66); every step pays the
@@ -631,11 +646,11 @@ def main():
                                (" + full reconstructions" if args.e2e_full_recon else
                                 "; reconstructions stay on the device (--e2e-full-recon copies them too)")),
                     "ms_per_step": e2e_ms / args.steps,
-                    "wall_ms_per_step": float(ms[1].item()) / args.steps,
+                    "wall_ms_per_step": e2e_wall_ms / args.steps,
                     "api": "TiTok.tokenize_reconstruct_(clips, token_counts) from pinned host clips, 2-slot pipeline, CUDA-graph replay "
                            "(the value leg launches the same kernels one by one so that each can be timed with CUDA events)"},
             "gpu_launches": launches, "roofline": roofline, "whole_step": whole, "kernels": kernels, "clocks": clocks,
-            "cpu_baseline": cpu, "quantizer_microbench": vq, "ragged_stream": ragged, "train_step": train, "scaled_config": scaled,
+            "cpu_baseline": cpu, "quantizer_microbench": vq, "ragged_stream": ragged, "train_step": train, "scaled_config": scaled, "e2e_u8": e2e_u8,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

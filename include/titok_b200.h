@@ -155,6 +155,11 @@ int ttk_rope_table_gather(const int32_t* pos, const float* cs_table, int n_ids, 
 int ttk_clip_error(const void* a, const void* b, const int64_t* clip_offset, const int64_t* clip_numel, int n_clips,
                    int64_t max_clip_numel, double* out, ttk_stream_t stream);
 
+/* The step before the path: decoded uint8 frames -> clips in [-1, 1] (dataset/video_dataset.py:118-119:
+ * `chunk.to(dtype) / 255; chunk * 2 - 1` on bf16 tensors), bit-identical to that torch expression, so that a job can
+ * ship uint8 frames over PCIe (half the bytes of bf16 clips). src uint8 [n], dst bf16 [n], both 16-byte aligned. */
+int ttk_normalize_u8(const void* src, void* dst, int64_t n, ttk_stream_t stream);
+
 /* TiTokEncoder embed (blocks.py:95-97). src_row int32 [M]: >= 0 row of proj (patch), < 0 latent row. */
 int ttk_enc_embed(const void* proj, int64_t ldp, const int32_t* src_row, const float* mask_token, const float* w_t,
                   const float* w_p, const float* w_next, void* x_out, void* xn_out, int M, int width, int64_t ld,

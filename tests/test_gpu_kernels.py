@@ -551,3 +551,17 @@ def test_device_built_plan_equals_host_planner():
         assert torch.equal(got, want), name
     assert torch.equal(dp.rope.cpu()[:hp.M], torch.from_numpy(hp.rope))
     assert torch.equal(dp.clip_offset.cpu(), torch.tensor(hp.clip_offset)) and torch.equal(dp.clip_numel.cpu(), torch.tensor(hp.clip_numel))
+
+
+def test_normalize_u8_is_bit_identical_to_the_reference_expression():
+    """dataset/video_dataset.py:118-119 on bf16 tensors: `chunk.to(bf16) / 255` then `chunk * 2 - 1`."""
+    g = torch.Generator().manual_seed(0)
+    for n in (256, 16 * 1000 + 7, 3 * 8 * 64 * 48):
+        src = torch.randint(0, 256, (n,), generator=g, dtype=torch.uint8)
+        src[:256] = torch.arange(256, dtype=torch.uint8)  # every possible value
+        ref = (src.to(BF) / 255) * 2 - 1
+        sd = src.to(DEV)
+        out = torch.empty(n, dtype=BF, device=DEV)
+        lib().call("ttk_normalize_u8", P(sd), P(out), n, ST())
+        torch.cuda.synchronize()
+        assert torch.equal(out.cpu().view(torch.int16), ref.view(torch.int16))

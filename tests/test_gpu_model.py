@@ -344,3 +344,22 @@ def test_scaled_config_long_sequences():
     for k, p in model.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
     assert sum(float(p.grad.abs().sum()) for p in model.parameters()) > 0
+
+
+def test_uint8_frames_equal_host_normalised_clips(golden_stress):
+    """Decoded uint8 frames handed straight to the model give bit-identical tokens and reconstructions to clips that
+    were normalised on the host the way the reference's dataset does (video_dataset.py:118-119)."""
+    model = build_model(True).cuda().eval()
+    g = torch.Generator().manual_seed(4)
+    shapes, tcs = [(8, 64, 48), (4, 16, 24)], [16, 3]
+    raw = [torch.randint(0, 256, (3, *s), generator=g, dtype=torch.uint8) for s in shapes]
+    host = [((r.to(torch.bfloat16) / 255) * 2 - 1) for r in raw]
+    with torch.no_grad():
+        rec_a, d_a = model([h.cuda() for h in host], tcs)
+        rec_b, d_b = model([r.cuda() for r in raw], tcs)
+        rec_c, d_c = model.tokenize_reconstruct_([r.cuda() for r in raw], tcs)
+        rec_c = [r.clone() for r in rec_c]
+    assert torch.equal(d_a["indices"], d_b["indices"]) and torch.equal(d_a["indices"], d_c["indices"])
+    for a, b, c in zip(rec_a, rec_b, rec_c):
+        assert b.dtype == torch.bfloat16
+        assert torch.equal(a, b) and torch.equal(a, c)

@@ -59,6 +59,7 @@ SIGNATURES = {
     "ttk_build_plan": [_vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ttk_rope_table_gather": [_vp, _vp, _i, _vp, _i64, _vp],
     "ttk_clip_error": [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp],
+    "ttk_normalize_u8": [_vp, _vp, _i64, _vp],
     "ttk_patchify": [_vp, _vp, _i, _i, _i, _i, _vp, _i64, _i64, _vp],
     "ttk_unpatchify": [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp, _i64, _vp],
     # ---- training path (backward kernels)

@@ -413,6 +413,39 @@ __global__ void __launch_bounds__(256) clip_error_kernel(const __nv_bfloat16* __
   }
 }
 
+// uint8 frames -> normalised bf16 clips, rounding like the reference's dataset code on bf16 tensors
+// (dataset/video_dataset.py:118-119): y = bf16(bf16(bf16(u8) / 255) * 2 - 1). 16 pixels per thread (one 16-byte load, two
+// 16-byte stores). The 256 possible results are exact images of that torch expression (tests/test_gpu_kernels.py).
+__global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                           int64_t n) {
+  const int64_t nv = n / 16;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint4 v = ldg16_stream(src + i * 16);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const float q = bf16r(static_cast<float>((w[k] >> (8 * b)) & 0xffu) / 255.0f);
+        f[b] = q * 2.0f - 1.0f;  // q * 2 is exact in bf16; the subtraction is rounded once by the packed convert below
+      }
+      o[2 * k] = pack_bf16x2(f[0], f[1]);
+      o[2 * k + 1] = pack_bf16x2(f[2], f[3]);
+    }
+    stg16(dst + i * 16, make_uint4(o[0], o[1], o[2], o[3]));
+    stg16(dst + i * 16 + 8, make_uint4(o[4], o[5], o[6], o[7]));
+  }
+  // tail (n % 16 elements)
+  if (blockIdx.x == 0 && threadIdx.x < n - nv * 16) {
+    const int64_t i = nv * 16 + threadIdx.x;
+    const float q = bf16r(static_cast<float>(src[i]) / 255.0f);
+    dst[i] = __float2bfloat16_rn(q * 2.0f - 1.0f);
+  }
+}
+
 int fsq_make_consts(FsqConsts& c, int D, const float* half_l, const float* offset, const float* shift,
                     const float* half_width, const int32_t* basis, const int32_t* levels);
 
@@ -582,6 +615,20 @@ int ttk_clip_error(const void* a, const void* b, const int64_t* clip_offset, con
   if (bx > 4LL * num_sms()) bx = 4LL * num_sms();
   clip_error_kernel<<<dim3(static_cast<unsigned>(bx), static_cast<unsigned>(n_clips)), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), clip_offset, clip_numel, out);
+  return launch_status();
+}
+
+// dst bf16 [n] = normalised src uint8 [n] (both 16-byte aligned).
+int ttk_normalize_u8(const void* src, void* dst, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return TTK_OK;
+  if (!src || !dst) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) != 0) return TTK_ERR_ALIGNMENT;
+  int64_t blocks = (n / 16 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+  normalize_u8_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const uint8_t*>(src),
+                                                                     static_cast<__nv_bfloat16*>(dst), n);
   return launch_status();
 }
 

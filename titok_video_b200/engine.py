@@ -421,7 +421,18 @@ def to_host_ints(v) -> List[int]:
 
 
 def flatten_clips(videos: Sequence[torch.Tensor], dp: DevicePlan, name: str = "clips_in") -> torch.Tensor:
-    """Concatenate the clips into the plan's static flat bf16 input buffer (one cat kernel)."""
+    """Concatenate the clips into the plan's static flat bf16 input buffer (one cat kernel). uint8 clips (decoded
+    frames, values 0..255) are normalised to [-1, 1] by ttk_normalize_u8 on the way."""
+    if videos[0].dtype == torch.uint8:
+        # decoded frames: one cat into the uint8 staging buffer, normalised on the device (dataset/video_dataset.py:118-119)
+        raw = dp.buf(name + "_u8", (dp.plan.total_numel,), torch.uint8)
+        if len(videos) == 1 and videos[0].is_contiguous():
+            raw.copy_(videos[0].reshape(-1))
+        else:
+            torch.cat([v.reshape(-1) for v in videos], out=raw)
+        buf = dp.buf(name, (dp.plan.total_numel,))
+        _lib.call("ttk_normalize_u8", _ptr(raw), _ptr(buf), dp.plan.total_numel, _stream())
+        return buf
     buf = dp.buf(name, (dp.plan.total_numel,))
     if len(videos) == 1 and videos[0].dtype == torch.bfloat16 and videos[0].is_contiguous():
         buf.copy_(videos[0].reshape(-1))

@@ -18,6 +18,10 @@ from ... import engine
 from .transformer import ResidualAttentionBlock
 from .utils import RMSNorm, geglu_inner_dim, get_model_dims
 
+def _float_dtype(t: torch.Tensor) -> torch.dtype:
+    return t.dtype if t.is_floating_point() else torch.bfloat16
+
+
 def _wants_grad(module: nn.Module, *inputs) -> bool:
     """True when autograd has to see this forward: grad mode on and a parameter (or a tensor input) requires grad.
     The training path (titok_video_b200/backward.py) then records the activations the backward kernels need."""
@@ -103,8 +107,8 @@ class TiTokEncoder(_Stack):
     def forward(self, videos, token_counts, grids=None):
         z, _, _, _ = self.forward_impl(videos, token_counts, grids)
         if z.requires_grad:
-            return z.to(videos[0].dtype)
-        return z.clone().to(videos[0].dtype)
+            return z.to(_float_dtype(videos[0]))
+        return z.clone().to(_float_dtype(videos[0]))
 
 
 class TiTokDecoder(_Stack):

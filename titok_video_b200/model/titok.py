@@ -15,6 +15,11 @@ from .base.utils import init_weights
 from .quantizer.fsq import FSQ
 
 
+def _float_dtype(t: torch.Tensor) -> torch.dtype:
+    """dtype of results derived from a clip: uint8 clips (decoded frames) produce bf16 results."""
+    return t.dtype if t.is_floating_point() else torch.bfloat16
+
+
 class TiTok(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -37,9 +42,9 @@ class TiTok(nn.Module):
         z, codes, idx, _ = self.encoder.forward_impl(x, token_counts, grids, fsq=self.quantize)
         if z.requires_grad:  # training: FSQ with its straight-through gradient (fsq.py:48-51)
             x_q, d = self.quantize(z)
-            x_q, indices = x_q.to(x[0].dtype), d["indices"]
+            x_q, indices = x_q.to(_float_dtype(x[0])), d["indices"]
         else:
-            x_q = codes.clone().to(x[0].dtype)
+            x_q = codes.clone().to(_float_dtype(x[0]))
             indices = idx.clone()
         if split_indices:
             indices = torch.split(indices, engine.to_host_ints(token_counts), dim=0)
@@ -72,13 +77,13 @@ class TiTok(nn.Module):
             out, _ = self.decoder.forward_impl(codes, tcs, grids)
             from .. import backward
 
-            return backward.split_clips_autograd(out.to(x[0].dtype), dp.plan), {"indices": d["indices"]}
+            return backward.split_clips_autograd(out.to(_float_dtype(x[0])), dp.plan), {"indices": d["indices"]}
         out, _ = self.decoder.forward_impl(codes, tcs, grids)
         if out.requires_grad:  # frozen encoder, trainable decoder
             from .. import backward
 
-            return backward.split_clips_autograd(out.to(x[0].dtype), dp.plan), {"indices": idx.clone()}
-        recon = engine.split_clips(out.clone().to(x[0].dtype), dp.plan)
+            return backward.split_clips_autograd(out.to(_float_dtype(x[0])), dp.plan), {"indices": idx.clone()}
+        recon = engine.split_clips(out.clone().to(_float_dtype(x[0])), dp.plan)
         return recon, {"indices": idx.clone()}
 
     # ---- throughput path: no defensive copies, results live in the plan's workspace ---------------
