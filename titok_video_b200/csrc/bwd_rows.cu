@@ -42,6 +42,28 @@ struct Row {
   }
 };
 
+// Raw (still packed) row: lets a warp issue the loads of its NEXT row before it works on the current one, so that two
+// rows per warp are in flight (the row kernels are latency-bound at 32 resident warps per SM otherwise).
+template <int NV>
+struct RawRow {
+  uint4 q[NV];
+  __device__ __forceinline__ void load(const __nv_bfloat16* row, int lane) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) q[i] = ldg16(row + i * 256 + lane * 8);
+  }
+  __device__ __forceinline__ void unpack(Row<NV>& r) const {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t rr[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        r.v[i * 8 + 2 * e] = bf16_lo(rr[e]);
+        r.v[i * 8 + 2 * e + 1] = bf16_hi(rr[e]);
+      }
+    }
+  }
+};
+
 template <int NV>
 __device__ __forceinline__ void load_w(const float* w, int lane, float (&out)[NV * 8]) {
 #pragma unroll
@@ -78,16 +100,33 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
 #pragma unroll
     for (int i = 0; i < NV * 8; ++i) acc2[i] = 0.f;
   }
-  for (int row = blockIdx.x * BW_WARPS + wid; row < M; row += gridDim.x * BW_WARPS) {
-    Row<NV> u, g;
-    u.load(x + row * ld, lane);
+  const int stride = gridDim.x * BW_WARPS;
+  int row = blockIdx.x * BW_WARPS + wid;
+  RawRow<NV> nx, ny, ng, na;
+  if (row < M) {
+    nx.load(x + row * ld, lane);
+    if (y) ny.load(y + row * ld, lane);
+    ng.load(dy + row * ld, lane);
+    if (add) na.load(add + row * ld, lane);
+  }
+  for (; row < M; row += stride) {
+    Row<NV> u, g, a;
+    nx.unpack(u);
     if (y) {
       Row<NV> b;
-      b.load(y + row * ld, lane);
+      ny.unpack(b);
 #pragma unroll
       for (int i = 0; i < NV * 8; ++i) u.v[i] = bf16r(bf16r(u.v[i] * alpha) + b.v[i]);
     }
-    g.load(dy + row * ld, lane);
+    ng.unpack(g);
+    if (add) na.unpack(a);
+    if (row + stride < M) {  // next row's loads go out before this row's reductions
+      const int64_t nr = row + stride;
+      nx.load(x + nr * ld, lane);
+      if (y) ny.load(y + nr * ld, lane);
+      ng.load(dy + nr * ld, lane);
+      if (add) na.load(add + nr * ld, lane);
+    }
     bool second = false;
     if constexpr (SEL) second = sel[row] < 0;
     float ss = 0.f;
@@ -114,8 +153,6 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
     }
     dot = warp_sum(dot) / static_cast<float>(W);
     if (add) {
-      Row<NV> a;
-      a.load(add + row * ld, lane);
 #pragma unroll
       for (int i = 0; i < NV * 8; ++i) g.v[i] = fmaf(add_scale, a.v[i], rstd * (g.v[i] - u.v[i] * dot));
     } else {
@@ -225,26 +262,50 @@ __global__ void __launch_bounds__(256) move_rows_kernel(const __nv_bfloat16* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// out[c] += sum_r x[r, c] (fp32), total[0] += sum of everything. blockIdx.x walks 256-row slabs, threads own
-// column pairs.
+// out[c] += sum_r x[r, c] (fp32), total[0] += sum of everything. Block = 32 column groups (8 columns, one 16-byte load
+// each) x 8 row lanes; a CTA covers 128 rows x 256 columns (16 rows per thread in flight), reduces its row lanes
+// through shared memory and issues one atomic per column.
 // ------------------------------------------------------------------------------------------------
+constexpr int CS_ROWS = 128;
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int64_t M, int N,
                                                      float* __restrict__ out, float* __restrict__ total) {
-  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 256;
-  const int64_t r1 = min(M, r0 + 256);
+  __shared__ float red[8][32][9];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = (blockIdx.y * 32 + cx) * 8;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * CS_ROWS;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (col < N) {
+#pragma unroll 4
+    for (int i = 0; i < CS_ROWS / 8; ++i) {
+      const int64_t r = r0 + ry + i * 8;
+      if (r < M) {
+        const uint4 v = ldg16_stream(x + r * ld + col);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e] += bf16_lo(w[e]);
+          acc[2 * e + 1] += bf16_hi(w[e]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[ry][cx][e] = acc[e];
+  __syncthreads();
   float tsum = 0.f;
-  for (int c = threadIdx.x * 2; c < N; c += 512) {
-    float s0 = 0.f, s1 = 0.f;
-    for (int64_t r = r0; r < r1; ++r) {
-      const uint32_t v = *reinterpret_cast<const uint32_t*>(x + r * ld + c);
-      s0 += bf16_lo(v);
-      s1 += bf16_hi(v);
+  {
+    // thread t sums column (t % 8) of column group (t / 8) over the 8 row lanes
+    const int g = threadIdx.x >> 3, e = threadIdx.x & 7;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][g][e];
+    const int c = (blockIdx.y * 32 + g) * 8 + e;
+    if (c < N) {
+      if (out) atomicAdd(out + c, s);
+      tsum = s;
     }
-    if (out) {
-      atomicAdd(out + c, s0);
-      atomicAdd(out + c + 1, s1);
-    }
-    tsum += s0 + s1;
   }
   if (total) {
     __shared__ float part[8];
@@ -473,11 +534,13 @@ int ttk_scatter_rows(const void* src, int64_t lds, const int32_t* idx, void* dst
 int ttk_colsum(const void* x, int64_t ld, int64_t M, int N, float* out, float* total, cudaStream_t stream) {
   if (!x || (!out && !total)) return TTK_ERR_BAD_ARG;
   if (int e = check_device_sm100()) return e;
-  if (N <= 0 || N % 2 || ld % 2) return TTK_ERR_BAD_SHAPE;
+  if (N <= 0 || N % 8 || ld % 8) return TTK_ERR_BAD_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0) return TTK_ERR_ALIGNMENT;
   if (M <= 0) return TTK_OK;
-  const int64_t blocks = (M + 255) / 256;
+  const int64_t blocks = (M + CS_ROWS - 1) / CS_ROWS;
   if (blocks > 0x7fffffffLL) return TTK_ERR_BAD_SHAPE;
-  colsum_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, M, N, out, total);
+  colsum_kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>((N + 255) / 256)), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), ld, M, N, out, total);
   return launch_status();
 }
 

@@ -763,6 +763,8 @@ int ttk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M,
   GemmIo io{A, lda, W, ldw};
   if (w_is_kn) {
     if (N % 8 != 0) return TTK_ERR_ALIGNMENT;
+    // input-gradient GEMMs of the training path (N = 256 / 704 / 768): 256-wide tiles read the A operand half as often
+    if (N > 128) return launch_gemm<256, EPI_STORE, true>(io, p, stream);
     return launch_gemm<128, EPI_STORE, true>(io, p, stream);
   }
   if (N > 128) {

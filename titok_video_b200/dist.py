@@ -91,7 +91,7 @@ class GradientAllReducer:
         self.rank, self.world = _world(group)
         self.buckets: List[List[torch.nn.Parameter]] = []
         self._pending: List[int] = []
-        self._work: List[Optional[Tuple[object, torch.Tensor]]] = []
+        self._work: List[Optional[tuple]] = []
         self._handles = []
         if self.world == 1:
             return
@@ -115,8 +115,10 @@ class GradientAllReducer:
 
     def _launch(self, b: int) -> None:
         flat = torch.cat([p.grad.reshape(-1).float() for p in self.buckets[b]])
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._work[b] = (work, flat)
+        # NCCL averages inside the collective; gloo (CPU tests) has no AVG: sum now, divide in finish()
+        avg = dist.get_backend(self.group) == "nccl"
+        work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._work[b] = (work, flat, avg)
 
     def finish(self) -> None:
         """Call after loss.backward(): completes the outstanding all-reduces and writes the averaged gradients."""
@@ -129,13 +131,19 @@ class GradientAllReducer:
                 else:
                     self._pending[b] = len(params)
                     continue
-            work, flat = self._work[b]
+            work, flat, averaged = self._work[b]
             work.wait()
-            flat.div_(self.world)
+            if not averaged:
+                flat.div_(self.world)
             off = 0
             for p in params:
                 n = p.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                g = flat[off:off + n].view_as(p)
+                # re-point .grad at the averaged bucket (no copy kernels) when the dtypes agree
+                if p.grad.dtype == g.dtype:
+                    p.grad = g
+                else:
+                    p.grad.copy_(g)
                 off += n
             self._work[b] = None
             self._pending[b] = len(params)
