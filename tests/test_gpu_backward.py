@@ -494,3 +494,61 @@ def test_discriminator_step_like_loss_module():
     assert all(p.grad is None for p in disc.parameters())
     for a, b in zip(fk, fo):
         assert cos_sim(a.grad.float().cpu(), b.grad) > 0.98
+
+
+def test_encode_then_decode_under_grad_equals_forward():
+    """TiTok.encode / TiTok.decode called separately with grad enabled (titok.py:47-66) record the same graph as
+    TiTok.forward: identical indices, reconstructions and parameter gradients; token_counts / grids may be tensors."""
+    model = build_model(True).to(DEV).train()
+    clips = [c.to(DEV) for c in O.make_clips([(8, 32, 32), (4, 16, 24)], 2)]
+    tcs = torch.tensor([8, 3], dtype=torch.int32)
+    grids = torch.tensor([[8, 32, 32], [4, 16, 24]], dtype=torch.int32)
+
+    def loss_of(recon):
+        return torch.stack([(r_.float() - c.float()).abs().mean() for c, r_ in zip(clips, recon)]).mean()
+
+    model.zero_grad(set_to_none=True)
+    rec_a, d_a = model(clips, tcs)
+    loss_of(rec_a).backward()
+    g_a = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    x_q, d_b = model.encode(clips, tcs.to(DEV), grids)
+    assert x_q.requires_grad and x_q.shape == (11, 5)
+    rec_b = model.decode(x_q, tcs, grids.to(DEV))
+    loss_of(rec_b).backward()
+    assert torch.equal(d_a["indices"], d_b["indices"])
+    for a, b in zip(rec_a, rec_b):
+        assert torch.equal(a.detach(), b.detach())
+    for k, p in model.named_parameters():
+        # the weight-gradient reductions use atomics: same values up to fp32 summation order
+        assert torch.allclose(p.grad, g_a[k], rtol=1e-3, atol=1e-6 + 1e-4 * float(g_a[k].abs().max())), k
+    # decoder alone on detached codes: only decoder parameters receive gradients
+    model.zero_grad(set_to_none=True)
+    rec_c = model.decode(x_q.detach(), tcs, grids)
+    loss_of(rec_c).backward()
+    assert all(p.grad is None for p in model.encoder.parameters())
+    assert all(p.grad is not None for p in model.decoder.parameters())
+
+
+def test_gradient_accumulation_over_two_microbatches():
+    """Two backward passes without zero_grad accumulate (`+=`) like autograd does for any module."""
+    model = build_model(False).to(DEV).train()
+    a = [c.to(DEV) for c in O.make_clips([(4, 32, 32)], 5)]
+    b = [c.to(DEV) for c in O.make_clips([(8, 16, 24)], 6)]
+
+    def run(clips, tcs):
+        rec, _ = model(clips, tcs)
+        (rec[0].float() - clips[0].float()).abs().mean().backward()
+
+    model.zero_grad(set_to_none=True)
+    run(a, [5])
+    ga = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    run(b, [7])
+    gb = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    run(a, [5])
+    run(b, [7])
+    for k, p in model.named_parameters():
+        want = ga[k] + gb[k]
+        assert torch.allclose(p.grad, want, rtol=2e-3, atol=1e-6 + 2e-4 * float(want.abs().max())), k
