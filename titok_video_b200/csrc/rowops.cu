@@ -270,16 +270,23 @@ __global__ void __launch_bounds__(256) patchify_kernel(const __nv_bfloat16* __re
                                                        const int64_t* __restrict__ geom, int C, int P0, int P1,
                                                        __nv_bfloat16* __restrict__ patches, int64_t ldp, int64_t G) {
   extern __shared__ uint4 patch_smem[];  // [PATCH_CHUNK][runs + 1] 16-byte cells (+1: bank-conflict padding)
+  __shared__ int64_t sgeom[PATCH_CHUNK * 4];  // the chunk's geometry, read once (not once per 16-byte run)
   const int runs = C * P0 * P1;
   const int pitch = runs + 1;
   const int64_t g0 = static_cast<int64_t>(blockIdx.x) * PATCH_CHUNK;
   const int np = static_cast<int>(min(static_cast<int64_t>(PATCH_CHUNK), G - g0));
-  for (int i = threadIdx.x; i < PATCH_CHUNK * runs; i += blockDim.x) {
+  if (threadIdx.x < np * 4) sgeom[threadIdx.x] = geom[g0 * 4 + threadIdx.x];
+  __syncthreads();
+  const int total = PATCH_CHUNK * runs;
+#pragma unroll 3
+  for (int i = threadIdx.x; i < total; i += 256) {
     const int pi = i % PATCH_CHUNK, rr = i / PATCH_CHUNK;
-    if (pi < np) patch_smem[pi * pitch + rr] = ldg16_stream(clips + patch_run_offset(geom + (g0 + pi) * 4, rr, P0, P1));
+    if (pi < np) patch_smem[pi * pitch + rr] = ldg16_stream(clips + patch_run_offset(sgeom + pi * 4, rr, P0, P1));
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < np * runs; i += blockDim.x) {
+  const int total_out = np * runs;
+#pragma unroll 3
+  for (int i = threadIdx.x; i < total_out; i += 256) {
     const int pi = i / runs, rr = i - pi * runs;
     stg16(patches + (g0 + pi) * ldp + rr * 8, patch_smem[pi * pitch + rr]);
   }
@@ -292,18 +299,27 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const __nv_bfloat16* __
                                                          const int64_t* __restrict__ geom, int C, int P0, int P1,
                                                          __nv_bfloat16* __restrict__ clips, int64_t G) {
   extern __shared__ uint4 patch_smem[];
+  __shared__ int64_t sgeom[PATCH_CHUNK * 4];
+  __shared__ int srow[PATCH_CHUNK];
   const int runs = C * P0 * P1;
   const int pitch = runs + 1;
   const int64_t g0 = static_cast<int64_t>(blockIdx.x) * PATCH_CHUNK;
   const int np = static_cast<int>(min(static_cast<int64_t>(PATCH_CHUNK), G - g0));
-  for (int i = threadIdx.x; i < np * runs; i += blockDim.x) {
+  if (threadIdx.x < np * 4) sgeom[threadIdx.x] = geom[g0 * 4 + threadIdx.x];
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + np) srow[threadIdx.x - 128] = patch_row[g0 + threadIdx.x - 128];
+  __syncthreads();
+  const int total_in = np * runs;
+#pragma unroll 3
+  for (int i = threadIdx.x; i < total_in; i += 256) {
     const int pi = i / runs, rr = i - pi * runs;
-    patch_smem[pi * pitch + rr] = ldg16_stream(proj + static_cast<int64_t>(patch_row[g0 + pi]) * ldp + rr * 8);
+    patch_smem[pi * pitch + rr] = ldg16_stream(proj + static_cast<int64_t>(srow[pi]) * ldp + rr * 8);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < PATCH_CHUNK * runs; i += blockDim.x) {
+  const int total = PATCH_CHUNK * runs;
+#pragma unroll 3
+  for (int i = threadIdx.x; i < total; i += 256) {
     const int pi = i % PATCH_CHUNK, rr = i / PATCH_CHUNK;
-    if (pi < np) stg16(clips + patch_run_offset(geom + (g0 + pi) * 4, rr, P0, P1), patch_smem[pi * pitch + rr]);
+    if (pi < np) stg16(clips + patch_run_offset(sgeom + pi * 4, rr, P0, P1), patch_smem[pi * pitch + rr]);
   }
 }
 
