@@ -255,6 +255,40 @@ int ttk_dec_embed_train(const void* codes, int token_size, const int32_t* src_ro
                         const float* mask_token, const float* w_t, const float* w_p, const float* w_next, void* x_out,
                         void* xn_out, void* e0_out, int M, int width, int64_t ld, ttk_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Native launch sequencers: one call enqueues every kernel of the transformer layers of a stack
+ * (ResidualAttentionBlock.forward, transformer.py:126-146, and its backward) -- the same kernels in the same order as
+ * the per-kernel entry points above; they exist because at the reference's batch size the step is bound by the host's
+ * launch rate. weights: HOST int64 [n_layers][9] of device pointers {to_qkv, out_proj, w12, w3 (bf16), pre_ln,
+ * attn_post_ln, ffn_norm, ffd_post_ln, next_ln (fp32; 0 = the layer has no such norm)}; next_ln = pre_ln of layer i+1,
+ * ln_post after the last layer.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ttk_layers_desc {
+  int32_t M, width, gqa, inner, n_layers, n_attn_work, n_dkv_work, n_dq_work;
+  float alpha, softmax_scale;
+  const float* rope;      /* [M,60] */
+  const void* attn_work;  /* ttk_attn_varlen_fwd work list */
+  const void* dkv_work;   /* ttk_attn_bwd_dkv work list (backward only) */
+  const void* dq_work;    /* ttk_attn_bwd_dq work list (backward only) */
+  const int64_t* weights; /* host */
+} ttk_layers_desc;
+
+/* Inference: x, xn [M,width] updated in place; qkv [M,2w+2g], att [M,w], h [M,inner] scratch; y [M,w] scratch selects the
+ * unfused residual path (required unless width == 256). */
+int ttk_layers_fwd(const ttk_layers_desc* d, void* x, void* xn, void* qkv, void* att, void* h, void* y, ttk_stream_t stream);
+
+/* Training forward: slab bf16 [n_layers][per_layer]; offs HOST int64 [11] = element offsets of {qkv, att, o, y_a, x_f, xn_f,
+ * h12, h, y_f, x_n, xn_n} in a layer's block; lse fp32 [n_layers][width/64][M]. */
+int ttk_layers_fwd_train(const ttk_layers_desc* d, const void* x0, const void* xn0, void* slab, int64_t per_layer,
+                         const int64_t* offs, float* lse, ttk_stream_t stream);
+
+/* Backward: g_in = dL/dx after the last layer; work bf16 scratch with HOST int64 [11] offsets woffs = {du_f, dh, dh12, dxn,
+ * g_f, du_a, d_att, dqkv, dO, g_a, g_b}; delta fp32 [width/64][M] scratch; grads HOST int64 [n_layers][8] device pointers of
+ * the fp32 gradients {ffd_post_ln, w3, w12, ffn_norm, attn_post_ln, out_proj, to_qkv, pre_ln}. *g_out = dL/dx0 (g_a or g_b). */
+int ttk_layers_bwd(const ttk_layers_desc* d, const void* x0, const void* xn0, const void* slab, int64_t per_layer,
+                   const int64_t* offs, const float* lse, const void* g_in, void* work, const int64_t* woffs, float* delta,
+                   const int64_t* grads, void** g_out, ttk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,4 +30,4 @@ print(f"host issue time {1e3*(t1-t0)/10:.2f} ms/step, with final sync {1e3*(t2-t
 pr = cProfile.Profile(); pr.enable()
 for _ in range(10): step()
 pr.disable(); torch.cuda.synchronize()
-s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(28); print(s.getvalue()[:6000])
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(22); print(s.getvalue()[:5000])

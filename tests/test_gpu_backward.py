@@ -573,3 +573,32 @@ def test_a_few_optimizer_steps_reduce_the_loss(enc, dec):
         opt.step()
         losses.append(float(loss.detach()))
     assert losses[-1] < losses[0] - 1e-3, losses
+
+
+def test_native_sequencer_equals_per_kernel_launches(monkeypatch):
+    """ttk_layers_fwd / ttk_layers_fwd_train / ttk_layers_bwd enqueue the same kernels as the per-kernel Python paths:
+    identical tokens and reconstructions (bit-exact), gradients equal up to the fp32 order of the atomic reductions."""
+    from titok_video_b200 import backward, engine
+
+    clips = [c.to(DEV) for c in O.make_clips([(8, 64, 48), (4, 16, 24), (8, 32, 40)], 3)]
+    tcs = [16, 3, 40]
+
+    def run(native):
+        monkeypatch.setattr(engine, "NATIVE_SEQ", native)
+        monkeypatch.setattr(backward, "NATIVE_SEQ", native)
+        model = build_model(True).to(DEV)
+        with torch.no_grad():
+            rec_i, d_i = model(clips, tcs)
+        model.train()
+        rec, d = model(clips, tcs)
+        torch.stack([(r_.float() - c.float()).abs().mean() for c, r_ in zip(clips, rec)]).mean().backward()
+        torch.cuda.synchronize()
+        return ([r_.clone() for r_ in rec_i], d_i["indices"].clone(), [r_.detach().clone() for r_ in rec], d["indices"].clone(),
+                {k: p.grad.clone() for k, p in model.named_parameters()})
+
+    a, b = run(True), run(False)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[3], b[3])
+    for x, y in zip(a[0] + a[2], b[0] + b[2]):
+        assert torch.equal(x, y)
+    for k in a[4]:
+        assert torch.allclose(a[4][k], b[4][k], rtol=1e-3, atol=1e-6 + 1e-4 * float(b[4][k].abs().max())), k

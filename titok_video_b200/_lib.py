@@ -77,6 +77,9 @@ SIGNATURES = {
     "ttk_head_bwd": [_vp, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "ttk_dec_in_bwd": [_vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "ttk_enc_embed_train": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp],
+    "ttk_layers_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ttk_layers_fwd_train": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "ttk_layers_bwd": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ttk_dec_embed_train": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp],
 }
 _RESTYPES = {"ttk_strerror": c_char_p}
@@ -109,10 +112,25 @@ def set_profiler(p) -> None:
     _PROFILER = p
 
 
-def call(name: str, *args) -> None:
-    """Invoke an int-returning kernel entry point and raise on a non-zero status."""
+class LayersDesc(ctypes.Structure):
+    """ttk_layers_desc of include/titok_b200.h."""
+    _fields_ = [("M", c_int32), ("width", c_int32), ("gqa", c_int32), ("inner", c_int32), ("n_layers", c_int32),
+                ("n_attn_work", c_int32), ("n_dkv_work", c_int32), ("n_dq_work", c_int32),
+                ("alpha", c_float), ("softmax_scale", c_float),
+                ("rope", c_void_p), ("attn_work", c_void_p), ("dkv_work", c_void_p), ("dq_work", c_void_p),
+                ("weights", c_void_p)]
+
+
+def profiling() -> bool:
+    """True while a per-kernel profiler is installed: launch sequences then go kernel by kernel through call()."""
+    return _PROFILER is not None
+
+
+def call(name: str, *args, launches: int = 1) -> None:
+    """Invoke an int-returning kernel entry point and raise on a non-zero status. `launches`: kernels the entry point
+    enqueues (1 for every kernel entry point, more for the native sequencers)."""
     global LAUNCHES
-    LAUNCHES += 1
+    LAUNCHES += launches
     if _PROFILER is None:
         check(getattr(_lib, name)(*args), name)
     else:

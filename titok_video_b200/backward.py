@@ -13,13 +13,15 @@ in flight before their backwards (generator + discriminator passes, gradient acc
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import Dict, List, Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
-from .engine import DevicePlan, PreparedStack, _ptr, _stream, _vp, patch_feature_perm, prepared
+from .engine import NATIVE_SEQ, DevicePlan, PreparedStack, _ptr, _stream, _vp, layers_desc, patch_feature_perm_on, prepared
 
 bf16 = torch.bfloat16
 
@@ -28,25 +30,11 @@ def _new(shape, device, dtype=bf16) -> torch.Tensor:
     return torch.empty(shape, dtype=dtype, device=device)
 
 
-class Slab:
-    """One allocation carved into contiguous 2-D bf16 blocks (torch.empty costs ~3 us a call; a layer needs a dozen)."""
-
-    def __init__(self, device, n_elems: int):
-        self.buf = torch.empty(n_elems + 8, dtype=bf16, device=device)
-        self.off = 0
-
-    def take(self, rows: int, cols: int) -> torch.Tensor:
-        n = rows * cols
-        t = self.buf[self.off:self.off + n].view(rows, cols)
-        self.off += (n + 7) // 8 * 8  # keep every block 16-byte aligned
-        return t
-
-
 class Tape:
     """Activations of one stack forward, kept for its backward."""
 
     def __init__(self):
-        self.layers: List[Dict[str, torch.Tensor]] = []
+        self.lt = None  # LayerTape of the transformer layers
         self.t: Dict[str, torch.Tensor] = {}
 
 
@@ -71,6 +59,49 @@ def _rmsnorm_bwd(st, x, w, dy, dx, dw, *, y=None, alpha=1.0, add=None, add_scale
               float(add_scale), _ptr(dx), _ptr(dw), _ptr(dw2), M, width, x.stride(0), st)
 
 
+# block order inside a layer's slab (ttk_layers_fwd_train) and inside the backward work buffer (ttk_layers_bwd)
+F_QKV, F_ATT, F_O, F_YA, F_XF, F_XNF, F_H12, F_H, F_YF, F_XN, F_XNN = range(11)
+B_DUF, B_DH, B_DH12, B_DXN, B_GF, B_DUA, B_DATT, B_DQKV, B_DO, B_G0, B_G1 = range(11)
+_LAYOUTS: Dict[tuple, tuple] = {}
+
+
+def _layouts(M: int, w: int, gqa: int, inner: int):
+    """(forward cols, forward offsets, per-layer elements, backward cols, backward offsets, work elements): element
+    offsets of the 2-D bf16 blocks, every block 16-byte aligned. Cached per shape."""
+    key = (M, w, gqa, inner)
+    hit = _LAYOUTS.get(key)
+    if hit is None:
+        ldq = 2 * w + 2 * gqa
+
+        def lay(cols):
+            offs, tot = [], 0
+            for c in cols:
+                offs.append(tot)
+                tot += (M * c + 7) // 8 * 8
+            return np.asarray(offs, dtype=np.int64), tot
+
+        fcols = [ldq, w, w, w, w, w, 2 * inner, inner, w, w, w]
+        bcols = [w, inner, 2 * inner, w, w, w, w, ldq, w, w, w]
+        foffs, ftot = lay(fcols)
+        boffs, btot = lay(bcols)
+        if len(_LAYOUTS) > 256:
+            _LAYOUTS.clear()
+        hit = (fcols, foffs, ftot, bcols, boffs, btot)
+        _LAYOUTS[key] = hit
+    return hit
+
+
+class LayerTape:
+    """Activations of all layers of one stack forward: one bf16 slab [n_layers][per_layer] + the log-sum-exps."""
+
+    def __init__(self, slab, per_layer, cols, offs, lse, x0, xn0, M):
+        self.slab, self.per_layer, self.cols, self.offs, self.lse, self.x0, self.xn0, self.M = slab, per_layer, cols, offs, lse, x0, xn0, M
+
+    def view(self, layer: int, col: int) -> torch.Tensor:
+        o = layer * self.per_layer + int(self.offs[col])
+        return self.slab[o:o + self.M * self.cols[col]].view(self.M, self.cols[col])
+
+
 def _layers_train(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tensor, tape: Tape):
     """ResidualAttentionBlock.forward (transformer.py:126-146), recording per-layer activations."""
     M, w = x.shape
@@ -81,36 +112,41 @@ def _layers_train(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torc
     L = m.num_layers
     alpha = float(2 * L)
     st = _stream()
+    fcols, foffs, per_layer, _, _, _ = _layouts(M, w, gqa, inner)
+    slab = torch.empty(L * per_layer, dtype=bf16, device=dev)
+    lse_all = torch.empty((L, hq, M), dtype=torch.float32, device=dev)
+    lt = LayerTape(slab, per_layer, fcols, foffs, lse_all, x, xn, M)
+    tape.lt = lt
+    if NATIVE_SEQ and not _lib.profiling():
+        d = layers_desc(m, W, dp, M)
+        _lib.call("ttk_layers_fwd_train", ctypes.byref(d), _ptr(x), _ptr(xn), _ptr(slab), per_layer, _vp(foffs.ctypes.data),
+                  _ptr(lse_all), st, launches=8 * L)
+        return lt.view(L - 1, F_XN), lt.view(L - 1, F_XNN)
     work = dp.attn_work(hq, hkv)
     scale = 1.0 / math.sqrt(64.0)
     T = W.t
     for i in range(L):
         mode = 0 if i == 0 else 1
-        sl = Slab(dev, M * (2 * w + 2 * gqa + 8 * w + 3 * inner) + 128)
-        qkv = sl.take(M, 2 * w + 2 * gqa)
-        att, o = sl.take(M, w), sl.take(M, w)
-        lse = _new((hq, M), dev, torch.float32)
+        qkv, att, o, lse = lt.view(i, F_QKV), lt.view(i, F_ATT), lt.view(i, F_O), lse_all[i]
         _lib.call("ttk_gemm_qkv_rope", _ptr(xn), xn.stride(0), _ptr(T[f"to_qkv{i}"]), w, M, w, w, gqa, _ptr(dp.rope),
                   _ptr(qkv), qkv.stride(0), st)
         _lib.call("ttk_attn_varlen_fwd_train", _ptr(qkv), qkv.stride(0), M, w, gqa, _ptr(work), work.shape[0], scale,
                   _ptr(att), att.stride(0), _ptr(o), _ptr(lse), st)
-        y_a = sl.take(M, w)
+        y_a = lt.view(i, F_YA)
         _gemm(st, att, T[f"out_proj{i}"], y_a, w, w)
-        x_f, xn_f = sl.take(M, w), sl.take(M, w)
+        x_f, xn_f = lt.view(i, F_XF), lt.view(i, F_XNF)
         _lib.call("ttk_resid_norm", _ptr(x), _ptr(y_a), _ptr(x_f), _ptr(xn_f), _ptr(T.get(f"attn_post_ln{i}")),
                   _ptr(T[f"ffn_norm{i}"]), alpha, mode, M, w, w, st)
-        h12 = sl.take(M, 2 * inner)
+        h12 = lt.view(i, F_H12)
         _gemm(st, xn_f, T[f"w12_{i}"], h12, 2 * inner, w)
-        h = sl.take(M, inner)
+        h = lt.view(i, F_H)
         _lib.call("ttk_geglu_fwd", _ptr(h12), h12.stride(0), inner, _ptr(h), h.stride(0), M, st)
-        y_f = sl.take(M, w)
+        y_f = lt.view(i, F_YF)
         _gemm(st, h, T[f"w3_{i}"], y_f, w, inner)
-        x_n, xn_n = sl.take(M, w), sl.take(M, w)
+        x_n, xn_n = lt.view(i, F_XN), lt.view(i, F_XNN)
         w_next = T[f"pre_ln{i + 1}"] if i + 1 < L else T["ln_post"]
         _lib.call("ttk_resid_norm", _ptr(x_f), _ptr(y_f), _ptr(x_n), _ptr(xn_n), _ptr(T.get(f"ffd_post_ln{i}")),
                   _ptr(w_next), alpha, mode, M, w, w, st)
-        tape.layers.append(dict(x_a=x, xn_a=xn, qkv=qkv, att=att, o=o, lse=lse, y_a=y_a, x_f=x_f, xn_f=xn_f, h12=h12,
-                                h=h, y_f=y_f))
         x, xn = x_n, xn_n
     return x, xn
 
@@ -174,16 +210,33 @@ def decoder_forward_train(m, dp: DevicePlan, codes: torch.Tensor):
 # --------------------------------------------------------------------------------------------------
 # backward
 # --------------------------------------------------------------------------------------------------
+_GRAD_KEYS = ("ffd_post_ln{i}", "w3_{i}", "w12_{i}", "ffn_norm{i}", "attn_post_ln{i}", "out_proj{i}", "to_qkv{i}", "pre_ln{i}")
+
+
 def _zero_grads(W: PreparedStack) -> Dict[str, torch.Tensor]:
     """fp32 zero buffers with the shapes of the prepared (kernel-layout) parameters: views of ONE flat buffer (one
     memset per stack; every view starts on a 16-byte boundary for the vector reductions of ttk_gemm_wgrad)."""
-    offs, total = {}, 0
-    for k, v in W.t.items():
-        offs[k] = total
-        total += (v.numel() + 3) // 4 * 4
+    lay = W.__dict__.get("_grad_layout")
+    if lay is None or lay[0] != tuple((k, tuple(v.shape)) for k, v in W.t.items()):
+        offs, total = {}, 0
+        for k, v in W.t.items():
+            offs[k] = total
+            total += (v.numel() + 3) // 4 * 4
+        L = W.module.num_layers
+        tab = np.full((L, len(_GRAD_KEYS)), -1, dtype=np.int64)  # element offsets of the layers' gradients, -1 = absent
+        for i in range(L):
+            for j, pat in enumerate(_GRAD_KEYS):
+                k = pat.format(i=i)
+                if k in offs:
+                    tab[i, j] = offs[k]
+        lay = (tuple((k, tuple(v.shape)) for k, v in W.t.items()), offs, total, tab)
+        W._grad_layout = lay
+    _, offs, total, _ = lay
     dev = next(iter(W.t.values())).device
     flat = torch.zeros(total, dtype=torch.float32, device=dev)
-    return {k: flat[offs[k]:offs[k] + v.numel()].view(v.shape) for k, v in W.t.items()}
+    grads = {k: flat[offs[k]:offs[k] + v.numel()].view(v.shape) for k, v in W.t.items()}
+    grads["__flat__"] = flat
+    return grads
 
 
 def _layers_backward(m, W: PreparedStack, dp: DevicePlan, tape: Tape, g: torch.Tensor, grads) -> torch.Tensor:
@@ -196,52 +249,74 @@ def _layers_backward(m, W: PreparedStack, dp: DevicePlan, tape: Tape, g: torch.T
     L = m.num_layers
     alpha = float(2 * L)
     st = _stream()
+    lt: LayerTape = tape.lt
+    _, _, _, bcols, boffs, btot = _layouts(M, w, gqa, inner)
+    work = torch.empty(btot, dtype=bf16, device=dev)  # temporaries are reused by every layer (stream order)
+    delta = _new((hq, M), dev, torch.float32)
+
+    def wv(col: int) -> torch.Tensor:
+        o = int(boffs[col])
+        return work[o:o + M * bcols[col]].view(M, bcols[col])
+
+    if NATIVE_SEQ and not _lib.profiling():
+        d = layers_desc(m, W, dp, M, backward=True)
+        flat = grads["__flat__"]
+        tab = W._grad_layout[3]
+        gptr = np.where(tab >= 0, flat.data_ptr() + 4 * tab, 0).astype(np.int64)
+        g_out = ctypes.c_void_p(0)
+        n_launch = sum(14 + (2 if i > 0 else 0) for i in range(L))
+        _lib.call("ttk_layers_bwd", ctypes.byref(d), _ptr(lt.x0), _ptr(lt.xn0), _ptr(lt.slab), lt.per_layer,
+                  _vp(lt.offs.ctypes.data), _ptr(lt.lse), _ptr(g), _ptr(work), _vp(boffs.ctypes.data), _ptr(delta),
+                  _vp(gptr.ctypes.data), ctypes.byref(g_out), st, launches=n_launch)
+        res = wv(B_G0) if g_out.value == wv(B_G0).data_ptr() else wv(B_G1)
+        assert res.data_ptr() == g_out.value
+        return res
     scale = 1.0 / math.sqrt(64.0)
     T = W.t
     wk_dkv, wk_dq = dp.attn_bwd_work(hq, hkv)
     for i in reversed(range(L)):
-        t = tape.layers[i]
         mode = 0 if i == 0 else 1
         c = alpha if mode == 1 else 1.0
-        sl = Slab(dev, M * (7 * w + 3 * inner + 2 * w + 2 * gqa) + 128)
+        x_a = lt.x0 if i == 0 else lt.view(i - 1, F_XN)
+        xn_a = lt.xn0 if i == 0 else lt.view(i - 1, F_XNN)
+        x_f = lt.view(i, F_XF)
         # ---- GEGLU block: x_out = x_f + y_f | RMSNorm(alpha x_f + y_f)
         if mode == 1:
-            du = sl.take(M, w)
-            _rmsnorm_bwd(st, t["x_f"], T[f"ffd_post_ln{i}"], g, du, grads[f"ffd_post_ln{i}"], y=t["y_f"], alpha=alpha)
+            du = wv(B_DUF)
+            _rmsnorm_bwd(st, x_f, T[f"ffd_post_ln{i}"], g, du, grads[f"ffd_post_ln{i}"], y=lt.view(i, F_YF), alpha=alpha)
         else:
             du = g
-        dh = sl.take(M, inner)
+        dh = wv(B_DH)
         _gemm(st, du, T[f"w3_{i}"], dh, inner, w, kn=1)
-        _wgrad(st, du, t["h"], grads[f"w3_{i}"])
-        dh12 = sl.take(M, 2 * inner)
-        _lib.call("ttk_geglu_bwd", _ptr(t["h12"]), 2 * inner, inner, _ptr(dh), inner, _ptr(dh12), 2 * inner, M, st)
-        dxn = sl.take(M, w)
+        _wgrad(st, du, lt.view(i, F_H), grads[f"w3_{i}"])
+        dh12 = wv(B_DH12)
+        _lib.call("ttk_geglu_bwd", _ptr(lt.view(i, F_H12)), 2 * inner, inner, _ptr(dh), inner, _ptr(dh12), 2 * inner, M, st)
+        dxn = wv(B_DXN)
         _gemm(st, dh12, T[f"w12_{i}"], dxn, w, 2 * inner, kn=1)
-        _wgrad(st, dh12, t["xn_f"], grads[f"w12_{i}"])
-        g_f = sl.take(M, w)
-        _rmsnorm_bwd(st, t["x_f"], T[f"ffn_norm{i}"], dxn, g_f, grads[f"ffn_norm{i}"], add=du, add_scale=c)
+        _wgrad(st, dh12, lt.view(i, F_XNF), grads[f"w12_{i}"])
+        g_f = wv(B_GF)
+        _rmsnorm_bwd(st, x_f, T[f"ffn_norm{i}"], dxn, g_f, grads[f"ffn_norm{i}"], add=du, add_scale=c)
         # ---- attention block: x_f = x_a + y_a | RMSNorm(alpha x_a + y_a)
         if mode == 1:
-            du = sl.take(M, w)
-            _rmsnorm_bwd(st, t["x_a"], T[f"attn_post_ln{i}"], g_f, du, grads[f"attn_post_ln{i}"], y=t["y_a"], alpha=alpha)
+            du = wv(B_DUA)
+            _rmsnorm_bwd(st, x_a, T[f"attn_post_ln{i}"], g_f, du, grads[f"attn_post_ln{i}"], y=lt.view(i, F_YA), alpha=alpha)
         else:
             du = g_f
-        d_att = sl.take(M, w)
+        d_att = wv(B_DATT)
         _gemm(st, du, T[f"out_proj{i}"], d_att, w, w, kn=1)
-        _wgrad(st, du, t["att"], grads[f"out_proj{i}"])
-        qkv = t["qkv"]
-        dqkv = sl.take(M, qkv.shape[1])
-        dO = sl.take(M, w)
-        delta = _new((hq, M), dev, torch.float32)
-        _lib.call("ttk_attn_bwd_prep", _ptr(d_att), w, _ptr(t["o"]), w, _ptr(qkv), qkv.stride(0), M, w, _ptr(dO), w,
+        _wgrad(st, du, lt.view(i, F_ATT), grads[f"out_proj{i}"])
+        qkv = lt.view(i, F_QKV)
+        dqkv, dO = wv(B_DQKV), wv(B_DO)
+        _lib.call("ttk_attn_bwd_prep", _ptr(d_att), w, _ptr(lt.view(i, F_O)), w, _ptr(qkv), qkv.stride(0), M, w, _ptr(dO), w,
                   _ptr(dqkv), dqkv.stride(0), _ptr(delta), st)
         for name, wk in (("ttk_attn_bwd_dkv", wk_dkv), ("ttk_attn_bwd_dq", wk_dq)):
-            _lib.call(name, _ptr(qkv), qkv.stride(0), _ptr(dO), w, M, w, gqa, _ptr(wk), wk.shape[0], _ptr(t["lse"]),
+            _lib.call(name, _ptr(qkv), qkv.stride(0), _ptr(dO), w, M, w, gqa, _ptr(wk), wk.shape[0], _ptr(lt.lse[i]),
                       _ptr(delta), _ptr(dp.rope), scale, _ptr(dqkv), dqkv.stride(0), st)
         _gemm(st, dqkv, T[f"to_qkv{i}"], dxn, w, 2 * w + 2 * gqa, kn=1)
-        _wgrad(st, dqkv, t["xn_a"], grads[f"to_qkv{i}"])
-        g = sl.take(M, w)
-        _rmsnorm_bwd(st, t["x_a"], T[f"pre_ln{i}"], dxn, g, grads[f"pre_ln{i}"], add=du, add_scale=c)
+        _wgrad(st, dqkv, xn_a, grads[f"to_qkv{i}"])
+        g_next = wv(B_G1 if ((L - 1 - i) & 1) else B_G0)
+        _rmsnorm_bwd(st, x_a, T[f"pre_ln{i}"], dxn, g_next, grads[f"pre_ln{i}"], add=du, add_scale=c)
+        g = g_next
     return g
 
 
@@ -322,7 +397,7 @@ def decoder_backward(m, dp: DevicePlan, tape: Tape, dout: torch.Tensor):
 # --------------------------------------------------------------------------------------------------
 def _param_grads(m, kind: str, grads: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     out: Dict[str, torch.Tensor] = {}
-    perm = patch_feature_perm(m.patch_size_tuple, m.patch_channels).to(grads["mask_token"].device)
+    perm = patch_feature_perm_on(m.patch_size_tuple, m.patch_channels, grads["mask_token"].device)
     out["mask_token"] = grads["mask_token"].view(1, 1)
     out["ln_pre_t.weight"] = grads["ln_pre_t"]
     out["ln_pre_p.weight"] = grads["ln_pre_p"]

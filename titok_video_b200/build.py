@@ -18,7 +18,7 @@ LIBDIR = os.path.join(ROOT, "lib")
 OBJDIR = os.path.join(ROOT, "build")
 LIB = os.path.join(LIBDIR, "libtitok_b200.so")
 
-SOURCES = ["api.cu", "host_util.cu", "fsq.cu", "rowops.cu", "gemm.cu", "attn.cu", "vq.cu", "wgrad.cu", "attn_bwd.cu", "bwd_rows.cu"]
+SOURCES = ["api.cu", "host_util.cu", "fsq.cu", "rowops.cu", "gemm.cu", "attn.cu", "vq.cu", "wgrad.cu", "attn_bwd.cu", "bwd_rows.cu", "sequence.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -216,6 +216,19 @@ def clear_caches() -> None:
 # --------------------------------------------------------------------------------------------------
 # prepared weights: bf16 GEMM operands, fp32 norm weights; refreshed in place when parameters change
 # --------------------------------------------------------------------------------------------------
+_PERM_CACHE: Dict[tuple, torch.Tensor] = {}
+
+
+def patch_feature_perm_on(patch_size: Sequence[int], channels: int, device) -> torch.Tensor:
+    """patch_feature_perm as a tensor on `device`, cached (an H2D copy per call would stall the launch stream)."""
+    key = (tuple(int(p) for p in patch_size), int(channels), str(device))
+    t = _PERM_CACHE.get(key)
+    if t is None:
+        t = patch_feature_perm(patch_size, channels).to(device)
+        _PERM_CACHE[key] = t
+    return t
+
+
 def patch_feature_perm(patch_size: Sequence[int], channels: int) -> torch.Tensor:
     """perm[j_new] = j_ref with j_ref = ((p0*P1+p1)*P2+p2)*C + c (einops '(p0 p1 p2 c)', utils.py:26-34) and
     j_new = ((c*P0+p0)*P1+p1)*P2+p2 (what patchify / unpatchify move as 16-byte runs)."""
@@ -236,6 +249,8 @@ class PreparedStack:
         self.module = module
         self.sig = None
         self.t: Dict[str, torch.Tensor] = {}
+        self._pending_dst: List[torch.Tensor] = []
+        self._pending_src: List[torch.Tensor] = []
 
     def _signature(self):
         ps = self.module.__dict__.get("_ttk_param_list")
@@ -247,9 +262,26 @@ class PreparedStack:
     def _set(self, name: str, value: torch.Tensor, dtype) -> None:
         cur = self.t.get(name)
         if cur is not None and cur.shape == value.shape and cur.dtype == dtype and cur.device == value.device:
-            cur.copy_(value.detach())  # keep the address stable: captured CUDA graphs stay valid
+            # keep the address stable (captured CUDA graphs stay valid); the copies of one refresh are batched into a few
+            # multi-tensor kernels (a refresh follows every optimizer step: 38 parameters per stack)
+            self._pending_dst.append(cur)
+            self._pending_src.append(value.detach())
         else:
             self.t[name] = value.detach().to(dtype, copy=True).contiguous()
+            self._table = None  # an address changed: the native sequencers' pointer table is stale
+
+    def layer_table(self) -> np.ndarray:
+        """HOST int64 [n_layers, 9] device pointers for the native sequencers (include/titok_b200.h: ttk_layers_desc)."""
+        if self.__dict__.get("_table") is None:
+            L = self.module.num_layers
+            tab = np.zeros((L, 9), dtype=np.int64)
+            for i in range(L):
+                nxt = self.t[f"pre_ln{i + 1}"] if i + 1 < L else self.t["ln_post"]
+                row = [self.t[f"to_qkv{i}"], self.t[f"out_proj{i}"], self.t[f"w12_{i}"], self.t[f"w3_{i}"], self.t[f"pre_ln{i}"],
+                       self.t.get(f"attn_post_ln{i}"), self.t[f"ffn_norm{i}"], self.t.get(f"ffd_post_ln{i}"), nxt]
+                tab[i] = [0 if t is None else t.data_ptr() for t in row]
+            self._table = tab
+        return self._table
 
     @torch.no_grad()
     def refresh(self) -> "PreparedStack":
@@ -258,7 +290,8 @@ class PreparedStack:
             return self
         m = self.module
         bf, f32 = torch.bfloat16, torch.float32
-        perm = patch_feature_perm(m.patch_size_tuple, m.patch_channels).to(m.mask_token.device)
+        perm = patch_feature_perm_on(m.patch_size_tuple, m.patch_channels, m.mask_token.device)
+        self._pending_dst, self._pending_src = [], []
         self._set("mask_token", m.mask_token.reshape(1), f32)
         self._set("ln_pre_t", m.ln_pre_t.weight, f32)
         self._set("ln_pre_p", m.ln_pre_p.weight, f32)
@@ -285,6 +318,9 @@ class PreparedStack:
             if i > 0:
                 self._set(f"attn_post_ln{i}", ml.attn_post_ln[i - 1].weight, f32)
                 self._set(f"ffd_post_ln{i}", ml.ffd_post_ln[i - 1].weight, f32)
+        if self._pending_dst:
+            torch._foreach_copy_(self._pending_dst, self._pending_src)
+        self._pending_dst, self._pending_src = [], []
         self.sig = sig
         return self
 
@@ -301,6 +337,24 @@ def prepared(module, kind: str) -> PreparedStack:
 # launch sequences
 # --------------------------------------------------------------------------------------------------
 FUSE_RESID_256 = os.environ.get("TTK_FUSE_RESID", "1") != "0"
+NATIVE_SEQ = os.environ.get("TTK_NATIVE_SEQ", "1") != "0"  # 0: enqueue the layers kernel by kernel from Python
+
+
+def layers_desc(m, W: PreparedStack, dp: DevicePlan, M: int, backward: bool = False) -> "_lib.LayersDesc":
+    """ttk_layers_desc for one stack and one packed batch (the weight table and the work lists stay referenced by W / dp)."""
+    hq, hkv = m.heads
+    work = dp.attn_work(hq, hkv)
+    d = _lib.LayersDesc()
+    d.M, d.width, d.gqa, d.inner, d.n_layers = M, m.width, hkv * 64, m.inner_dim, m.num_layers
+    d.n_attn_work = work.shape[0]
+    d.alpha, d.softmax_scale = float(2 * m.num_layers), 1.0 / math.sqrt(64.0)
+    d.rope, d.attn_work = dp.rope.data_ptr(), work.data_ptr()
+    if backward:
+        wk_dkv, wk_dq = dp.attn_bwd_work(hq, hkv)
+        d.n_dkv_work, d.n_dq_work = wk_dkv.shape[0], wk_dq.shape[0]
+        d.dkv_work, d.dq_work = wk_dkv.data_ptr(), wk_dq.data_ptr()
+    d.weights = W.layer_table().ctypes.data
+    return d
 
 
 def _layers(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tensor) -> None:
@@ -320,6 +374,11 @@ def _layers(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tens
     work = dp.attn_work(hq, hkv)
     scale = 1.0 / math.sqrt(64.0)
     T = W.t
+    if NATIVE_SEQ and not _lib.profiling():
+        d = layers_desc(m, W, dp, M)
+        _lib.call("ttk_layers_fwd", ctypes.byref(d), _ptr(x), _ptr(xn), _ptr(qkv), _ptr(att), _ptr(h), _ptr(y), st,
+                  launches=L * (5 if y is None else 7))
+        return
 
     def out_update(a: torch.Tensor, wmat: torch.Tensor, K: int, mode: int, w_post, w_next) -> None:
         if y is None:
