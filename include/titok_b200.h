@@ -236,7 +236,8 @@ int ttk_gather_rows(const void* src, int64_t lds, const int32_t* idx, void* dst,
 int ttk_scatter_rows(const void* src, int64_t lds, const int32_t* idx, void* dst, int64_t ldd, int64_t n, int width,
                      ttk_stream_t stream);
 
-/* Bias / mask_token gradients: out[c] (optional) += sum_r x[r,c]; total[0] (optional) += sum of all of x. */
+/* Bias / mask_token gradients: out[c] (optional) += sum_r x[r,c]; total[0] (optional) += sum of all of x.
+ * x bf16 [M, N], N and ld multiples of 8, 16-byte aligned. */
 int ttk_colsum(const void* x, int64_t ld, int64_t M, int N, float* out, float* total, ttk_stream_t stream);
 
 /* Backward of the encoder head Linear(width -> token_size) on the latent rows (blocks.py:101-103). */
