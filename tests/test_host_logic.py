@@ -203,3 +203,55 @@ def test_attention_backward_work_lists_cover_every_tile_once(hq, hkv):
     # longest work first
     cost = dkv[:, 4].astype(np.int64) * ((dkv[:, 6] + 127) // 128)
     assert (np.diff(cost) <= 0).all()
+
+
+def _reference_dynamic_batching(data, patch_size, token_range, max_grid, max_seq_len, eval, max_samples, rnd):
+    """Restatement of dataset/video_dataset.py:130-172 for the test (the reference module needs webdataset / decord, which
+    this image does not have): same control flow, written independently from titok_video_b200.data.batching."""
+    assert math.prod(x // y for x, y in zip(max_grid, patch_size)) + token_range[1] <= max_seq_len
+    batches, chunks, tcs, cur, seen = [], [], [], 0, 0
+    for sample in data:
+        g = math.prod(x // y for x, y in zip(sample["video"].shape[1:], patch_size))
+        t = rnd.randrange(token_range[0], token_range[1] + 1)
+        if eval:
+            if seen > max_samples:
+                break
+            seen += 1
+        if cur + g + t > max_seq_len:
+            batches.append(([c["key"] for c in chunks], list(tcs)))
+            chunks, tcs, cur = [], [], 0
+        cur += g + t
+        chunks.append(sample)
+        tcs.append(t)
+    return batches
+
+
+@pytest.mark.parametrize("eval_mode", [False, True])
+def test_dynamic_batches_follow_the_reference_semantics(eval_mode):
+    import random
+
+    from titok_video_b200.data import canonical_order, dynamic_batches
+
+    rnd = random.Random(3)
+    samples = []
+    for i in range(60):
+        shp = (3, rnd.choice([8, 12, 16]), rnd.choice([128, 136, 152, 168]), rnd.choice([128, 144, 168]))
+        samples.append({"video": torch.empty(shp, dtype=torch.bfloat16, device="meta"), "key": i})
+    kw = dict(patch_size=[4, 8, 8], token_range=[1, 128], max_grid=[16, 168, 168], max_seq_len=6144)
+    want = _reference_dynamic_batching(samples, eval=eval_mode, max_samples=20, rnd=random.Random(11), **kw)
+    got = list(dynamic_batches(samples, eval=eval_mode, max_samples=20, randrange=random.Random(11).randrange, **kw))
+    assert [(b["key"], b["token_counts"].tolist()) for b in got] == want
+    assert len(got) > 3
+    for b in got:
+        assert b["token_counts"].dtype == torch.int32
+        s = sum(math.prod(x // y for x, y in zip(v.shape[1:], [4, 8, 8])) + int(t) for v, t in zip(b["video"], b["token_counts"]))
+        assert s <= 6144
+    with pytest.raises(AssertionError):
+        list(dynamic_batches(samples, [4, 8, 8], [1, 128], [16, 168, 168], 1800))
+    # canonical order: a permutation with its inverse; batches with the same multiset of (shape, tokens) get the same key
+    shapes, tcs = [(8, 128, 128), (16, 168, 168), (8, 128, 128)], [5, 7, 3]
+    perm, inv = canonical_order(shapes, tcs)
+    assert sorted(perm) == [0, 1, 2] and [perm[inv[i]] for i in range(3)] == [0, 1, 2]
+    key = lambda sh, tc, p: tuple((sh[i], tc[i]) for i in p)
+    perm2, _ = canonical_order(shapes[::-1], tcs[::-1])
+    assert key(shapes, tcs, perm) == key(shapes[::-1], tcs[::-1], perm2)
