@@ -255,3 +255,32 @@ def test_dynamic_batches_follow_the_reference_semantics(eval_mode):
     key = lambda sh, tc, p: tuple((sh[i], tc[i]) for i in p)
     perm2, _ = canonical_order(shapes[::-1], tcs[::-1])
     assert key(shapes, tcs, perm) == key(shapes[::-1], tcs[::-1], perm2)
+
+
+def test_token_container_roundtrip_and_validation(tmp_path):
+    import io
+
+    from titok_video_b200.data import read_tokens, write_tokens
+
+    g = torch.Generator().manual_seed(0)
+    idx = [torch.randint(0, 4375, (n,), generator=g, dtype=torch.int32) for n in (128, 1, 0, 77)]
+    grids = [(16, 168, 168), (8, 128, 128), (4, 8, 8), (12, 136, 152)]
+    p = str(tmp_path / "clips.ttkv")
+    n = write_tokens(p, idx, grids, 4375)
+    assert n == 6 + 10 + 8 * 4 + 2 * (128 + 1 + 0 + 77)
+    got, gg, K = read_tokens(p)
+    assert K == 4375 and gg == grids
+    for a, b in zip(got, idx):
+        assert a.dtype == torch.int32 and torch.equal(a, b)
+    # wide codebooks use 32-bit indices; in-memory streams work too
+    buf = io.BytesIO()
+    wide = [torch.tensor([0, 70000, 99999])]
+    write_tokens(buf, wide, [(4, 8, 8)], 100000)
+    got, _, K = read_tokens(buf.getvalue())
+    assert K == 100000 and got[0].tolist() == [0, 70000, 99999]
+    with pytest.raises(ValueError):
+        write_tokens(io.BytesIO(), [torch.tensor([4375])], [(4, 8, 8)], 4375)
+    with pytest.raises(ValueError):
+        read_tokens(open(p, "rb").read()[:-1])
+    with pytest.raises(ValueError):
+        read_tokens(b"nope" + bytes(40))
