@@ -26,7 +26,10 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 // epilogue warps per kind: 8 (two per TMEM lane quarter) for the store-only epilogues, 16 (four per quarter) for the
 // arithmetic-heavy ones (GELU, residual + norms) so that each scheduler has four warps to hide latencies with
-__host__ __device__ constexpr int epi_warps(int epi) { return (epi == 2 || epi == 3) ? 16 : 8; }
+// the weight-stationary qkv kernel (BN = 192: three 64-column heads per tile) gives every head box its own warp (12 warps)
+__host__ __device__ constexpr int epi_warps(int epi, int bn = 256) {
+  return (epi == 2 || epi == 3) ? 16 : ((epi == 1 && bn == 192) ? 12 : 8);
+}
 constexpr int BOX_BYTES = 32 * 128;  // one [32 rows x 64 bf16] staging box
 
 struct GemmParams {
@@ -70,7 +73,8 @@ struct GemmSmem {
   // EPI_RESID: the [128 x 256] residual tile (4 swizzled boxes of 128 rows x 64 cols), updated in place and stored
   // from there. Other epilogues: staging boxes per epilogue warp (double-buffered unless the weights are resident).
   static constexpr int OUT_BUFS = WS ? 1 : 2;
-  static constexpr int OUT_BYTES = (EPI == EPI_RESID) ? BM * 256 * 2 : 8 * OUT_BUFS * BOX_BYTES;
+  static constexpr int OUT_BOXES = (EPI == EPI_QKV) ? epi_warps(EPI, BN) : 8;  // staging boxes (GEGLU: one per warp pair)
+  static constexpr int OUT_BYTES = (EPI == EPI_RESID) ? BM * 256 * 2 : OUT_BOXES * OUT_BUFS * BOX_BYTES;
   static constexpr int AUX_BYTES = (EPI == EPI_RESID) ? 2 * 256 * 4 + 2 * 4 * 128 * 4 : 0;  // norm weights + partial sums
   static constexpr int BAR_BYTES = 256;
   static constexpr int BUDGET = 227 * 1024 - 1024 - RES_BYTES - OUT_BYTES - AUX_BYTES - BAR_BYTES;
@@ -166,7 +170,7 @@ __device__ __forceinline__ void box_write_row(uint8_t* box, int lane, const uint
 }
 
 template <int BN, int EPI, bool B_MN, bool WS>
-__global__ void __launch_bounds__(128 + 32 * epi_warps(EPI), 1)
+__global__ void __launch_bounds__(128 + 32 * epi_warps(EPI, BN), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO,   // out / x_out: box [32 rows x 64 cols]
             const __grid_constant__ CUtensorMap tmO2,  // EPI_RESID: xn_out, same box
@@ -174,7 +178,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const GemmParams p) {
   using S = GemmSmem<BN, EPI, WS>;
   constexpr int STAGES = S::STAGES;
-  constexpr int EPI_WARPS = epi_warps(EPI);
+  constexpr int EPI_WARPS = epi_warps(EPI, BN);
   static_assert(!WS || (!B_MN && EPI != EPI_RESID), "weight-stationary mode: K-major weights, store-type epilogues");
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
@@ -434,7 +438,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else if constexpr (EPI == EPI_QKV) {
         // column classes: [0,w) q (RoPE) | [w,2w) gate | [2w,2w+g) k (RoPE) | [2w+g,2w+2g) v; one 64-col box == one head
-        constexpr int CPW = BN / 2;
+        constexpr int CPW = BN / (EPI_WARPS / 4);  // columns per warp: 128 (BN = 256, 8 warps) or 64 (BN = 192, 12 warps)
         // RoPE second pass runs with lane == complex pair over the staged box; the (cos, sin) of the 32 rows of this
         // warp's slice are fetched up front (one contiguous 240-byte run per row), before the accumulator is ready.
         // Complex lanes 30, 31 (head dims 60..63) are not rotated (rope.py:22-24).
@@ -720,7 +724,7 @@ static int launch_gemm(const GemmIo& io, GemmParams& p, cudaStream_t stream) {
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 128 + 32 * epi_warps(EPI), S::TOTAL, stream>>>(tmA, tmB, tmO, tmO2, tmR, p);
+  kern<<<grid, 128 + 32 * epi_warps(EPI, BN), S::TOTAL, stream>>>(tmA, tmB, tmO, tmO2, tmR, p);
   return launch_status();
 }
 
@@ -790,7 +794,9 @@ int ttk_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldw, in
   p.width = width;
   p.gqa = gqa;
   GemmIo io{A, lda, W, ldw};
-  // (weight-stationary mode measured slower here: its single staging box per warp serialises the RoPE pass and the store)
+  // Weight-stationary variants measured slower here, twice: 256-wide tiles (two boxes per warp through one staging buffer
+  // serialise the RoPE pass and the store) and 192-wide tiles with a warp per head box (0.78 ms vs 0.53 ms per step: four
+  // n-blocks of 192 re-read every A tile four times and leave only 37 CTAs per n-block). Streaming 128x256 tiles it is.
   return launch_gemm<256, EPI_QKV, false>(io, p, stream);
 }
 
