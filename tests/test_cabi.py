@@ -66,3 +66,17 @@ def test_cpu_tensors_are_rejected():
     q = T.FSQ([7, 5, 5, 5, 5])
     with pytest.raises(T._lib.TitokB200Error):
         q(torch.zeros(4, 5))
+
+
+def test_sequencers_reject_null_arguments_without_a_gpu():
+    """Argument validation happens before any CUDA call: callable (and checkable) on a machine without a GPU."""
+    from titok_video_b200 import _lib
+
+    z = ctypes.c_void_p(0)
+    assert _lib.fn("ttk_layers_fwd")(z, z, z, z, z, z, z, z) == -1
+    assert _lib.fn("ttk_layers_fwd_train")(z, z, z, z, 0, z, z, z) == -1
+    assert _lib.fn("ttk_layers_bwd")(z, z, z, z, 0, z, z, z, z, z, z, z, z, z) == -1
+    d = _lib.LayersDesc()
+    assert ctypes.sizeof(d) == 8 * 4 + 2 * 4 + 5 * 8  # layout of ttk_layers_desc in include/titok_b200.h
+    with pytest.raises(_lib.TitokB200Error):
+        _lib.call("ttk_layers_fwd", ctypes.byref(d), z, z, z, z, z, z, z)
