@@ -284,3 +284,16 @@ def test_token_container_roundtrip_and_validation(tmp_path):
         read_tokens(open(p, "rb").read()[:-1])
     with pytest.raises(ValueError):
         read_tokens(b"nope" + bytes(40))
+
+
+def test_cached_parameter_list_matches_named_parameters_and_notices_replacement():
+    from titok_video_b200 import engine
+
+    m = build_model(False)
+    for stack in (m.encoder, m.decoder):
+        a, b = engine.cached_named_params(stack), list(stack.named_parameters())
+        assert [n for n, _ in a] == [n for n, _ in b] and all(x is y for (_, x), (_, y) in zip(a, b))
+    old = m.encoder.proj_in.weight
+    m.encoder.proj_in.weight = torch.nn.Parameter(torch.zeros_like(old))
+    c = dict(engine.cached_named_params(m.encoder))
+    assert c["proj_in.weight"] is m.encoder.proj_in.weight and c["proj_in.weight"] is not old

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import NATIVE_SEQ, DevicePlan, PreparedStack, _ptr, _stream, _vp, layers_desc, patch_feature_perm_on, prepared
+from .engine import NATIVE_SEQ, DevicePlan, cached_named_params, PreparedStack, _ptr, _stream, _vp, layers_desc, patch_feature_perm_on, prepared
 
 bf16 = torch.bfloat16
 
@@ -444,12 +444,7 @@ def _ordered(m, kind: str, grads, params_meta) -> Tuple[Optional[torch.Tensor], 
 
 
 def _named_params(m):
-    """[(name, parameter)] of a stack, cached on the module (walking the module tree costs ~50 us per call)."""
-    c = m.__dict__.get("_ttk_named_params")
-    if c is None:
-        c = list(m.named_parameters())
-        m.__dict__["_ttk_named_params"] = c
-    return c
+    return cached_named_params(m)
 
 
 def stack_params(m):

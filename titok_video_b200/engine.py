@@ -241,6 +241,22 @@ def patch_feature_perm(patch_size: Sequence[int], channels: int) -> torch.Tensor
     return ((p0 * P1 + p1) * P2 + p2) * channels + c
 
 
+def cached_named_params(module) -> list:
+    """[(qualified name, parameter)] of a module, cached on it: walking the module tree costs ~50 us per call and the launch
+    sequences need the list several times per step. The cache is validated against the owners' `_parameters` dicts (76
+    identity checks), so replacing a parameter object (not just its data) is noticed."""
+    c = module.__dict__.get("_ttk_param_cache")
+    if c is not None and all(owner._parameters.get(leaf) is p for owner, leaf, _, p in c):
+        return [(name, p) for _, _, name, p in c]
+    c = []
+    for mod_name, sub in module.named_modules():
+        for leaf, p in sub._parameters.items():
+            if p is not None:
+                c.append((sub, leaf, (mod_name + "." if mod_name else "") + leaf, p))
+    module.__dict__["_ttk_param_cache"] = c
+    return [(name, p) for _, _, name, p in c]
+
+
 class PreparedStack:
     """bf16 / fp32 device copies of one TiTokEncoder / TiTokDecoder's parameters in kernel layout."""
 
@@ -253,11 +269,7 @@ class PreparedStack:
         self._pending_src: List[torch.Tensor] = []
 
     def _signature(self):
-        ps = self.module.__dict__.get("_ttk_param_list")
-        if ps is None:  # cached: walking the module tree on every launch sequence costs ~50 us
-            ps = list(self.module.parameters())
-            self.module.__dict__["_ttk_param_list"] = ps
-        return tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+        return tuple((p.data_ptr(), p._version, p.dtype) for _, p in cached_named_params(self.module))
 
     def _set(self, name: str, value: torch.Tensor, dtype) -> None:
         cur = self.t.get(name)
