@@ -297,3 +297,22 @@ def test_cached_parameter_list_matches_named_parameters_and_notices_replacement(
     m.encoder.proj_in.weight = torch.nn.Parameter(torch.zeros_like(old))
     c = dict(engine.cached_named_params(m.encoder))
     assert c["proj_in.weight"] is m.encoder.proj_in.weight and c["proj_in.weight"] is not old
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) needs no GPU: one JSON line with the keys of
+    the bench contract, `impl: reference`, a cpu_baseline block and an e2e block that repeats the line's value."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+              "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "clips/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
