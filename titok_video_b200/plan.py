@@ -191,7 +191,7 @@ def make_plan(grids_px: Sequence[Sequence[int]], token_counts: Sequence[int], pa
     plan = PackedPlan(grids_px=grids_px, grids=tuple(grids), token_counts=token_counts, patch_size=patch_size,
                       channels=channels)
 
-    gsz = [int(np.prod(g)) for g in grids]
+    gsz = [g[0] * g[1] * g[2] for g in grids]
     seq = [g + t for g, t in zip(gsz, token_counts)]
     plan.seq_lens = tuple(seq)
     plan.cu_seqlens = np.concatenate([[0], np.cumsum(seq)]).astype(np.int32)
@@ -282,21 +282,31 @@ def attn_bwd_work_lists(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: 
       dkv: one record per (128-key tile, kv head); streams the clip's query tiles of the `hq // hkv` grouped query heads
       dq : one record per (128-row query tile, query head); streams the clip's key tiles of kv head `h // (hq // hkv)`."""
     grp = hq // hkv
-    dkv, dq = [], []
-    for start, n in zip(seq_starts, seq_lens):
-        start, n = int(start), int(n)
-        for t0 in range(0, n, 128):
-            valid = min(128, n - t0)
-            for kh in range(hkv):
-                dkv.append((start + t0, valid, kh, kh * grp, grp, start, n, 0))
-            for qh in range(hq):
-                dq.append((start + t0, valid, qh, qh // grp, 1, start, n, 0))
-    a = np.asarray(dkv, dtype=np.int32).reshape(-1, 8)
-    b = np.asarray(dq, dtype=np.int32).reshape(-1, 8)
-    if len(a):
-        a = a[np.argsort(-(a[:, 4].astype(np.int64) * ((a[:, 6] + 127) // 128)), kind="stable")]
-    if len(b):
-        b = b[np.argsort(-((b[:, 6] + 127) // 128), kind="stable")]
+    st = np.asarray(seq_starts, dtype=np.int64).reshape(-1)
+    sl = np.asarray(seq_lens, dtype=np.int64).reshape(-1)
+    if len(sl) == 0:
+        return np.zeros((0, 8), dtype=np.int32), np.zeros((0, 8), dtype=np.int32)
+    # vectorised over all 128-row tiles of the batch (a ragged stream builds these lists every step)
+    nt = (sl + ATTN_TILE - 1) // ATTN_TILE
+    clip = np.repeat(np.arange(len(sl)), nt)
+    ti = np.arange(int(nt.sum()), dtype=np.int64) - np.repeat(np.cumsum(nt) - nt, nt)
+    row0 = st[clip] + ti * ATTN_TILE
+    valid = np.minimum(ATTN_TILE, sl[clip] - ti * ATTN_TILE)
+    n_t = len(ti)
+
+    def records(n_heads_out, head, other0, n_heads):
+        rec = np.zeros((n_t * n_heads_out, 8), dtype=np.int32)
+        rep = lambda v: np.repeat(v, n_heads_out)
+        rec[:, 0], rec[:, 1], rec[:, 2], rec[:, 3], rec[:, 4] = rep(row0), rep(valid), head, other0, n_heads
+        rec[:, 5], rec[:, 6] = rep(st[clip]), rep(sl[clip])
+        return rec
+
+    kh = np.tile(np.arange(hkv), n_t)
+    qh = np.tile(np.arange(hq), n_t)
+    a = records(hkv, kh, kh * grp, grp)
+    b = records(hq, qh, qh // grp, 1)
+    a = a[np.argsort(-(a[:, 4].astype(np.int64) * ((a[:, 6] + 127) // 128)), kind="stable")]
+    b = b[np.argsort(-((b[:, 6] + 127) // 128), kind="stable")]
     return np.ascontiguousarray(a), np.ascontiguousarray(b)
 
 
