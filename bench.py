@@ -295,6 +295,58 @@ def train_leg(T, _lib, dev, world, rank, dist, batch, steps, warmup):
                     + "fused AdamW + codebook histogram; synthetic clips 3x16x168x168 / 128 tokens, random-init weights"}
 
 
+def train_ragged_leg(T, _lib, dev, rank, steps):
+    """The regime train.py really runs in: every step a NEW batch composition from the dataloader's token-budget batching
+    (titok_video_b200.data.dynamic_batches = video_dataset.py:130-172: shapes in [min_grid, max_grid], 1..128 tokens,
+    6144 packed rows per batch), so every step pays the host planner, the metadata upload and the work-list construction
+    on top of forward + loss + backward + AdamW. Wall clock around a synchronised loop, rank 0 only."""
+    import random
+
+    from titok_video_b200 import engine as _eng
+    from titok_video_b200.config import tiny_config
+    from titok_video_b200.data import dynamic_batches
+
+    torch.manual_seed(42)
+    model = T.TiTok(tiny_config(LEVELS, PATCH)).to(dev).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.5, 0.96), weight_decay=1e-4, fused=True)
+    rnd = random.Random(1)
+
+    def samples():
+        while True:
+            shp = (rnd.choice([8, 12, 16]), rnd.choice([128, 136, 144, 152, 160, 168]), rnd.choice([128, 136, 144, 152, 160, 168]))
+            yield {"video": (torch.rand((3, *shp), device=dev) * 2 - 1).to(torch.bfloat16)}
+
+    it = dynamic_batches(samples(), list(PATCH), [1, 128], [16, 168, 168], 6144, randrange=rnd.randrange)
+    batches = [next(it) for _ in range(steps + 3)]
+
+    def step(b):
+        clips, tcs = b["video"], b["token_counts"]
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            recon, d = model(clips, tcs)
+        loss = torch.stack([(r_.float() - c.float()).abs().mean() for c, r_ in zip(clips, recon)]).mean()
+        loss.backward()
+        opt.step()
+        return loss
+
+    _eng.clear_caches()
+    for b in batches[:3]:
+        step(b)
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    for b in batches[3:]:
+        step(b)
+    torch.cuda.synchronize()
+    w1 = time.perf_counter()
+    n_clips = sum(len(b["video"]) for b in batches[3:])
+    rows = sum(int(b["token_counts"].sum()) + sum((v.shape[1] // 4) * (v.shape[2] // 8) * (v.shape[3] // 8) for v in b["video"])
+               for b in batches[3:])
+    return {"clips_per_s": n_clips / (w1 - w0), "ms_per_step_wall": 1e3 * (w1 - w0) / steps, "steps": steps,
+            "clips_per_step": n_clips / steps, "packed_rows_per_step": rows / steps,
+            "note": "new shapes / token counts every step (dynamic_batches, 6144-row budget): host planning + metadata upload + "
+                    "forward + L1 loss + backward + fused AdamW; wall clock"}
+
+
 def scaled_leg(T, dev, world, rank, dist, steps, warmup, clips_per_gpu=4):
     """BASELINE configs[4]: the scaled-up variant that stresses the attention sequence length -- clips of
     32x256x256 with 256 latent tokens (8192 patches, 8448 packed rows per clip; attention is 84 % of the FLOPs), tiny
@@ -585,6 +637,8 @@ def main():
         train = {}
         for tb in [int(v) for v in args.train_batch.split(",") if v]:
             train[f"batch{tb}"] = train_leg(T, _lib, dev, world, rank, dist, tb, max(4, args.steps // 2), args.warmup)
+        if rank == 0:
+            train["ragged"] = train_ragged_leg(T, _lib, dev, rank, 8)
 
     # ---------------- scaled-up variant (BASELINE configs[4]) ----------------
     scaled = None
