@@ -554,12 +554,14 @@ def test_gradient_accumulation_over_two_microbatches():
         assert torch.allclose(p.grad, want, rtol=2e-3, atol=1e-6 + 2e-4 * float(want.abs().max())), k
 
 
-@pytest.mark.parametrize("enc,dec", [("tiny", "tiny"), ("large", "small")])
-def test_a_few_optimizer_steps_reduce_the_loss(enc, dec):
+@pytest.mark.parametrize("enc,dec,fused", [("tiny", "tiny", False), ("tiny", "tiny", True), ("large", "small", True)])
+def test_a_few_optimizer_steps_reduce_the_loss(enc, dec, fused):
     """Direction check at sizes the CPU oracle is too slow for ('large': width 1024, 24 layers, 16/4 heads): five AdamW
-    steps on one fixed batch lower the L1 reconstruction loss and keep every gradient finite."""
+    steps on one fixed batch lower the L1 reconstruction loss and keep every gradient finite. `fused=True`: the fused
+    optimizer kernel does not bump `p._version`, so this also checks that updated weights reach the kernels
+    (PreparedStack.refresh: optimizer-step hook + forced refresh of training forwards)."""
     model = build_model(False, enc=enc, dec=dec).to(DEV).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=3e-4, betas=(0.5, 0.96), weight_decay=1e-4)
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-4, betas=(0.5, 0.96), weight_decay=1e-4, fused=fused)
     clips = [c.to(DEV) for c in O.make_clips([(4, 32, 32), (8, 16, 24)], 9)]
     tcs = [6, 20]
     losses = []
@@ -602,3 +604,29 @@ def test_native_sequencer_equals_per_kernel_launches(monkeypatch):
         assert torch.equal(x, y)
     for k in a[4]:
         assert torch.allclose(a[4][k], b[4][k], rtol=1e-3, atol=1e-6 + 1e-4 * float(b[4][k].abs().max())), k
+
+
+def test_inference_sees_weights_updated_by_a_fused_optimizer_or_through_data():
+    """Weights changed by a fused optimizer step (no version bump) are picked up by the next no-grad forward through the
+    optimizer-step hook; edits through `p.data` need engine.invalidate()."""
+    from titok_video_b200 import engine
+
+    model = build_model(True).to(DEV)
+    clips = [c.to(DEV) for c in O.make_clips([(4, 32, 32)], 1)]
+    with torch.no_grad():
+        rec0, _ = model(clips, [6])
+    rec0 = rec0[0].clone()
+    opt = torch.optim.SGD(model.parameters(), lr=0.5, fused=True)
+    for p in model.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()
+    with torch.no_grad():
+        rec1, _ = model(clips, [6])
+    assert not torch.equal(rec1[0], rec0), "stale weights after a fused optimizer step"
+    rec1 = rec1[0].clone()
+    for p in model.decoder.parameters():
+        p.data.mul_(0.5)
+    engine.invalidate(model)
+    with torch.no_grad():
+        rec2, _ = model(clips, [6])
+    assert not torch.equal(rec2[0], rec1)

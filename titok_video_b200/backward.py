@@ -153,7 +153,7 @@ def _layers_train(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torc
 
 def encoder_forward_train(m, dp: DevicePlan, clips_flat: torch.Tensor, fsq_consts):
     """TiTokEncoder.forward recording a tape. Returns (z, codes, idx, tape); z/codes bf16 [T, ts]."""
-    W = prepared(m, "enc")
+    W = prepared(m, "enc", force=True)  # a training step always re-reads the parameters (see PreparedStack.refresh)
     pl = dp.plan
     M, G, Tn, w = pl.M, pl.G, pl.T, m.width
     P0, P1, P2 = pl.patch_size
@@ -184,7 +184,7 @@ def encoder_forward_train(m, dp: DevicePlan, clips_flat: torch.Tensor, fsq_const
 
 def decoder_forward_train(m, dp: DevicePlan, codes: torch.Tensor):
     """TiTokDecoder.forward recording a tape. Returns (out_flat bf16 [sum 3*T*H*W], tape)."""
-    W = prepared(m, "dec")
+    W = prepared(m, "dec", force=True)
     pl = dp.plan
     M, G, w = pl.M, pl.G, m.width
     P0, P1, P2 = pl.patch_size

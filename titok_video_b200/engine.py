@@ -267,6 +267,8 @@ class PreparedStack:
         self.t: Dict[str, torch.Tensor] = {}
         self._pending_dst: List[torch.Tensor] = []
         self._pending_src: List[torch.Tensor] = []
+        self._all_dst: List[torch.Tensor] = []
+        self._all_src: List[torch.Tensor] = []
 
     def _signature(self):
         return tuple((p.data_ptr(), p._version, p.dtype) for _, p in cached_named_params(self.module))
@@ -281,6 +283,8 @@ class PreparedStack:
         else:
             self.t[name] = value.detach().to(dtype, copy=True).contiguous()
             self._table = None  # an address changed: the native sequencers' pointer table is stale
+        self._all_dst.append(self.t[name])
+        self._all_src.append(value.detach())
 
     def layer_table(self) -> np.ndarray:
         """HOST int64 [n_layers, 9] device pointers for the native sequencers (include/titok_b200.h: ttk_layers_desc)."""
@@ -296,28 +300,51 @@ class PreparedStack:
         return self._table
 
     @torch.no_grad()
-    def refresh(self) -> "PreparedStack":
-        sig = self._signature()
-        if sig == self.sig:
+    def refresh(self, force: bool = False) -> "PreparedStack":
+        """Bring the kernel-layout copies up to date with the module's parameters.
+
+        Staleness cannot be detected from the parameters alone: fused optimizer kernels (`AdamW(fused=True)`) and in-place
+        edits through `p.data` do not bump `p._version`. So (a) every optimizer step in the process bumps a counter that
+        is part of the signature (`_OPT_STEPS`, a global optimizer post-step hook), and (b) callers that are about to
+        record a training step pass `force=True`. A refresh with unchanged parameter objects is cheap: two or three
+        index_selects for the permuted patch projections and ONE multi-tensor copy for all 38 parameters of the stack."""
+        sig = (self._signature(), _OPT_STEPS[0])
+        if not force and sig == self.sig:
+            return self
+        fast = self.__dict__.get("_fast")
+        key = tuple((id(p), p.data_ptr(), p.dtype) for _, p in cached_named_params(self.module))
+        if fast is not None and fast[0] == key:
+            _, gathers, dst, src = fast
+            for w, dim, perm, tmp in gathers:
+                torch.index_select(w, dim, perm, out=tmp)
+            torch._foreach_copy_(dst, src)
+            self.sig = sig
             return self
         m = self.module
         bf, f32 = torch.bfloat16, torch.float32
         perm = patch_feature_perm_on(m.patch_size_tuple, m.patch_channels, m.mask_token.device)
-        self._pending_dst, self._pending_src = [], []
+        self._pending_dst, self._pending_src, self._all_dst, self._all_src = [], [], [], []
+        gathers = []  # (source parameter, dim, perm, persistent fp32 temporary) of the permuted patch projections
+
+        def permuted(w: torch.Tensor, dim: int) -> torch.Tensor:
+            tmp = torch.index_select(w.detach(), dim, perm)
+            gathers.append((w.detach(), dim, perm, tmp))
+            return tmp
+
         self._set("mask_token", m.mask_token.reshape(1), f32)
         self._set("ln_pre_t", m.ln_pre_t.weight, f32)
         self._set("ln_pre_p", m.ln_pre_p.weight, f32)
         self._set("ln_post", m.ln_post.weight, f32)
         if self.kind == "enc":
-            self._set("proj_in_w", m.proj_in.weight[:, perm], bf)
+            self._set("proj_in_w", permuted(m.proj_in.weight, 1), bf)
             self._set("proj_in_b", m.proj_in.bias, bf)
             self._set("proj_out_w", m.proj_out.weight, bf)
             self._set("proj_out_b", m.proj_out.bias, bf)
         else:
             self._set("proj_in_w", m.proj_in.weight, bf)
             self._set("proj_in_b", m.proj_in.bias, bf)
-            self._set("proj_out_w", m.proj_out.weight[perm, :], bf)
-            self._set("proj_out_b", m.proj_out.bias[perm], bf)
+            self._set("proj_out_w", permuted(m.proj_out.weight, 0), bf)
+            self._set("proj_out_b", permuted(m.proj_out.bias, 0), bf)
         ml = m.model_layers
         for i in range(m.num_layers):
             a, f = ml.attn_layer[i], ml.ffd_layer[i]
@@ -332,17 +359,48 @@ class PreparedStack:
                 self._set(f"ffd_post_ln{i}", ml.ffd_post_ln[i - 1].weight, f32)
         if self._pending_dst:
             torch._foreach_copy_(self._pending_dst, self._pending_src)
-        self._pending_dst, self._pending_src = [], []
+        # the (destination, source) pairs of this refresh are the recipe of every later one, as long as the parameter
+        # objects and their storages stay the same (sources are aliases of the parameters / the persistent temporaries)
+        if len(self._all_dst) == len(self.t):
+            self._fast = (key, gathers, list(self._all_dst), list(self._all_src))
+        else:
+            self._fast = None
+        self._pending_dst, self._pending_src, self._all_dst, self._all_src = [], [], [], []
         self.sig = sig
         return self
 
 
-def prepared(module, kind: str) -> PreparedStack:
+def prepared(module, kind: str, force: bool = False) -> PreparedStack:
     ps = module.__dict__.get("_ttk_prepared")
     if ps is None or ps.kind != kind:
         ps = PreparedStack(module, kind)
         module.__dict__["_ttk_prepared"] = ps
-    return ps.refresh()
+    return ps.refresh(force)
+
+
+def invalidate(module: torch.nn.Module) -> None:
+    """Force the next launch sequence of every stack under `module` to re-read its parameters. Needed only after editing
+    parameters in a way PyTorch does not record (e.g. `p.data.add_(...)`) outside of a training step."""
+    for sub in module.modules():
+        ps = sub.__dict__.get("_ttk_prepared")
+        if ps is not None:
+            ps.sig = None
+
+
+# every optimizer step in the process (fused kernels do not bump parameter versions) invalidates the prepared weights
+_OPT_STEPS = [0]
+
+
+def _count_optimizer_step(*_args, **_kwargs) -> None:
+    _OPT_STEPS[0] += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_opt_hook
+
+    _reg_opt_hook(_count_optimizer_step)
+except Exception:  # pragma: no cover  (very old torch: training forwards still refresh unconditionally)
+    pass
 
 
 # --------------------------------------------------------------------------------------------------
