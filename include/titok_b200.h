@@ -240,6 +240,11 @@ int ttk_scatter_rows(const void* src, int64_t lds, const int32_t* idx, void* dst
  * x bf16 [M, N], N and ld multiples of 8, 16-byte aligned. */
 int ttk_colsum(const void* x, int64_t ld, int64_t M, int N, float* out, float* total, ttk_stream_t stream);
 
+/* Weight refresh after an optimizer step: the master parameters of a stack -> their kernel-layout copies in one launch.
+ * table: DEVICE int64 [n][4] = {src pointer, dst pointer, numel, kind}; kind = 2 * (src is bf16, else fp32) + (dst is fp32,
+ * else bf16). Replaces the `.to(bfloat16)` casts autocast performs on every nn.Linear weight in every forward. */
+int ttk_multi_cast(const int64_t* table, int n, int64_t max_numel, ttk_stream_t stream);
+
 /* Backward of the encoder head Linear(width -> token_size) on the latent rows (blocks.py:101-103). */
 int ttk_head_bwd(const void* dz, int token_size, const void* xn, int64_t ld, const int32_t* latent_row, const void* w_out,
                  void* dxn, float* dw, float* db, int T, int width, ttk_stream_t stream);

@@ -74,6 +74,7 @@ SIGNATURES = {
     "ttk_gather_rows": [_vp, _i64, _vp, _vp, _i64, _i64, _i, _vp],
     "ttk_scatter_rows": [_vp, _i64, _vp, _vp, _i64, _i64, _i, _vp],
     "ttk_colsum": [_vp, _i64, _i64, _i, _vp, _vp, _vp],
+    "ttk_multi_cast": [_vp, _i, _i64, _vp],
     "ttk_head_bwd": [_vp, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "ttk_dec_in_bwd": [_vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "ttk_enc_embed_train": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp],

@@ -439,6 +439,25 @@ dec_in_bwd_kernel(const __nv_bfloat16* __restrict__ de, int64_t ld, const int32_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight refresh: the fp32 (or bf16) master parameters of a stack -> their kernel-layout copies (bf16 GEMM operands, fp32
+// norm weights) in ONE launch. table: device int64 [n][4] = {src pointer, dst pointer, numel, kind}, kind = 2 * (src is
+// bf16) + (dst is fp32). blockIdx.y = tensor, blockIdx.x strides over its elements.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) multi_cast_kernel(const int64_t* __restrict__ table) {
+  const int64_t* e = table + static_cast<int64_t>(blockIdx.y) * 4;
+  const int64_t n = e[2];
+  const int kind = static_cast<int>(e[3]);
+  const void* src = reinterpret_cast<const void*>(static_cast<uintptr_t>(e[0]));
+  void* dst = reinterpret_cast<void*>(static_cast<uintptr_t>(e[1]));
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = (kind & 2) ? __bfloat162float(static_cast<const __nv_bfloat16*>(src)[i]) : static_cast<const float*>(src)[i];
+    if (kind & 1) static_cast<float*>(dst)[i] = v;
+    else static_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(v);
+  }
+}
+
 static inline bool bw_width_ok(int width) { return width > 0 && width % 256 == 0 && width <= 1024; }
 
 }  // namespace ttk
@@ -541,6 +560,18 @@ int ttk_colsum(const void* x, int64_t ld, int64_t M, int N, float* out, float* t
   if (blocks > 0x7fffffffLL) return TTK_ERR_BAD_SHAPE;
   colsum_kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>((N + 255) / 256)), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(x), ld, M, N, out, total);
+  return launch_status();
+}
+
+int ttk_multi_cast(const int64_t* table, int n, int64_t max_numel, cudaStream_t stream) {
+  if (n <= 0) return TTK_OK;
+  if (!table || max_numel <= 0) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (n > 65535) return TTK_ERR_BAD_SHAPE;
+  int64_t bx = (max_numel + 256 * 4 - 1) / (256 * 4);
+  if (bx < 1) bx = 1;
+  if (bx > 64) bx = 64;
+  multi_cast_kernel<<<dim3(static_cast<unsigned>(bx), static_cast<unsigned>(n)), 256, 0, stream>>>(table);
   return launch_status();
 }
 

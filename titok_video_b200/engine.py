@@ -286,6 +286,22 @@ class PreparedStack:
         self._all_dst.append(self.t[name])
         self._all_src.append(value.detach())
 
+    @staticmethod
+    def _cast_table(dst: List[torch.Tensor], src: List[torch.Tensor]):
+        """(device int64 [n,4] table, n, max numel) for ttk_multi_cast, or None when a dtype / layout is outside what the
+        kernel handles (then the refresh uses torch's multi-tensor copy)."""
+        rows = []
+        for d, s_ in zip(dst, src):
+            if s_.dtype not in (torch.float32, torch.bfloat16) or d.dtype not in (torch.float32, torch.bfloat16):
+                return None
+            if not (s_.is_contiguous() and d.is_contiguous()) or s_.numel() != d.numel() or not s_.is_cuda:
+                return None
+            rows.append([s_.data_ptr(), d.data_ptr(), d.numel(), 2 * int(s_.dtype == torch.bfloat16) + int(d.dtype == torch.float32)])
+        if not rows:
+            return None
+        tab = torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(dst[0].device)
+        return tab, len(rows), max(r[2] for r in rows)
+
     def layer_table(self) -> np.ndarray:
         """HOST int64 [n_layers, 9] device pointers for the native sequencers (include/titok_b200.h: ttk_layers_desc)."""
         if self.__dict__.get("_table") is None:
@@ -314,10 +330,13 @@ class PreparedStack:
         fast = self.__dict__.get("_fast")
         key = tuple((id(p), p.data_ptr(), p.dtype) for _, p in cached_named_params(self.module))
         if fast is not None and fast[0] == key:
-            _, gathers, dst, src = fast
+            _, gathers, dst, src, table = fast
             for w, dim, perm, tmp in gathers:
                 torch.index_select(w, dim, perm, out=tmp)
-            torch._foreach_copy_(dst, src)
+            if table is not None:
+                _lib.call("ttk_multi_cast", _ptr(table[0]), table[1], table[2], _stream())
+            else:
+                torch._foreach_copy_(dst, src)
             self.sig = sig
             return self
         m = self.module
@@ -362,7 +381,7 @@ class PreparedStack:
         # the (destination, source) pairs of this refresh are the recipe of every later one, as long as the parameter
         # objects and their storages stay the same (sources are aliases of the parameters / the persistent temporaries)
         if len(self._all_dst) == len(self.t):
-            self._fast = (key, gathers, list(self._all_dst), list(self._all_src))
+            self._fast = (key, gathers, list(self._all_dst), list(self._all_src), self._cast_table(self._all_dst, self._all_src))
         else:
             self._fast = None
         self._pending_dst, self._pending_src, self._all_dst, self._all_src = [], [], [], []
