@@ -130,3 +130,45 @@ def test_gradient_allreducer_averages_per_stack_buckets(tmp_path):
     for k in want:
         for r in range(world):
             assert torch.allclose(got[r][k], want[k] / world, rtol=1e-5, atol=1e-6), k
+
+
+def _accum_worker(rank, world, port, out_dir):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from titok_video_b200 import dist as D
+
+    torch.manual_seed(0)
+    net = torch.nn.ModuleDict({"encoder": torch.nn.Linear(6, 4), "decoder": torch.nn.Linear(4, 3)})
+    red = D.GradientAllReducer(net)
+    net.zero_grad(set_to_none=True)
+    with red.no_sync():  # first micro-batch: accumulate only
+        net["decoder"](net["encoder"](torch.full((5, 6), float(rank + 1)))).square().sum().backward()
+    net["decoder"](net["encoder"](torch.full((5, 6), float(rank + 3)))).square().sum().backward()
+    red.finish()
+    torch.save({k: p.grad.clone() for k, p in net.named_parameters()}, os.path.join(out_dir, f"a{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreducer_no_sync_accumulates_before_reducing(tmp_path):
+    """Two micro-batches per rank, the first under no_sync(): every rank ends with the mean over ranks of the SUM of its
+    two micro-batch gradients."""
+    world = 2
+    mp.spawn(_accum_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = [torch.load(tmp_path / f"a{r}.pt") for r in range(world)]
+    torch.manual_seed(0)
+    net = torch.nn.ModuleDict({"encoder": torch.nn.Linear(6, 4), "decoder": torch.nn.Linear(4, 3)})
+    want = None
+    for r in range(world):
+        net.zero_grad(set_to_none=True)
+        for v in (r + 1, r + 3):
+            net["decoder"](net["encoder"](torch.full((5, 6), float(v)))).square().sum().backward()
+        g = {k: p.grad.clone() for k, p in net.named_parameters()}
+        want = g if want is None else {k: want[k] + g[k] for k in g}
+    for k in want:
+        for r in range(world):
+            assert torch.allclose(got[r][k], want[k] / world, rtol=1e-5, atol=1e-6), k

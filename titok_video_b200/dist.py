@@ -93,6 +93,7 @@ class GradientAllReducer:
         self._pending: List[int] = []
         self._work: List[Optional[tuple]] = []
         self._handles = []
+        self._sync = True
         if self.world == 1:
             return
         by_child = {}
@@ -106,8 +107,25 @@ class GradientAllReducer:
             for p in params:
                 self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
 
+    def no_sync(self):
+        """Context manager for gradient accumulation (same contract as DistributedDataParallel.no_sync): backward passes
+        inside it only accumulate into `.grad`; the first backward outside it all-reduces the accumulated gradients."""
+        reducer = self
+
+        class _NoSync:
+            def __enter__(self_inner):
+                reducer._sync = False
+
+            def __exit__(self_inner, *exc):
+                reducer._sync = True
+                return False
+
+        return _NoSync()
+
     def _make_hook(self, b: int):
         def hook(_param):
+            if not self._sync:
+                return
             self._pending[b] -= 1
             if self._pending[b] == 0:
                 self._launch(b)
