@@ -630,3 +630,17 @@ def test_inference_sees_weights_updated_by_a_fused_optimizer_or_through_data():
     with torch.no_grad():
         rec2, _ = model(clips, [6])
     assert not torch.equal(rec2[0], rec1)
+
+
+def test_backward_twice_with_retain_graph():
+    """`loss.backward(retain_graph=True)` followed by a second backward re-runs the backward kernels on the same tapes and
+    accumulates: gradients double."""
+    model = build_model(False).to(DEV).train()
+    clips = [c.to(DEV) for c in O.make_clips([(4, 32, 32)], 5)]
+    rec, _ = model(clips, [5])
+    loss = (rec[0].float() - clips[0].float()).abs().mean()
+    loss.backward(retain_graph=True)
+    g1 = {k: p.grad.clone() for k, p in model.named_parameters()}
+    loss.backward()
+    for k, p in model.named_parameters():
+        assert torch.allclose(p.grad, 2 * g1[k], rtol=2e-3, atol=1e-6 + 2e-4 * float(g1[k].abs().max())), k

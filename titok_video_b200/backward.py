@@ -470,8 +470,7 @@ class EncoderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dz, _dcodes, _didx):
         dz = dz.to(bf16).contiguous()
-        grads, dflat = encoder_backward(ctx.m, ctx.dp, ctx.tape, dz, ctx.need_input)
-        ctx.tape = None
+        grads, dflat = encoder_backward(ctx.m, ctx.dp, ctx.tape, dz, ctx.need_input)  # (the tape dies with the graph node)
         return (None, None, None, dflat) + _ordered(ctx.m, "enc", grads, ctx.meta)
 
 
@@ -491,7 +490,6 @@ class DecoderFn(torch.autograd.Function):
     def backward(ctx, dout):
         dout = dout.to(bf16).contiguous()
         grads, dcodes = decoder_backward(ctx.m, ctx.dp, ctx.tape, dout)
-        ctx.tape = None
         dc = dcodes.to(ctx.codes_dtype) if ctx.need_codes else None
         return (None, None, dc) + _ordered(ctx.m, "dec", grads, ctx.meta)
 
