@@ -52,7 +52,9 @@ constexpr int AB_H = 64;             // rows of the streamed tile per stream
 constexpr int AB_D = 64;
 constexpr int AB_TILE = AB_T * AB_D * 2;  // 16 KB
 constexpr int AB_STAGES = 3;
-constexpr int AB_SMEM = 2 * AB_TILE + AB_STAGES * 2 * AB_TILE + 2 * 2 * 128 * 4 + 256 + 1024;
+constexpr int AB_STAT_IT = 32;  // dkv: iterations whose per-column statistics (lse, D) are staged in shared memory at once
+constexpr int AB_STAT_BYTES = AB_STAT_IT * 256 * 4;
+constexpr int AB_SMEM = 2 * AB_TILE + AB_STAGES * 2 * AB_TILE + AB_STAT_BYTES + 256 + 1024;
 constexpr int AB_THREADS = 128 + 16 * 32;  // 4 control warps + 16 math warps (four per scheduler: latency hiding)
 // TMEM columns. Two STREAMS per CTA: stream s owns rows [64 s, 64 s + 64) of every streamed tile, i.e. a [128 x 64] slice
 // of S and dP, its own P / dS buffers and its own barriers; both streams accumulate into the same acc0 / acc1. While the
@@ -80,8 +82,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sX1 = smem;                 // stationary: dkv K | dq Q
   uint8_t* sX2 = smem + AB_TILE;       //             dkv V | dq dO
   uint8_t* sY = smem + 2 * AB_TILE;    // ring of [Y1 | Y2]: dkv (Q, dO) | dq (K, V)
-  float* cols = reinterpret_cast<float*>(sY + AB_STAGES * 2 * AB_TILE);  // dkv: [2 parities][2 streams][lse 64 | delta 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(cols) + 2 * 2 * 128 * 4);
+  float* cols = reinterpret_cast<float*>(sY + AB_STAGES * 2 * AB_TILE);  // dkv: [AB_STAT_IT iterations][lse 128 | delta 128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(cols) + AB_STAT_BYTES);
   uint64_t* x_full = bars;
   uint64_t* y_full = bars + 1;
   uint64_t* y_empty = y_full + AB_STAGES;
@@ -226,7 +228,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const float c = p.scale_log2;
-    const int ct = (threadIdx.x - 128) & 255;  // index within the stream's 256 threads
     const int c0 = h * 32;                     // first column (within the stream's slice) of this thread
     float lse_r = 0.f, delta_r = 0.f;
     if (!DKV && r < w.st_valid) {
@@ -237,21 +238,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t par = it & 1;
       const int tile = it % n_tiles;
       const int y_valid = w.clip_len - tile * AB_T - s * AB_H;  // valid rows of the stream's slice (>= 64: all)
-      float* cl = cols + (par * 2 + s) * 128;                   // [lse 64 | delta 64]
-      if (DKV) {
-        // per-column (query row) log-sum-exp and D of the stream's slice; +inf / 0 beyond the clip => P = dS = 0
-        if (ct < 128) {
-          const int head = w.o_head0 + it / n_tiles;
-          const int cc = ct & 63;
-          const bool ok = cc < y_valid;
-          const int64_t gi = static_cast<int64_t>(head) * p.M + w.clip_row0 + tile * AB_T + s * AB_H + cc;
+      // per-column (query row) log-sum-exp and D of the streamed tiles: staged for AB_STAT_IT iterations at a time by all
+      // 512 math threads (one barrier pair per 32 iterations instead of one per iteration); +inf / 0 beyond the clip => P = dS = 0
+      if (DKV && (it % AB_STAT_IT) == 0) {
+        named_bar_sync(3, 512);  // nobody reads the previous chunk any more
+        const int chunk = min(AB_STAT_IT, n_it - it) * 256;
+        for (int j = threadIdx.x - 128; j < chunk; j += 512) {
+          const int it2 = it + (j >> 8);
+          const int cidx = j & 255, cc = cidx & 127;
+          const int rowc = (it2 % n_tiles) * AB_T + cc;
+          const bool ok = rowc < w.clip_len;
+          const int64_t gi = static_cast<int64_t>(w.o_head0 + it2 / n_tiles) * p.M + w.clip_row0 + rowc;
           float v;
-          if (ct < 64) v = ok ? p.lse[gi] : __int_as_float(0x7f800000);
+          if (cidx < 128) v = ok ? p.lse[gi] : __int_as_float(0x7f800000);
           else v = ok ? p.delta[gi] : 0.f;
-          cl[ct] = v;
+          cols[j] = v;
         }
-        named_bar_sync(1 + s, 256);
+        named_bar_sync(3, 512);
       }
+      const float* cl = cols + (it % AB_STAT_IT) * 256 + s * AB_H;  // lse at cl[c], D at cl[128 + c] for the stream's column c
       mbar_wait(&sdp_full[s], par);
       tc_fence_after();
       uint32_t sv[32], dv[32];
@@ -267,7 +272,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float l[4], d[4];
         if (DKV) {
           const float4 lv = *reinterpret_cast<const float4*>(cl + c0 + i);
-          const float4 dl = *reinterpret_cast<const float4*>(cl + 64 + c0 + i);
+          const float4 dl = *reinterpret_cast<const float4*>(cl + 128 + c0 + i);
           l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
           d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = dl.w;
         } else {
