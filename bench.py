@@ -182,14 +182,52 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path on the host cores
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, sample_clips=1):
+def _runner(args, timeout=900):
+    """oracle/reference_runner.py in a SEPARATE process (the reference's stack never shares a process with the product);
+    returns its JSON line or {"unavailable": why}."""
+    env = dict(os.environ)
+    env.setdefault("TRITON_CACHE_DIR", "/tmp/triton_cache_ref")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "reference_runner.py"), *args], capture_output=True,
+                           text=True, timeout=timeout, env=env, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "reference runner timed out"}
+    if r.returncode != 0:
+        return {"unavailable": (r.stderr or "").strip().splitlines()[-1][:300] if r.stderr else f"rc {r.returncode}"}
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    return {"unavailable": "no JSON line from the reference runner"}
+
+
+def reference_available():
+    return any(os.path.isdir(os.path.join(c, "model")) for c in
+               (os.environ.get("TITOK_REFERENCE_ROOT") or "/nonexistent", "/root/reference", os.path.join(ROOT, "baseline", "_ref")))
+
+
+def cpu_reference_run(steps, warmup, sample_clips=1, in_process=False):
+    """CPU arm. kind "reference+shims": the UNMODIFIED reference files (baseline/_ref, vendored by
+    scripts/vendor_reference.sh) on the host cores with the three CPU stand-ins for its CUDA-only third-party kernels
+    (oracle/ref_shim.py); weights drawn by the reference's own TiTok(cfg). kind "port" (only when no reference copy
+    travelled): the oracle restatement. Never imports titok_video_b200."""
+    if reference_available():
+        if in_process:
+            from oracle import reference_runner as RR
+
+            r = RR.cpu_bench(sample_clips, steps, warmup)
+        else:
+            r = _runner(["bench", "--mode", "cpu", "--batch", str(sample_clips), "--steps", str(steps), "--warmup", str(warmup)])
+        if "unavailable" not in r:
+            r["kind"] = "reference"  # the reference's own files; its three CUDA-only third-party symbols are stand-ins
+            r["shims"] = ["flash_attn.flash_attn_varlen_func -> per-segment SDPA", "flash_attn Triton RMSNorm -> torch fp32",
+                          "xformers.ops.SwiGLU -> placeholder (dead code)"]
+            return r
     from oracle import titok_oracle as O
-    import titok_video_b200 as T
-    from titok_video_b200.config import tiny_config
 
     torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(42)
-    sd = {k: v.detach().clone() for k, v in T.TiTok(tiny_config(LEVELS, PATCH)).state_dict().items()}
+    sd = O.random_state_dict(42)
     clips = O.make_clips([CLIP_A] * sample_clips, 0)
     tcs = [TOKENS_A] * sample_clips
     times = []
@@ -202,8 +240,14 @@ def cpu_reference_run(steps, warmup, sample_clips=1):
                 times.append(dt)
     total = sum(times)
     return {"clips_per_s": sample_clips * len(times) / total, "ms_per_step": 1e3 * total / len(times),
-            "cores": torch.get_num_threads(),
+            "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{sample_clips} clip(s) 3x16x168x168 / 128 tokens per step, {len(times)} timed steps, torch CPU oracle port"}
+
+
+def workload_string(B):
+    _, s, _ = clip_flops()
+    return (f"configs/tiny.yaml batch tokenise+reconstruct (C3): per GPU {B} clips 3x16x168x168 bf16, "
+            f"128 latent tokens each, packed rows/step {B * s}")
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -392,15 +436,18 @@ def scaled_leg(T, dev, world, rank, dist, steps, warmup, clips_per_gpu=4):
 def run_reference(args, rank):
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, max(args.warmup, 1))
+    r = cpu_reference_run(args.steps, max(args.warmup, 1), in_process=True)
     line = {"impl": "reference", "metric": "clips/sec encode+decode", "value": r["clips_per_s"], "unit": "clips/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs/tiny.yaml batch tokenise+reconstruct, clips 3x16x168x168 / 128 latent tokens",
-                       "note": "CPU arm: oracle port of the reference path (the reference has no CPU path of its own: "
-                               "flash-attn / Triton RMSNorm are CUDA-only), all host threads, bounded sample per step"},
-            "cpu_baseline": {"value": r["clips_per_s"], "unit": "clips/s", "cores": r["cores"], "kind": "port",
-                             "sample": r["sample"]},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"bfloat16": "bf16", "float32": "f32"}.get(r.get("dtype"), "bf16"), "data": "synthetic",
+            "config": {"workload": workload_string(args.batch), "clips_per_gpu_per_step": args.batch,
+                       "sample": "each timed step is a bounded sample of that workload: " + r["sample"],
+                       "note": "CPU arm: the reference has no CPU path of its own (flash-attn / Triton RMSNorm are CUDA-only); "
+                               "its unmodified files run on all host threads with stand-ins for those third-party kernels. "
+                               "The same-box GPU run of the reference (real flash-attn 2.8.3 / Triton / cuBLAS) is reported "
+                               "by the product arm as config.gpu_reference"},
+            "cpu_baseline": {"value": r["clips_per_s"], "unit": "clips/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": r["sample"], "shims": r.get("shims")},
             "e2e": {"value": r["clips_per_s"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -424,8 +471,11 @@ def main():
                     help="clips per GPU per step of the training-step leg(s) (BASELINE configs[3]; 3 clips A = tiny.yaml's "
                          "6144-token budget); empty = skip")
     ap.add_argument("--no-scaled", action="store_true", help="skip the scaled-up (32x256x256) leg (BASELINE configs[4])")
-    ap.add_argument("--e2e-full-recon", action="store_true",
-                    help="e2e leg copies the full reconstructions back to the host (default: token indices + per-clip error)")
+    ap.add_argument("--e2e-tokens-only", action="store_true",
+                    help="skip the full-result e2e leg (default: `e2e` brings the decoded clips back to the host too; "
+                         "`e2e.tokens_only` is the same leg with token indices + per-clip error only)")
+    ap.add_argument("--no-gpu-reference", action="store_true",
+                    help="skip the same-box GPU run of the unmodified reference (config.gpu_reference)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -441,7 +491,6 @@ def main():
     import titok_video_b200 as T
     from titok_video_b200 import _lib
     from titok_video_b200.config import tiny_config
-    from oracle import titok_oracle as O  # only for deterministic synthetic clips and the cpu_baseline leg
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -516,7 +565,6 @@ def main():
     # ---------------- e2e: pinned host clips -> H2D -> public API -> D2H of indices + reconstructions ----------------
     h2d_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
     SLOTS = 2
-    full = args.e2e_full_recon
     main_stream = torch.cuda.current_stream()
 
     def _flat_of(recon):
@@ -525,7 +573,7 @@ def main():
         n = B * 3 * CLIP_A[0] * CLIP_A[1] * CLIP_A[2]
         return base.reshape(-1).as_strided((n,), (1,), base.storage_offset())
 
-    def e2e_leg(host_bufs, in_dtype):
+    def e2e_leg(host_bufs, in_dtype, full):
         """Timed region per step: H2D of the step's clips from pinned host memory (side stream), the public API call,
         D2H of the results into pinned host memory (side stream). Returns (device ms, wall ms) per step, max over ranks."""
         in_flat = [torch.empty((B * clip_numel,), dtype=in_dtype, device=dev) for _ in range(SLOTS)]
@@ -585,12 +633,43 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0].item()), float(t[1].item())
 
-    e2e_ms, e2e_wall_ms = e2e_leg(host_flat, torch.bfloat16)
+    full = not args.e2e_tokens_only
+    e2e_ms, e2e_wall_ms = e2e_leg(host_flat, torch.bfloat16, full)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    tok_ms, tok_wall_ms = e2e_leg(host_flat, torch.bfloat16, False) if full else (e2e_ms, e2e_wall_ms)
+
+    # plain pinned-copy ceiling of this box at N ranks: the same 173 MB H2D (and D2H) per step with NO compute, all ranks
+    # at once -- what `e2e` cannot beat (shows whether the e2e scaling curve is the platform's host<->device path)
+    def copy_probe():
+        dbuf = torch.empty((B * clip_numel,), dtype=torch.bfloat16, device=dev)
+        hout = torch.empty((B * clip_numel,), dtype=torch.bfloat16).pin_memory()
+        res = {}
+        for name, fn in (("h2d", lambda i: dbuf.copy_(host_flat[i % INPUT_SETS], non_blocking=True)),
+                         ("d2h", lambda i: hout.copy_(dbuf, non_blocking=True))):
+            for i in range(2):
+                fn(i)
+            barrier()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            n = 8
+            for i in range(n):
+                fn(i)
+            eb.record()
+            barrier()
+            t = torch.tensor([ea.elapsed_time(eb) / n], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res[name + "_ms_per_step"] = float(t.item())
+            res[name + "_gbs_per_gpu"] = B * clip_bytes / (float(t.item()) * 1e-3) / 1e9
+        res["note"] = (f"{B * clip_bytes / 1e6:.0f} MB pinned<->device copies, all {world} rank(s) at once, no compute: "
+                       "the floor of an e2e step is max(compute, h2d, d2h) since the three overlap")
+        return res
+
+    probe = copy_probe()
     # same leg fed with decoded uint8 frames (what the reference's dataset holds before `/255*2-1`, video_dataset.py:111-119):
     # half the PCIe bytes, normalised on the device by ttk_normalize_u8 (bit-identical to the host expression)
     host_u8 = [torch.randint(0, 256, (B * clip_numel,), generator=gen, dtype=torch.uint8).pin_memory() for _ in range(INPUT_SETS)]
-    u8_ms, u8_wall_ms = e2e_leg(host_u8, torch.uint8)
+    u8_ms, u8_wall_ms = e2e_leg(host_u8, torch.uint8, full)
     e2e_u8 = {"value": world * B * args.steps / (u8_ms * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": B * clip_numel,
               "d2h_bytes_per_step": (B * clip_bytes if full else 0) + B * TOKENS_A * 4 + B * 16, "ms_per_step": u8_ms / args.steps,
               "wall_ms_per_step": u8_wall_ms / args.steps,
@@ -671,36 +750,76 @@ def main():
     whole = {"tflops": value * flops_clip / 1e12, "frac_of_tensor_peak": value * flops_clip / 1e12 / pk["bf16_tflops_sustained"]}
 
     vq = None
-    if rank == 0 and world == 1 and not args.no_vq:
+    if rank == 0 and not args.no_vq:
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         import vq_bench
 
         vq = vq_bench.main(quick=True, quiet=True)
+    if world > 1:
+        dist.barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(steps=6, warmup=1)
-        cpu = {"value": r["clips_per_s"], "unit": "clips/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        cpu = {"value": r["clips_per_s"], "unit": "clips/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+               "shims": r.get("shims")}
+
+    # same-box GPU run of the UNMODIFIED reference (flash-attn 2.8.3 varlen + Triton RMSNorm + cuBLAS), separate process
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        if reference_available():
+            gpu_ref = _runner(["bench", "--mode", "gpu", "--batch", str(B), "--steps", str(max(4, args.steps // 2)), "--warmup", "3"])
+            if "unavailable" not in gpu_ref:
+                gpu_ref["ours_over_reference"] = value / gpu_ref["clips_per_s"]
+                top_attn = ksum.get("ttk_attn_varlen_fwd")
+                if top_attn and gpu_ref.get("attn_alone_us_per_launch"):
+                    gpu_ref["ours_attn_us_per_launch"] = 1e3 * top_attn[0] / top_attn[1]
+        else:
+            gpu_ref = {"unavailable": "no reference copy under baseline/_ref (scripts/vendor_reference.sh not run)"}
 
     if rank == 0:
+        def vq_line(r):
+            return {"K": r["K"], "D": r["D"], "N": r["N"], "ms": r["ms"], "tflops": r["tflops_algorithmic"],
+                    "frac_burst": r["frac_of_tensor_peak"], "mma_frac_burst": r["mma_frac_of_tensor_peak"]}
+
+        if roofline is not None and vq:
+            roofline["vq"] = [vq_line(r) for r in vq if r["kernel"] == "ttk_vq_argmin"]
+            roofline["fsq"] = [{"dtype": r["dtype"], "N": r["N"], "ms": r["ms"], "gbs": r["gbs"], "frac_hbm": r["frac_of_hbm_peak"]}
+                               for r in vq if r["kernel"] == "ttk_fsq_fwd"]
+            roofline["vq_peak"] = {"tflops": pk["bf16_tflops"], "source": pk["source"] + " (burst bf16: kernel timed alone)"}
+        cfg = {"workload": workload_string(B), "clips_per_gpu_per_step": B,
+               "global_clips_per_step": world * B, "latent_tokens_per_s": value * TOKENS_A,
+               "parallelism": f"clip-sharded x{world}, no data-path collective",
+               "l2": f"inputs rotate over {INPUT_SETS} sets ({INPUT_SETS * B * clip_bytes / 1e6:.0f} MB) and the per-step "
+                     f"activation working set exceeds the 126 MB L2",
+               "weights": "random init, seed 42 (reference initialiser)", "codebook_usage_percent": usage,
+               "whole_step_tflops": whole["tflops"], "whole_step_frac_of_tensor_peak": whole["frac_of_tensor_peak"],
+               "gpu_reference": gpu_ref}
+        if train:
+            for k, v in train.items():
+                cfg["train_step_" + k] = {kk: vv for kk, vv in v.items() if kk not in ("kernels", "what", "note")}
+        if scaled:
+            cfg["scaled_config"] = scaled
+        if ragged:
+            cfg["ragged_stream"] = {k: v for k, v in ragged.items() if k != "note"}
+        d2h_small = B * TOKENS_A * 4 + B * 16
         line = {
             "metric": "clips/sec encode+decode", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"configs/tiny.yaml batch tokenise+reconstruct (C3): per GPU {B} clips 3x16x168x168 bf16, "
-                                   f"128 latent tokens each, packed rows/step {B * s}", "clips_per_gpu_per_step": B,
-                       "global_clips_per_step": world * B, "latent_tokens_per_s": value * TOKENS_A,
-                       "parallelism": f"clip-sharded x{world}, no data-path collective",
-                       "l2": f"inputs rotate over {INPUT_SETS} sets ({INPUT_SETS * B * clip_bytes / 1e6:.0f} MB) and the per-step "
-                             f"activation working set exceeds the 126 MB L2",
-                       "weights": "random init, seed 42 (reference initialiser)", "codebook_usage_percent": usage},
+            "config": cfg,
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": B * clip_bytes,
-                    "d2h_bytes_per_step": (B * clip_bytes if args.e2e_full_recon else 0) + B * TOKENS_A * 4 + B * 16,
+                    "d2h_bytes_per_step": (B * clip_bytes if full else 0) + d2h_small,
                     "result": ("token indices + per-clip (L1, squared) reconstruction error" +
-                               (" + full reconstructions" if args.e2e_full_recon else
-                                "; reconstructions stay on the device (--e2e-full-recon copies them too)")),
+                               (" + the decoded clips (full reconstructions)" if full else
+                                "; reconstructions stay on the device (--e2e-tokens-only)")),
                     "ms_per_step": e2e_ms / args.steps,
                     "wall_ms_per_step": e2e_wall_ms / args.steps,
+                    "tokens_only": {"value": world * B * args.steps / (tok_ms * 1e-3), "ms_per_step": tok_ms / args.steps,
+                                    "d2h_bytes_per_step": d2h_small,
+                                    "result": "token indices + per-clip error only (a tokenisation job; the decoded clips stay on the device)"},
+                    "copy_probe": probe,
+                    "u8": e2e_u8,
                     "api": "TiTok.tokenize_reconstruct_(clips, token_counts) from pinned host clips, 2-slot pipeline, CUDA-graph replay "
                            "(the value leg launches the same kernels one by one so that each can be timed with CUDA events)"},
             "gpu_launches": launches, "roofline": roofline, "whole_step": whole, "kernels": kernels, "clocks": clocks,

@@ -11,9 +11,20 @@ the reference's own files, which then run unchanged:
     for GQA (q head h uses kv head h // (Hq/Hkv)), softmax scale d^-0.5, non-causal
   * xformers.ops.SwiGLU                      -> placeholder class (never instantiated)
 
-It exists to (a) generate the golden fixtures under tests/golden/ (make_golden.py) and (b) pin the oracle
-restatement (oracle/titok_oracle.py) against the real reference. It only works where /root/reference is mounted
-(this build container); nothing on the GPU box imports it.
+It exists to (a) generate the golden fixtures under tests/golden/ (make_golden.py), (b) pin the oracle
+restatement (oracle/titok_oracle.py) against the real reference, (c) run the reference itself as the baseline arm of
+bench.py (`--impl reference` on the host cores, `config.gpu_reference` on the GPU) and as the live GPU oracle of
+tests/test_gpu_reference.py.
+
+Where the reference comes from: $TITOK_REFERENCE_ROOT, else /root/reference (the build container), else the git-ignored
+copy under <repo>/baseline/_ref/ that scripts/vendor_reference.sh makes at build time and that travels to the GPU box
+with the gpurun snapshot.
+
+Two modes (one per process, sys.modules is global):
+  install("cpu")  the three stand-ins above (no CUDA needed)
+  install("gpu")  ONLY the xformers placeholder: the reference then runs its REAL third-party kernels -- flash-attn
+                  2.8.3 `flash_attn_varlen_func` (transformer.py:100), flash-attn's Triton RMSNorm (blocks.py:27) and
+                  cuBLAS through nn.Linear -- i.e. the same-box bar of SURVEY 2.1 K1-K3.
 """
 from __future__ import annotations
 
@@ -26,7 +37,18 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REFERENCE_ROOT = os.environ.get("TITOK_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VENDORED_ROOT = os.path.join(_REPO, "baseline", "_ref")
+
+
+def _find_root() -> str:
+    for cand in (os.environ.get("TITOK_REFERENCE_ROOT"), "/root/reference", VENDORED_ROOT):
+        if cand and os.path.isdir(os.path.join(cand, "model")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:
@@ -61,35 +83,49 @@ def _flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, m
     return out
 
 
-_installed = False
+_installed = None  # "cpu" | "gpu"
 
 
-def install():
+def install(mode: str = "cpu"):
     global _installed
-    if _installed:
+    if _installed == mode:
         return
+    if _installed is not None:
+        raise RuntimeError(f"reference already imported in {_installed!r} mode in this process")
+    if mode not in ("cpu", "gpu"):
+        raise ValueError(mode)
     if not available():
-        raise RuntimeError(f"reference not mounted at {REFERENCE_ROOT}")
-    fa = types.ModuleType("flash_attn")
-    fa.flash_attn_varlen_func = _flash_attn_varlen_func
-    fa_ops = types.ModuleType("flash_attn.ops")
-    fa_tr = types.ModuleType("flash_attn.ops.triton")
-    fa_ln = types.ModuleType("flash_attn.ops.triton.layer_norm")
-    fa_ln.RMSNorm = _RMSNorm
-    xf = types.ModuleType("xformers")
-    xf_ops = types.ModuleType("xformers.ops")
-    xf_ops.SwiGLU = type("SwiGLU", (), {})
-    for name, mod in [("flash_attn", fa), ("flash_attn.ops", fa_ops), ("flash_attn.ops.triton", fa_tr),
-                      ("flash_attn.ops.triton.layer_norm", fa_ln), ("xformers", xf), ("xformers.ops", xf_ops)]:
+        raise RuntimeError(f"reference not found (looked at $TITOK_REFERENCE_ROOT, /root/reference, {VENDORED_ROOT})")
+    mods = []
+    if mode == "cpu":
+        fa = types.ModuleType("flash_attn")
+        fa.flash_attn_varlen_func = _flash_attn_varlen_func
+        fa_ops = types.ModuleType("flash_attn.ops")
+        fa_tr = types.ModuleType("flash_attn.ops.triton")
+        fa_ln = types.ModuleType("flash_attn.ops.triton.layer_norm")
+        fa_ln.RMSNorm = _RMSNorm
+        mods += [("flash_attn", fa), ("flash_attn.ops", fa_ops), ("flash_attn.ops.triton", fa_tr),
+                 ("flash_attn.ops.triton.layer_norm", fa_ln)]
+    try:
+        import xformers.ops  # noqa: F401  (not installed in this image; if it ever is, use it)
+        if not hasattr(sys.modules["xformers.ops"], "SwiGLU"):
+            raise ImportError
+    except Exception:
+        xf = types.ModuleType("xformers")
+        xf_ops = types.ModuleType("xformers.ops")
+        xf_ops.SwiGLU = type("SwiGLU", (), {})
+        xf.ops = xf_ops
+        mods += [("xformers", xf), ("xformers.ops", xf_ops)]
+    for name, mod in mods:
         sys.modules[name] = mod
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
-    _installed = True
+    _installed = mode
 
 
-def reference_modules():
+def reference_modules(mode: str = "cpu"):
     """(model.titok, model.base.blocks, model.quantizer.fsq, train_utils.codebook_logging) of the reference."""
-    install()
+    install(mode)
     return (importlib.import_module("model.titok"), importlib.import_module("model.base.blocks"),
             importlib.import_module("model.quantizer.fsq"), importlib.import_module("train_utils.codebook_logging"))
 
@@ -105,8 +141,8 @@ class AttrDict(dict):
 
 
 def build_reference_titok(fsq_levels=(7, 5, 5, 5, 5), patch_size=(4, 8, 8), encoder_size="tiny", decoder_size="tiny",
-                          seed=42):
-    titok_mod, _, _, _ = reference_modules()
+                          seed=42, mode="cpu"):
+    titok_mod, _, _, _ = reference_modules(mode)
     cfg = AttrDict.wrap({"tokenizer": {"model": {"patch_size": list(patch_size), "fsq_levels": list(fsq_levels),
                                                   "encoder_size": encoder_size, "decoder_size": decoder_size}}})
     torch.manual_seed(seed)

@@ -328,6 +328,43 @@ def stress_init_(sd: Dict[str, torch.Tensor], seed: int = 1) -> Dict[str, torch.
     return sd
 
 
+def random_state_dict(seed: int = 42, enc: str = "tiny", dec: str = "tiny", patch: Sequence[int] = (4, 8, 8),
+                      token_size: int = 5) -> Dict[str, torch.Tensor]:
+    """A state dict with the reference's 76-key layout and initialiser STATISTICS (Linear ~ N(0, 0.02^2), bias 0, norm
+    weights 1, mask_token ~ width^-0.5 N(0,1); utils.py:54-66, blocks.py:50,126) -- NOT the reference's RNG stream. Only for
+    timing the port when no reference copy is at hand (bench.py fallback); parity tests draw weights through the modules."""
+    g = torch.Generator().manual_seed(seed)
+    pf = 3 * patch[0] * patch[1] * patch[2]
+    sd: Dict[str, torch.Tensor] = {}
+
+    def lin(name, out_f, in_f, bias):
+        sd[name + ".weight"] = torch.randn((out_f, in_f), generator=g) * 0.02
+        if bias:
+            sd[name + ".bias"] = torch.zeros(out_f)
+
+    for prefix, size, fin, fout in (("encoder", enc, pf, token_size), ("decoder", dec, token_size, pf)):
+        w, n_layers, (hq, hkv) = model_dims(size)
+        inner = 32 * ((int(4.0 * (2 / 3) * w) + 31) // 32)  # transformer.py:39-40
+        sd[f"{prefix}.mask_token"] = torch.randn((1, 1), generator=g) * w ** -0.5
+        lin(f"{prefix}.proj_in", w, fin, True)
+        sd[f"{prefix}.ln_pre_t.weight"] = torch.ones(w)
+        sd[f"{prefix}.ln_pre_p.weight"] = torch.ones(w)
+        for i in range(n_layers):
+            ml = f"{prefix}.model_layers"
+            sd[f"{ml}.attn_layer.{i}.pre_ln.weight"] = torch.ones(w)
+            lin(f"{ml}.attn_layer.{i}.to_qkv", 2 * w + 2 * hkv * 64, w, False)
+            lin(f"{ml}.attn_layer.{i}.out_proj", w, w, False)
+            sd[f"{ml}.ffd_layer.{i}.norm.weight"] = torch.ones(w)
+            lin(f"{ml}.ffd_layer.{i}.w12", 2 * inner, w, False)
+            lin(f"{ml}.ffd_layer.{i}.w3", w, inner, False)
+            if i < n_layers - 1:
+                sd[f"{ml}.attn_post_ln.{i}.weight"] = torch.ones(w)
+                sd[f"{ml}.ffd_post_ln.{i}.weight"] = torch.ones(w)
+        sd[f"{prefix}.ln_post.weight"] = torch.ones(w)
+        lin(f"{prefix}.proj_out", fout, w, True)
+    return sd
+
+
 def make_clips(shapes: Sequence[Sequence[int]], seed: int = 0) -> List[torch.Tensor]:
     """uniform [-1, 1) clips in bf16 (torch.manual_seed(0); rand*2-1)."""
     g = torch.Generator().manual_seed(seed)

@@ -644,3 +644,31 @@ def test_backward_twice_with_retain_graph():
     loss.backward()
     for k, p in model.named_parameters():
         assert torch.allclose(p.grad, 2 * g1[k], rtol=2e-3, atol=1e-6 + 2e-4 * float(g1[k].abs().max())), k
+
+
+def test_frozen_encoder_tape_survives_an_intervening_encoder_launch():
+    """Frozen encoder / trainable decoder (titok.py:81-85): the codes on the decoder's tape must be a private copy. An
+    inference encoder launch between the forward and the backward (exactly what loss_module._forward_generator does with
+    its discriminator on the detached target) overwrites the device-wide 'codes' arena; gradients must not change."""
+    shapes, tcs = [(8, 64, 48), (4, 16, 24)], [16, 3]
+    clips = [c.to(DEV) for c in O.make_clips(shapes, 0)]
+    other = [c.to(DEV) for c in O.make_clips(shapes, 9)]
+
+    def run(intervene):
+        model = build_model(True).to(DEV).train()
+        for p in model.encoder.parameters():
+            p.requires_grad_(False)
+        recon, _ = model(clips, tcs)
+        if intervene:
+            with torch.no_grad():
+                model.encoder(other, tcs)          # same plan, different codes -> same arena slots
+                model(other, tcs)
+        loss = torch.stack([(r_.float() - c.float()).abs().mean() for c, r_ in zip(clips, recon)]).mean()
+        loss.backward()
+        torch.cuda.synchronize()
+        assert all(p.grad is None for p in model.encoder.parameters())
+        return {k: p.grad.detach().clone() for k, p in model.decoder.named_parameters()}
+
+    a, b = run(False), run(True)
+    for k in a:
+        assert torch.equal(a[k], b[k]), f"decoder gradient of {k} changed after an intervening encoder launch"

@@ -23,6 +23,8 @@ def _load() -> ctypes.CDLL:
             f"{LIB_PATH} not found: the CUDA extension has not been built. "
             "Run `python titok_video_b200/build.py` (needs nvcc); there is no CPU fallback."
         )
+    import torch  # noqa: F401  (loads libcudart.so.12 into the process: the library links the CUDA runtime dynamically)
+
     return ctypes.CDLL(LIB_PATH)
 
 

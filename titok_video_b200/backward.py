@@ -479,7 +479,9 @@ class DecoderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, m, dp, codes, *params):
-        codes_b = codes.detach().to(bf16).contiguous()
+        # always a private copy: `codes` may be a view of the device-wide 'codes' arena (engine.encoder_launch under
+        # no_grad, the frozen-encoder case), which any later encoder launch overwrites before this node's backward runs
+        codes_b = codes.detach().to(bf16).clone(memory_format=torch.contiguous_format)
         out, tape = decoder_forward_train(m, dp, codes_b)
         ctx.m, ctx.dp, ctx.tape, ctx.meta = m, dp, tape, _meta(m)
         ctx.codes_dtype = codes.dtype

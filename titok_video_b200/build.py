@@ -70,7 +70,9 @@ def build(force: bool = False, verbose: bool = False, tag: str = "", defines: tu
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         list(ex.map(run, jobs))
     if force or jobs or _stale(LIB, objs):
-        run([nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static"])
+        # the CUDA runtime is linked dynamically: PyTorch has already loaded libcudart in-process, and the shipped binary then
+        # carries no copy of the runtime
+        run([nvcc, "-shared", "-o", LIB, *objs, "-cudart", "shared"])
     return LIB
 
 

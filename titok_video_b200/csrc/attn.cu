@@ -440,13 +440,9 @@ static int attn_fwd_launch(const void* qkv, int64_t ld, int M, int width, int gq
   p.o_save = static_cast<__nv_bfloat16*>(o_save);
   p.lse = lse;
   p.M = M;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess)
-      return TTK_ERR_CUDA;
-    attr_done = true;
-  }
+  static PerDeviceOnce once_plain, once_train;
+  if (int e = set_smem_attr_once(once_plain, reinterpret_cast<const void*>(attn_fwd_kernel<false>), AT_SMEM)) return e;
+  if (int e = set_smem_attr_once(once_train, reinterpret_cast<const void*>(attn_fwd_kernel<true>), AT_SMEM)) return e;
   if (o_save)
     attn_fwd_kernel<true><<<n_work, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
   else

@@ -435,11 +435,8 @@ static int launch_attn_bwd(const void* qkv, int64_t ld, const void* dO, int64_t 
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   auto kern = attn_bwd_kernel<DKV>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM) != cudaSuccess) return TTK_ERR_CUDA;
-    attr_done = true;
-  }
+  static PerDeviceOnce once;  // one per template instantiation
+  if (int e = set_smem_attr_once(once, reinterpret_cast<const void*>(kern), AB_SMEM)) return e;
   kern<<<n_work, AB_THREADS, AB_SMEM, stream>>>(tmQ, tmK, tmV, tmDO, p);
   return launch_status();
 }

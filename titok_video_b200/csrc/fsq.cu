@@ -329,13 +329,8 @@ int ttk_hist_u32(const int32_t* idx, int64_t n, int K, uint32_t* counts, cudaStr
   if (blocks < 1) blocks = 1;
   const size_t smem = static_cast<size_t>(K) * 4;
   if (smem <= 96 * 1024) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      if (cudaFuncSetAttribute(hist_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) !=
-          cudaSuccess)
-        return TTK_ERR_CUDA;
-      attr_done = true;
-    }
+    static PerDeviceOnce once;
+    if (int e = set_smem_attr_once(once, reinterpret_cast<const void*>(hist_smem_kernel), 96 * 1024)) return e;
     hist_smem_kernel<<<static_cast<int>(blocks), threads, smem, stream>>>(idx, n, K, counts);
   } else {
     hist_gmem_kernel<<<static_cast<int>(blocks * 4), threads, 0, stream>>>(idx, n, K, counts);

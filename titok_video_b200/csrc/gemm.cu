@@ -716,12 +716,8 @@ static int launch_gemm(const GemmIo& io, GemmParams& p, cudaStream_t stream) {
     p.num_n_tiles = (p.N + BN - 1) / BN;
   p.num_k_blocks = (p.K + BK - 1) / BK;
   auto kern = gemm_kernel<BN, EPI, B_MN, WS>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
-      return TTK_ERR_CUDA;
-    attr_done = true;
-  }
+  static PerDeviceOnce once;  // one per template instantiation
+  if (int e = set_smem_attr_once(once, reinterpret_cast<const void*>(kern), S::TOTAL)) return e;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, 128 + 32 * epi_warps(EPI, BN), S::TOTAL, stream>>>(tmA, tmB, tmO, tmO2, tmR, p);

@@ -1,5 +1,6 @@
 #include "host_util.cuh"
 
+#include <atomic>
 #include <mutex>
 
 namespace ttk {
@@ -38,25 +39,51 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 
 long long* g_trace = nullptr;
 
-static int g_sm_major = -1, g_sm_minor = -1, g_num_sms = 0;
-static std::once_flag g_dev_once;
-static void query_dev() {
-  std::call_once(g_dev_once, []() {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return;
-    cudaDeviceGetAttribute(&g_sm_major, cudaDevAttrComputeCapabilityMajor, dev);
-    cudaDeviceGetAttribute(&g_sm_minor, cudaDevAttrComputeCapabilityMinor, dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  });
+// Per-device state (the library is re-entrant across devices and threads: nothing is cached for "the first device seen").
+struct DevInfo {
+  std::atomic<int> ready{0};
+  int major = -1, minor = -1, sms = 0;
+};
+static DevInfo g_dev[TTK_MAX_DEVICES];
+
+static const DevInfo* dev_info() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= TTK_MAX_DEVICES) return nullptr;
+  DevInfo& d = g_dev[dev];
+  if (!d.ready.load(std::memory_order_acquire)) {
+    int mj = -1, mn = -1, sms = 0;  // racing threads write identical values
+    cudaDeviceGetAttribute(&mj, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&mn, cudaDevAttrComputeCapabilityMinor, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    d.major = mj;
+    d.minor = mn;
+    d.sms = sms;
+    d.ready.store(1, std::memory_order_release);
+  }
+  return &d;
 }
 
 int check_device_sm100() {
-  query_dev();
-  return (g_sm_major == 10) ? TTK_OK : TTK_ERR_ARCH;
+  const DevInfo* d = dev_info();
+  return (d && d->major == 10) ? TTK_OK : TTK_ERR_ARCH;
 }
 int num_sms() {
-  query_dev();
-  return g_num_sms > 0 ? g_num_sms : 148;
+  const DevInfo* d = dev_info();
+  return (d && d->sms > 0) ? d->sms : 148;
+}
+
+int set_smem_attr_once(PerDeviceOnce& once, const void* kernel, int bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return TTK_ERR_CUDA;
+  if (dev < 0 || dev >= TTK_MAX_DEVICES) {  // beyond the cache: set it every time (cheap, idempotent)
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? TTK_OK : TTK_ERR_CUDA;
+  }
+  const unsigned long long bit = 1ull << dev;
+  if (once.mask.load(std::memory_order_acquire) & bit) return TTK_OK;
+  // function attributes are per device; two threads racing here set the same value twice, which is harmless
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return TTK_ERR_CUDA;
+  once.mask.fetch_or(bit, std::memory_order_release);
+  return TTK_OK;
 }
 
 }  // namespace ttk

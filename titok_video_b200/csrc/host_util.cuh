@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace ttk {
@@ -25,8 +27,17 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 // development aid: device buffer for clock64 pipeline stamps (ttk_debug_set_trace), null in production
 extern long long* g_trace;
 
+// Both are answered for the CURRENT device of the calling thread (cached per device ordinal).
 int check_device_sm100();
 int num_sms();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: set it once per (kernel, device).
+// Usage in a launcher:  static PerDeviceOnce once;  if (int e = set_smem_attr_once(once, (const void*)kern, bytes)) return e;
+constexpr int TTK_MAX_DEVICES = 64;
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+};
+int set_smem_attr_once(PerDeviceOnce& once, const void* kernel, int bytes);
 
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? TTK_OK : TTK_ERR_CUDA; }
 inline int launch_status() { return cuda_status(cudaGetLastError()); }

@@ -562,13 +562,9 @@ int ttk_vq_argmin(const void* z, int64_t ldz, const void* cb_aug, int64_t lda, i
   // inner extent = true D for z (columns >= D read as zero, then patched with ones), DA for the codebook
   if (int e = make_tmap_bf16_2d(&tmZ, z, static_cast<uint64_t>(N), D, ldz, VQ_BM)) return e;
   if (int e = make_tmap_bf16_2d(&tmC, cb_aug, K, DA, lda, VQ_BN)) return e;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(vq_argmin2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return TTK_ERR_CUDA;
-    attr_done = true;
-  }
+  static PerDeviceOnce once1, once2;
+  if (int e = set_smem_attr_once(once1, reinterpret_cast<const void*>(vq_argmin_kernel), 227 * 1024)) return e;
+  if (int e = set_smem_attr_once(once2, reinterpret_cast<const void*>(vq_argmin2_kernel), 227 * 1024)) return e;
   if (num_kb <= 3 && p.num_m_tiles > num_sms()) {
     // two z tiles per CTA share every codebook tile (vq_argmin2_kernel)
     int bs2 = (VQ_SMEM_BUDGET - 2 * a_one) / VQ_B_BYTES;

@@ -189,11 +189,8 @@ static int launch_wgrad(const void* dy, int64_t ldy, const void* x, int64_t ldx,
   splits = (p.num_k_blocks + per - 1) / per;
   p.splits = splits;
   auto kern = wgrad_kernel<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return TTK_ERR_CUDA;
-    attr_done = true;
-  }
+  static PerDeviceOnce once;  // one per template instantiation
+  if (int e = set_smem_attr_once(once, reinterpret_cast<const void*>(kern), S::TOTAL)) return e;
   kern<<<tiles * splits, 256, S::TOTAL, stream>>>(tmA, tmB, p);
   return launch_status();
 }
