@@ -82,6 +82,15 @@ int ttk_vq_argmin(const void* z, int64_t ldz, const void* cb_aug, int64_t lda, i
  * (numerator of the commitment / codebook loss of a learned-codebook VQ; the reference's FSQ has no such loss). */
 int ttk_vq_gather_loss(const void* z, int64_t ldz, const void* codebook, int64_t ldc, const int32_t* idx, int64_t N,
                        int D, void* zq, int64_t ldq, float* loss_sum, ttk_stream_t stream);
+/* Backward of the learned-codebook quantizer z_q = z + sg(C[idx] - z) with commitment = mean((z - sg(c))^2) and
+ * codebook = mean((sg(z) - c)^2):  dz = dzq + commit_scale * (z - c),  dC[idx] += codebook_scale * (c - z)
+ * (commit_scale = dL/dcommitment * 2/(N D), codebook_scale = dL/dcodebook * 2/(N D)). bf16 activations, dC fp32
+ * [K, lddc], ACCUMULATED (zero it first). dzq / dz / dC may be NULL. dev_scales (device float[2], may be NULL)
+ * multiplies the two scales on the device, so the loss gradients never visit the host. (The reference's FSQ has only the
+ * straight-through part, fsq.py:48-51; this is north_star's generic VQ.) */
+int ttk_vq_bwd(const void* dzq, int64_t lddq, const void* z, int64_t ldz, const void* codebook, int64_t ldc,
+               const int32_t* idx, int64_t N, int D, float commit_scale, float codebook_scale, const float* dev_scales,
+               void* dz, int64_t lddz, float* dC, int64_t lddc, ttk_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Linear layers (tcgen05 GEMMs).  C[M,N] = A[M,K] @ W[N,K]^T, bf16 in, fp32 accumulate, bf16 out.

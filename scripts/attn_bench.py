@@ -29,28 +29,33 @@ print(f"{os.environ.get('TTK_LIB_PATH', 'default')}: B={B} {ms * 1e3:.1f} us/lau
 
 if "--trace" in sys.argv:
     from titok_video_b200.engine import _vp
-    tr = torch.zeros(2048, 64, dtype=torch.int64, device=dev)
+    n_cta = 2 * work.shape[0]  # one CTA per query tile (two per work record)
+    tr = torch.zeros(n_cta, 64, dtype=torch.int64, device=dev)
     _lib.check(_lib.fn("ttk_debug_set_trace")(_ptr(tr)))
     run()
     torch.cuda.synchronize()
     _lib.check(_lib.fn("ttk_debug_set_trace")(_vp(0)))
     t = tr.cpu()
-    names = ["S ready", "S in regs", "max+xchg", "exps done", "pv_done ok", "P stored", "t1 S ready", "t1 P stored", "MMA S0 issue", "MMA S1 issue", "MMA PV0 issue", "MMA PV1 issue"]
-    # whole-CTA phases and back-to-back CTAs on one SM (globaltimer-free: clock64 is per SM, so compare CTAs on the same SM)
-    by_sm = {}
-    for cta in range(work.shape[0]):
-        r = t[cta]
-        if int(r[63]):
-            by_sm.setdefault(int(r[59]), []).append((int(r[60]), int(r[58]), int(r[61]), int(r[62]), int(r[63]), cta))
-    for sm in (0, 77):
-        seq = sorted(by_sm.get(sm, []))
-        print(f"SM {sm}: per CTA [setup->firstS | kv loop | epilogue | teardown] and gap to the next CTA's setup stamp")
-        for a, b in zip(seq[:6], seq[1:7]):
-            print(f"   cta {a[5]}: {a[1]-a[0]} | {a[2]-a[1]} | {a[3]-a[2]} | {a[4]-a[3]} | gap {b[0]-a[4]}")
-    for cta in (0, 500):
+    names = ["S ready", "S in regs", "max+xchg", "exps done", "pv_done ok", "P stored", "-", "-", "MMA S(j+1) issue", "-", "MMA PV issue", "-"]
+    for cta in (0, 1, 1001, 2500):
         r = t[cta]
         t0 = int(r[0])
-        print(f"cta {cta}: cycles relative to 'S ready' of kv iteration 3 (tile 0)")
+        print(f"cta {cta}: cycles relative to 'S ready' of kv iteration 3")
         for jj in range(4):
             ev = [int(r[jj * 12 + k]) - t0 for k in range(12)]
-            print(f"  j={jj + 3}: " + "  ".join(f"{n}={v}" for n, v in zip(names, ev)))
+            print(f"  j={jj + 3}: " + "  ".join(f"{n}={v}" for n, v in zip(names, ev) if n != "-"))
+    # iteration period statistics over all CTAs: S ready(j=6) - S ready(j=3)
+    d = (t[:, 36] - t[:, 0]).float() / 3
+    ok = (t[:, 36] > 0) & (t[:, 0] > 0)
+    print(f"mean kv-iteration period {d[ok].mean().item():.0f} cycles (median {d[ok].median().item():.0f}) over {int(ok.sum())} CTAs")
+    for k in range(1, 6):
+        seg = (t[:, k] - t[:, k - 1]).float()
+        print(f"  {names[k - 1]} -> {names[k]}: mean {seg[ok].mean().item():.0f} median {seg[ok].median().item():.0f}")
+    seg = (t[:, 12] - t[:, 5]).float()
+    print(f"  P stored(j) -> S ready(j+1): mean {seg[ok].mean().item():.0f} median {seg[ok].median().item():.0f}")
+    seg = (t[:, 8] - t[:, 1]).float()
+    print(f"  S in regs(j) -> MMA S(j+1) issue: mean {seg[ok].mean().item():.0f} median {seg[ok].median().item():.0f}")
+    seg = (t[:, 10] - t[:, 5]).float()
+    print(f"  P stored(j) -> MMA PV(j) issue: mean {seg[ok].mean().item():.0f} median {seg[ok].median().item():.0f}")
+    seg = (t[:, 12] - t[:, 8]).float()
+    print(f"  MMA S(j+1) issue -> S ready(j+1) seen by softmax: mean {seg[ok].mean().item():.0f} median {seg[ok].median().item():.0f}")

@@ -670,5 +670,6 @@ def test_frozen_encoder_tape_survives_an_intervening_encoder_launch():
         return {k: p.grad.detach().clone() for k, p in model.decoder.named_parameters()}
 
     a, b = run(False), run(True)
-    for k in a:
-        assert torch.equal(a[k], b[k]), f"decoder gradient of {k} changed after an intervening encoder launch"
+    for k in a:  # split-K weight gradients are accumulated with float atomics: equal up to summation order
+        d = (a[k].double() - b[k].double()).norm() / (a[k].double().norm() + 1e-30)
+        assert d < 1e-4, f"decoder gradient of {k} changed after an intervening encoder launch: rel {float(d):.3g}"

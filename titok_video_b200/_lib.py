@@ -47,6 +47,7 @@ SIGNATURES = {
     "ttk_vq_prepare_codebook": [_vp, _i64, _i, _i, _vp, _i64, _vp],
     "ttk_vq_argmin": [_vp, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp],
     "ttk_vq_gather_loss": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _i64, _vp, _vp],
+    "ttk_vq_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _f, _f, _vp, _vp, _i64, _vp, _i64, _vp],
     "ttk_gemm_bf16": [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _i64, _vp, _i, _vp],
     "ttk_debug_set_trace": [_vp],
     "ttk_gemm_qkv_rope": [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _vp],

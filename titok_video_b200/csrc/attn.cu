@@ -60,22 +60,35 @@ __device__ __forceinline__ void at_stamp(const AttnParams& p, int j, int ev) {
 }
 
 constexpr int AT_BM = 128;  // query rows per tile
-constexpr int AT_BN = 128;  // keys per kv tile
+constexpr int AT_BN = 64;   // keys per kv sub-tile (one S accumulator)
 constexpr int AT_D = 64;
-constexpr int AT_KST = 4;  // K / V ring depth
+constexpr int AT_KST = 6;  // K ring depth (sub-tiles)
+constexpr int AT_VST = 4;  // V ring depth
 constexpr int AT_Q_BYTES = AT_BM * AT_D * 2;   // 16 KB
-constexpr int AT_KV_BYTES = AT_BN * AT_D * 2;  // 16 KB
-constexpr int AT_XCH_BYTES = 3 * 2 * 2 * 128 * 4;  // half-row exchange: row max (two parities) and row sum
-constexpr int AT_SMEM = 2 * AT_Q_BYTES + 2 * AT_KST * AT_KV_BYTES + 512 + AT_XCH_BYTES + 1024;
-constexpr int AT_THREADS = 128 + 16 * 32;
-// TMEM columns
-constexpr uint32_t AT_TM_S = 0;    // S0 [0,128)   S1 [128,256)
-constexpr uint32_t AT_TM_O = 256;  // O0 [256,320) O1 [320,384)
-constexpr uint32_t AT_TM_P = 384;  // P0 [384,448) P1 [448,512)   (128 keys x bf16 = 64 columns)
-#ifndef AT_STAGGER_NS
-#define AT_STAGGER_NS 600
-#endif
+constexpr int AT_KV_BYTES = AT_BN * AT_D * 2;  // 8 KB
+constexpr int AT_XCH_BYTES = 4 * 128 * 4;  // per-row reference maximum, the two groups' row sums
+// ~100 KB per CTA: two CTAs are resident per SM (2 x 256 tensor-memory columns, 2 x 384 threads)
+constexpr int AT_SMEM = AT_Q_BYTES + (AT_KST + AT_VST) * AT_KV_BYTES + 512 + AT_XCH_BYTES + 1024;
+constexpr int AT_THREADS = 128 + 8 * 32;
+// TMEM columns (256 per CTA)
+constexpr uint32_t AT_TM_S = 0;    // S_a [0,64)  S_b [64,128)   (even / odd kv sub-tiles)
+constexpr uint32_t AT_TM_O = 128;  // O [128,192)
+constexpr uint32_t AT_TM_P = 192;  // P_a [192,224)  P_b [224,256)   (64 keys x bf16 = 32 columns)
+constexpr uint32_t AT_TM_COLS = 256;
 constexpr float AT_RESCALE_LOG2 = 8.0f;  // rescale O only when the row maximum grew by more than 2^8
+// named barriers: token hand-over between the two softmax groups, end-of-loop exchange
+constexpr uint32_t AT_BAR_TOK = 1;  // + group that WAITS on it (1, 2)
+constexpr uint32_t AT_BAR_FIN = 3;
+
+// (immediate barrier ids: a register id makes ptxas reserve all 16 named barriers of the CTA)
+template <int ID>
+__device__ __forceinline__ void nbar_sync256() {
+  asm volatile("bar.sync %0, 256;" ::"n"(ID) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void nbar_arrive256() {
+  asm volatile("bar.arrive %0, 256;" ::"n"(ID) : "memory");
+}
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
@@ -93,33 +106,91 @@ __device__ __forceinline__ float ex2_approx(float x) {
 #endif
 }
 
+// 2^x for a packed pair on the FMA / ALU pipes instead of MUFU (the kv loop is bound by the 16 ex2 / clk / SM of the XU
+// pipe at head dim 64): x = n + f, n = rn(x) through the 1.5 * 2^23 magic constant, f in [-0.5, 0.5],
+// 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5 -- P is rounded to bf16, 3.9e-3, right after),
+// 2^n by adding n to the exponent field. x is clamped to >= -126 (masked keys hold -inf).
+__device__ __forceinline__ void ex2_poly_pair(uint64_t t, float& o0, float& o1) {
+  float x0, x1;
+  f32x2_unpack(t, x0, x1);
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  const uint64_t x = f32x2_pack(x0, x1);
+  const uint64_t u = f32x2_add(x, f32x2_pack(12582912.f, 12582912.f));    // low mantissa bits = rn(x)
+  const uint64_t nf = f32x2_add(u, f32x2_pack(-12582912.f, -12582912.f));  // rn(x) as a float
+  const uint64_t f = f32x2_fma(nf, f32x2_pack(-1.f, -1.f), x);
+  uint64_t q = f32x2_fma(f32x2_pack(0.05517164617776871f, 0.05517164617776871f), f,
+                         f32x2_pack(0.2426111251115799f, 0.2426111251115799f));
+  q = f32x2_fma(q, f, f32x2_pack(0.6932609677314758f, 0.6932609677314758f));
+  q = f32x2_fma(q, f, f32x2_pack(0.9999280571937561f, 0.9999280571937561f));
+  float u0, u1, q0, q1;
+  f32x2_unpack(u, u0, u1);
+  f32x2_unpack(q, q0, q1);
+  o0 = __uint_as_float((__float_as_uint(u0) << 23) + __float_as_uint(q0));
+  o1 = __uint_as_float((__float_as_uint(u1) << 23) + __float_as_uint(q1));
+}
+
+// which of the 16 groups of four scores per thread take the polynomial: bit g of AT_EMU_B -> elements 4g+2, 4g+3,
+// bit g of AT_EMU_A -> elements 4g, 4g+1. Default: 8 of 64 exponentials (12.5 %) off the MUFU pipe -- the loop is
+// bound by instruction issue almost as much as by MUFU, and a polynomial pair costs ~14 issue slots against 5
+// (measured at 64 clips: 0 % 366 us, 12.5 % 355 us, 25 % 371 us, 37.5 % 379 us, 50 % 405 us per launch).
+#ifndef AT_EMU_A
+#define AT_EMU_A 0x0000
+#endif
+#ifndef AT_EMU_B
+#define AT_EMU_B 0x1111
+#endif
+
+// Work item of a CTA: ONE 128-row query tile (tile blockIdx & 1 of work record blockIdx >> 1) against the K/V stream
+// of its clip, in kv sub-tiles of 64 keys. Two CTAs are resident per SM, so one CTA's prologue (barrier init, tensor
+// memory allocation, first loads) and epilogue (gate, normalisation, stores) run under the other's kv loop, and the
+// two tiles of a record -- launched side by side -- find each other's K/V tiles in L2.
+//
+// Warp roles: warp 0 TMA producer (Q once, K and V sub-tiles through rings), warp 1 MMA issuer, warp 2 tensor-memory
+// allocator, warps 4-7 softmax group a (even sub-tiles), warps 8-11 softmax group b (odd sub-tiles); thread == one
+// query row x the 64 keys of a sub-tile, so a sub-tile's row maximum needs no exchange. Each group has its own S and P
+// buffers in tensor memory (S(j+2) is issued as soon as S(j) sits in registers); both accumulate into the same O.
+//
+// The exponential phases of the two groups are serialised by a token (named barriers): at any time at most one group
+// of a CTA is on the MUFU pipe while the other one loads / reduces / stores, which keeps the pipe that bounds the loop
+// busy instead of having all warps of a scheduler hit it in phase and then leave it idle together. The token also
+// carries the per-row reference maximum (shared memory): the holder decides about the lazy rescale (only when a row
+// maximum grew by more than 2^8), rescales O itself once every product issued so far has retired, and publishes the new
+// reference before it hands the token over; the other group folds the change into its partial row sum when it next
+// reads the reference. The final division by l makes the result exact.
 template <bool TRAIN>  // TRAIN: also store the un-gated output and the log-sum-exp (compiled out of the inference kernel)
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  const AttnWork* wp = p.work + (blockIdx.x >> 1);
+  const int t = blockIdx.x & 1;
+  const int q_valid = wp->q_valid[t];
+  if (q_valid <= 0) return;  // (whole CTA: nothing has been allocated yet)
+  const int q_row0 = wp->q_row0[t], q_head = wp->q_head[t];
+  const int kv_head = wp->kv_head, kv_row0 = wp->kv_row0, kv_len = wp->kv_len;
+
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                       // [2][128][64]
-  uint8_t* sK = sQ + 2 * AT_Q_BYTES;        // [KST][128][64]
-  uint8_t* sV = sK + AT_KST * AT_KV_BYTES;  // [KST][128][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AT_KST * AT_KV_BYTES);
+  uint8_t* sQ = smem;                       // [128][64]
+  uint8_t* sK = sQ + AT_Q_BYTES;            // [KST][64][64]
+  uint8_t* sV = sK + AT_KST * AT_KV_BYTES;  // [VST][64][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AT_VST * AT_KV_BYTES);
   uint64_t* q_full = bars;              // [1]
   uint64_t* k_full = bars + 1;          // [KST]
   uint64_t* k_empty = k_full + AT_KST;  // [KST]
-  uint64_t* v_full = k_empty + AT_KST;  // [KST]
-  uint64_t* v_empty = v_full + AT_KST;  // [KST]
-  uint64_t* s_full = v_empty + AT_KST;  // [2]  S_t(j) is in tensor memory
-  uint64_t* s_empty = s_full + 2;       // [2]  the softmax warps hold S_t(j) in registers
-  uint64_t* p_full = s_empty + 2;       // [2]  P_t(j) is in tensor memory (and O_t has been rescaled if needed)
-  uint64_t* pv_done = p_full + 2;       // [2]  O_t += P_t(j) V(j) has retired
+  uint64_t* v_full = k_empty + AT_KST;  // [VST]
+  uint64_t* v_empty = v_full + AT_VST;  // [VST]
+  uint64_t* s_full = v_empty + AT_VST;  // [2] S_g is in tensor memory
+  uint64_t* s_empty = s_full + 2;       // [2] group g holds S_g in registers
+  uint64_t* p_full = s_empty + 2;       // [2] P_g is in tensor memory
+  uint64_t* pv_done = p_full + 2;       // [2] O += P_g V has retired
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
-  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // [3][tile][half][128]
+  float* m_sh = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // [128] reference maximum per row
+  float* l_sh = m_sh + 128;                                                        // [2][128] row sums of the groups
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const AttnWork w = p.work[blockIdx.x];
-  const int n_kv = (w.kv_len + AT_BN - 1) / AT_BN;
-  const bool act0 = w.q_valid[0] > 0, act1 = w.q_valid[1] > 0;
+  const int n_sub = (kv_len + AT_BN - 1) / AT_BN;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -131,283 +202,293 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int s = 0; s < AT_KST; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < AT_VST; ++s) {
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
     }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&s_empty[t], 8);
-      mbar_init(&p_full[t], 8);
-      mbar_init(&pv_done[t], 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&s_empty[g], 4);
+      mbar_init(&p_full[g], 4);
+      mbar_init(&pv_done[g], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_ptr, 512);
+  if (warp == 2) tmem_alloc(tmem_ptr, AT_TM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // Register re-distribution: 640 threads start with 96 registers; the control warpgroup drops to 40 and the 16
-  // softmax warps (64 scores per thread live) grow to 104 (4 x 32 x 56 freed >= 16 x 32 x 8 taken).
-  // setmaxnreg sits at the top of each role branch.
+  // Register re-distribution: 384 threads start with 80 registers (two CTAs per SM); the control warpgroup drops to 32
+  // and the 8 softmax warps (64 scores per thread live) grow to 104 (128 x 48 freed = 256 x 24 taken).
   if (warp == 0) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (elect_one()) {
-      const uint32_t q_bytes = (act0 ? AT_Q_BYTES : 0) + (act1 ? AT_Q_BYTES : 0);
-      mbar_arrive_expect_tx(q_full, q_bytes);
-      if (act0) tma_load_2d(sQ, &tmQ, q_full, w.q_head[0] * AT_D, w.q_row0[0]);
-      if (act1) tma_load_2d(sQ + AT_Q_BYTES, &tmQ, q_full, w.q_head[1] * AT_D, w.q_row0[1]);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % AT_KST;
-        const uint32_t ph = (j / AT_KST) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], AT_KV_BYTES);
-        tma_load_2d(sK + st * AT_KV_BYTES, &tmK, &k_full[st], w.kv_head * AT_D, w.kv_row0 + j * AT_BN);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], AT_KV_BYTES);
-        tma_load_2d(sV + st * AT_KV_BYTES, &tmV, &v_full[st], w.kv_head * AT_D, w.kv_row0 + j * AT_BN);
+      mbar_arrive_expect_tx(q_full, AT_Q_BYTES);
+      tma_load_2d(sQ, &tmQ, q_full, q_head * AT_D, q_row0);
+      for (int j = 0; j < n_sub; ++j) {
+        const int sk = j % AT_KST, sv = j % AT_VST;
+        mbar_wait(&k_empty[sk], ((j / AT_KST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[sk], AT_KV_BYTES);
+        tma_load_2d(sK + sk * AT_KV_BYTES, &tmK, &k_full[sk], kv_head * AT_D, kv_row0 + j * AT_BN);
+        mbar_wait(&v_empty[sv], ((j / AT_VST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[sv], AT_KV_BYTES);
+        tma_load_2d(sV + sv * AT_KV_BYTES, &tmV, &v_full[sv], kv_head * AT_D, kv_row0 + j * AT_BN);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);  // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_D, 0, 1);   // P (tmem, K-major) x V (MN-major)
-      const bool act[2] = {act0, act1};
-      auto issue_s = [&](int t, int st) {
-        const uint32_t sa = smem_u32(sQ + t * AT_Q_BYTES);
+      auto issue_s = [&](int g, int st) {
+        const uint32_t sa = smem_u32(sQ);
         const uint32_t sb = smem_u32(sK + st * AT_KV_BYTES);
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16_ss(tmem_base + AT_TM_S + t * AT_BN, umma_smem_desc_sw128(sa + k * 32, 1024, 0),
+          umma_bf16_ss(tmem_base + AT_TM_S + g * AT_BN, umma_smem_desc_sw128(sa + k * 32, 1024, 0),
                        umma_smem_desc_sw128(sb + k * 32, 1024, 0), idesc_s, k != 0 ? 1u : 0u);
       };
-      auto issue_pv = [&](int t, int st, bool accumulate) {
+      auto issue_pv = [&](int g, int st, bool accumulate) {
         const uint32_t sb = smem_u32(sV + st * AT_KV_BYTES);
 #pragma unroll
         for (int k = 0; k < AT_BN / 16; ++k)  // 16 keys == 8 packed columns of P
-          umma_bf16_ts(tmem_base + AT_TM_O + t * AT_D, tmem_base + AT_TM_P + t * (AT_BN / 2) + k * 8,
+          umma_bf16_ts(tmem_base + AT_TM_O, tmem_base + AT_TM_P + g * (AT_BN / 2) + k * 8,
                        umma_smem_desc_sw128(sb + k * 2048, 1024, 0), idesc_o, (accumulate || k != 0) ? 1u : 0u);
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      for (int t = 0; t < 2; ++t) {
-        if (!act[t]) continue;
-        // Stagger the two query tiles by roughly half a kv iteration: their softmax groups share the four MUFU
-        // pipes, and nothing else would ever move them out of phase (measured: in phase, every exponential phase
-        // runs at half speed while the pipes idle during the load / max / store phases of both tiles).
-        if (t == 1 && act[0]) __nanosleep(AT_STAGGER_NS);
-        issue_s(t, 0);
-        umma_commit(&s_full[t]);
+      for (int j = 0; j < 2 && j < n_sub; ++j) {
+        mbar_wait(&k_full[j], 0);
+        tc_fence_after();
+        issue_s(j, j);
+        umma_commit(&s_full[j]);
+        umma_commit(&k_empty[j]);
       }
-      umma_commit(&k_empty[0]);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % AT_KST;
-        const uint32_t ph = (j / AT_KST) & 1;
-        const uint32_t par = j & 1;
-        if (j + 1 < n_kv) {
-          // ---- S_t(j+1) = Q_t K(j+1)^T as soon as S_t(j) has been read out of tensor memory
-          const int st1 = (j + 1) % AT_KST;
-          mbar_wait(&k_full[st1], ((j + 1) / AT_KST) & 1);
-          for (int t = 0; t < 2; ++t) {
-            if (!act[t]) continue;
-            mbar_wait(&s_empty[t], par);
-            tc_fence_after();
-            at_stamp(p, j, 8 + t);
-            issue_s(t, st1);
-            umma_commit(&s_full[t]);
-          }
-          umma_commit(&k_empty[st1]);
-        }
-        // ---- O_t += P_t(j) V(j)
-        mbar_wait(&v_full[st], ph);
-        for (int t = 0; t < 2; ++t) {
-          if (!act[t]) continue;
-          mbar_wait(&p_full[t], par);
+      // Fixed issue order (S(j+2), then P(j) V(j), j ascending): the accumulation order into O is the same in every run
+      // and for every batch composition, so results are bit-reproducible. (Issuing whichever group's operation is
+      // ready first was measured: no faster, and it reorders the fp32 accumulation.)
+      for (int j = 0; j < n_sub; ++j) {
+        const int g = j & 1;
+        const uint32_t par = (j >> 1) & 1;
+        if (j + 2 < n_sub) {
+          // ---- S(j+2) = Q K(j+2)^T into group g's accumulator as soon as S(j) has been read out of tensor memory
+          const int sk = (j + 2) % AT_KST;
+          mbar_wait(&k_full[sk], ((j + 2) / AT_KST) & 1);
+          mbar_wait(&s_empty[g], par);
           tc_fence_after();
-          at_stamp(p, j, 10 + t);
-          issue_pv(t, st, j > 0);
-          umma_commit(&pv_done[t]);
+          if (g == 0) at_stamp(p, j >> 1, 8);
+          issue_s(g, sk);
+          umma_commit(&s_full[g]);
+          umma_commit(&k_empty[sk]);
         }
-        umma_commit(&v_empty[st]);
+        // ---- O += P(j) V(j)
+        const int sv = j % AT_VST;
+        mbar_wait(&v_full[sv], (j / AT_VST) & 1);
+        mbar_wait(&p_full[g], par);
+        tc_fence_after();
+        if (g == 0) at_stamp(p, j >> 1, 10);
+        issue_pv(g, sv, j > 0);
+        umma_commit(&pv_done[g]);
+        umma_commit(&v_empty[sv]);
       }
     }
     __syncwarp();
   } else if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    const int sw = warp - 4;        // 0..15
-    const int t = sw >> 3;          // query tile of this softmax group
-    const int half = (sw >> 2) & 1; // key half [64*half, +64) of every kv tile
+    const int g = (warp - 4) >> 2;      // softmax group: kv sub-tiles j == g (mod 2)
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row within the tile == TMEM lane
-    const bool active = t == 0 ? act0 : act1;
-    if (active) {
-      const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-      const uint32_t t_s = tmem_base + lane_off + AT_TM_S + t * AT_BN + half * 64;
-      const uint32_t t_o = tmem_base + lane_off + AT_TM_O + t * AT_D + half * 32;
-      const uint32_t t_p = tmem_base + lane_off + AT_TM_P + t * (AT_BN / 2) + half * 32;
-      const uint32_t pair_bar = 1 + t;  // named barrier of this tile's 8 softmax warps
-      float* x_mine = xch + (t * 2 + half) * 128 + r;        // + parity * 512 (max) / + 1024 (sum)
-      float* x_other = xch + (t * 2 + (half ^ 1)) * 128 + r;
-      const float c = p.scale_log2;
-      const uint64_t c2 = f32x2_pack(c, c);
-      float m_ref = 0.f, l_run = 0.f;  // l_run: this half's share of the row sum
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_off + AT_TM_S + g * AT_BN;
+    const uint32_t t_o = tmem_base + lane_off + AT_TM_O;
+    const uint32_t t_p = tmem_base + lane_off + AT_TM_P + g * (AT_BN / 2);
+    const float c = p.scale_log2;
+    const uint64_t c2 = f32x2_pack(c, c);
+    // l_run: this group's share of the row sum, relative to m_ref (-inf until the group has seen a reference:
+    // adopting one then scales the empty sum by 2^-inf = 0)
+    float m_ref = __int_as_float(0xff800000), l_run = 0.f;
 
-      for (int j = 0; j < n_kv; ++j) {
-        const uint32_t par = j & 1;
-        // ---- S(j): this thread's 64 scores into registers with one wait, then hand S back to the tensor core
-        mbar_wait(&s_full[t], par);
-        tc_fence_after();
-        if (threadIdx.x == 128) at_stamp(p, j, 0);
-        if (threadIdx.x == 384) at_stamp(p, j, 6);
-        // the epilogue's gate values: pull this thread's 64-byte segment towards L2 a few kv tiles ahead of its use
-        // (measured: the epilogue of a CTA drops from ~9k to ~5.5k cycles)
-        if (j == n_kv - 3 || (n_kv < 3 && j == 0)) {
-          const __nv_bfloat16* gp = p.gate + static_cast<int64_t>(w.q_row0[t] + min(r, w.q_valid[t] - 1)) * p.ld +
-                                    w.q_head[t] * AT_D + half * 32;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(gp));
-        }
-        uint32_t sv[64];
-        tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-        tmem_ld_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[t]);  // S_t(j+1) may overwrite the accumulator once all 8 warps arrived
-        if (threadIdx.x == 128) at_stamp(p, j, 1);
+    for (int j = g; j < n_sub; j += 2) {
+      const uint32_t par = (j >> 1) & 1;
+      // ---- S(j): this thread's 64 scores into registers with one wait, then hand S_g back to the tensor core
+      mbar_wait(&s_full[g], par);
+      tc_fence_after();
+      if (threadIdx.x == 128) at_stamp(p, j >> 1, 0);
+      // the epilogue's gate values: pull this thread's 64-byte segment towards L2 a few kv tiles ahead of its use
+      if (j + 6 >= n_sub && j + 4 < n_sub) {
+        const __nv_bfloat16* gp = p.gate + static_cast<int64_t>(q_row0 + min(r, q_valid - 1)) * p.ld + q_head * AT_D + g * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(gp));
+      }
+      uint32_t sv[64];
+      tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+      tmem_ld_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[g]);  // S(j+2) may overwrite the accumulator once the 4 warps arrived
+      if (threadIdx.x == 128) at_stamp(p, j >> 1, 1);
 
-        const int kv_valid = w.kv_len - j * AT_BN - half * 64;  // valid keys of this half; < 64 only in the last kv tile
-        if (kv_valid < 64) {
+      const int kv_valid = kv_len - j * AT_BN;  // < 64 only in the last sub-tile
+      if (kv_valid < 64) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (i >= kv_valid) sv[i] = 0xff800000u;  // -inf: exp2 -> 0, never the max
-        }
-        float m0 = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
-        float m1 = fmaxf(__uint_as_float(sv[2]), __uint_as_float(sv[3]));
+        for (int i = 0; i < 64; ++i)
+          if (i >= kv_valid) sv[i] = 0xff800000u;  // -inf: exp2 -> 0, never the max
+      }
+      float m0 = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
+      float m1 = fmaxf(__uint_as_float(sv[2]), __uint_as_float(sv[3]));
 #pragma unroll
-        for (int i = 4; i < 64; i += 4) {
-          m0 = fmax3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
-          m1 = fmax3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
-        }
-        // both halves of a row take the same decisions: exchange the half maxima (parity-alternating slots)
-#ifdef AT_EXP_NOBAR  // timing experiment only: cost of the half-row exchange
-        const float m_tile = fmaxf(m0, m1);
-#else
-        x_mine[par * 512] = fmaxf(m0, m1);
-        named_bar_sync(pair_bar, 256);
-        const float m_tile = fmaxf(fmaxf(m0, m1), x_other[par * 512]);  // the first half always holds >= 1 valid key
-#endif
+      for (int i = 4; i < 64; i += 4) {
+        m0 = fmax3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+        m1 = fmax3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+      }
+      const float m_sub = fmaxf(m0, m1);  // a sub-tile always holds >= 1 valid key
 
-        if (threadIdx.x == 128) at_stamp(p, j, 2);
-        // ---- lazy maximum: keep the old reference unless some row of this warp outgrew it by 2^8
-        if (j == 0) {
-          m_ref = m_tile;
-        } else if (__any_sync(0xffffffffu, (m_tile - m_ref) * c > AT_RESCALE_LOG2)) {
-          const float m_new = fmaxf(m_ref, m_tile);
+      // ---- take the token: the other group's exponentials of sub-tile j-1 are done, its reference is published
+      if (j == 0) {
+        m_ref = m_sub;
+        m_sh[r] = m_sub;
+      } else {
+        if (g == 0) nbar_sync256<AT_BAR_TOK>(); else nbar_sync256<AT_BAR_TOK + 1>();
+        const float m_cur = m_sh[r];
+        if (m_cur != m_ref) {  // the other group moved the reference (rare)
+          l_run *= ex2_approx((m_ref - m_cur) * c);
+          m_ref = m_cur;
+        }
+        // lazy maximum: keep the reference unless some row of this warp outgrew it by 2^8
+        // (rows past the clip's end hold another clip's queries: they must not take part in the decision, or the
+        // rounding of this clip's rows would depend on what it is packed with)
+        if (__any_sync(0xffffffffu, r < q_valid && (m_sub - m_ref) * c > AT_RESCALE_LOG2)) {
+          const float m_new = fmaxf(m_ref, m_sub);
           const float alpha = ex2_approx((m_ref - m_new) * c);
-          mbar_wait(&pv_done[t], (j - 1) & 1);  // O_t holds every product up to kv tile j-1
+          // O holds every product up to sub-tile j-1 once the latest PV of either group has retired
+          mbar_wait(&pv_done[g ^ 1], ((j - 1) >> 1) & 1);
+          if (j >= 2) mbar_wait(&pv_done[g], ((j - 2) >> 1) & 1);
           tc_fence_after();
-          uint32_t o[32];  // this half rescales 32 of the 64 output columns
-          tmem_ld_32x32b_x32(t_o, o);
-          tmem_ld_wait();
+#pragma unroll 1
+          for (int q = 0; q < 4; ++q) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(t_o + q * 16, o);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32b_x32(t_o, o);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x16(t_o + q * 16, o);
+          }
           tmem_st_wait();
+          tc_fence_before();
           l_run *= alpha;
           m_ref = m_new;
+          m_sh[r] = m_new;
         }
+      }
+      if (threadIdx.x == 128) at_stamp(p, j >> 1, 2);
 
-        // ---- P(j) = 2^(s*c - m*c): packed FMA, MUFU ex2, packed row-sum, bf16 pairs (in place, sv[0..31])
-        const float nmc = -m_ref * c;
-        const uint64_t nmc2 = f32x2_pack(nmc, nmc);
-        uint64_t la = f32x2_pack(0.f, 0.f), lb = la;
+      // ---- P(j) = 2^(s*c - m*c): packed FMA, MUFU ex2 / polynomial, packed row-sum, bf16 pairs (in place, sv[0..31])
+      const float nmc = -m_ref * c;
+      const uint64_t nmc2 = f32x2_pack(nmc, nmc);
+      uint64_t la = f32x2_pack(0.f, 0.f), lb = la;
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          const uint64_t ta = f32x2_fma(f32x2_pack(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), c2, nmc2);
-          const uint64_t tb = f32x2_fma(f32x2_pack(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), c2, nmc2);
-          float a0, a1, b0, b1;
+      for (int i = 0; i < 64; i += 4) {
+        const uint64_t ta = f32x2_fma(f32x2_pack(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), c2, nmc2);
+        const uint64_t tb = f32x2_fma(f32x2_pack(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), c2, nmc2);
+        float a0, a1, b0, b1;
+        if ((AT_EMU_A >> (i >> 2)) & 1) {
+          ex2_poly_pair(ta, a0, a1);
+        } else {
           f32x2_unpack(ta, a0, a1);
-          f32x2_unpack(tb, b0, b1);
           a0 = ex2_approx(a0);
           a1 = ex2_approx(a1);
+        }
+        if ((AT_EMU_B >> (i >> 2)) & 1) {
+          ex2_poly_pair(tb, b0, b1);
+        } else {
+          f32x2_unpack(tb, b0, b1);
           b0 = ex2_approx(b0);
           b1 = ex2_approx(b1);
-          la = f32x2_add(la, f32x2_pack(a0, a1));
-          lb = f32x2_add(lb, f32x2_pack(b0, b1));
-          sv[i >> 1] = pack_bf16x2(a0, a1);
-          sv[(i >> 1) + 1] = pack_bf16x2(b0, b1);
         }
-        {
-          float x0, x1;
-          f32x2_unpack(f32x2_add(la, lb), x0, x1);
-          l_run += x0 + x1;
-        }
-        // ---- P(j) -> tensor memory once P V(j-1) no longer reads the buffer
-        if (threadIdx.x == 128) at_stamp(p, j, 3);
-        if (j > 0) {
-          mbar_wait(&pv_done[t], (j - 1) & 1);
-          tc_fence_after();
-        }
-        if (threadIdx.x == 128) at_stamp(p, j, 4);
-        tmem_st_32x32b_x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
-        if (threadIdx.x == 128) at_stamp(p, j, 5);
-        if (threadIdx.x == 384) at_stamp(p, j, 7);
+        la = f32x2_add(la, f32x2_pack(a0, a1));
+        lb = f32x2_add(lb, f32x2_pack(b0, b1));
+        sv[i >> 1] = pack_bf16x2(a0, a1);
+        sv[(i >> 1) + 1] = pack_bf16x2(b0, b1);
       }
+      {
+        float x0, x1;
+        f32x2_unpack(f32x2_add(la, lb), x0, x1);
+        l_run += x0 + x1;
+      }
+      // ---- hand the token over: the other group may start the exponentials of sub-tile j+1
+      if (j + 1 < n_sub) {
+        if (g == 0) nbar_arrive256<AT_BAR_TOK + 1>(); else nbar_arrive256<AT_BAR_TOK>();
+      }
+      if (threadIdx.x == 128) at_stamp(p, j >> 1, 3);
+      // ---- P(j) -> tensor memory once this group's previous P V no longer reads the buffer
+      if (j >= 2) {
+        mbar_wait(&pv_done[g], ((j - 2) >> 1) & 1);
+        tc_fence_after();
+      }
+      if (threadIdx.x == 128) at_stamp(p, j >> 1, 4);
+      tmem_st_32x32b_x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      if (threadIdx.x == 128) at_stamp(p, j >> 1, 5);
+    }
 
-      // ---- epilogue: out = bf16(O / l) * bf16(sigmoid(gate)); this half writes 32 of the 64 head dims
-      x_mine[1024] = l_run;
-      named_bar_sync(pair_bar, 256);
-      const float l_tot = l_run + x_other[1024];
-      const float inv_l = __fdividef(1.0f, l_tot);
-      if (TRAIN && half == 0 && r < w.q_valid[t])  // the backward kernels recompute P = 2^(s*c - lse)
-        p.lse[static_cast<int64_t>(w.q_head[t]) * p.M + w.q_row0[t] + r] = fmaf(m_ref, c, __log2f(l_tot));
-      mbar_wait(&pv_done[t], (n_kv - 1) & 1);
-      tc_fence_after();
-      uint32_t o[32];
-      tmem_ld_32x32b_x32(t_o, o);
-      tmem_ld_wait();
-      const int qv = w.q_valid[t];
-      if (r < qv) {
-        const int row = w.q_row0[t] + r;
-        const int col = w.q_head[t] * AT_D + half * 32;
-        const __nv_bfloat16* g = p.gate + static_cast<int64_t>(row) * p.ld + col;
-        __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + col;
-        __nv_bfloat16* osv = TRAIN ? p.o_save + static_cast<int64_t>(row) * p.ldo + col : nullptr;
+    // ---- epilogue: out = bf16(O / l) * bf16(sigmoid(gate)); group g writes 32 of the 64 head dims
+    nbar_sync256<AT_BAR_FIN>();  // every exponential phase is over: the reference is final
+    {
+      const float m_fin = m_sh[r];
+      if (m_fin != m_ref) {
+        l_run *= ex2_approx((m_ref - m_fin) * c);
+        m_ref = m_fin;
+      }
+    }
+    l_sh[g * 128 + r] = l_run;
+    nbar_sync256<AT_BAR_FIN>();
+    const float l_tot = l_run + l_sh[(g ^ 1) * 128 + r];
+    const float inv_l = __fdividef(1.0f, l_tot);
+    if (TRAIN && g == 0 && r < q_valid)  // the backward kernels recompute P = 2^(s*c - lse)
+      p.lse[static_cast<int64_t>(q_head) * p.M + q_row0 + r] = fmaf(m_ref, c, __log2f(l_tot));
+    mbar_wait(&pv_done[(n_sub - 1) & 1], ((n_sub - 1) >> 1) & 1);  // the last product issued (in-order completion)
+    tc_fence_after();
+    uint32_t o[32];
+    tmem_ld_32x32b_x32(t_o + g * 32, o);
+    tmem_ld_wait();
+    if (r < q_valid) {
+      const int row = q_row0 + r;
+      const int col = q_head * AT_D + g * 32;
+      const __nv_bfloat16* gt = p.gate + static_cast<int64_t>(row) * p.ld + col;
+      __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + col;
+      __nv_bfloat16* osv = TRAIN ? p.o_save + static_cast<int64_t>(row) * p.ldo + col : nullptr;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 gv = ldg16(g + q * 8);
-          const uint32_t gg[4] = {gv.x, gv.y, gv.z, gv.w};
-          uint32_t ov[4], av[4];
+      for (int q = 0; q < 4; ++q) {
+        const uint4 gv = ldg16(gt + q * 8);
+        const uint32_t gg[4] = {gv.x, gv.y, gv.z, gv.w};
+        uint32_t ov[4], av[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float g0 = bf16_lo(gg[e]), g1 = bf16_hi(gg[e]);
-            const float s0 = bf16r(__fdividef(1.0f, 1.0f + __expf(-g0)));
-            const float s1 = bf16r(__fdividef(1.0f, 1.0f + __expf(-g1)));
-            const float a0 = bf16r(__uint_as_float(o[q * 8 + 2 * e]) * inv_l);
-            const float a1 = bf16r(__uint_as_float(o[q * 8 + 2 * e + 1]) * inv_l);
-            ov[e] = pack_bf16x2(a0 * s0, a1 * s1);
-            av[e] = pack_bf16x2(a0, a1);
-          }
-          stg16(dst + q * 8, make_uint4(ov[0], ov[1], ov[2], ov[3]));
-          if (TRAIN) stg16(osv + q * 8, make_uint4(av[0], av[1], av[2], av[3]));
+        for (int e = 0; e < 4; ++e) {
+          const float g0 = bf16_lo(gg[e]), g1 = bf16_hi(gg[e]);
+          const float s0 = bf16r(__fdividef(1.0f, 1.0f + __expf(-g0)));
+          const float s1 = bf16r(__fdividef(1.0f, 1.0f + __expf(-g1)));
+          const float a0 = bf16r(__uint_as_float(o[q * 8 + 2 * e]) * inv_l);
+          const float a1 = bf16r(__uint_as_float(o[q * 8 + 2 * e + 1]) * inv_l);
+          ov[e] = pack_bf16x2(a0 * s0, a1 * s1);
+          av[e] = pack_bf16x2(a0, a1);
         }
+        stg16(dst + q * 8, make_uint4(ov[0], ov[1], ov[2], ov[3]));
+        if (TRAIN) stg16(osv + q * 8, make_uint4(av[0], av[1], av[2], av[3]));
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) tmem_dealloc(tmem_base, AT_TM_COLS);
 }
 
 }  // namespace ttk
@@ -427,7 +508,7 @@ static int attn_fwd_launch(const void* qkv, int64_t ld, int M, int width, int gq
   const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
   CUtensorMap tmQ, tmK, tmV;
   if (int e = make_tmap_bf16_2d(&tmQ, base, M, width, ld, AT_BM)) return e;
-  if (int e = make_tmap_bf16_2d(&tmK, base + 2 * width, M, gqa, ld, AT_BN)) return e;
+  if (int e = make_tmap_bf16_2d(&tmK, base + 2 * width, M, gqa, ld, AT_BN)) return e;  // boxes of 64 keys
   if (int e = make_tmap_bf16_2d(&tmV, base + 2 * width + gqa, M, gqa, ld, AT_BN)) return e;
   AttnParams p{};
   p.work = static_cast<const AttnWork*>(work);
@@ -444,9 +525,9 @@ static int attn_fwd_launch(const void* qkv, int64_t ld, int M, int width, int gq
   if (int e = set_smem_attr_once(once_plain, reinterpret_cast<const void*>(attn_fwd_kernel<false>), AT_SMEM)) return e;
   if (int e = set_smem_attr_once(once_train, reinterpret_cast<const void*>(attn_fwd_kernel<true>), AT_SMEM)) return e;
   if (o_save)
-    attn_fwd_kernel<true><<<n_work, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+    attn_fwd_kernel<true><<<2 * n_work, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
   else
-    attn_fwd_kernel<false><<<n_work, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+    attn_fwd_kernel<false><<<2 * n_work, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
   return launch_status();
 }
 

@@ -511,6 +511,54 @@ __global__ void __launch_bounds__(256) vq_gather_kernel(const __nv_bfloat16* __r
   }
 }
 
+// Backward of the learned-codebook quantizer z_q = z + sg(C[idx] - z) with the two VQ-VAE losses
+//   commitment = mean((z - sg(C[idx]))^2)      codebook = mean((sg(z) - C[idx])^2)
+// dz = dzq (straight-through) + a * (z - c),  dC[idx] += b * (c - z)   (fp32 atomics, 4-wide vector red),
+// a = dL/d(commitment) * 2 / (N D), b = dL/d(codebook) * 2 / (N D). One thread per 8-element run.
+__global__ void __launch_bounds__(256) vq_bwd_kernel(const __nv_bfloat16* __restrict__ dzq, int64_t lddq,
+                                                     const __nv_bfloat16* __restrict__ z, int64_t ldz,
+                                                     const __nv_bfloat16* __restrict__ cb, int64_t ldc,
+                                                     const int32_t* __restrict__ idx, int64_t N, int D8, float a, float b,
+                                                     const float* __restrict__ dev_scales,
+                                                     __nv_bfloat16* __restrict__ dz, int64_t lddz,
+                                                     float* __restrict__ dC, int64_t lddc) {
+  if (dev_scales) {  // upstream gradients of the two loss scalars, still on the device (no host sync in backward)
+    a *= dev_scales[0];
+    b *= dev_scales[1];
+  }
+  const int64_t total = N * D8;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t n = i / D8;
+    const int c = static_cast<int>(i - n * D8);
+    const int64_t k = idx[n];
+    const uint4 q = ldg16(cb + k * ldc + c * 8);
+    const uint4 zz = ldg16_stream(z + n * ldz + c * 8);
+    uint4 g = make_uint4(0u, 0u, 0u, 0u);
+    if (dzq) g = ldg16_stream(dzq + n * lddq + c * 8);
+    const uint32_t qq[4] = {q.x, q.y, q.z, q.w}, aa[4] = {zz.x, zz.y, zz.z, zz.w}, gg[4] = {g.x, g.y, g.z, g.w};
+    uint32_t out[4];
+    float dc[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float d0 = bf16_lo(aa[e]) - bf16_lo(qq[e]);
+      const float d1 = bf16_hi(aa[e]) - bf16_hi(qq[e]);
+      out[e] = pack_bf16x2(fmaf(a, d0, bf16_lo(gg[e])), fmaf(a, d1, bf16_hi(gg[e])));
+      dc[2 * e] = -b * d0;
+      dc[2 * e + 1] = -b * d1;
+    }
+    if (dz) stg16(dz + n * lddz + c * 8, make_uint4(out[0], out[1], out[2], out[3]));
+    if (dC && b != 0.f) {
+      float* dst = dC + k * lddc + c * 8;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(dc[0]), "f"(dc[1]), "f"(dc[2]), "f"(dc[3])
+                   : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(dc[4]), "f"(dc[5]), "f"(dc[6]),
+                   "f"(dc[7])
+                   : "memory");
+    }
+  }
+}
+
 }  // namespace ttk
 
 using namespace ttk;
@@ -596,6 +644,28 @@ int ttk_vq_gather_loss(const void* z, int64_t ldz, const void* codebook, int64_t
   vq_gather_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(z), ldz,
                                              static_cast<const __nv_bfloat16*>(codebook), ldc, idx, N, D / 8,
                                              static_cast<__nv_bfloat16*>(zq), ldq, loss_sum);
+  return launch_status();
+}
+
+// Backward of the quantizer (see vq_bwd_kernel). dzq may be NULL (no upstream gradient on z_q), dz / dC may be NULL.
+// dC is fp32 [K, lddc] and is ACCUMULATED into (zero it first); lddc % 4 == 0 and 16-byte aligned rows.
+// dev_scales (optional, device float[2]) multiplies commit_scale / codebook_scale on the device.
+int ttk_vq_bwd(const void* dzq, int64_t lddq, const void* z, int64_t ldz, const void* codebook, int64_t ldc,
+               const int32_t* idx, int64_t N, int D, float commit_scale, float codebook_scale, const float* dev_scales,
+               void* dz, int64_t lddz, float* dC, int64_t lddc, cudaStream_t stream) {
+  if (!z || !codebook || !idx || (!dz && !dC)) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (D <= 0 || D % 8 || ldc % 8 || ldz % 8 || (dzq && lddq % 8) || (dz && lddz % 8) || (dC && lddc % 4))
+    return TTK_ERR_BAD_SHAPE;
+  if (dC && (reinterpret_cast<uintptr_t>(dC) & 15u)) return TTK_ERR_ALIGNMENT;
+  if (N <= 0) return TTK_OK;
+  const int64_t total = N * (D / 8);
+  const int64_t blocks = (total + 255) / 256;
+  const int grid = static_cast<int>(blocks < 16LL * num_sms() ? blocks : 16LL * num_sms());
+  vq_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dzq), lddq,
+                                          static_cast<const __nv_bfloat16*>(z), ldz,
+                                          static_cast<const __nv_bfloat16*>(codebook), ldc, idx, N, D / 8, commit_scale,
+                                          codebook_scale, dev_scales, static_cast<__nv_bfloat16*>(dz), lddz, dC, lddc);
   return launch_status();
 }
 

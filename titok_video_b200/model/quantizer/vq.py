@@ -1,0 +1,189 @@
+"""Learned-codebook vector quantizer on the tcgen05 distance + fused-argmin kernel (csrc/vq.cu).
+
+This is BASELINE.json north_star's generic quantizer -- `torch.cdist(z, C).argmin(-1)`, quantized latents, commitment /
+codebook losses and a straight-through backward. The reference itself ships only FSQ (model/quantizer/fsq.py, no
+learned codebook, no losses: SURVEY 0-D1/D2), so the oracle of this module is the standard VQ-VAE formulation written in
+plain torch (tests/test_gpu_kernels.py), anchored on the reference where it can be: with `C = FSQ.implicit_codebook`
+(fsq.py:75-76) the indices equal `FSQ.forward`'s.
+
+    q = VectorQuantizer(codebook_size=4096, dim=128).cuda()
+    z_q, d = q(z)            # z [..., dim] bf16 / fp32 (fp32 is rounded to bf16 for the distance GEMM, like autocast)
+    d["indices"]             # int32 [...]           argmin_k ||z - c_k||^2 (first minimum)
+    d["commitment_loss"]     # mean((z - sg(c))^2)   gradient flows to z
+    d["codebook_loss"]       # mean((sg(z) - c)^2)   gradient flows to the codebook
+    d["loss"]                # commitment_weight * commitment_loss + codebook_weight * codebook_loss
+    z_q                      # z + sg(c - z): value c[idx], straight-through gradient to z
+
+The return contract mirrors FSQ's `(codes, {'indices': ...})` (fsq.py:123-135) with the loss entries added.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+BF = torch.bfloat16
+
+
+class _VqFn(torch.autograd.Function):
+    """(z_q, indices, sum ||c - z||^2) with the straight-through / commitment / codebook gradients (ttk_vq_bwd)."""
+
+    @staticmethod
+    def forward(ctx, z2: torch.Tensor, codebook: torch.Tensor, vq: "VectorQuantizer"):
+        from ... import _lib, engine
+
+        n, d = z2.shape
+        cb_bf, aug, da = vq._prepared(codebook)
+        d8 = cb_bf.shape[1]
+        if d8 != d or z2.dtype != BF or not z2.is_contiguous():
+            zp = torch.zeros((n, d8), dtype=BF, device=z2.device)
+            zp[:, :d] = z2
+        else:
+            zp = z2
+        idx = torch.empty((n,), dtype=torch.int32, device=z2.device)
+        st = engine._stream()
+        _lib.call("ttk_vq_argmin", engine._ptr(zp), d8, engine._ptr(aug), da, n, cb_bf.shape[0], d, engine._ptr(idx),
+                  engine._vp(0), st)
+        zq = torch.empty((n, d8), dtype=BF, device=z2.device)
+        sq = torch.zeros((1,), dtype=torch.float32, device=z2.device)
+        _lib.call("ttk_vq_gather_loss", engine._ptr(zp), d8, engine._ptr(cb_bf), d8, engine._ptr(idx), n, d8,
+                  engine._ptr(zq), d8, engine._ptr(sq), st)
+        ctx.save_for_backward(zp, cb_bf, idx)
+        ctx.shape = (n, d, d8, codebook.shape, codebook.dtype, z2.dtype)
+        ctx.need = (z2.requires_grad, codebook.requires_grad)
+        ctx.mark_non_differentiable(idx)
+        mse = sq / float(n * d)  # padded columns are zero on both sides
+        return zq[:, :d].to(z2.dtype), idx, mse
+
+    @staticmethod
+    def backward(ctx, dzq, _didx, dmse):
+        """`mse` is consumed twice by the module (commitment: gradient to z only; codebook: to C only), which hands the
+        two upstream gradients over through ctx.vq_scales; dmse itself is their sum and is not used."""
+        from ... import _lib, engine
+
+        zp, cb_bf, idx = ctx.saved_tensors
+        n, d, d8, cshape, cdtype, zdtype = ctx.shape
+        need_z, need_c = ctx.need
+        scales = ctx.vq_scales  # device float[2]: upstream gradients of (commitment, codebook) loss
+        k = 2.0 / float(n * d)
+        dz = torch.empty((n, d8), dtype=BF, device=zp.device) if need_z else None
+        dC = torch.zeros((cb_bf.shape[0], d8), dtype=torch.float32, device=zp.device) if need_c else None
+        if dzq is not None:
+            g = torch.zeros((n, d8), dtype=BF, device=zp.device)
+            g[:, :d] = dzq
+        else:
+            g = None
+        if dz is not None or dC is not None:
+            _lib.call("ttk_vq_bwd", engine._ptr(g), d8, engine._ptr(zp), d8, engine._ptr(cb_bf), d8, engine._ptr(idx), n, d8,
+                      k, k, engine._ptr(scales), engine._ptr(dz), d8, engine._ptr(dC), d8, engine._stream())
+        return (dz[:, :d].to(zdtype) if dz is not None else None,
+                dC[:, :d].to(cdtype).reshape(cshape) if dC is not None else None, None)
+
+
+class VectorQuantizer(nn.Module):
+    def __init__(self, codebook_size: int, dim: int, commitment_weight: float = 0.25, codebook_weight: float = 1.0):
+        super().__init__()
+        self.codebook_size, self.dim = int(codebook_size), int(dim)
+        self.commitment_weight, self.codebook_weight = float(commitment_weight), float(codebook_weight)
+        self.codebook = nn.Embedding(self.codebook_size, self.dim)
+        nn.init.uniform_(self.codebook.weight, -1.0 / self.codebook_size, 1.0 / self.codebook_size)
+        self._cache = None
+
+    def _prepared(self, w: torch.Tensor):
+        """bf16 codebook padded to a multiple of 8 columns + the augmented operand of the distance GEMM
+        ([-2c | split of |c|^2]); rebuilt when the parameter changed (version / storage)."""
+        from ... import _lib, engine
+
+        key = (w.data_ptr(), w._version, str(w.device))
+        if self._cache is None or self._cache[0] != key:
+            k, d = w.shape
+            d8 = (d + 7) // 8 * 8
+            cb = torch.zeros((k, d8), dtype=BF, device=w.device)
+            cb[:, :d] = w.detach()
+            da = int(_lib.fn("ttk_vq_aug_dim")(d))
+            aug = torch.empty((k, da), dtype=BF, device=w.device)
+            _lib.call("ttk_vq_prepare_codebook", engine._ptr(cb), d8, k, d, engine._ptr(aug), da, engine._stream())
+            self._cache = (key, cb, aug, da)
+        return self._cache[1], self._cache[2], self._cache[3]
+
+    def indices_to_codes(self, indices: torch.Tensor) -> torch.Tensor:
+        """C[idx] in bf16 (the values the forward returns), 16-byte gather kernel."""
+        from ... import _lib, engine
+
+        engine.require_cuda(indices.device)
+        cb, _, _ = self._prepared(self.codebook.weight)
+        flat = indices.reshape(-1).to(torch.int32).contiguous()
+        out = torch.empty((flat.numel(), cb.shape[1]), dtype=BF, device=flat.device)
+        _lib.call("ttk_vq_gather_loss", engine._vp(0), cb.shape[1], engine._ptr(cb), cb.shape[1], engine._ptr(flat),
+                  flat.numel(), cb.shape[1], engine._ptr(out), cb.shape[1], engine._vp(0), engine._stream())
+        return out[:, :self.dim].reshape(*indices.shape, self.dim)
+
+    @torch.compiler.disable()
+    def forward(self, z: torch.Tensor):
+        from ... import engine
+
+        engine.require_cuda(z.device)
+        if z.shape[-1] != self.dim:
+            raise ValueError(f"expected last dim {self.dim}, got {tuple(z.shape)}")
+        w = self.codebook.weight
+        z2 = z.reshape(-1, self.dim)
+        if z2.dtype not in (BF, torch.float32):
+            z2 = z2.float()
+        grad = torch.is_grad_enabled() and (z2.requires_grad or w.requires_grad)
+        if grad:
+            holder = _ScaleHolder()
+            zq, idx, mse = _VqCall.apply(z2, w, self, holder)
+            commit, code = _Split.apply(mse, holder)
+        else:
+            zq, idx, mse = _VqFn.forward(_NoCtx(), z2.detach(), w.detach(), self)
+            commit = code = mse
+        commit, code = commit.reshape(()), code.reshape(())
+        out = {"indices": idx.view(z.shape[:-1]), "commitment_loss": commit, "codebook_loss": code,
+               "loss": self.commitment_weight * commit + self.codebook_weight * code}
+        return zq.view(z.shape).to(z.dtype), out
+
+
+class _ScaleHolder:
+    """carries the upstream gradients of the two losses (a device float[2], no host sync) from _Split.backward to
+    _VqCall.backward: same graph, and _Split's backward always runs first because it is downstream. If neither loss is
+    used, the scales stay zero and only the straight-through gradient flows."""
+    scales = None
+
+
+class _VqCall(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z2, w, vq, holder):
+        ctx.holder = holder
+        return _VqFn.forward(ctx, z2, w, vq)
+
+    @staticmethod
+    def backward(ctx, dzq, didx, dmse):
+        sc = ctx.holder.scales
+        if sc is None:
+            sc = torch.zeros(2, dtype=torch.float32, device=ctx.saved_tensors[0].device)
+        ctx.vq_scales = sc
+        return _VqFn.backward(ctx, dzq, didx, dmse) + (None,)
+
+
+class _Split(torch.autograd.Function):
+    """mse -> (commitment, codebook): identical values; the backward records each upstream gradient separately."""
+
+    @staticmethod
+    def forward(ctx, mse, holder):
+        ctx.holder, ctx.dev, ctx.shape = holder, mse.device, mse.shape
+        return mse.clone(), mse.clone()
+
+    @staticmethod
+    def backward(ctx, g_commit, g_code):
+        z = torch.zeros((), dtype=torch.float32, device=ctx.dev)
+        gc = g_commit.reshape(()).float() if g_commit is not None else z
+        gk = g_code.reshape(()).float() if g_code is not None else z
+        ctx.holder.scales = torch.stack([gc, gk]).contiguous()
+        return (gc + gk).reshape(ctx.shape), None
+
+
+class _NoCtx:
+    def save_for_backward(self, *a):
+        pass
+
+    def mark_non_differentiable(self, *a):
+        pass
