@@ -99,15 +99,20 @@ def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.T
     return r(out)
 
 
-def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, q_chunk: int = 2048) -> torch.Tensor:
     """One clip: q [s,Hq,64], k/v [s,Hkv,64]; exact softmax(q k^T / 8) v per head, q head h reads kv head
-    h // (Hq/Hkv), output stored in bf16.  [transformer.py:100 -> flash_attn_varlen_func, non-causal, default scale]"""
+    h // (Hq/Hkv), output stored in bf16.  [transformer.py:100 -> flash_attn_varlen_func, non-causal, default scale]
+    Query rows are independent, so long sequences are processed `q_chunk` rows at a time (bounds the [H, q, s] score
+    matrix: 12 heads x 8448^2 fp32 would be 3.4 GB)."""
     hq, hk = q.shape[1], k.shape[1]
     kk = k.repeat_interleave(hq // hk, dim=1)
     vv = v.repeat_interleave(hq // hk, dim=1)
-    s = torch.einsum("qhd,khd->hqk", q, kk) * (1.0 / math.sqrt(q.shape[-1]))
-    p = torch.softmax(s, dim=-1)
-    return r(torch.einsum("hqk,khd->qhd", p, vv))
+    out = []
+    for a in range(0, q.shape[0], q_chunk):
+        s = torch.einsum("qhd,khd->hqk", q[a:a + q_chunk], kk) * (1.0 / math.sqrt(q.shape[-1]))
+        p = torch.softmax(s, dim=-1)
+        out.append(torch.einsum("hqk,khd->qhd", p, vv))
+    return r(torch.cat(out, dim=0))
 
 
 def gelu_erf(x: torch.Tensor) -> torch.Tensor:

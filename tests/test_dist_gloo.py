@@ -172,3 +172,51 @@ def test_gradient_allreducer_no_sync_accumulates_before_reducing(tmp_path):
     for k in want:
         for r in range(world):
             assert torch.allclose(got[r][k], want[k] / world, rtol=1e-5, atol=1e-6), k
+
+
+def _stats_worker(rank, world, port, out_dir):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from titok_video_b200 import dist as D
+
+    hist = torch.tensor([1, 0, 2 + rank, 0, 5 * rank], dtype=torch.int32)
+    h, means = D.allreduce_step_stats(hist, {"l1": torch.tensor(3.0 * (rank + 1)), "psnr": 10.0 + rank},
+                                      {"l1": 2 + rank, "psnr": torch.tensor(1)})
+    torch.save({"hist": h, "l1": means["l1"], "psnr": means["psnr"]}, os.path.join(out_dir, f"s{rank}.pt"))
+    # a second backward before finish() is an error, not a silent overwrite
+    net = torch.nn.ModuleDict({"encoder": torch.nn.Linear(3, 2)})
+    red = D.GradientAllReducer(net)
+    net["encoder"](torch.ones(1, 3)).sum().backward()
+    try:
+        net["encoder"](torch.ones(1, 3)).sum().backward()
+        raised = False
+    except RuntimeError:
+        raised = True
+    red.finish()
+    torch.save({"raised": raised, "path": red.last_path}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fused_small_allreduce_of_histogram_losses_and_counts(tmp_path):
+    """histogram + loss numerators + counts travel in ONE all-reduce; means are global sum / global count."""
+    world = 2
+    mp.spawn(_stats_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        got = torch.load(tmp_path / f"s{r}.pt")
+        assert got["hist"].dtype == torch.int32 and got["hist"].tolist() == [2, 0, 5, 0, 5]
+        assert abs(float(got["l1"]) - (3.0 + 6.0) / (2 + 3)) < 1e-12
+        assert abs(float(got["psnr"]) - (10.0 + 11.0) / 2) < 1e-12
+        rr = torch.load(tmp_path / f"r{r}.pt")
+        assert rr["raised"] and rr["path"] == "cat"
+    # single process: same arithmetic, no collective
+    from titok_video_b200 import dist as D
+
+    h, m = D.allreduce_step_stats(torch.tensor([1, 2], dtype=torch.int64), {"a": 6.0}, {"a": 4})
+    assert h.tolist() == [1, 2] and float(m["a"]) == 1.5
+    h, m = D.allreduce_step_stats(None, {"a": 6.0}, {"a": 0})
+    assert h is None and float(m["a"]) == 6.0

@@ -346,6 +346,32 @@ def test_scaled_config_long_sequences():
     assert sum(float(p.grad.abs().sum()) for p in model.parameters()) > 0
 
 
+@pytest.mark.parametrize("size,stress,shape", [
+    ("tiny", False, (32, 256, 256)), ("tiny", True, (32, 256, 256)),
+    # base: ~8 TFLOP of CPU oracle for the full clip (about 25 s on the GPU box's host cores)
+    ("base", False, (32, 256, 256)),
+])
+def test_scaled_config_matches_oracle(size, stress, shape):
+    """BASELINE configs[4] / SURVEY C5 against the ORACLE at full size: one 32x256x256 clip with 256 latent tokens (8448
+    packed rows, 132 kv sub-tiles per attention row) through `tiny` and `base` stacks (base: width 768, 12 layers, 12/4
+    heads -- the unfused residual path and 3-head kv groups). Same tolerances as the C1 cases."""
+    t = 256
+    model = build_model(stress, enc=size, dec=size)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda().eval()
+    clip = O.make_clips([shape], 21)
+    with torch.no_grad():
+        z = model.encoder([clip[0].cuda()], [t])
+        x_q, d = model.encode([clip[0].cuda()], [t])
+        rec = model.decode(x_q, [t], [shape])
+    z_o = O.encoder_forward(sd, size, PATCH, clip, [t])
+    _check(z, z_o, stress, f"C5 {size} z vs oracle")
+    res_idx = O.fsq_forward(z_o, LEVELS)[1]
+    _check_indices(d["indices"], res_idx, z, z_o, f"C5 {size} indices vs oracle")
+    rec_o = O.decoder_forward(sd, size, PATCH, x_q.float().cpu(), [t], [shape])  # decoder on OUR codes: no flip coupling
+    _check(rec[0], rec_o[0], stress, f"C5 {size} recon vs oracle")
+
+
 def test_uint8_frames_equal_host_normalised_clips(golden_stress):
     """Decoded uint8 frames handed straight to the model give bit-identical tokens and reconstructions to clips that
     were normalised on the host the way the reference's dataset does (video_dataset.py:118-119)."""

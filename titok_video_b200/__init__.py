@@ -8,8 +8,9 @@ from . import _lib  # noqa: F401  (fails loudly when the CUDA extension is missi
 from .model.titok import TiTok
 from .model.base.blocks import TiTokEncoder, TiTokDecoder
 from .model.quantizer.fsq import FSQ
+from .model.quantizer.vq import VectorQuantizer
 from .train_utils.codebook_logging import CodebookLogger
 from .config import load_config, AttrDict
 
-__all__ = ["TiTok", "TiTokEncoder", "TiTokDecoder", "FSQ", "CodebookLogger", "load_config", "AttrDict"]
+__all__ = ["TiTok", "TiTokEncoder", "TiTokDecoder", "FSQ", "VectorQuantizer", "CodebookLogger", "load_config", "AttrDict"]
 __version__ = "0.1.0"

@@ -402,10 +402,13 @@ def _param_grads(m, kind: str, grads: Dict[str, torch.Tensor]) -> Dict[str, torc
     out["ln_pre_t.weight"] = grads["ln_pre_t"]
     out["ln_pre_p.weight"] = grads["ln_pre_p"]
     out["ln_post.weight"] = grads["ln_post"]
+    # the two permuted tensors are un-permuted back INTO their slots of the stack's flat gradient buffer, so that every
+    # parameter gradient of a stack is a view of ONE buffer (dist.GradientAllReducer all-reduces that buffer in place)
     if kind == "enc":
         gw = torch.empty_like(grads["proj_in_w"])
         gw[:, perm] = grads["proj_in_w"]  # kernel layout is weight[:, perm]
-        out["proj_in.weight"] = gw
+        grads["proj_in_w"].copy_(gw)
+        out["proj_in.weight"] = grads["proj_in_w"]
         out["proj_in.bias"] = grads["proj_in_b"]
         out["proj_out.weight"] = grads["proj_out_w"]
         out["proj_out.bias"] = grads["proj_out_b"]
@@ -416,8 +419,10 @@ def _param_grads(m, kind: str, grads: Dict[str, torch.Tensor]) -> Dict[str, torc
         gw[perm, :] = grads["proj_out_w"]
         gb = torch.empty_like(grads["proj_out_b"])
         gb[perm] = grads["proj_out_b"]
-        out["proj_out.weight"] = gw
-        out["proj_out.bias"] = gb
+        grads["proj_out_w"].copy_(gw)
+        grads["proj_out_b"].copy_(gb)
+        out["proj_out.weight"] = grads["proj_out_w"]
+        out["proj_out.bias"] = grads["proj_out_b"]
     for i in range(m.num_layers):
         out[f"model_layers.attn_layer.{i}.pre_ln.weight"] = grads[f"pre_ln{i}"]
         out[f"model_layers.attn_layer.{i}.to_qkv.weight"] = grads[f"to_qkv{i}"]
