@@ -71,9 +71,12 @@ int ttk_codebook_stats(const uint32_t* counts, int K, double* out, ttk_stream_t 
 
 /* Generic VQ (BASELINE.json north_star): idx[n] = argmin_k ||z_n - c_k||^2 over a [K,D] bf16 codebook, the
  * oracle being torch.cdist(z, C).argmin(-1) (for FSQ: C = FSQ.implicit_codebook, fsq.py:75-76).
- * The codebook is augmented once: cb_aug [K, ttk_vq_aug_dim(D)] = [-2c | 3-term bf16 split of |c|^2 | 0].
+ * The codebook is augmented once: cb_aug [ttk_vq_aug_rows(K,D), ttk_vq_aug_dim(D)]: K rows [-2c | 3-term bf16 split
+ * of |c|^2 | 0] followed by the fp32 squared norms of ceil256(K) codes (+inf past K; used when D % 64 == 0, where the
+ * kernel adds |c|^2 in its epilogue instead of spending a k block on the norm columns).
  * z is [N,D] bf16 with row pitch ldz (multiple of 8 elements). best (optional) = |c|^2 - 2 z.c of the winner. */
 int ttk_vq_aug_dim(int D);
+int ttk_vq_aug_rows(int K, int D);
 int ttk_vq_prepare_codebook(const void* codebook, int64_t ldc, int K, int D, void* cb_aug, int64_t lda,
                             ttk_stream_t stream);
 int ttk_vq_argmin(const void* z, int64_t ldz, const void* cb_aug, int64_t lda, int64_t N, int K, int D, int32_t* idx,

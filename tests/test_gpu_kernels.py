@@ -457,7 +457,7 @@ def _vq_run(z, cb):
     zp = torch.zeros((N, D8), dtype=BF, device=DEV)
     zp[:, :D] = z.to(DEV)
     cbd = cb.to(DEV).contiguous()
-    aug = torch.empty((K, DA), dtype=BF, device=DEV)
+    aug = torch.empty((lib().fn("ttk_vq_aug_rows")(K, D), DA), dtype=BF, device=DEV)
     lib().call("ttk_vq_prepare_codebook", P(cbd), D, K, D, P(aug), DA, ST())
     idx = torch.full((N,), -1, dtype=torch.int32, device=DEV)
     best = torch.empty((N,), dtype=torch.float32, device=DEV)

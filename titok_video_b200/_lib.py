@@ -44,6 +44,7 @@ SIGNATURES = {
     "ttk_hist_u32": [_vp, _i64, _i, _vp, _vp],
     "ttk_codebook_stats": [_vp, _i, _vp, _vp],
     "ttk_vq_aug_dim": [_i],
+    "ttk_vq_aug_rows": [_i, _i],
     "ttk_vq_prepare_codebook": [_vp, _i64, _i, _i, _vp, _i64, _vp],
     "ttk_vq_argmin": [_vp, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp],
     "ttk_vq_gather_loss": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _i64, _vp, _vp],

@@ -35,13 +35,20 @@ constexpr int VQ_SMEM_BUDGET = 220 * 1024;
 struct VqParams {
   int64_t N;
   int K, D, DA;  // DA = augmented feature count (multiple of 8)
-  int num_kb;    // ceil(DA / 64)
+  int num_kb;    // 64-wide k blocks that are actually multiplied: ceil(DA / 64), or D / 64 in the no-augmentation mode
   int a_bufs;    // 1 or 2
   int b_stages;
   int num_m_tiles, num_n_tiles;
   int32_t* idx;
   float* best;
+  // D % 64 == 0: the three norm columns would cost a whole extra k block (D = 128: 9 instead of 8 MMA steps per tile,
+  // 96 instead of 64 KB of codebook per tile through L2 -> shared memory). Instead |c_k|^2 (fp32, +inf past K) is
+  // added by the epilogue from a [256]-float slice that travels beside each codebook tile (bulk copy, own ring).
+  int noaug;
+  const float* norms;  // [ceil256(K)] fp32, behind the augmented codebook (ttk_vq_aug_rows)
 };
+constexpr int VQ_NSLOTS = 4;                      // norm-slice ring
+constexpr int VQ_N_BYTES = VQ_BN * 4;             // 1 KB per slice
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
   float r;
@@ -75,13 +82,42 @@ __device__ __forceinline__ void vq_chunk_update(const uint32_t (&v)[32], int col
   }
 }
 
+// the same with |c_k|^2 added from shared memory (no-augmentation mode; codes past K carry +inf)
+__device__ __forceinline__ void vq_chunk_update_n(const uint32_t (&v)[32], const float* __restrict__ nrm, int col0, float& best,
+                                                  int& best_i) {
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 n4 = *reinterpret_cast<const float4*>(nrm + i);  // same address in every lane: broadcast
+    f[i] = __uint_as_float(v[i]) + n4.x;
+    f[i + 1] = __uint_as_float(v[i + 1]) + n4.y;
+    f[i + 2] = __uint_as_float(v[i + 2]) + n4.z;
+    f[i + 3] = __uint_as_float(v[i + 3]) + n4.w;
+  }
+  float m[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) m[i] = fmin3(f[3 * i], f[3 * i + 1], f[3 * i + 2]);
+  m[10] = fminf(f[30], f[31]);
+  const float a = fmin3(m[0], m[1], m[2]), b = fmin3(m[3], m[4], m[5]), c = fmin3(m[6], m[7], m[8]);
+  const float mm = fminf(fmin3(a, b, c), fminf(m[9], m[10]));
+  if (mm < best) {
+    best = mm;
+    int bi = 31;
+#pragma unroll
+    for (int i = 30; i >= 0; --i)
+      if (f[i] == mm) bi = i;
+    best_i = col0 + bi;
+  }
+}
+
 __global__ void __launch_bounds__(384, 1)
 vq_argmin_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmC, const VqParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                               // [a_bufs][num_kb][128 x 64]
   uint8_t* sB = sA + p.a_bufs * p.num_kb * VQ_A_KB_BYTES;           // [b_stages][256 x 64]
-  uint8_t* tail = sB + p.b_stages * VQ_B_BYTES;
+  float* sN = reinterpret_cast<float*>(sB + p.b_stages * VQ_B_BYTES);  // [VQ_NSLOTS][256] norm slices (no-aug mode)
+  uint8_t* tail = reinterpret_cast<uint8_t*>(sN) + VQ_NSLOTS * VQ_N_BYTES;
   float* m_best = reinterpret_cast<float*>(tail);                   // [128] merge buffer
   int* m_idx = reinterpret_cast<int*>(tail + 512);                  // [128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 1024);
@@ -92,7 +128,9 @@ vq_argmin_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant_
   uint64_t* t_empty = bars + 8;     // [2]
   uint64_t* b_full = bars + 10;     // [b_stages <= 8]
   uint64_t* b_empty = bars + 18;    // [b_stages <= 8]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 26);
+  uint64_t* n_full = bars + 26;     // [VQ_NSLOTS]
+  uint64_t* n_empty = bars + 30;    // [VQ_NSLOTS]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 34);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,6 +151,10 @@ vq_argmin_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant_
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
+    for (int s = 0; s < VQ_NSLOTS; ++s) {
+      mbar_init(&n_full[s], 1);
+      mbar_init(&n_empty[s], 8);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, 512);
@@ -125,9 +167,15 @@ vq_argmin_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant_
     // ===================== codebook (B) producer =====================
     if (elect_one()) {
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, tc = 0;  // tc: codebook tiles streamed so far (norm-slice ring position)
       for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x) {
-        for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+        for (int nt = 0; nt < p.num_n_tiles; ++nt, ++tc) {
+          if (p.noaug) {
+            const int sl = tc & (VQ_NSLOTS - 1);
+            mbar_wait(&n_empty[sl], ((tc / VQ_NSLOTS) & 1) ^ 1);
+            mbar_arrive_expect_tx(&n_full[sl], VQ_N_BYTES);
+            bulk_load_1d(sN + sl * VQ_BN, p.norms + static_cast<int64_t>(nt) * VQ_BN, VQ_N_BYTES, &n_full[sl]);
+          }
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(&b_empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&b_full[stage], VQ_B_BYTES);
@@ -157,7 +205,7 @@ vq_argmin_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant_
       __syncwarp();
       mbar_wait(&a_full[ab], ph);
       // columns D, D+1, D+2 of every row := 1.0 (they multiply the hi/mid/lo norm terms of c')
-      for (int e = lane; e < VQ_BM * 3; e += 32) {
+      for (int e = lane; e < VQ_BM * 3 && !p.noaug; e += 32) {
         const int r = e / 3;
         const int col = p.D + (e - r * 3);
         const int kb = col >> 6;
@@ -192,7 +240,7 @@ vq_argmin_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant_
             tc_fence_after();
             const uint32_t sa = a_addr + kb * VQ_A_KB_BYTES;
             const uint32_t sb = smem_u32(sB + stage * VQ_B_BYTES);
-            const int rem = p.DA - kb * VQ_BK;
+            const int rem = (p.noaug ? p.D : p.DA) - kb * VQ_BK;
             const int ksteps = rem >= VQ_BK ? 4 : (rem + 15) / 16;
             for (int k = 0; k < ksteps; ++k)
               umma_bf16_ss(d_tmem, umma_smem_desc_sw128(sa + k * 32, 1024, 0),
@@ -219,11 +267,14 @@ vq_argmin_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant_
     const int chalf = (warp - 4) >> 2;
     const int r = quarter * 32 + lane;
     int as = 0;
-    uint32_t aphase = 0;
+    uint32_t aphase = 0, tc = 0;
     for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x) {
       float best = INFINITY;
       int best_i = 0;
-      for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+      for (int nt = 0; nt < p.num_n_tiles; ++nt, ++tc) {
+        const int sl = tc & (VQ_NSLOTS - 1);
+        const float* nrm = sN + sl * VQ_BN + chalf * 128;
+        if (p.noaug) mbar_wait(&n_full[sl], (tc / VQ_NSLOTS) & 1);
         mbar_wait(&t_full[as], aphase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * VQ_BN + chalf * 128;
@@ -234,12 +285,20 @@ vq_argmin_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant_
           tmem_ld_32x32b_x32(t_row + c0, v0);
           tmem_ld_32x32b_x32(t_row + c0 + 32, v1);
           tmem_ld_wait();
-          if (colbase + c0 < p.K) vq_chunk_update(v0, colbase + c0, p.K, best, best_i);
-          if (colbase + c0 + 32 < p.K) vq_chunk_update(v1, colbase + c0 + 32, p.K, best, best_i);
+          if (p.noaug) {
+            vq_chunk_update_n(v0, nrm + c0, colbase + c0, best, best_i);
+            vq_chunk_update_n(v1, nrm + c0 + 32, colbase + c0 + 32, best, best_i);
+          } else {
+            if (colbase + c0 < p.K) vq_chunk_update(v0, colbase + c0, p.K, best, best_i);
+            if (colbase + c0 + 32 < p.K) vq_chunk_update(v1, colbase + c0 + 32, p.K, best, best_i);
+          }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[as]);
+        if (lane == 0) {
+          mbar_arrive(&t_empty[as]);
+          if (p.noaug) mbar_arrive(&n_empty[sl]);
+        }
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -275,27 +334,35 @@ vq_argmin_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant_
 
 // Variant for feature dims up to 189 (num_kb <= 3): the CTA owns TWO 128-row z tiles (256 rows) and every codebook
 // tile that streams through shared memory feeds both, which halves the L2 -> SM traffic per MMA -- at D <= 128 the
-// single-tile kernel is bound by streaming the codebook (96 KB per 1152 MMA cycles), not by the tensor core.
-// TMEM holds one accumulator per z tile; while the tensor core works on one, four epilogue warps drain the other
-// (thread == row, all 256 columns of the tile: no cross-warp merge).
-//   warp 0      B producer      warp 1   MMA issuer      warp 2   TMEM allocator      warp 3   A producer + ones patch
-//   warps 4-7   argmin epilogue of z tile 0            warps 8-11   argmin epilogue of z tile 1
+// single-tile kernel is bound by streaming the codebook, not by the tensor core.
+// TMEM holds one accumulator per z tile. The MMAs are issued TILE-major -- all k blocks of z tile 0, then all of z
+// tile 1, against the same resident codebook tile -- so that while the tensor core fills one accumulator, all eight
+// epilogue warps drain the other one (thread == row x half of the 256 columns): an accumulator is free again long before
+// its next tile starts (k-block-major order left ~1 MMA step between the completion of an accumulator and its reuse, and the tensor
+// core waited for the drain: 53-59 % of peak at D = 128).
+//   warp 0      B producer (+ norm slices)   warp 1   MMA issuer   warp 2   TMEM allocator   warp 3   A producer (+ ones patch)
+//   warps 4-11  argmin epilogue: quarter = TMEM lanes, warps 4-7 columns [0,128), warps 8-11 columns [128,256)
 __global__ void __launch_bounds__(384, 1)
 vq_argmin2_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmC, const VqParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                     // [2 tiles][num_kb][128 x 64]
   uint8_t* sB = sA + 2 * p.num_kb * VQ_A_KB_BYTES;        // [b_stages][256 x 64]
-  uint8_t* tail = sB + p.b_stages * VQ_B_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* a_full = bars;          // [1]
-  uint64_t* a_ready = bars + 1;     // [1]
-  uint64_t* a_empty = bars + 2;     // [1]
-  uint64_t* t_full = bars + 3;      // [2]
-  uint64_t* t_empty = bars + 5;     // [2]
-  uint64_t* b_full = bars + 7;      // [b_stages <= 8]
-  uint64_t* b_empty = bars + 15;    // [b_stages <= 8]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 23);
+  float* sN = reinterpret_cast<float*>(sB + p.b_stages * VQ_B_BYTES);  // [VQ_NSLOTS][256] norm slices (no-aug mode)
+  uint8_t* tail = reinterpret_cast<uint8_t*>(sN) + VQ_NSLOTS * VQ_N_BYTES;
+  float* m_best = reinterpret_cast<float*>(tail);         // [2 tiles][128] merge buffer of the column halves
+  int* m_idx = reinterpret_cast<int*>(tail + 1024);       // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2048);
+  uint64_t* a_full = bars;          // [2] per z tile: the next block's tile 0 is loaded while tile 1 still computes
+  uint64_t* a_ready = bars + 2;     // [2]
+  uint64_t* a_empty = bars + 4;     // [2]
+  uint64_t* t_full = bars + 6;      // [2]
+  uint64_t* t_empty = bars + 8;     // [2]
+  uint64_t* b_full = bars + 10;     // [b_stages <= 8]
+  uint64_t* b_empty = bars + 18;    // [b_stages <= 8]
+  uint64_t* n_full = bars + 26;     // [VQ_NSLOTS]
+  uint64_t* n_empty = bars + 30;    // [VQ_NSLOTS]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 34);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -306,16 +373,20 @@ vq_argmin2_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
     tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(a_full, 1);
-    mbar_init(a_ready, 1);
-    mbar_init(a_empty, 1);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_ready[s], 1);
+      mbar_init(&a_empty[s], 1);
       mbar_init(&t_full[s], 1);
-      mbar_init(&t_empty[s], 4);
+      mbar_init(&t_empty[s], 8);
     }
     for (int s = 0; s < p.b_stages; ++s) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < VQ_NSLOTS; ++s) {
+      mbar_init(&n_full[s], 1);
+      mbar_init(&n_empty[s], 8);
     }
     fence_barrier_init();
   }
@@ -329,9 +400,15 @@ vq_argmin2_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
     // ===================== codebook (B) producer =====================
     if (elect_one()) {
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, tc = 0;
       for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
-        for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+        for (int nt = 0; nt < p.num_n_tiles; ++nt, ++tc) {
+          if (p.noaug) {
+            const int sl = tc & (VQ_NSLOTS - 1);
+            mbar_wait(&n_empty[sl], ((tc / VQ_NSLOTS) & 1) ^ 1);
+            mbar_arrive_expect_tx(&n_full[sl], VQ_N_BYTES);
+            bulk_load_1d(sN + sl * VQ_BN, p.norms + static_cast<int64_t>(nt) * VQ_BN, VQ_N_BYTES, &n_full[sl]);
+          }
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(&b_empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&b_full[stage], VQ_B_BYTES);
@@ -346,99 +423,150 @@ vq_argmin2_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
     }
     __syncwarp();
   } else if (warp == 3) {
-    // ===================== z (A) producer + ones patch: both tiles of the block =====================
+    // ===================== z (A) producer + ones patch: the two tiles of a block, each on its own barriers =====================
     uint32_t it = 0;
     for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
-      if (lane == 0) {
-        mbar_wait(a_empty, (it & 1) ^ 1);
-        mbar_arrive_expect_tx(a_full, 2 * p.num_kb * VQ_A_KB_BYTES);
+      if (lane == 0 && blk + static_cast<int>(gridDim.x) < num_blocks) {  // next block's rows towards L2 now
         for (int a = 0; a < 2; ++a)
           for (int kb = 0; kb < p.num_kb; ++kb)
-            tma_load_2d(sA + (a * p.num_kb + kb) * VQ_A_KB_BYTES, &tmZ, a_full, kb * VQ_BK, (blk * 2 + a) * VQ_BM);
+            tma_prefetch_l2_2d(&tmZ, kb * VQ_BK, ((blk + gridDim.x) * 2 + a) * VQ_BM);
       }
-      __syncwarp();
-      mbar_wait(a_full, it & 1);
-      // columns D, D+1, D+2 of every row := 1.0 (they multiply the hi/mid/lo norm terms of c')
-      for (int e = lane; e < 2 * VQ_BM * 3; e += 32) {
-        const int a = e / (VQ_BM * 3);
-        const int r = (e / 3) % VQ_BM;
-        const int col = p.D + (e % 3);
-        const int kb = col >> 6;
-        const int cc = col & 63;
-        uint8_t* dst = sA + (a * p.num_kb + kb) * VQ_A_KB_BYTES + sw128_offset(r, cc >> 3) + (cc & 7) * 2;
-        *reinterpret_cast<unsigned short*>(dst) = 0x3f80;  // bf16(1.0)
+      for (int a = 0; a < 2; ++a) {
+        if (lane == 0) {
+          mbar_wait(&a_empty[a], (it & 1) ^ 1);
+          mbar_arrive_expect_tx(&a_full[a], p.num_kb * VQ_A_KB_BYTES);
+          for (int kb = 0; kb < p.num_kb; ++kb)
+            tma_load_2d(sA + (a * p.num_kb + kb) * VQ_A_KB_BYTES, &tmZ, &a_full[a], kb * VQ_BK, (blk * 2 + a) * VQ_BM);
+        }
+        __syncwarp();
+        mbar_wait(&a_full[a], it & 1);
+        // columns D, D+1, D+2 of every row := 1.0 (they multiply the hi/mid/lo norm terms of c')
+        for (int e = lane; e < VQ_BM * 3 && !p.noaug; e += 32) {
+          const int r = e / 3;
+          const int col = p.D + (e % 3);
+          const int kb = col >> 6;
+          const int cc = col & 63;
+          uint8_t* dst = sA + (a * p.num_kb + kb) * VQ_A_KB_BYTES + sw128_offset(r, cc >> 3) + (cc & 7) * 2;
+          *reinterpret_cast<unsigned short*>(dst) = 0x3f80;  // bf16(1.0)
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[a]);
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready);
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (tile-major) =====================
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(VQ_BM, VQ_BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0, tcount = 0;  // tcount: codebook tiles processed so far (parity of the accumulator barriers)
+      const int kdim = p.noaug ? p.D : p.DA;
       for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
-        mbar_wait(a_ready, it & 1);
         for (int nt = 0; nt < p.num_n_tiles; ++nt, ++tcount) {
-          for (int kb = 0; kb < p.num_kb; ++kb) {
-            mbar_wait(&b_full[stage], phase);
-            const uint32_t sb = smem_u32(sB + stage * VQ_B_BYTES);
-            const int rem = p.DA - kb * VQ_BK;
-            const int ksteps = rem >= VQ_BK ? 4 : (rem + 15) / 16;
-            for (int a = 0; a < 2; ++a) {
-              if (kb == 0) mbar_wait(&t_empty[a], (tcount & 1) ^ 1);  // the epilogue has drained this accumulator
-              tc_fence_after();
+          const int stage0 = stage;
+          for (int a = 0; a < 2; ++a) {
+            if (nt == 0) mbar_wait(&a_ready[a], it & 1);
+            mbar_wait(&t_empty[a], (tcount & 1) ^ 1);  // the epilogue has drained this accumulator
+            tc_fence_after();
+            int st = stage0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+              if (a == 0) {  // the codebook tile's k blocks arrive once and stay until z tile 1 has used them too
+                mbar_wait(&b_full[stage], phase);
+                tc_fence_after();
+                if (++stage == p.b_stages) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
               const uint32_t sa = smem_u32(sA + (a * p.num_kb + kb) * VQ_A_KB_BYTES);
+              const uint32_t sb = smem_u32(sB + st * VQ_B_BYTES);
+              const int rem = kdim - kb * VQ_BK;
+              const int ksteps = rem >= VQ_BK ? 4 : (rem + 15) / 16;
               for (int k = 0; k < ksteps; ++k)
                 umma_bf16_ss(tmem_base + a * VQ_BN, umma_smem_desc_sw128(sa + k * 32, 1024, 0),
                              umma_smem_desc_sw128(sb + k * 32, 1024, 0), idesc, (kb | k) != 0 ? 1u : 0u);
-              if (kb == p.num_kb - 1) umma_commit(&t_full[a]);
+              if (++st == p.b_stages) st = 0;
             }
-            umma_commit(&b_empty[stage]);
-            if (++stage == p.b_stages) {
-              stage = 0;
-              phase ^= 1;
-            }
+            umma_commit(&t_full[a]);
+            if (nt == p.num_n_tiles - 1) umma_commit(&a_empty[a]);  // this z tile's rows are free for the next block
+          }
+          int st = stage0;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            umma_commit(&b_empty[st]);
+            if (++st == p.b_stages) st = 0;
           }
         }
-        umma_commit(a_empty);
       }
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================== epilogue: running argmin, one accumulator per warpgroup =====================
+    // ===================== epilogue: running argmin, all eight warps on one accumulator at a time =====================
     const int quarter = warp & 3;
-    const int a = (warp - 4) >> 2;  // z tile / accumulator of this warpgroup
+    const int chalf = (warp - 4) >> 2;
     const int r = quarter * 32 + lane;
     uint32_t tcount = 0;
     for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
-      float best = INFINITY;
-      int best_i = 0;
+      float best[2] = {INFINITY, INFINITY};
+      int best_i[2] = {0, 0};
       for (int nt = 0; nt < p.num_n_tiles; ++nt, ++tcount) {
-        mbar_wait(&t_full[a], tcount & 1);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + a * VQ_BN;
-        const int colbase = nt * VQ_BN;
+        const int sl = tcount & (VQ_NSLOTS - 1);
+        const float* nrm = sN + sl * VQ_BN + chalf * 128;
+        if (p.noaug) mbar_wait(&n_full[sl], (tcount / VQ_NSLOTS) & 1);
+        const int colbase = nt * VQ_BN + chalf * 128;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          mbar_wait(&t_full[a], tcount & 1);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + a * VQ_BN + chalf * 128;
 #pragma unroll 1
-        for (int c0 = 0; c0 < VQ_BN; c0 += 64) {
-          uint32_t v0[32], v1[32];
-          tmem_ld_32x32b_x32(t_row + c0, v0);
-          tmem_ld_32x32b_x32(t_row + c0 + 32, v1);
-          tmem_ld_wait();
-          if (colbase + c0 < p.K) vq_chunk_update(v0, colbase + c0, p.K, best, best_i);
-          if (colbase + c0 + 32 < p.K) vq_chunk_update(v1, colbase + c0 + 32, p.K, best, best_i);
+          for (int c0 = 0; c0 < 128; c0 += 64) {
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32b_x32(t_row + c0, v0);
+            tmem_ld_32x32b_x32(t_row + c0 + 32, v1);
+            tmem_ld_wait();
+            if (p.noaug) {
+              vq_chunk_update_n(v0, nrm + c0, colbase + c0, best[a], best_i[a]);
+              vq_chunk_update_n(v1, nrm + c0 + 32, colbase + c0 + 32, best[a], best_i[a]);
+            } else {
+              if (colbase + c0 < p.K) vq_chunk_update(v0, colbase + c0, p.K, best[a], best_i[a]);
+              if (colbase + c0 + 32 < p.K) vq_chunk_update(v1, colbase + c0 + 32, p.K, best[a], best_i[a]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[a]);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[a]);
+        if (p.noaug && lane == 0) mbar_arrive(&n_empty[sl]);
       }
-      const int64_t row = (static_cast<int64_t>(blk) * 2 + a) * VQ_BM + r;
-      if (row < p.N) {
-        p.idx[row] = best_i;
-        if (p.best) p.best[row] = best;
+      // merge the two column halves of each row (lower index wins ties)
+      if (chalf == 1) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          m_best[a * 128 + r] = best[a];
+          m_idx[a * 128 + r] = best_i[a];
+        }
       }
+      named_bar_sync(1, 256);
+      if (chalf == 0) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const float ob = m_best[a * 128 + r];
+          const int oi = m_idx[a * 128 + r];
+          float bb = best[a];
+          int bi = best_i[a];
+          if (ob < bb || (ob == bb && oi < bi)) {
+            bb = ob;
+            bi = oi;
+          }
+          const int64_t row = (static_cast<int64_t>(blk) * 2 + a) * VQ_BM + r;
+          if (row < p.N) {
+            p.idx[row] = bi;
+            if (p.best) p.best[row] = bb;
+          }
+        }
+      }
+      named_bar_sync(1, 256);
     }
   }
 
@@ -448,12 +576,16 @@ vq_argmin2_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
 }
 
 // c'_k = [-2 c_k | hi, mid, lo of |c_k|^2 | 0..]; one warp per code.
+// Also norms[k] = |c_k|^2 in fp32 for k < K and +inf for K <= k < ceil256(K) (no-augmentation mode of the kernels).
 __global__ void __launch_bounds__(256) vq_prepare_kernel(const __nv_bfloat16* __restrict__ cb, int64_t ldc, int K,
                                                          int D, __nv_bfloat16* __restrict__ out, int64_t lda,
-                                                         int DA) {
+                                                         int DA, float* __restrict__ norms) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (k >= K) return;
+  if (k >= K) {
+    if (k < (K + 255) / 256 * 256 && lane == 0) norms[k] = INFINITY;
+    return;
+  }
   float s = 0.f;
   for (int d = lane; d < D; d += 32) {
     const float c = __bfloat162float(cb[k * ldc + d]);
@@ -469,6 +601,7 @@ __global__ void __launch_bounds__(256) vq_prepare_kernel(const __nv_bfloat16* __
     out[k * lda + D] = __float2bfloat16_rn(hi);
     out[k * lda + D + 1] = __float2bfloat16_rn(mid);
     out[k * lda + D + 2] = __float2bfloat16_rn(lo);
+    norms[k] = s;
   }
   for (int d = D + 3 + lane; d < DA; d += 32) out[k * lda + d] = __float2bfloat16_rn(0.f);
 }
@@ -568,15 +701,26 @@ extern "C" {
 // Number of bf16 columns of the augmented codebook for feature dim D.
 int ttk_vq_aug_dim(int D) { return ((D + 3 + 7) / 8) * 8; }
 
-// codebook [K, D] bf16 (row pitch ldc) -> cb_aug [K, ttk_vq_aug_dim(D)] bf16 (row pitch lda).
+// Rows the caller allocates for the augmented codebook (row pitch lda >= ttk_vq_aug_dim(D)): K rows of codes followed by
+// the fp32 squared norms of ceil256(K) codes (+inf past K), which start at element K * lda.
+int ttk_vq_aug_rows(int K, int D) {
+  if (K <= 0 || D <= 0) return 0;
+  const int64_t norm_bytes = static_cast<int64_t>((K + 255) / 256) * 256 * 4;
+  const int64_t row_bytes = static_cast<int64_t>(ttk_vq_aug_dim(D)) * 2;
+  return K + static_cast<int>((norm_bytes + row_bytes - 1) / row_bytes);
+}
+
+// codebook [K, D] bf16 (row pitch ldc) -> cb_aug [ttk_vq_aug_rows(K, D), ttk_vq_aug_dim(D)] bf16 (row pitch lda).
 int ttk_vq_prepare_codebook(const void* codebook, int64_t ldc, int K, int D, void* cb_aug, int64_t lda,
                             cudaStream_t stream) {
   if (!codebook || !cb_aug) return TTK_ERR_BAD_ARG;
   if (int e = check_device_sm100()) return e;
   const int DA = ttk_vq_aug_dim(D);
-  if (K <= 0 || D <= 0 || lda < DA) return TTK_ERR_BAD_SHAPE;
-  vq_prepare_kernel<<<(K + 7) / 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(codebook), ldc, K, D,
-                                                     static_cast<__nv_bfloat16*>(cb_aug), lda, DA);
+  if (K <= 0 || D <= 0 || lda < DA || lda % 8) return TTK_ERR_BAD_SHAPE;
+  float* norms = reinterpret_cast<float*>(static_cast<__nv_bfloat16*>(cb_aug) + static_cast<int64_t>(K) * lda);
+  const int kpad = (K + 255) / 256 * 256;
+  vq_prepare_kernel<<<(kpad + 7) / 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(codebook), ldc, K, D,
+                                                        static_cast<__nv_bfloat16*>(cb_aug), lda, DA, norms);
   return launch_status();
 }
 
@@ -587,18 +731,24 @@ int ttk_vq_argmin(const void* z, int64_t ldz, const void* cb_aug, int64_t lda, i
   if (!z || !cb_aug || !idx) return TTK_ERR_BAD_ARG;
   if (int e = check_device_sm100()) return e;
   const int DA = ttk_vq_aug_dim(D);
-  const int num_kb = (DA + VQ_BK - 1) / VQ_BK;
   if (N <= 0) return TTK_OK;
-  if (K <= 0 || D <= 0 || num_kb > VQ_MAX_KB || N > (int64_t(1) << 31) - VQ_BM) return TTK_ERR_BAD_SHAPE;
+  if (K <= 0 || D <= 0 || lda % 8) return TTK_ERR_BAD_SHAPE;
+  const int noaug = (D % VQ_BK == 0) ? 1 : 0;  // the norm columns would need a k block of their own: add |c|^2 in the epilogue
+  const int num_kb = noaug ? D / VQ_BK : (DA + VQ_BK - 1) / VQ_BK;
+  if (num_kb > VQ_MAX_KB || N > (int64_t(1) << 31) - VQ_BM) return TTK_ERR_BAD_SHAPE;
   VqParams p{};
   p.N = N;
   p.K = K;
   p.D = D;
   p.DA = DA;
   p.num_kb = num_kb;
+  p.noaug = noaug;
+  p.norms = reinterpret_cast<const float*>(static_cast<const __nv_bfloat16*>(cb_aug) + static_cast<int64_t>(K) * lda);
+  constexpr int kTail = VQ_NSLOTS * VQ_N_BYTES + 2048 + 512 + 1024;  // norm ring, merge buffers, barriers, alignment
+  const int budget = VQ_SMEM_BUDGET - kTail;
   const int a_one = num_kb * VQ_A_KB_BYTES;
-  p.a_bufs = (2 * a_one + 3 * VQ_B_BYTES <= VQ_SMEM_BUDGET) ? 2 : 1;
-  int bs = (VQ_SMEM_BUDGET - p.a_bufs * a_one) / VQ_B_BYTES;
+  p.a_bufs = (2 * a_one + 3 * VQ_B_BYTES <= budget) ? 2 : 1;
+  int bs = (budget - p.a_bufs * a_one) / VQ_B_BYTES;
   if (bs > 6) bs = 6;
   if (bs < 2) return TTK_ERR_BAD_SHAPE;
   p.b_stages = bs;
@@ -614,18 +764,20 @@ int ttk_vq_argmin(const void* z, int64_t ldz, const void* cb_aug, int64_t lda, i
   if (int e = set_smem_attr_once(once1, reinterpret_cast<const void*>(vq_argmin_kernel), 227 * 1024)) return e;
   if (int e = set_smem_attr_once(once2, reinterpret_cast<const void*>(vq_argmin2_kernel), 227 * 1024)) return e;
   if (num_kb <= 3 && p.num_m_tiles > num_sms()) {
-    // two z tiles per CTA share every codebook tile (vq_argmin2_kernel)
-    int bs2 = (VQ_SMEM_BUDGET - 2 * a_one) / VQ_B_BYTES;
+    // two z tiles per CTA share every codebook tile (vq_argmin2_kernel); the ring holds whole codebook tiles
+    int bs2 = (budget - 2 * a_one) / VQ_B_BYTES;
     if (bs2 > 6) bs2 = 6;
-    p.b_stages = bs2;
-    p.a_bufs = 1;
-    const int num_blocks = (p.num_m_tiles + 1) / 2;
-    const int smem2 = 2 * a_one + p.b_stages * VQ_B_BYTES + 256 + 1024;
-    const int grid2 = num_blocks < num_sms() ? num_blocks : num_sms();
-    vq_argmin2_kernel<<<grid2, 384, smem2, stream>>>(tmZ, tmC, p);
-    return launch_status();
+    if (bs2 >= num_kb) {
+      p.b_stages = bs2;
+      p.a_bufs = 1;
+      const int num_blocks = (p.num_m_tiles + 1) / 2;
+      const int smem2 = 2 * a_one + p.b_stages * VQ_B_BYTES + kTail;
+      const int grid2 = num_blocks < num_sms() ? num_blocks : num_sms();
+      vq_argmin2_kernel<<<grid2, 384, smem2, stream>>>(tmZ, tmC, p);
+      return launch_status();
+    }
   }
-  const int smem = p.a_bufs * a_one + p.b_stages * VQ_B_BYTES + 1024 + 256 + 1024;
+  const int smem = p.a_bufs * a_one + p.b_stages * VQ_B_BYTES + kTail;
   const int grid = p.num_m_tiles < num_sms() ? p.num_m_tiles : num_sms();
   vq_argmin_kernel<<<grid, 384, smem, stream>>>(tmZ, tmC, p);
   return launch_status();

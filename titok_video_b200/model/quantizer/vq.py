@@ -100,7 +100,7 @@ class VectorQuantizer(nn.Module):
             cb = torch.zeros((k, d8), dtype=BF, device=w.device)
             cb[:, :d] = w.detach()
             da = int(_lib.fn("ttk_vq_aug_dim")(d))
-            aug = torch.empty((k, da), dtype=BF, device=w.device)
+            aug = torch.empty((int(_lib.fn("ttk_vq_aug_rows")(k, d)), da), dtype=BF, device=w.device)
             _lib.call("ttk_vq_prepare_codebook", engine._ptr(cb), d8, k, d, engine._ptr(aug), da, engine._stream())
             self._cache = (key, cb, aug, da)
         return self._cache[1], self._cache[2], self._cache[3]
