@@ -52,8 +52,8 @@ def peaks():
 def ncu_traffic(kernel, batch):
     """dram bytes (read + write) per launch of `kernel` from the committed ncu --set full summary of this same bench
     command (profiles/r1_traffic.json, written by scripts/summarize_profiles.py); None when no capture matches."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if not os.path.exists(p):
+    p = next((q for q in (os.path.join(ROOT, "profiles", f"r{r}_traffic.json") for r in (2, 1)) if os.path.exists(q)), None)
+    if p is None:
         return None
     try:
         d = json.load(open(p))

@@ -113,6 +113,69 @@ def cmd_kernels(a):
     print(json.dumps({"ok": True}))
 
 
+def cmd_disc(a):
+    """The reference's ReconstructionLoss (model/losses/loss_module.py, unmodified) on seeded clips: generator-side GAN
+    loss and the discriminator step's loss dict + parameter gradients. LPIPS / gram are switched off in the config
+    (their weights need a download); the discriminator is the reference's TiTokEncoder(out_channels=1)."""
+    import importlib
+
+    from oracle import ref_shim, titok_oracle as O
+
+    ref_shim.install(a.mode)
+    lm = importlib.import_module("model.losses.loss_module")
+    A = ref_shim.AttrDict.wrap
+    cfg = A({"tokenizer": {"losses": {"disc_weight": 0.4, "perceptual_weight": 0.0, "gram_weight": 0.0,
+                                      "perceptual_samples_per_step": 24, "perceptual_sampling_size": 128}},
+             "discriminator": {"model": {"patch_size": PATCH, "model_size": "tiny"},
+                               "losses": {"gp_weight": 0.1, "gp_noise": 0.1, "centering_weight": 0.01}},
+             "training": {"main": {"torch_compile": False, "max_steps": 1000}}})
+    torch.manual_seed(5)
+    loss = lm.ReconstructionLoss(cfg)
+    dev = torch.device("cuda" if a.mode == "gpu" else "cpu")
+    sd = {k: v.detach().clone() for k, v in loss.disc_model.state_dict().items()}
+    if a.stress:
+        O.stress_init_(sd, 2)
+        loss.disc_model.load_state_dict(sd)
+    loss = loss.to(torch.bfloat16).to(dev)
+    shapes = [tuple(s) for s in json.loads(a.shapes)]
+    target = [c.to(dev) for c in O.make_clips(shapes, 31)]
+    recon = [c.to(dev) for c in O.make_clips(shapes, 32)]
+    g = torch.Generator().manual_seed(33)
+    unit = [torch.randn(c.shape, generator=g).to(torch.bfloat16).to(dev) for c in target]
+    noise = [u * 0.1 for u in unit]  # what `torch.randn_like(x) * self.gp_noise` (loss_module.py:186) evaluates to
+    # the reference draws its noise with randn_like; make that call return ours so both sides see the same numbers
+    it = iter(unit)
+    real_randn_like = torch.randn_like
+    torch.randn_like = lambda x, *aa, **kw: next(it)
+    try:
+        total, logs = loss(target, recon, disc_forward=True)
+    finally:
+        torch.randn_like = real_randn_like
+    total.backward()
+    arrays = {"shapes": np.array(shapes), "total": np.array(float(total)), "weight_checksum": _checksum(sd)}
+    for k, v in logs.items():
+        arrays["log/" + k] = np.array(float(v))
+    for k, p_ in loss.disc_model.named_parameters():
+        gg = (p_.grad if p_.grad is not None else torch.zeros_like(p_)).float().reshape(-1).cpu()
+        arrays["norm/" + k] = np.array(float(gg.double().norm()))
+        stride = max(1, -(-gg.numel() // 2048))
+        arrays["sample/" + k] = gg[::stride].numpy()
+    for i, n in enumerate(noise):
+        arrays[f"noise{i}_bits"] = _bits(n)
+    # generator side: frozen discriminator, gradient w.r.t. the fake pixels
+    rec_leaf = [r.detach().clone().requires_grad_(True) for r in recon]
+    for p_ in loss.disc_model.parameters():
+        p_.requires_grad = False
+    lr, lf = loss.disc_wrapper([t.detach() for t in target]), loss.disc_wrapper(rec_leaf)
+    g_loss = torch.nn.functional.softplus(-(lf - lr))
+    g_loss.mean().backward()
+    arrays["g_loss"] = g_loss.detach().float().cpu().numpy()
+    for i, r_ in enumerate(rec_leaf):
+        arrays[f"g_pixgrad{i}_norm"] = np.array(float(r_.grad.float().double().norm()))
+    np.savez_compressed(a.out, **arrays)
+    print(json.dumps({"ok": True, "total": float(total)}))
+
+
 def _bench_inputs(batch, dev, dtype, shape=CLIP_A, tokens=TOKENS_A, sets=2):
     g = torch.Generator().manual_seed(1000)
     out = []
@@ -259,6 +322,12 @@ def main():
     p.add_argument("--seed", type=int, default=11)
     p.add_argument("--out", required=True)
     p.set_defaults(fn=cmd_kernels)
+    p = sub.add_parser("disc")
+    p.add_argument("--mode", default="cpu", choices=["gpu", "cpu"])
+    p.add_argument("--shapes", default="[[8, 32, 32], [4, 16, 24], [8, 64, 48]]")
+    p.add_argument("--stress", type=int, default=1)
+    p.add_argument("--out", required=True)
+    p.set_defaults(fn=cmd_disc)
     p = sub.add_parser("bench")
     p.add_argument("--mode", default="gpu", choices=["gpu", "cpu"])
     p.add_argument("--batch", type=int, default=64)

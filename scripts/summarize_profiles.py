@@ -51,7 +51,7 @@ def main(tag, batch):
         scale = 1e-3 if unit in ("ns", "nsecond") else 1.0
         tot = sum(a[0] for a in agg.values())
         md += ["## Launch list (cold-cache, serialised: shares, not absolutes)", "",
-               f"{sum(a[1] for a in agg.values())} launches captured (`-s 200 -c 80`, about 1.6 steps incl. torch copy kernels).", "",
+               f"{sum(a[1] for a in agg.values())} launches captured (about 1.6-2.5 steps incl. torch copy kernels).", "",
                "| kernel | launches | total us | share |", "|---|---|---|---|"]
         for k, (v, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
             md.append(f"| `{k}` | {n} | {v * scale:.1f} | {100 * v / tot:.1f} % |")
@@ -59,7 +59,7 @@ def main(tag, batch):
         with open(os.path.join(PROF, f"{tag}_launches.csv"), "w") as f:
             f.writelines(lines)
     traffic = {}
-    for kind in ("attn", "gemm"):
+    for kind in ("attn", "gemm", "vq"):
         rep = os.path.join(OUT, f"{kind}_{tag}.ncu-rep")
         if not os.path.exists(rep):
             continue
@@ -81,7 +81,7 @@ def main(tag, batch):
         md.append("")
     open(os.path.join(PROF, f"{tag}_kernels.md"), "w").write("\n".join(md) + "\n")
     if traffic:
-        json.dump(traffic, open(os.path.join(PROF, "r1_traffic.json"), "w"), indent=1)
+        json.dump(traffic, open(os.path.join(PROF, f"{tag[:2]}_traffic.json"), "w"), indent=1)
     print("\n".join(md[:40]))
 
 

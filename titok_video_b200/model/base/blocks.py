@@ -87,16 +87,17 @@ class TiTokEncoder(_Stack):
         dp = self._plan(gpx, tcs, device)
         consts = (fsq if fsq is not None else _dummy_fsq(self.token_size))._consts(device)
         if _wants_grad(self, *videos):
-            # training path: recorded by autograd (backward.EncoderFn); pixels get a gradient if they ask for one
-            # (the discriminator's gradient penalties differentiate w.r.t. the input, loss_module.py:149-152)
-            from ... import backward
+            # training path: recorded by autograd through the registered operator titok_b200::encoder_stack (ops.py);
+            # pixels get a gradient if they ask for one (the discriminator's gradient penalties differentiate w.r.t.
+            # the input, loss_module.py:149-152)
+            from ... import ops
 
             if any(v.requires_grad for v in videos):
                 flat = torch.cat([v.reshape(-1).to(torch.bfloat16) for v in videos])
             else:
                 with torch.no_grad():
                     flat = engine.flatten_clips(videos, dp)
-            z, codes, idx = backward.EncoderFn.apply(self, dp, consts, flat, *backward.stack_params(self))
+            z, codes, idx = ops.encoder_call(self, dp, consts, flat, True)
             return z, codes, idx, dp
         with torch.no_grad():
             flat = engine.flatten_clips(videos, dp)
@@ -131,9 +132,9 @@ class TiTokDecoder(_Stack):
             raise ValueError(f"tokens {tuple(tokens.shape)} do not match token_counts (sum {sum(tcs)})")
         dp = self._plan(gpx, tcs, device)
         if _wants_grad(self, tokens):
-            from ... import backward
+            from ... import ops
 
-            return backward.DecoderFn.apply(self, dp, tokens, *backward.stack_params(self)), dp
+            return ops.decoder_call(self, dp, tokens, True), dp
         with torch.no_grad():
             codes = tokens.detach().to(torch.bfloat16).contiguous()
             out = dp.buf("clips_out", (dp.plan.total_numel,))
