@@ -339,6 +339,83 @@ def train_leg(T, _lib, dev, world, rank, dist, batch, steps, warmup):
                     + "fused AdamW + codebook histogram; synthetic clips 3x16x168x168 / 128 tokens, random-init weights"}
 
 
+def gan_leg(T, _lib, dev, batch, steps, warmup):
+    """The full training step of train.py:48-115 around the path: generator step (TiTok forward, L1, the
+    GAN term through the discriminator = a TiTokEncoder(out_channels=1), backward, AdamW) and discriminator step
+    (relativistic loss + noise R1/R2 + centering, loss_module.py:166-214, backward, AdamW). LPIPS is not on the path (a
+    VGG whose weights need a download). Measured twice: the discriminator's forwards of each step PACKED into one launch
+    sequence (train_utils.PackedDiscriminator) and issued one by one like the reference does (6 encoder calls)."""
+    import torch.nn.functional as F
+
+    from titok_video_b200.config import tiny_config
+    from titok_video_b200.model.base.utils import init_weights
+    from titok_video_b200.train_utils.disc_step import PackedDiscriminator
+
+    torch.manual_seed(42)
+    model = T.TiTok(tiny_config(LEVELS, PATCH)).to(dev).train()
+    disc = T.TiTokEncoder("tiny", PATCH, 3, 1).apply(init_weights).to(dev).train()
+    opt_g = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.5, 0.96), weight_decay=1e-4, fused=True)
+    opt_d = torch.optim.AdamW(disc.parameters(), lr=1.5e-5, betas=(0.5, 0.96), weight_decay=1e-4, fused=True)
+    pd = PackedDiscriminator(disc, 4)
+    gen = torch.Generator().manual_seed(4000)
+    clips = [(torch.rand((3, *CLIP_A), generator=gen) * 2 - 1).to(torch.bfloat16).to(dev) for _ in range(batch)]
+    tcs = [TOKENS_A] * batch
+
+    def sep_logits(groups):
+        return [pd.logits([g])[0] for g in groups]
+
+    def step(packed):
+        logits = pd.logits if packed else sep_logits
+        # ---- generator
+        pd.set_requires_grad(False)
+        opt_g.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            recon, d = model(clips, tcs)
+            recon_loss = torch.stack([(r_.float() - c.float()).abs().mean() for c, r_ in zip(clips, recon)])
+            lr_, lf_ = logits([[c.detach() for c in clips], list(recon)])
+            g_loss = F.softplus(-(lf_ - lr_))
+            total = (recon_loss + 0.4 * g_loss.float()).mean()
+        total.backward()
+        opt_g.step()
+        # ---- discriminator
+        opt_d.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if packed:
+                total_d, _ = pd.discriminator_loss(clips, [r_.detach() for r_ in recon], 0.1, 0.1, 0.01)
+            else:
+                pd.set_requires_grad(True)
+                rec = [r_.detach() for r_ in recon]
+                noise = [torch.randn_like(x) * 0.1 for x in clips]
+                a, b, c2, d2 = sep_logits([clips, rec, [x + n for x, n in zip(clips, noise)], [x + n for x, n in zip(rec, noise)]])
+                total_d = (F.softplus(-(a - b)) + 0.1 / 0.01 * ((a - c2) ** 2 + (b - d2) ** 2) + 0.01 * ((a + b) ** 2) / 2).mean()
+        total_d.backward()
+        opt_d.step()
+        return total.detach()
+
+    out = {}
+    for name, packed in (("packed", True), ("separate", False)):
+        for _ in range(max(warmup, 3)):
+            step(packed)
+        torch.cuda.synchronize()
+        l0 = _lib.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            step(packed)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = {"ms_per_step": e0.elapsed_time(e1) / steps, "wall_ms_per_step": (time.perf_counter() - w0) * 1e3 / steps,
+                     "gpu_launches_per_step": (_lib.LAUNCHES - l0) / steps}
+    out["clips_per_gpu_per_step"] = batch
+    out["clips_per_s_packed"] = batch / (out["packed"]["ms_per_step"] * 1e-3)
+    out["what"] = ("generator step (TiTok fwd + L1 + GAN term via the frozen discriminator + backward + AdamW) and discriminator "
+                   "step (relativistic + noise R1/R2 + centering, backward, AdamW); discriminator = TiTokEncoder(out_channels=1), "
+                   "4 register tokens; `packed` = each step's discriminator forwards as one launch sequence, `separate` = the "
+                   "reference's 6 encoder calls")
+    return out
+
+
 def train_ragged_leg(T, _lib, dev, rank, steps):
     """The regime train.py really runs in: every step a NEW batch composition from the dataloader's token-budget batching
     (titok_video_b200.data.dynamic_batches = video_dataset.py:130-172: shapes in [min_grid, max_grid], 1..128 tokens,
@@ -718,6 +795,8 @@ def main():
             train[f"batch{tb}"] = train_leg(T, _lib, dev, world, rank, dist, tb, max(4, args.steps // 2), args.warmup)
         if rank == 0:
             train["ragged"] = train_ragged_leg(T, _lib, dev, rank, 8)
+        if rank == 0 and world == 1:
+            train["gan"] = gan_leg(T, _lib, dev, 3, max(4, args.steps // 2), args.warmup)
 
     # ---------------- scaled-up variant (BASELINE configs[4]) ----------------
     scaled = None

@@ -144,3 +144,65 @@ def test_kernels_match_flash_attn_and_triton_rmsnorm(tmp_path):
         bad = (y - y_ref).abs() > 2.0 * ulp + 1e-30
         assert bad.float().mean() < 1e-2, f"rmsnorm width {w}: {int(bad.sum())} of {bad.numel()} beyond 2 ulp"
         assert (y - y_ref).abs().max() <= 8 * ulp.max()
+
+
+@needs_ref
+def test_packed_discriminator_step_matches_the_reference_loss_module(tmp_path):
+    """the reference's ReconstructionLoss discriminator step (loss_module.py:166-214; 4 encoder forwards)
+    and generator-side GAN loss (:140-153; 2 forwards), UNMODIFIED and run on the host cores under the CPU stand-ins,
+    against train_utils.PackedDiscriminator, which evaluates each step's forwards as ONE packed launch sequence on the
+    drop-in TiTokEncoder(out_channels=1). Same discriminator weights (the reference's RNG stream, re-drawn wide so the
+    logits are not all ~0), same clips, same noise. Tolerances: logged scalars |d| <= 2e-2 + 3e-2*|ref| (bf16, 4 layers,
+    mean over 4 register tokens); parameter-gradient cosine >= 0.98 on every 2-D weight."""
+    import titok_video_b200 as T
+    from titok_video_b200.model.base.utils import init_weights
+    from titok_video_b200.train_utils.disc_step import PackedDiscriminator
+
+    out = str(tmp_path / "disc.npz")
+    shapes = [(8, 32, 32), (4, 16, 24), (8, 64, 48)]
+    _run(["disc", "--mode", "cpu", "--shapes", json.dumps(shapes), "--stress", "1", "--out", out])
+    ref = np.load(out)
+    torch.manual_seed(5)
+    disc = T.TiTokEncoder("tiny", (4, 8, 8), 3, 1).apply(init_weights)
+    sd = {k: v.detach().clone() for k, v in disc.state_dict().items()}
+    O.stress_init_(sd, 2)
+    assert checksum_matches(sd, ref["weight_checksum"]), "discriminator weights differ from the ones the reference drew"
+    disc.load_state_dict(sd)
+    disc = disc.cuda().train()
+    target = [c.cuda() for c in O.make_clips(shapes, 31)]
+    recon = [c.cuda() for c in O.make_clips(shapes, 32)]
+    noise = [from_bits(ref[f"noise{i}_bits"]).view(3, *s).cuda() for i, s in enumerate(shapes)]
+    pd = PackedDiscriminator(disc, disc_tokens=4)
+    from titok_video_b200 import _lib
+
+    n0 = _lib.LAUNCHES
+    total, logs = pd.discriminator_loss(target, recon, gp_weight=0.1, gp_noise=0.1, centering_weight=0.01, noise=noise)
+    fwd_launches = _lib.LAUNCHES - n0
+    total.backward()
+    torch.cuda.synchronize()
+    assert fwd_launches <= 60, f"{fwd_launches} launches: the four forwards were not packed into one sequence"
+    for k in ("d_loss", "logits_relative", "r1_penalty", "r2_penalty", "centering_loss", "total_loss"):
+        a, b = float(logs["disc/" + k]), float(ref["log/disc/" + k])
+        assert abs(a - b) <= 2e-2 + 3e-2 * abs(b), f"{k}: {a} vs reference {b}"
+    for k, p in disc.named_parameters():
+        g = p.grad.detach().float().reshape(-1).cpu()
+        stride = max(1, -(-g.numel() // 2048))
+        gs, rs = g[::stride].double(), torch.from_numpy(ref["sample/" + k]).double()
+        if p.dim() == 2 and min(p.shape) > 1:
+            cos = float((gs @ rs) / (gs.norm() * rs.norm() + 1e-300))
+            assert cos >= 0.98, f"{k}: gradient cosine {cos:.4f}"
+            assert abs(float(g.double().norm()) / float(ref["norm/" + k]) - 1.0) < 0.1, k
+    # generator side: frozen discriminator, the loss reaches the fake pixels
+    fake = [r.detach().clone().requires_grad_(True) for r in recon]
+    g_loss = pd.generator_loss(target, fake)
+    g_loss.mean().backward()
+    gr = torch.from_numpy(ref["g_loss"])
+    assert (g_loss.detach().float().cpu() - gr).abs().max() <= 2e-2 + 3e-2 * gr.abs().max()
+    for i, f in enumerate(fake):
+        assert f.grad is not None and abs(float(f.grad.float().double().norm()) / float(ref[f"g_pixgrad{i}_norm"]) - 1.0) < 0.15
+    assert all(p.grad is not None for p in disc.parameters())  # (from the D step; the G step adds nothing to them)
+    # packing is exact: the packed logits equal the four separate calls bit for bit
+    with torch.no_grad():
+        lg = pd.logits([target, recon])
+        sep = [pd.logits([target])[0], pd.logits([recon])[0]]
+    assert torch.equal(lg[0], sep[0]) and torch.equal(lg[1], sep[1])
