@@ -194,6 +194,10 @@ int ttk_enc_head_fsq(const void* x, int64_t ld, const int32_t* latent_row, const
  * geom int64 [G,4] = {element offset of the patch origin in the flat clip buffer, W, H*W, T*H*W}. P2 must be 8. */
 int ttk_patchify(const void* clips, const int64_t* geom, int C, int P0, int P1, int P2, void* patches, int64_t ldp,
                  int64_t G, ttk_stream_t stream);
+/* ttk_patchify on decoded uint8 frames: patch gather + the dataset's normalisation `x / 255 * 2 - 1`
+ * (dataset/video_dataset.py:118-119) in one pass; bit-identical to ttk_normalize_u8 followed by ttk_patchify. */
+int ttk_patchify_u8(const void* clips, const int64_t* geom, int C, int P0, int P1, int P2, void* patches, int64_t ldp,
+                    int64_t G, ttk_stream_t stream);
 int ttk_unpatchify(const void* proj, int64_t ldp, const int32_t* patch_row, const int64_t* geom, int C, int P0,
                    int P1, int P2, void* clips, int64_t G, ttk_stream_t stream);
 

@@ -385,10 +385,31 @@ def test_uint8_frames_equal_host_normalised_clips(golden_stress):
         rec_b, d_b = model([r.cuda() for r in raw], tcs)
         rec_c, d_c = model.tokenize_reconstruct_([r.cuda() for r in raw], tcs)
         rec_c = [r.clone() for r in rec_c]
+        rec_e, d_e = model.tokenize_reconstruct_([r.cuda() for r in raw], tcs, with_error=True)  # separate normalise pass
+        rec_e = [r.clone() for r in rec_e]
     assert torch.equal(d_a["indices"], d_b["indices"]) and torch.equal(d_a["indices"], d_c["indices"])
-    for a, b, c in zip(rec_a, rec_b, rec_c):
+    assert torch.equal(d_a["indices"], d_e["indices"])
+    for a, b, c, e, h in zip(rec_a, rec_b, rec_c, rec_e, host):
         assert b.dtype == torch.bfloat16
-        assert torch.equal(a, b) and torch.equal(a, c)
+        assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(a, e)
+    l1 = torch.stack([(h.cuda().float() - a.float()).abs().sum() for h, a in zip(host, rec_a)]).double()
+    assert torch.allclose(d_e["clip_error"][:, 0], l1, rtol=1e-5)
+    # kernel level: the fused gather (ttk_patchify_u8) == ttk_normalize_u8 followed by ttk_patchify, bit for bit
+    from titok_video_b200 import _lib, engine
+    from titok_video_b200.plan import make_plan
+
+    pl = make_plan(shapes, tcs, (4, 8, 8))
+    flat8 = torch.cat([r.reshape(-1) for r in raw]).cuda()
+    flatb = torch.empty(flat8.numel(), dtype=torch.bfloat16, device="cuda")
+    geom = torch.from_numpy(pl.geom).cuda()
+    pa = torch.empty((pl.G, 768), dtype=torch.bfloat16, device="cuda")
+    pb = torch.empty_like(pa)
+    st = engine._stream()
+    _lib.call("ttk_normalize_u8", engine._ptr(flat8), engine._ptr(flatb), flat8.numel(), st)
+    _lib.call("ttk_patchify", engine._ptr(flatb), engine._ptr(geom), 3, 4, 8, 8, engine._ptr(pa), 768, pl.G, st)
+    _lib.call("ttk_patchify_u8", engine._ptr(flat8), engine._ptr(geom), 3, 4, 8, 8, engine._ptr(pb), 768, pl.G, st)
+    torch.cuda.synchronize()
+    assert torch.equal(pa, pb)
 
 
 def test_tokens_written_to_a_container_decode_to_the_same_clips(tmp_path, golden_stress):

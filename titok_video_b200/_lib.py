@@ -65,6 +65,7 @@ SIGNATURES = {
     "ttk_clip_error": [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp],
     "ttk_normalize_u8": [_vp, _vp, _i64, _vp],
     "ttk_patchify": [_vp, _vp, _i, _i, _i, _i, _vp, _i64, _i64, _vp],
+    "ttk_patchify_u8": [_vp, _vp, _i, _i, _i, _i, _vp, _i64, _i64, _vp],
     "ttk_unpatchify": [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp, _i64, _vp],
     # ---- training path (backward kernels)
     "ttk_attn_varlen_fwd_train": [_vp, _i64, _i, _i, _i, _vp, _i, _f, _vp, _i64, _vp, _vp, _vp],

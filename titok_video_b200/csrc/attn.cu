@@ -162,6 +162,7 @@ template <bool TRAIN>  // TRAIN: also store the un-gated output and the log-sum-
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  // (the work list is plan metadata, written long before the predecessor kernel: reading it ahead of pdl_wait is safe)
   const AttnWork* wp = p.work + (blockIdx.x >> 1);
   const int t = blockIdx.x & 1;
   const int q_valid = wp->q_valid[t];
@@ -220,6 +221,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // programmatic dependent launch: the set-up above ran under the predecessor's tail
 
   // Register re-distribution: 384 threads start with 80 registers (two CTAs per SM); the control warpgroup drops to 32
   // and the 8 softmax warps (64 scores per thread live) grow to 104 (128 x 48 freed = 256 x 24 taken).
@@ -440,6 +442,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
 
     // ---- epilogue: out = bf16(O / l) * bf16(sigmoid(gate)); group g writes 32 of the 64 head dims
+    pdl_launch_dependents();  // once the LAST CTAs of the grid are here, the successor may start setting itself up
     nbar_sync256<AT_BAR_FIN>();  // every exponential phase is over: the reference is final
     {
       const float m_fin = m_sh[r];
@@ -525,10 +528,8 @@ static int attn_fwd_launch(const void* qkv, int64_t ld, int M, int width, int gq
   if (int e = set_smem_attr_once(once_plain, reinterpret_cast<const void*>(attn_fwd_kernel<false>), AT_SMEM)) return e;
   if (int e = set_smem_attr_once(once_train, reinterpret_cast<const void*>(attn_fwd_kernel<true>), AT_SMEM)) return e;
   if (o_save)
-    attn_fwd_kernel<true><<<2 * n_work, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
-  else
-    attn_fwd_kernel<false><<<2 * n_work, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
-  return launch_status();
+    return cuda_status(launch_pdl(attn_fwd_kernel<true>, dim3(2 * n_work), dim3(AT_THREADS), AT_SMEM, stream, tmQ, tmK, tmV, p));
+  return cuda_status(launch_pdl(attn_fwd_kernel<false>, dim3(2 * n_work), dim3(AT_THREADS), AT_SMEM, stream, tmQ, tmK, tmV, p));
 }
 
 int ttk_attn_varlen_fwd(const void* qkv, int64_t ld, int M, int width, int gqa, const void* work, int n_work,

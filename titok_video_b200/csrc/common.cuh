@@ -150,6 +150,14 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 
 // ----------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with the attribute may start (barrier init, tensor-memory
+// allocation, descriptor prefetch) while its predecessor in the stream drains; it must not touch global memory before
+// pdl_wait() (which returns once the predecessor has completed and flushed; a no-op without the attribute)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------
 // TMA (tiled tensor maps)
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

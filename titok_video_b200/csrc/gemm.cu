@@ -233,6 +233,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   if (threadIdx.x == 0) trace_stamp(p, 0);
+  // everything above overlapped the predecessor's tail (programmatic dependent launch); its results are needed from here
+  pdl_wait();
+  pdl_launch_dependents();  // persistent grid: every CTA is resident, the successor may set itself up whenever an SM frees
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -720,8 +723,7 @@ static int launch_gemm(const GemmIo& io, GemmParams& p, cudaStream_t stream) {
   if (int e = set_smem_attr_once(once, reinterpret_cast<const void*>(kern), S::TOTAL)) return e;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 128 + 32 * epi_warps(EPI, BN), S::TOTAL, stream>>>(tmA, tmB, tmO, tmO2, tmR, p);
-  return launch_status();
+  return cuda_status(launch_pdl(kern, dim3(grid), dim3(128 + 32 * epi_warps(EPI, BN)), S::TOTAL, stream, tmA, tmB, tmO, tmO2, tmR, p));
 }
 
 // weight-stationary mode pays off when K fits the resident tile and every n group gets a few m tiles per CTA

@@ -1,6 +1,7 @@
 #include "host_util.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -76,6 +77,14 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 }
 
 long long* g_trace = nullptr;
+
+bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = std::getenv("TTK_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 // Per-device state (the library is re-entrant across devices and threads: nothing is cached for "the first device seen").
 struct DevInfo {

@@ -39,6 +39,24 @@ struct PerDeviceOnce {
 };
 int set_smem_attr_once(PerDeviceOnce& once, const void* kernel, int bytes);
 
+// Launch with the programmatic-stream-serialization attribute (TTK_PDL=0 switches it off): only for kernels that call
+// pdl_wait() before their first global-memory access.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? TTK_OK : TTK_ERR_CUDA; }
 inline int launch_status() { return cuda_status(cudaGetLastError()); }
 

@@ -266,9 +266,33 @@ __device__ __forceinline__ int64_t patch_run_offset(const int64_t* ge, int rr, i
   return ge[0] + c * ge[3] + p0 * ge[2] + p1 * ge[1];
 }
 
-__global__ void __launch_bounds__(256) patchify_kernel(const __nv_bfloat16* __restrict__ clips,
+// 8 uint8 pixels -> 8 normalised bf16 values with the rounding sequence of the reference's dataset code on bf16 tensors
+// (dataset/video_dataset.py:118-119): y = bf16(bf16(bf16(u8) / 255) * 2 - 1).
+__device__ __forceinline__ uint4 normalize_u8x8(uint32_t lo, uint32_t hi) {
+  const uint32_t w[2] = {lo, hi};
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    float f[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const float q = bf16r(static_cast<float>((w[k] >> (8 * b)) & 0xffu) / 255.0f);
+      f[b] = q * 2.0f - 1.0f;  // q * 2 is exact in bf16; the subtraction is rounded once by the packed convert below
+    }
+    o[2 * k] = pack_bf16x2(f[0], f[1]);
+    o[2 * k + 1] = pack_bf16x2(f[2], f[3]);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// U8: `clips` holds decoded uint8 frames (same geometry, 8-byte runs); they are normalised on the way through (the
+// separate ttk_normalize_u8 pass -- 3 bytes of HBM traffic per pixel -- disappears from the tokenisation path).
+template <bool U8>
+__global__ void __launch_bounds__(256) patchify_kernel(const void* __restrict__ clips_v,
                                                        const int64_t* __restrict__ geom, int C, int P0, int P1,
                                                        __nv_bfloat16* __restrict__ patches, int64_t ldp, int64_t G) {
+  const __nv_bfloat16* clips = static_cast<const __nv_bfloat16*>(clips_v);
+  const uint8_t* clips8 = static_cast<const uint8_t*>(clips_v);
   extern __shared__ uint4 patch_smem[];  // [PATCH_CHUNK][runs + 1] 16-byte cells (+1: bank-conflict padding)
   __shared__ int64_t sgeom[PATCH_CHUNK * 4];  // the chunk's geometry, read once (not once per 16-byte run)
   const int runs = C * P0 * P1;
@@ -281,7 +305,15 @@ __global__ void __launch_bounds__(256) patchify_kernel(const __nv_bfloat16* __re
 #pragma unroll 3
   for (int i = threadIdx.x; i < total; i += 256) {
     const int pi = i % PATCH_CHUNK, rr = i / PATCH_CHUNK;
-    if (pi < np) patch_smem[pi * pitch + rr] = ldg16_stream(clips + patch_run_offset(sgeom + pi * 4, rr, P0, P1));
+    if (pi < np) {
+      const int64_t off = patch_run_offset(sgeom + pi * 4, rr, P0, P1);
+      if (U8) {
+        const uint2 v = *reinterpret_cast<const uint2*>(clips8 + off);
+        patch_smem[pi * pitch + rr] = normalize_u8x8(v.x, v.y);
+      } else {
+        patch_smem[pi * pitch + rr] = ldg16_stream(clips + off);
+      }
+    }
   }
   __syncthreads();
   const int total_out = np * runs;
@@ -598,8 +630,27 @@ int ttk_patchify(const void* clips, const int64_t* geom, int C, int P0, int P1, 
   if (smem > 48 * 1024) return TTK_ERR_BAD_SHAPE;
   const int64_t blocks = (G + PATCH_CHUNK - 1) / PATCH_CHUNK;
   if (blocks > 0x7fffffffLL) return TTK_ERR_BAD_SHAPE;
-  patchify_kernel<<<static_cast<int>(blocks), 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(clips), geom, C, P0, P1,
-                                            static_cast<__nv_bfloat16*>(patches), ldp, G);
+  patchify_kernel<false><<<static_cast<int>(blocks), 256, smem, stream>>>(clips, geom, C, P0, P1,
+                                                                        static_cast<__nv_bfloat16*>(patches), ldp, G);
+  return launch_status();
+}
+
+// ttk_patchify on decoded uint8 frames (the reference's dataset output before `chunk.to(dtype) / 255; chunk * 2 - 1`,
+// dataset/video_dataset.py:118-119): gathers the patches and normalises them in one pass. clips: uint8, every clip
+// starting on an 8-byte boundary; patches: bf16 [G, ldp], bit-identical to ttk_normalize_u8 followed by ttk_patchify.
+int ttk_patchify_u8(const void* clips, const int64_t* geom, int C, int P0, int P1, int P2, void* patches, int64_t ldp,
+                    int64_t G, cudaStream_t stream) {
+  if (!clips || !geom || !patches) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (P2 != 8 || C < 1 || P0 < 1 || P1 < 1 || ldp % 8) return TTK_ERR_BAD_SHAPE;
+  if (reinterpret_cast<uintptr_t>(clips) & 7u) return TTK_ERR_ALIGNMENT;
+  if (G <= 0) return TTK_OK;
+  const size_t smem = static_cast<size_t>(PATCH_CHUNK) * (C * P0 * P1 + 1) * 16;
+  if (smem > 48 * 1024) return TTK_ERR_BAD_SHAPE;
+  const int64_t blocks = (G + PATCH_CHUNK - 1) / PATCH_CHUNK;
+  if (blocks > 0x7fffffffLL) return TTK_ERR_BAD_SHAPE;
+  patchify_kernel<true><<<static_cast<int>(blocks), 256, smem, stream>>>(clips, geom, C, P0, P1,
+                                                                       static_cast<__nv_bfloat16*>(patches), ldp, G);
   return launch_status();
 }
 

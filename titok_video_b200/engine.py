@@ -510,7 +510,9 @@ def encoder_launch(m, dp: DevicePlan, clips_flat: torch.Tensor, fsq_consts) -> T
     codes = dp.buf("codes", (max(Tn, 1), ts))
     idx = dp.buf("idx", (max(Tn, 1),), torch.int32)
     T = W.t
-    _lib.call("ttk_patchify", _ptr(clips_flat), _ptr(dp.geom), pl.channels, P0, P1, P2, _ptr(patches), feat, G, st)
+    # decoded uint8 frames are normalised inside the patch gather (no separate pass over the pixels)
+    _lib.call("ttk_patchify_u8" if clips_flat.dtype == torch.uint8 else "ttk_patchify", _ptr(clips_flat), _ptr(dp.geom),
+              pl.channels, P0, P1, P2, _ptr(patches), feat, G, st)
     _lib.call("ttk_gemm_bf16", _ptr(patches), feat, _ptr(T["proj_in_w"]), feat, G, w, feat, _ptr(T["proj_in_b"]),
               _ptr(proj), w, _vp(0), 0, st)
     _lib.call("ttk_enc_embed", _ptr(proj), w, _ptr(dp.enc_src_row), _ptr(T["mask_token"]), _ptr(T["ln_pre_t"]),
@@ -568,9 +570,10 @@ def to_host_ints(v) -> List[int]:
     return [(to_host_ints(e) if isinstance(e, (list, tuple, torch.Tensor)) else int(e)) for e in v]
 
 
-def flatten_clips(videos: Sequence[torch.Tensor], dp: DevicePlan, name: str = "clips_in") -> torch.Tensor:
+def flatten_clips(videos: Sequence[torch.Tensor], dp: DevicePlan, name: str = "clips_in", keep_u8: bool = False) -> torch.Tensor:
     """Concatenate the clips into the plan's static flat bf16 input buffer (one cat kernel). uint8 clips (decoded
-    frames, values 0..255) are normalised to [-1, 1] by ttk_normalize_u8 on the way."""
+    frames, values 0..255) are normalised to [-1, 1] by ttk_normalize_u8 on the way -- or, with keep_u8, returned as the
+    flat uint8 buffer for the inference encoder launch, whose patch gather normalises them itself (ttk_patchify_u8)."""
     if videos[0].dtype == torch.uint8:
         # decoded frames: one cat into the uint8 staging buffer, normalised on the device (dataset/video_dataset.py:118-119)
         raw = dp.buf(name + "_u8", (dp.plan.total_numel,), torch.uint8)
@@ -578,6 +581,8 @@ def flatten_clips(videos: Sequence[torch.Tensor], dp: DevicePlan, name: str = "c
             raw.copy_(videos[0].reshape(-1))
         else:
             torch.cat([v.reshape(-1) for v in videos], out=raw)
+        if keep_u8:
+            return raw
         buf = dp.buf(name, (dp.plan.total_numel,))
         _lib.call("ttk_normalize_u8", _ptr(raw), _ptr(buf), dp.plan.total_numel, _stream())
         return buf

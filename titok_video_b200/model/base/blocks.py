@@ -100,7 +100,7 @@ class TiTokEncoder(_Stack):
             z, codes, idx = ops.encoder_call(self, dp, consts, flat, True)
             return z, codes, idx, dp
         with torch.no_grad():
-            flat = engine.flatten_clips(videos, dp)
+            flat = engine.flatten_clips(videos, dp, keep_u8=True)
             z, codes, idx = engine.encoder_launch(self, dp, flat, consts)
         return z, codes, idx, dp
 

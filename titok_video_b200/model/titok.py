@@ -109,7 +109,8 @@ class TiTok(nn.Module):
             raise ValueError("len(token_counts) must equal the number of clips")
         enc, dec = self.encoder, self.decoder
         dp = enc._plan(grids, tcs, dev)
-        flat = engine.flatten_clips(x, dp)
+        # (the per-clip error compares against the normalised clips, so it needs them materialised)
+        flat = engine.flatten_clips(x, dp, keep_u8=not with_error)
         consts = self.quantize._consts(dev)
         engine.prepared(enc, "enc")
         engine.prepared(dec, "dec")
