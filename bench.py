@@ -639,6 +639,53 @@ def main():
     value = world * B * args.steps / (total_ms * 1e-3)
     ksum = timer.summary()
 
+    # ---------------- the same step with wide ("stress") weights: tokens spread over the codebook, attention rows are peaked and
+    # the lazy rescale of the attention kernel (rare at the reference initialiser, whose attention is near-uniform) fires
+    stress = None
+    if rank == 0:
+        import math
+
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        gs = torch.Generator().manual_seed(1)
+        for k in sorted(sd):
+            v = sd[k]
+            if v.dim() == 2 and v.shape[0] > 1 and v.shape[1] > 1:
+                v.copy_((torch.randn(v.shape, generator=gs) * (2.0 / math.sqrt(v.shape[1]))).to(v.device))
+            elif k.endswith(".bias"):
+                v.copy_((torch.randn(v.shape, generator=gs) * 0.1).to(v.device))
+        torch.manual_seed(42)
+        model_s = T.TiTok(tiny_config(LEVELS, PATCH)).to(dev).eval()
+        model_s.load_state_dict(sd)
+        hist_s = torch.zeros_like(hist)
+
+        def step_s(clips):
+            with torch.no_grad():
+                _, d = model_s.tokenize_reconstruct_(clips, tcs, use_graph=False)
+                _lib.call("ttk_hist_u32", T.engine._ptr(d["indices"]), d["indices"].numel(), hist_s.numel(),
+                          T.engine._ptr(hist_s), T.engine._stream())
+
+        for i in range(3):
+            step_s(dev_sets[i % INPUT_SETS])
+        torch.cuda.synchronize()
+        timer_s = KernelTimer()
+        _lib.set_profiler(timer_s)
+        es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es0.record()
+        n_s = max(4, args.steps // 2)
+        for i in range(n_s):
+            step_s(dev_sets[i % INPUT_SETS])
+        es1.record()
+        torch.cuda.synchronize()
+        _lib.set_profiler(None)
+        ks = timer_s.summary().get("ttk_attn_varlen_fwd")
+        stress = {"ms_per_step": es0.elapsed_time(es1) / n_s, "clips_per_s": B * n_s / (es0.elapsed_time(es1) * 1e-3),
+                  "attn_avg_launch_ms": (ks[0] / ks[1]) if ks else None,
+                  "codebook_usage_percent": float((hist_s > 0).sum().item()) / hist_s.numel() * 100.0,
+                  "weights": "every 2-D parameter ~ N(0, (2/sqrt(fan_in))^2), seed 1 (the parity tests' stress initialiser)"}
+        del model_s
+    if world > 1:
+        dist.barrier()
+
     # ---------------- e2e: pinned host clips -> H2D -> public API -> D2H of indices + reconstructions ----------------
     h2d_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
     SLOTS = 2
@@ -835,11 +882,17 @@ def main():
     if top is not None:
         fl = kernel_flops_per_launch(top, B, s, g, TOKENS_A)
         avg_ms = ksum[top][0] / ksum[top][1]
-        peak = pk["bf16_tflops_sustained"]
+        # the timed region is ~0.1 s at full clocks (see `clocks`), not a seconds-long power-capped loop: the burst figure
+        # is the like-for-like denominator; the fraction of the sustained figure is given beside it
+        peak = pk["bf16_tflops"]
         ach = fl / (avg_ms * 1e-3) / 1e12 if fl else None
         roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (ach / peak) if ach else None, "traffic": ncu_traffic(top, B), "peak_source": pk["source"] + " (sustained bf16)",
-                    "avg_launch_ms": avg_ms, "share_of_step": ksum[top][0] / tot_k}
+                    "frac": (ach / peak) if ach else None, "traffic": ncu_traffic(top, B), "peak_source": pk["source"] + " (burst bf16)",
+                    "frac_of_sustained": (ach / pk["bf16_tflops_sustained"]) if ach else None,
+                    "avg_launch_ms": avg_ms, "share_of_step": ksum[top][0] / tot_k,
+                    "mufu_bound_tflops": 16 * 148 * 1.965e9 * 256 / 1e12,
+                    "note": "head dim 64: 256 FLOP per exponential; the XU pipe's 16 ex2/clk/SM caps the kernel at 1191 TFLOP/s "
+                            "(75 % of the burst tensor peak) before any other limit"}
     whole = {"tflops": value * flops_clip / 1e12, "frac_of_tensor_peak": value * flops_clip / 1e12 / pk["bf16_tflops_sustained"]}
 
     vq = None
@@ -880,6 +933,8 @@ def main():
             roofline["fsq"] = [{"dtype": r["dtype"], "N": r["N"], "ms": r["ms"], "gbs": r["gbs"], "frac_hbm": r["frac_of_hbm_peak"]}
                                for r in vq if r["kernel"] == "ttk_fsq_fwd"]
             roofline["vq_peak"] = {"tflops": pk["bf16_tflops"], "source": pk["source"] + " (burst bf16: kernel timed alone)"}
+        if roofline is not None and stress is not None:
+            roofline["stress_init"] = stress
         cfg = {"workload": workload_string(B), "clips_per_gpu_per_step": B,
                "global_clips_per_step": world * B, "latent_tokens_per_s": value * TOKENS_A,
                "parallelism": f"clip-sharded x{world}, no data-path collective",

@@ -47,6 +47,8 @@ struct VqParams {
   int noaug;
   const float* norms;  // [ceil256(K)] fp32, behind the augmented codebook (ttk_vq_aug_rows)
 };
+constexpr int VQ2_EPI_WARPS = 16;                 // epilogue warps of the two-tile kernel (four per scheduler)
+constexpr int VQ2_THREADS = 128 + 32 * VQ2_EPI_WARPS;
 constexpr int VQ_NSLOTS = 4;                      // norm-slice ring
 constexpr int VQ_N_BYTES = VQ_BN * 4;             // 1 KB per slice
 
@@ -54,6 +56,36 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
   float r;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
+}
+
+// First index i with f[i] == mm, given the partial minima of the tree: a = min f[0..8], b = min f[9..17], c = min
+// f[18..26]. The branch on "some row of the warp found a new minimum" is not rare for small codebooks (a warp sees few
+// chunks per row), and a flat 31-step scan made it the most expensive part of the epilogue: only the 9-element group
+// that holds the minimum is scanned (a warp executes the union of the groups its lanes need, usually one).
+__device__ __forceinline__ int vq_first_index(const float (&f)[32], float mm, float a, float b, float c) {
+  int bi;
+  if (a == mm) {
+    bi = 8;
+#pragma unroll
+    for (int i = 7; i >= 0; --i)
+      if (f[i] == mm) bi = i;
+  } else if (b == mm) {
+    bi = 17;
+#pragma unroll
+    for (int i = 16; i >= 9; --i)
+      if (f[i] == mm) bi = i;
+  } else if (c == mm) {
+    bi = 26;
+#pragma unroll
+    for (int i = 25; i >= 18; --i)
+      if (f[i] == mm) bi = i;
+  } else {
+    bi = 31;
+#pragma unroll
+    for (int i = 30; i >= 27; --i)
+      if (f[i] == mm) bi = i;
+  }
+  return bi;
 }
 
 // running (min, argmin) over one 32-column chunk held in registers
@@ -72,13 +104,9 @@ __device__ __forceinline__ void vq_chunk_update(const uint32_t (&v)[32], int col
   m[10] = fminf(f[30], f[31]);
   const float a = fmin3(m[0], m[1], m[2]), b = fmin3(m[3], m[4], m[5]), c = fmin3(m[6], m[7], m[8]);
   const float mm = fminf(fmin3(a, b, c), fminf(m[9], m[10]));
-  if (mm < best) {  // rare after the first few chunks; strict '<' keeps the first minimum (argmin tie rule)
+  if (mm < best) {  // strict '<' keeps the first minimum (argmin tie rule)
     best = mm;
-    int bi = 31;
-#pragma unroll
-    for (int i = 30; i >= 0; --i)
-      if (f[i] == mm) bi = i;
-    best_i = col0 + bi;
+    best_i = col0 + vq_first_index(f, mm, a, b, c);
   }
 }
 
@@ -100,13 +128,9 @@ __device__ __forceinline__ void vq_chunk_update_n(const uint32_t (&v)[32], const
   m[10] = fminf(f[30], f[31]);
   const float a = fmin3(m[0], m[1], m[2]), b = fmin3(m[3], m[4], m[5]), c = fmin3(m[6], m[7], m[8]);
   const float mm = fminf(fmin3(a, b, c), fminf(m[9], m[10]));
-  if (mm < best) {
+  if (mm < best) {  // strict '<' keeps the first minimum (argmin tie rule)
     best = mm;
-    int bi = 31;
-#pragma unroll
-    for (int i = 30; i >= 0; --i)
-      if (f[i] == mm) bi = i;
-    best_i = col0 + bi;
+    best_i = col0 + vq_first_index(f, mm, a, b, c);
   }
 }
 
@@ -341,8 +365,8 @@ vq_argmin_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant_
 // its next tile starts (k-block-major order left ~1 MMA step between the completion of an accumulator and its reuse, and the tensor
 // core waited for the drain: 53-59 % of peak at D = 128).
 //   warp 0      B producer (+ norm slices)   warp 1   MMA issuer   warp 2   TMEM allocator   warp 3   A producer (+ ones patch)
-//   warps 4-11  argmin epilogue: quarter = TMEM lanes, warps 4-7 columns [0,128), warps 8-11 columns [128,256)
-__global__ void __launch_bounds__(384, 1)
+//   warps 4-19  argmin epilogue: quarter = TMEM lanes (warp & 3), column quarter [64 q, +64) with q = (warp - 4) / 4
+__global__ void __launch_bounds__(VQ2_THREADS, 1)
 vq_argmin2_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmC, const VqParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -350,9 +374,9 @@ vq_argmin2_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
   uint8_t* sB = sA + 2 * p.num_kb * VQ_A_KB_BYTES;        // [b_stages][256 x 64]
   float* sN = reinterpret_cast<float*>(sB + p.b_stages * VQ_B_BYTES);  // [VQ_NSLOTS][256] norm slices (no-aug mode)
   uint8_t* tail = reinterpret_cast<uint8_t*>(sN) + VQ_NSLOTS * VQ_N_BYTES;
-  float* m_best = reinterpret_cast<float*>(tail);         // [2 tiles][128] merge buffer of the column halves
-  int* m_idx = reinterpret_cast<int*>(tail + 1024);       // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2048);
+  float* m_best = reinterpret_cast<float*>(tail);         // [2 tiles][3][128] merge buffer of column quarters 1..3
+  int* m_idx = reinterpret_cast<int*>(tail + 3072);       // [2][3][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 6144);
   uint64_t* a_full = bars;          // [2] per z tile: the next block's tile 0 is loaded while tile 1 still computes
   uint64_t* a_ready = bars + 2;     // [2]
   uint64_t* a_empty = bars + 4;     // [2]
@@ -378,7 +402,7 @@ vq_argmin2_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       mbar_init(&a_ready[s], 1);
       mbar_init(&a_empty[s], 1);
       mbar_init(&t_full[s], 1);
-      mbar_init(&t_empty[s], 8);
+      mbar_init(&t_empty[s], VQ2_EPI_WARPS);
     }
     for (int s = 0; s < p.b_stages; ++s) {
       mbar_init(&b_full[s], 1);
@@ -386,7 +410,7 @@ vq_argmin2_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
     }
     for (int s = 0; s < VQ_NSLOTS; ++s) {
       mbar_init(&n_full[s], 1);
-      mbar_init(&n_empty[s], 8);
+      mbar_init(&n_empty[s], VQ2_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -501,9 +525,11 @@ vq_argmin2_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================== epilogue: running argmin, all eight warps on one accumulator at a time =====================
+    // ===================== epilogue: running argmin, all sixteen warps on one accumulator at a time =====================
+    // (four warps per scheduler: the drain is a chain of tensor-memory loads and short dependent min trees, and with two
+    // warps per scheduler it took twice as long as the MMAs of the other z tile)
     const int quarter = warp & 3;
-    const int chalf = (warp - 4) >> 2;
+    const int cq = (warp - 4) >> 2;  // column quarter [64 cq, +64) of every 256-code tile
     const int r = quarter * 32 + lane;
     uint32_t tcount = 0;
     for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
@@ -511,53 +537,64 @@ vq_argmin2_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       int best_i[2] = {0, 0};
       for (int nt = 0; nt < p.num_n_tiles; ++nt, ++tcount) {
         const int sl = tcount & (VQ_NSLOTS - 1);
-        const float* nrm = sN + sl * VQ_BN + chalf * 128;
+        const float* nrm = sN + sl * VQ_BN + cq * 64;
         if (p.noaug) mbar_wait(&n_full[sl], (tcount / VQ_NSLOTS) & 1);
-        const int colbase = nt * VQ_BN + chalf * 128;
+        const int colbase = nt * VQ_BN + cq * 64;
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
           mbar_wait(&t_full[a], tcount & 1);
           tc_fence_after();
-          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + a * VQ_BN + chalf * 128;
-#pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 64) {
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32b_x32(t_row + c0, v0);
-            tmem_ld_32x32b_x32(t_row + c0 + 32, v1);
-            tmem_ld_wait();
-            if (p.noaug) {
-              vq_chunk_update_n(v0, nrm + c0, colbase + c0, best[a], best_i[a]);
-              vq_chunk_update_n(v1, nrm + c0 + 32, colbase + c0 + 32, best[a], best_i[a]);
-            } else {
-              if (colbase + c0 < p.K) vq_chunk_update(v0, colbase + c0, p.K, best[a], best_i[a]);
-              if (colbase + c0 + 32 < p.K) vq_chunk_update(v1, colbase + c0 + 32, p.K, best[a], best_i[a]);
-            }
-          }
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + a * VQ_BN + cq * 64;
+          uint32_t v0[32], v1[32];
+#ifndef VQ_EXP_NOLD  // (timing experiments: where does the accumulator hand-over spend its time?)
+          tmem_ld_32x32b_x32(t_row, v0);
+          tmem_ld_32x32b_x32(t_row + 32, v1);
+          tmem_ld_wait();
+#else
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v0[i] = v1[i] = __float_as_uint(1.0f + i + t_row);
+#endif
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&t_empty[a]);
+          if (lane == 0) mbar_arrive(&t_empty[a]);  // the scores are in registers: the accumulator may be refilled
+#ifdef VQ_EXP_NOMIN
+          if (__uint_as_float(v0[lane]) + __uint_as_float(v1[lane]) == 12345.f) best[a] = 0.f;
+#else
+          if (p.noaug) {
+            vq_chunk_update_n(v0, nrm, colbase, best[a], best_i[a]);
+            vq_chunk_update_n(v1, nrm + 32, colbase + 32, best[a], best_i[a]);
+          } else
+#endif
+          {
+            if (colbase < p.K) vq_chunk_update(v0, colbase, p.K, best[a], best_i[a]);
+            if (colbase + 32 < p.K) vq_chunk_update(v1, colbase + 32, p.K, best[a], best_i[a]);
+          }
         }
+        __syncwarp();
         if (p.noaug && lane == 0) mbar_arrive(&n_empty[sl]);
       }
-      // merge the two column halves of each row (lower index wins ties)
-      if (chalf == 1) {
+      // merge the four column quarters of each row (lower index wins ties: quarters in ascending order)
+      if (cq > 0) {
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
-          m_best[a * 128 + r] = best[a];
-          m_idx[a * 128 + r] = best_i[a];
+          m_best[(a * 3 + cq - 1) * 128 + r] = best[a];
+          m_idx[(a * 3 + cq - 1) * 128 + r] = best_i[a];
         }
       }
-      named_bar_sync(1, 256);
-      if (chalf == 0) {
+      named_bar_sync(1, VQ2_EPI_WARPS * 32);
+      if (cq == 0) {
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
-          const float ob = m_best[a * 128 + r];
-          const int oi = m_idx[a * 128 + r];
           float bb = best[a];
           int bi = best_i[a];
-          if (ob < bb || (ob == bb && oi < bi)) {
-            bb = ob;
-            bi = oi;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const float ob = m_best[(a * 3 + q) * 128 + r];
+            const int oi = m_idx[(a * 3 + q) * 128 + r];
+            if (ob < bb || (ob == bb && oi < bi)) {
+              bb = ob;
+              bi = oi;
+            }
           }
           const int64_t row = (static_cast<int64_t>(blk) * 2 + a) * VQ_BM + r;
           if (row < p.N) {
@@ -566,7 +603,7 @@ vq_argmin2_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
           }
         }
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(1, VQ2_EPI_WARPS * 32);
     }
   }
 
@@ -744,7 +781,7 @@ int ttk_vq_argmin(const void* z, int64_t ldz, const void* cb_aug, int64_t lda, i
   p.num_kb = num_kb;
   p.noaug = noaug;
   p.norms = reinterpret_cast<const float*>(static_cast<const __nv_bfloat16*>(cb_aug) + static_cast<int64_t>(K) * lda);
-  constexpr int kTail = VQ_NSLOTS * VQ_N_BYTES + 2048 + 512 + 1024;  // norm ring, merge buffers, barriers, alignment
+  constexpr int kTail = VQ_NSLOTS * VQ_N_BYTES + 6144 + 512 + 1024;  // norm ring, merge buffers, barriers, alignment
   const int budget = VQ_SMEM_BUDGET - kTail;
   const int a_one = num_kb * VQ_A_KB_BYTES;
   p.a_bufs = (2 * a_one + 3 * VQ_B_BYTES <= budget) ? 2 : 1;
@@ -773,7 +810,7 @@ int ttk_vq_argmin(const void* z, int64_t ldz, const void* cb_aug, int64_t lda, i
       const int num_blocks = (p.num_m_tiles + 1) / 2;
       const int smem2 = 2 * a_one + p.b_stages * VQ_B_BYTES + kTail;
       const int grid2 = num_blocks < num_sms() ? num_blocks : num_sms();
-      vq_argmin2_kernel<<<grid2, 384, smem2, stream>>>(tmZ, tmC, p);
+      vq_argmin2_kernel<<<grid2, VQ2_THREADS, smem2, stream>>>(tmZ, tmC, p);
       return launch_status();
     }
   }
