@@ -468,20 +468,33 @@ def train_ragged_leg(T, _lib, dev, rank, steps):
                     "forward + L1 loss + backward + fused AdamW; wall clock"}
 
 
-def scaled_leg(T, dev, world, rank, dist, steps, warmup, clips_per_gpu=4):
+def model_flops(size, shape, t):
+    """Forward FLOPs of one clip through encoder + decoder stacks of a given size (SURVEY 8d formula)."""
+    w, layers, hq, hkv = {"tiny": (256, 4, 4, 2), "small": (512, 8, 8, 2), "base": (768, 12, 12, 4), "large": (1024, 24, 16, 4)}[size]
+    inner = 32 * ((int(4.0 * (2 / 3) * w) + 31) // 32)
+    g = (shape[0] // PATCH[0]) * (shape[1] // PATCH[1]) * (shape[2] // PATCH[2])
+    s = g + t
+    lin = layers * s * 2 * (w * (2 * w + 2 * hkv * 64) + w * w + 3 * w * inner)
+    attn = layers * 4 * s * s * w
+    io = 2 * 768 * w * g * 2 + 2 * 5 * w * t * 2
+    return 2 * (lin + attn) + io, s
+
+
+def scaled_leg(T, dev, world, rank, dist, steps, warmup, size="tiny", clips_per_gpu=4):
     """BASELINE configs[4]: the scaled-up variant that stresses the attention sequence length -- clips of
-    32x256x256 with 256 latent tokens (8192 patches, 8448 packed rows per clip; attention is 84 % of the FLOPs), tiny
-    stacks, forward tokenise + reconstruct through TiTok.tokenize_reconstruct_ (CUDA-graph replay), device-timed."""
+    32x256x256 with 256 latent tokens (8192 patches, 8448 packed rows per clip; attention is 84 % of the FLOPs at tiny),
+    tiny / base / large stacks, forward tokenise + reconstruct through TiTok.tokenize_reconstruct_ (CUDA-graph replay),
+    device-timed."""
     from titok_video_b200.config import tiny_config
 
     shape, t = (32, 256, 256), 256
     torch.manual_seed(42)
-    model = T.TiTok(tiny_config(LEVELS, PATCH)).to(dev).eval()
+    model = T.TiTok(tiny_config(LEVELS, PATCH, size, size)).to(dev).eval()
     gen = torch.Generator().manual_seed(3000 + rank)
     sets = [[(torch.rand((3, *shape), generator=gen) * 2 - 1).to(torch.bfloat16).to(dev) for _ in range(clips_per_gpu)]
             for _ in range(2)]
     tcs = [t] * clips_per_gpu
-    fl, s_rows, _ = clip_flops(shape, t)
+    fl, s_rows = model_flops(size, shape, t)
 
     def barrier():
         if world > 1:
@@ -504,8 +517,10 @@ def scaled_leg(T, dev, world, rank, dist, steps, warmup, clips_per_gpu=4):
     ms_step = float(ms.item()) / steps
     cps = world * clips_per_gpu / (ms_step * 1e-3)
     tf = cps / world * fl / 1e12
+    del model
+    torch.cuda.empty_cache()
     return {"workload": f"per GPU {clips_per_gpu} clips 3x32x256x256 bf16, 256 latent tokens each ({s_rows} packed rows per clip), "
-                        "tiny encoder / decoder, forward tokenise + reconstruct",
+                        f"{size} encoder / decoder, forward tokenise + reconstruct",
             "clips_per_s": cps, "latent_tokens_per_s": cps * t, "ms_per_step": ms_step, "gflop_per_clip": fl / 1e9,
             "tflops_per_gpu": tf, "frac_of_tensor_peak": tf / peaks()["bf16_tflops_sustained"]}
 
@@ -863,6 +878,9 @@ def main():
     scaled = None
     if not args.no_scaled:
         scaled = scaled_leg(T, dev, world, rank, dist, max(4, args.steps // 2), args.warmup)
+        # the wider stacks of the size table (utils.py:8-23): widths 768 / 1024 take the unfused residual path
+        scaled["base"] = scaled_leg(T, dev, world, rank, dist, 4, 3, size="base", clips_per_gpu=2)
+        scaled["large"] = scaled_leg(T, dev, world, rank, dist, 3, 3, size="large", clips_per_gpu=1)
 
     # ---------------- codebook usage over the whole job (the only data-path collective) ----------------
     if world > 1:

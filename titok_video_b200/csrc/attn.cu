@@ -96,6 +96,12 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return r;
 }
 
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
 #ifdef AT_EXP_NOMUFU  // timing experiment only (scripts/attn_bench.py): how much of the kernel is MUFU time?
   return fmaf(x, 1e-3f, 1e-2f);
@@ -197,8 +203,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-  }
-  if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < AT_KST; ++s) {
       mbar_init(&k_full[s], 1);
@@ -215,6 +219,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&pv_done[g], 1);
     }
     fence_barrier_init();
+    // The first loads wait for nothing inside the CTA: they go out before the tensor-memory allocation and the CTA-wide
+    // barrier, so their L2 / HBM latency runs under the rest of the set-up. (Programmatic dependent launch: the
+    // predecessor's results are needed from here.)
+    pdl_wait();
+    mbar_arrive_expect_tx(q_full, AT_Q_BYTES);
+    tma_load_2d(sQ, &tmQ, q_full, q_head * AT_D, q_row0);
+    for (int j = 0; j < AT_KST && j < n_sub; ++j) {
+      mbar_arrive_expect_tx(&k_full[j], AT_KV_BYTES);
+      tma_load_2d(sK + j * AT_KV_BYTES, &tmK, &k_full[j], kv_head * AT_D, kv_row0 + j * AT_BN);
+      if (j < AT_VST) {
+        mbar_arrive_expect_tx(&v_full[j], AT_KV_BYTES);
+        tma_load_2d(sV + j * AT_KV_BYTES, &tmV, &v_full[j], kv_head * AT_D, kv_row0 + j * AT_BN);
+      }
+    }
   }
   if (warp == 2) tmem_alloc(tmem_ptr, AT_TM_COLS);
   tc_fence_before();
@@ -227,14 +245,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // and the 8 softmax warps (64 scores per thread live) grow to 104 (128 x 48 freed = 256 x 24 taken).
   if (warp == 0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, AT_Q_BYTES);
-      tma_load_2d(sQ, &tmQ, q_full, q_head * AT_D, q_row0);
-      for (int j = 0; j < n_sub; ++j) {
+    if (lane == 0) {  // (the thread that issued the first ring fill above)
+      for (int j = AT_VST; j < n_sub; ++j) {
         const int sk = j % AT_KST, sv = j % AT_VST;
-        mbar_wait(&k_empty[sk], ((j / AT_KST) & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[sk], AT_KV_BYTES);
-        tma_load_2d(sK + sk * AT_KV_BYTES, &tmK, &k_full[sk], kv_head * AT_D, kv_row0 + j * AT_BN);
+        if (j >= AT_KST) {
+          mbar_wait(&k_empty[sk], ((j / AT_KST) & 1) ^ 1);
+          mbar_arrive_expect_tx(&k_full[sk], AT_KV_BYTES);
+          tma_load_2d(sK + sk * AT_KV_BYTES, &tmK, &k_full[sk], kv_head * AT_D, kv_row0 + j * AT_BN);
+        }
         mbar_wait(&v_empty[sv], ((j / AT_VST) & 1) ^ 1);
         mbar_arrive_expect_tx(&v_full[sv], AT_KV_BYTES);
         tma_load_2d(sV + sv * AT_KV_BYTES, &tmV, &v_full[sv], kv_head * AT_D, kv_row0 + j * AT_BN);
@@ -311,6 +329,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t t_p = tmem_base + lane_off + AT_TM_P + g * (AT_BN / 2);
     const float c = p.scale_log2;
     const uint64_t c2 = f32x2_pack(c, c);
+    // shared-memory addresses of this group's barriers and of this row's exchange slots, converted once
+    const uint32_t a_sfull = smem_u32(&s_full[g]), a_sempty = smem_u32(&s_empty[g]), a_pfull = smem_u32(&p_full[g]);
+    const uint32_t a_pvdone = smem_u32(&pv_done[g]), a_pvdone_o = smem_u32(&pv_done[g ^ 1]);
+    const uint32_t a_msh = smem_u32(m_sh + r);
     // l_run: this group's share of the row sum, relative to m_ref (-inf until the group has seen a reference:
     // adopting one then scales the empty sum by 2^-inf = 0)
     float m_ref = __int_as_float(0xff800000), l_run = 0.f;
@@ -318,7 +340,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = g; j < n_sub; j += 2) {
       const uint32_t par = (j >> 1) & 1;
       // ---- S(j): this thread's 64 scores into registers with one wait, then hand S_g back to the tensor core
-      mbar_wait(&s_full[g], par);
+      mbar_wait_a(a_sfull, par);
       tc_fence_after();
       if (threadIdx.x == 128) at_stamp(p, j >> 1, 0);
       // the epilogue's gate values: pull this thread's 64-byte segment towards L2 a few kv tiles ahead of its use
@@ -332,7 +354,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[g]);  // S(j+2) may overwrite the accumulator once the 4 warps arrived
+      if (lane == 0) mbar_arrive_a(a_sempty);  // S(j+2) may overwrite the accumulator once the 4 warps arrived
       if (threadIdx.x == 128) at_stamp(p, j >> 1, 1);
 
       const int kv_valid = kv_len - j * AT_BN;  // < 64 only in the last sub-tile
@@ -353,10 +375,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // ---- take the token: the other group's exponentials of sub-tile j-1 are done, its reference is published
       if (j == 0) {
         m_ref = m_sub;
-        m_sh[r] = m_sub;
+        sts_f32(a_msh, m_sub);
       } else {
         if (g == 0) nbar_sync256<AT_BAR_TOK>(); else nbar_sync256<AT_BAR_TOK + 1>();
-        const float m_cur = m_sh[r];
+        const float m_cur = lds_f32(a_msh);
         if (m_cur != m_ref) {  // the other group moved the reference (rare)
           l_run *= ex2_approx((m_ref - m_cur) * c);
           m_ref = m_cur;
@@ -368,8 +390,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float m_new = fmaxf(m_ref, m_sub);
           const float alpha = ex2_approx((m_ref - m_new) * c);
           // O holds every product up to sub-tile j-1 once the latest PV of either group has retired
-          mbar_wait(&pv_done[g ^ 1], ((j - 1) >> 1) & 1);
-          if (j >= 2) mbar_wait(&pv_done[g], ((j - 2) >> 1) & 1);
+          mbar_wait_a(a_pvdone_o, ((j - 1) >> 1) & 1);
+          if (j >= 2) mbar_wait_a(a_pvdone, ((j - 2) >> 1) & 1);
           tc_fence_after();
 #pragma unroll 1
           for (int q = 0; q < 4; ++q) {
@@ -384,7 +406,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tc_fence_before();
           l_run *= alpha;
           m_ref = m_new;
-          m_sh[r] = m_new;
+          sts_f32(a_msh, m_new);
         }
       }
       if (threadIdx.x == 128) at_stamp(p, j >> 1, 2);
@@ -429,7 +451,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (threadIdx.x == 128) at_stamp(p, j >> 1, 3);
       // ---- P(j) -> tensor memory once this group's previous P V no longer reads the buffer
       if (j >= 2) {
-        mbar_wait(&pv_done[g], ((j - 2) >> 1) & 1);
+        mbar_wait_a(a_pvdone, ((j - 2) >> 1) & 1);
         tc_fence_after();
       }
       if (threadIdx.x == 128) at_stamp(p, j >> 1, 4);
@@ -437,7 +459,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[g]);
+      if (lane == 0) mbar_arrive_a(a_pfull);
       if (threadIdx.x == 128) at_stamp(p, j >> 1, 5);
     }
 
@@ -445,15 +467,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     pdl_launch_dependents();  // once the LAST CTAs of the grid are here, the successor may start setting itself up
     nbar_sync256<AT_BAR_FIN>();  // every exponential phase is over: the reference is final
     {
-      const float m_fin = m_sh[r];
+      const float m_fin = lds_f32(a_msh);
       if (m_fin != m_ref) {
         l_run *= ex2_approx((m_ref - m_fin) * c);
         m_ref = m_fin;
       }
     }
-    l_sh[g * 128 + r] = l_run;
+    sts_f32(smem_u32(l_sh + g * 128 + r), l_run);
     nbar_sync256<AT_BAR_FIN>();
-    const float l_tot = l_run + l_sh[(g ^ 1) * 128 + r];
+    const float l_tot = l_run + lds_f32(smem_u32(l_sh + (g ^ 1) * 128 + r));
     const float inv_l = __fdividef(1.0f, l_tot);
     if (TRAIN && g == 0 && r < q_valid)  // the backward kernels recompute P = 2^(s*c - lse)
       p.lse[static_cast<int64_t>(q_head) * p.M + q_row0 + r] = fmaf(m_ref, c, __log2f(l_tot));
@@ -476,8 +498,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float g0 = bf16_lo(gg[e]), g1 = bf16_hi(gg[e]);
-          const float s0 = bf16r(__fdividef(1.0f, 1.0f + __expf(-g0)));
-          const float s1 = bf16r(__fdividef(1.0f, 1.0f + __expf(-g1)));
+          // sigmoid(x) = 0.5 tanh(0.5 x) + 0.5: one MUFU op per value instead of two (exp + reciprocal); the epilogue's
+          // MUFU work was one extra kv sub-tile per row. tanh.approx is good to 2^-11, the result is rounded to bf16 (2^-9)
+          const float s0 = bf16r(fmaf(0.5f, tanh_approx(0.5f * g0), 0.5f));
+          const float s1 = bf16r(fmaf(0.5f, tanh_approx(0.5f * g1), 0.5f));
           const float a0 = bf16r(__uint_as_float(o[q * 8 + 2 * e]) * inv_l);
           const float a1 = bf16r(__uint_as_float(o[q * 8 + 2 * e + 1]) * inv_l);
           ov[e] = pack_bf16x2(a0 * s0, a1 * s1);
