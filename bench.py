@@ -260,7 +260,7 @@ def train_flops(B):
     return 3.0 * B * f
 
 
-def train_leg(T, _lib, dev, world, rank, dist, batch, steps, warmup):
+def train_leg(T, _lib, dev, world, rank, dist, batch, steps, warmup, graphed=False):
     """One generator training step per iteration through the public module API (train.py:68-80): bf16 autocast forward of
     TiTok (fp32 master parameters), L1 reconstruction loss (loss_module.py:118, plain torch: the loss module is not on
     the path), backward through the CUDA backward kernels, gradient all-reduce over NCCL (N > 1, decoder bucket
@@ -279,12 +279,24 @@ def train_leg(T, _lib, dev, world, rank, dist, batch, steps, warmup):
             for _ in range(2)]
     tcs = [TOKENS_A] * batch
 
+    gstep = None
+    if graphed:
+        from titok_video_b200.train_utils.graphed_step import GraphedTrainStep
+
+        gstep = GraphedTrainStep(model, warmup=1)
+
     def step(clips):
         opt.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            recon, d = model(clips, tcs)
-        loss = torch.stack([(r_.float() - c.float()).abs().mean() for c, r_ in zip(clips, recon)]).mean()
-        loss.backward()
+        if gstep is not None:
+            # forward + loss + backward replayed as ONE CUDA graph once the composition has been seen (the bench's fixed
+            # batch repeats every step); the all-reduce and the optimizer stay eager
+            loss, d = gstep(clips, tcs)
+            red.reduce_now()
+        else:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                recon, d = model(clips, tcs)
+            loss = torch.stack([(r_.float() - c.float()).abs().mean() for c, r_ in zip(clips, recon)]).mean()
+            loss.backward()
         red.finish()
         opt.step()
         idx = d["indices"]
@@ -312,12 +324,13 @@ def train_leg(T, _lib, dev, world, rank, dist, batch, steps, warmup):
     launches = _lib.LAUNCHES - l0
     # per-kernel breakdown: separate pass (the per-launch CUDA events cost host time, so they stay out of the timed region)
     timer = KernelTimer()
-    _lib.set_profiler(timer)
     prof_steps = 2
-    for i in range(prof_steps):
-        step(sets[i % 2])
-    barrier()
-    _lib.set_profiler(None)
+    if gstep is None:
+        _lib.set_profiler(timer)
+        for i in range(prof_steps):
+            step(sets[i % 2])
+        barrier()
+        _lib.set_profiler(None)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -334,7 +347,10 @@ def train_leg(T, _lib, dev, world, rank, dist, batch, steps, warmup):
             "packed_rows_per_gpu": batch * clip_flops()[1], "loss": float(loss.detach()), "gpu_launches_per_step": launches / steps,
             "tflops_algorithmic": tf, "frac_of_tensor_peak": tf / pk["bf16_tflops_sustained"],
             "wall_ms_per_step": wall_ms, "kernel_ms_per_step": sum(v[0] for v in ks.values()) / prof_steps, "kernels": kernels,
-            "what": "TiTok.forward under bf16 autocast + L1 loss + backward (CUDA backward kernels) + "
+            "graph_replays": (gstep.replays if gstep is not None else 0),
+            "what": ("forward + L1 loss + backward REPLAYED AS ONE CUDA GRAPH (train_utils.GraphedTrainStep; the fixed bench "
+                     "batch repeats every step -- the reference's ragged batches would not) + " if graphed else "")
+                    + "TiTok.forward under bf16 autocast + L1 loss + backward (CUDA backward kernels) + "
                     + ("NCCL gradient all-reduce (per-stack buckets, overlapped) + " if world > 1 else "")
                     + "fused AdamW + codebook histogram; synthetic clips 3x16x168x168 / 128 tokens, random-init weights"}
 
@@ -869,6 +885,8 @@ def main():
         train = {}
         for tb in [int(v) for v in args.train_batch.split(",") if v]:
             train[f"batch{tb}"] = train_leg(T, _lib, dev, world, rank, dist, tb, max(4, args.steps // 2), args.warmup)
+            train[f"batch{tb}_graph"] = train_leg(T, _lib, dev, world, rank, dist, tb, max(4, args.steps // 2), args.warmup,
+                                                  graphed=True)
         if rank == 0:
             train["ragged"] = train_ragged_leg(T, _lib, dev, rank, 8)
         if rank == 0 and world == 1:

@@ -673,3 +673,40 @@ def test_frozen_encoder_tape_survives_an_intervening_encoder_launch():
     for k in a:  # split-K weight gradients are accumulated with float atomics: equal up to summation order
         d = (a[k].double() - b[k].double()).norm() / (a[k].double().norm() + 1e-30)
         assert d < 1e-4, f"decoder gradient of {k} changed after an intervening encoder launch: rel {float(d):.3g}"
+
+
+def test_graphed_train_step_replays_match_eager_steps():
+    """train_utils.GraphedTrainStep: forward + L1 loss + backward of a repeated batch composition replayed as one CUDA
+    graph gives the loss and gradients of the eager step on the same clips (split-K atomics: up to summation order), also
+    after an optimizer step changed the weights and with fresh clip contents; a new composition falls back to eager."""
+    from titok_video_b200.train_utils.graphed_step import GraphedTrainStep
+
+    shapes, tcs = [(8, 64, 48), (4, 16, 24)], [16, 3]
+    model = build_model(True).to(DEV).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    step = GraphedTrainStep(model, warmup=1)
+    sets = [[c.to(DEV) for c in O.make_clips(shapes, s)] for s in (0, 1, 2, 3)]
+    for i, clips in enumerate(sets):
+        opt.zero_grad(set_to_none=True)
+        loss_g, out_g = step(clips, tcs)
+        loss_g = float(loss_g)
+        idx_g = out_g["indices"].clone()
+        grads_g = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+        # the eager reference of the SAME step (same weights, same clips)
+        opt.zero_grad(set_to_none=True)
+        loss_e, idx_e, grads_e = _train_step_grads(model, [c.cpu() for c in clips], tcs)
+        assert abs(loss_g - loss_e) < 1e-5 * abs(loss_e) + 1e-7, (i, loss_g, loss_e)
+        assert torch.equal(idx_g.cpu(), idx_e)
+        for k in grads_e:
+            a, b = grads_g[k].float().cpu().double(), grads_e[k].double()
+            assert (a - b).norm() <= 1e-4 * b.norm() + 1e-12, (i, k)
+        # now really step the optimizer so that the next replay sees new weights
+        for k, p in model.named_parameters():
+            p.grad = grads_g[k]
+        opt.step()
+    assert step.eager_steps == 1 and step.replays == 3
+    # an unseen composition runs eagerly
+    other = [c.to(DEV) for c in O.make_clips([(4, 16, 24)], 9)]
+    opt.zero_grad(set_to_none=True)
+    loss_o, _ = step(other, [2])
+    assert step.eager_steps == 2 and torch.isfinite(loss_o)

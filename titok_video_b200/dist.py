@@ -206,6 +206,15 @@ class GradientAllReducer:
         work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group, async_op=True)
         self._work[b] = (work, flat, avg, inplace)
 
+    def reduce_now(self) -> None:
+        """Launch every bucket's all-reduce on the gradients as they are (no autograd hooks involved): for steps whose
+        backward did not run through autograd in this process -- a CUDA-graph replay (train_utils.GraphedTrainStep)."""
+        if self.world == 1:
+            return
+        for b, params in enumerate(self.buckets):
+            if self._work[b] is None and all(p.grad is not None for p in params):
+                self._launch(b)
+
     def finish(self) -> None:
         """Call after loss.backward(): completes the outstanding all-reduces and writes the averaged gradients."""
         if self.world == 1:
