@@ -290,7 +290,8 @@ def train_leg(T, _lib, dev, world, rank, dist, batch, steps, warmup, graphed=Fal
         if gstep is not None:
             # forward + loss + backward replayed as ONE CUDA graph once the composition has been seen (the bench's fixed
             # batch repeats every step); the all-reduce and the optimizer stay eager
-            loss, d = gstep(clips, tcs)
+            with red.no_sync():  # (autograd hooks must not fire collectives inside a capture)
+                loss, d = gstep(clips, tcs)
             red.reduce_now()
         else:
             with torch.autocast("cuda", dtype=torch.bfloat16):

@@ -13,8 +13,9 @@ that has not been seen simply runs eagerly the first time. This is the training-
 `TiTok.tokenize_reconstruct_`'s graph replay.
 
     step = GraphedTrainStep(model, loss_fn)          # loss_fn(clips, recon, out_dict) -> scalar loss
-    loss, out = step(clips, token_counts)            # forward + loss + backward; model.parameters() have their .grad
-    reducer.reduce_now(); reducer.finish()           # DDP (dist.GradientAllReducer), then optimizer.step()
+    with reducer.no_sync():                          # DDP (dist.GradientAllReducer): its autograd hooks must not fire
+        loss, out = step(clips, token_counts)        #   collectives inside a capture; forward + loss + backward
+    reducer.reduce_now(); reducer.finish()           # all-reduce the gradients as they are, then optimizer.step()
 """
 from __future__ import annotations
 
