@@ -32,6 +32,11 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+try:
+    ORIG_AFFINITY = os.sched_getaffinity(0)  # the reference / CPU-baseline child processes get all host cores back
+except Exception:
+    ORIG_AFFINITY = None
+
 CLIP_A = (16, 168, 168)
 TOKENS_A = 128
 PATCH = (4, 8, 8)
@@ -190,8 +195,12 @@ def _runner(args, timeout=900):
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
         env.pop(k, None)
     try:
+        def _all_cores():
+            if ORIG_AFFINITY:
+                os.sched_setaffinity(0, ORIG_AFFINITY)
+
         r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "reference_runner.py"), *args], capture_output=True,
-                           text=True, timeout=timeout, env=env, cwd=ROOT)
+                           text=True, timeout=timeout, env=env, cwd=ROOT, preexec_fn=_all_cores)
     except subprocess.TimeoutExpired:
         return {"unavailable": "reference runner timed out"}
     if r.returncode != 0:
@@ -242,6 +251,26 @@ def cpu_reference_run(steps, warmup, sample_clips=1, in_process=False):
     return {"clips_per_s": sample_clips * len(times) / total, "ms_per_step": 1e3 * total / len(times),
             "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{sample_clips} clip(s) 3x16x168x168 / 128 tokens per step, {len(times)} timed steps, torch CPU oracle port"}
+
+
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, so that the pinned staging buffers of
+    the e2e legs are allocated (first touch) on the GPU's own NUMA node. Returns a short description for the JSON line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"{len(allowed)} CPUs local to GPU {gpu_index} (NVML affinity)"
+        return "NVML affinity empty or outside the cgroup: unchanged"
+    except Exception as e:  # no NVML / not permitted: leave the affinity alone
+        return f"unchanged ({type(e).__name__})"
 
 
 def workload_string(B):
@@ -608,6 +637,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation: first touch decides the NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -983,6 +1013,7 @@ def main():
                "l2": f"inputs rotate over {INPUT_SETS} sets ({INPUT_SETS * B * clip_bytes / 1e6:.0f} MB) and the per-step "
                      f"activation working set exceeds the 126 MB L2",
                "weights": "random init, seed 42 (reference initialiser)", "codebook_usage_percent": usage,
+               "host_affinity": numa,
                "whole_step_tflops": whole["tflops"], "whole_step_frac_of_tensor_peak": whole["frac_of_tensor_peak"],
                "gpu_reference": gpu_ref}
         if train:

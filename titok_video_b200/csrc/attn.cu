@@ -377,7 +377,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         m_ref = m_sub;
         sts_f32(a_msh, m_sub);
       } else {
+#ifndef AT_EXP_NOTOKEN  // (timing experiment only: what does the token cost? results are wrong whenever a rescale fires)
         if (g == 0) nbar_sync256<AT_BAR_TOK>(); else nbar_sync256<AT_BAR_TOK + 1>();
+#endif
         const float m_cur = lds_f32(a_msh);
         if (m_cur != m_ref) {  // the other group moved the reference (rare)
           l_run *= ex2_approx((m_ref - m_cur) * c);
@@ -445,9 +447,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         l_run += x0 + x1;
       }
       // ---- hand the token over: the other group may start the exponentials of sub-tile j+1
+#ifndef AT_EXP_NOTOKEN
       if (j + 1 < n_sub) {
         if (g == 0) nbar_arrive256<AT_BAR_TOK + 1>(); else nbar_arrive256<AT_BAR_TOK>();
       }
+#endif
       if (threadIdx.x == 128) at_stamp(p, j >> 1, 3);
       // ---- P(j) -> tensor memory once this group's previous P V no longer reads the buffer
       if (j >= 2) {
