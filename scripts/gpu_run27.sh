@@ -1,0 +1,3 @@
+timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "attn" 2>&1 | tail -2
+timeout 120 python scripts/attn_bench.py 64 2>&1 | tail -1
+timeout 120 python scripts/attn_bench.py 16 2>&1 | tail -1

@@ -710,3 +710,17 @@ def test_graphed_train_step_replays_match_eager_steps():
     opt.zero_grad(set_to_none=True)
     loss_o, _ = step(other, [2])
     assert step.eager_steps == 2 and torch.isfinite(loss_o)
+
+
+def test_backward_after_the_weights_changed_raises():
+    """A forward whose graph is kept across an optimizer step must not silently combine old activations with new
+    weights in its backward: like PyTorch's version-counter check, the backward raises."""
+    model = build_model(True).to(DEV).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
+    clips = [c.to(DEV) for c in O.make_clips([(4, 16, 24)], 0)]
+    recon, _ = model(clips, [3])
+    loss = (recon[0].float() - clips[0].float()).abs().mean()
+    loss.backward(retain_graph=True)   # fine: weights unchanged
+    opt.step()                         # fused AdamW: no version bump, but the step counter moves
+    with pytest.raises(RuntimeError, match="parameters of this stack were modified"):
+        loss.backward()

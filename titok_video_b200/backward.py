@@ -36,6 +36,26 @@ class Tape:
     def __init__(self):
         self.lt = None  # LayerTape of the transformer layers
         self.t: Dict[str, torch.Tensor] = {}
+        self.weights_sig = None  # (parameter signature, optimizer-step counter) the forward ran with
+
+
+def _weights_sig(m):
+    """What identifies the parameter values a stack's prepared bf16 copies were made from: parameter objects / versions /
+    storages (PreparedStack._signature) and the process-wide optimizer-step counter (fused optimizers do not bump
+    versions)."""
+    from . import engine
+
+    ps = m.__dict__.get("_ttk_prepared")
+    return (ps._signature() if ps is not None else None, engine._OPT_STEPS[0])
+
+
+def _check_tape_weights(m, tape: "Tape") -> None:
+    """The backward kernels read the stack's CURRENT prepared weights: if the parameters changed between a forward and its
+    backward (an optimizer step in between, retain_graph reuse after a step), old activations would be combined with new
+    weights without any error. PyTorch raises a version-counter error in that situation; so do we."""
+    if tape.weights_sig is not None and tape.weights_sig != _weights_sig(m):
+        raise RuntimeError("titok_video_b200: the parameters of this stack were modified (optimizer step / in-place edit) "
+                           "between the forward that recorded this graph and its backward")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -179,6 +199,7 @@ def encoder_forward_train(m, dp: DevicePlan, clips_flat: torch.Tensor, fsq_const
               _ptr(T["proj_out_b"]), ts, _ptr(z), _ptr(codes), _ptr(idx), Tn, w, half_l, offset, shift, half_width,
               basis, levels, st)
     tape.t.update(patches=patches, e0=e0, x_fin=x_fin, xn_fin=xn_fin)
+    tape.weights_sig = _weights_sig(m)
     return z[:Tn], codes[:Tn], idx[:Tn], tape
 
 
@@ -204,6 +225,7 @@ def decoder_forward_train(m, dp: DevicePlan, codes: torch.Tensor):
     _lib.call("ttk_unpatchify", _ptr(rows), feat, _ptr(dp.patch_row), _ptr(dp.geom), pl.channels, P0, P1, P2, _ptr(out),
               G, st)
     tape.t.update(codes=codes, e0=e0, x_fin=x_fin, xn_fin=xn_fin)
+    tape.weights_sig = _weights_sig(m)
     return out, tape
 
 
@@ -322,6 +344,7 @@ def _layers_backward(m, W: PreparedStack, dp: DevicePlan, tape: Tape, g: torch.T
 
 def encoder_backward(m, dp: DevicePlan, tape: Tape, dz: torch.Tensor, need_input_grad: bool = False):
     """dz bf16 [T, ts] -> (grads in kernel layout, d clips_flat or None)."""
+    _check_tape_weights(m, tape)
     W = prepared(m, "enc")
     pl = dp.plan
     M, G, Tn, w = pl.M, pl.G, pl.T, m.width
@@ -359,6 +382,7 @@ def encoder_backward(m, dp: DevicePlan, tape: Tape, dz: torch.Tensor, need_input
 
 def decoder_backward(m, dp: DevicePlan, tape: Tape, dout: torch.Tensor):
     """dout bf16 flat [sum 3*T*H*W] -> (grads in kernel layout, dcodes fp32 [T, ts])."""
+    _check_tape_weights(m, tape)
     W = prepared(m, "dec")
     pl = dp.plan
     M, G, Tn, w = pl.M, pl.G, pl.T, m.width
