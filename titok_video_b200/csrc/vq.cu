@@ -106,7 +106,11 @@ __device__ __forceinline__ void vq_chunk_update(const uint32_t (&v)[32], int col
   const float mm = fminf(fmin3(a, b, c), fminf(m[9], m[10]));
   if (mm < best) {  // strict '<' keeps the first minimum (argmin tie rule)
     best = mm;
+#ifdef VQ_EXP_NOINDEX  // timing experiment: upper bound of tracking only (min, chunk) in the sweep
+    best_i = col0;
+#else
     best_i = col0 + vq_first_index(f, mm, a, b, c);
+#endif
   }
 }
 
@@ -130,7 +134,11 @@ __device__ __forceinline__ void vq_chunk_update_n(const uint32_t (&v)[32], const
   const float mm = fminf(fmin3(a, b, c), fminf(m[9], m[10]));
   if (mm < best) {  // strict '<' keeps the first minimum (argmin tie rule)
     best = mm;
+#ifdef VQ_EXP_NOINDEX  // timing experiment: upper bound of tracking only (min, chunk) in the sweep
+    best_i = col0;
+#else
     best_i = col0 + vq_first_index(f, mm, a, b, c);
+#endif
   }
 }
 
