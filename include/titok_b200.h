@@ -155,6 +155,15 @@ int ttk_build_plan(const int64_t* desc, int n_clips, int64_t M, int P0, int P1, 
                    int32_t* dec_src_row, int32_t* latent_row, int32_t* patch_row, int64_t* geom, int32_t* rope_pos,
                    ttk_stream_t stream);
 
+/* ttk_build_plan for a BUCKET of batch compositions: the launch extents (M_max, T_max, G_max) are fixed -- they are baked
+ * into one captured CUDA graph -- and the real sizes of the step live in device memory: hdr int64[8] = {n_clips, M, T, G,
+ * element offset of a 768-element scratch patch behind the clips, 0, 0, 0}. Padded rows / tokens / patches get harmless
+ * defaults (mask-token rows, token row 0, the scratch patch), see csrc/rowops.cu. Replaces, like ttk_build_plan, the
+ * metadata code of blocks.py:72-89 / rope.py:57-71 for the reference's ragged batches (video_dataset.py:130-172). */
+int ttk_build_plan_bucket(const int64_t* desc, const int64_t* hdr, int64_t M_max, int64_t T_max, int64_t G_max, int P0,
+                          int P1, int P2, int32_t* enc_src_row, int32_t* dec_src_row, int32_t* latent_row,
+                          int32_t* patch_row, int64_t* geom, int32_t* rope_pos, ttk_stream_t stream);
+
 /* RoPE table of a packed batch (RoPE.forward + _get_freqs_cis, rope.py:48-71): rope [M,60] fp32 (cos, sin) pairs,
  * complex lane = freq*3 + axis, gathered from cs_table [n_ids,10,2] fp32 = (cos, sin)(inv_freq[f] * id), evaluated once
  * in float64 by the host planner, by the integer position ids pos [M,3] int32. */

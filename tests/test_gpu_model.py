@@ -429,3 +429,48 @@ def test_tokens_written_to_a_container_decode_to_the_same_clips(tmp_path, golden
         rec2 = model.decode_indices([i.cuda() for i in idx], grids)
     for a, b in zip(rec, rec2):
         assert torch.equal(a, b)
+
+
+def test_bucketed_graph_replay_equals_the_per_composition_path():
+    """ragged batch compositions that fall into ONE shape bucket are served by ONE captured launch sequence
+    (TiTok.tokenize_reconstruct_bucketed_); tokens, reconstructions and per-clip errors are bit-identical to the eager
+    per-composition path for every composition, including uint8 frames and a batch that opens a second bucket."""
+    from titok_video_b200 import engine
+
+    model = build_model(True).cuda().eval()
+    g = torch.Generator().manual_seed(12)
+    comps = [
+        ([(8, 64, 48), (4, 16, 24), (8, 32, 32)], [16, 3, 8]),
+        ([(4, 16, 24), (8, 64, 48)], [1, 40]),
+        ([(12, 40, 24), (8, 32, 32), (4, 16, 24), (4, 24, 16), (8, 16, 16)], [7, 7, 2, 30, 5]),
+        ([(16, 168, 168), (16, 168, 168)], [128, 64]),               # a different (larger) bucket: 3528 patches
+        ([(8, 64, 48), (4, 16, 24), (8, 32, 32)], [16, 3, 8]),        # the first composition again
+    ]
+    engine._BUCKET_CACHE.clear()
+    graphs_before = None
+    for n, (shapes, tcs) in enumerate(comps):
+        clips = [(torch.rand((3, *s), generator=g) * 2 - 1).to(torch.bfloat16).cuda() for s in shapes]
+        with torch.no_grad():
+            rec_e, d_e = model.tokenize_reconstruct_(clips, tcs, use_graph=False, with_error=True)
+            rec_e = [r.clone() for r in rec_e]
+            idx_e, err_e = d_e["indices"].clone(), d_e["clip_error"].clone()
+            rec_b, d_b = model.tokenize_reconstruct_bucketed_(clips, tcs, with_error=True)
+        assert torch.equal(d_b["indices"], idx_e), n
+        # (the per-clip sums are reduced over a grid sized by the bucket's upper bound: same values, other summation order)
+        assert torch.allclose(d_b["clip_error"], err_e, rtol=1e-6, atol=0), n
+        for a, b in zip(rec_b, rec_e):
+            assert a.shape == b.shape and torch.equal(a, b), n
+        if n == 2:
+            graphs_before = sum(len(bp.graphs) for bp in engine._BUCKET_CACHE.values())
+            assert len(engine._BUCKET_CACHE) == 1 and graphs_before == 1  # three compositions, one bucket, one graph
+    assert len(engine._BUCKET_CACHE) == 2
+    # uint8 frames through the same bucket (own graph: the patch gather differs)
+    shapes, tcs = comps[1]
+    raw = [torch.randint(0, 256, (3, *s), generator=g, dtype=torch.uint8).cuda() for s in shapes]
+    with torch.no_grad():
+        rec_e, d_e = model.tokenize_reconstruct_(raw, tcs, use_graph=False)
+        rec_e, idx_e = [r.clone() for r in rec_e], d_e["indices"].clone()
+        rec_b, d_b = model.tokenize_reconstruct_bucketed_(raw, tcs)
+    assert torch.equal(d_b["indices"], idx_e)
+    for a, b in zip(rec_b, rec_e):
+        assert torch.equal(a, b)

@@ -61,6 +61,7 @@ SIGNATURES = {
     "ttk_dec_embed": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp],
     "ttk_enc_head_fsq": [_vp, _i64, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _fp, _fp, _fp, _fp, _ip, _ip, _vp],
     "ttk_build_plan": [_vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ttk_build_plan_bucket": [_vp, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ttk_rope_table_gather": [_vp, _vp, _i, _vp, _i64, _vp],
     "ttk_clip_error": [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp],
     "ttk_normalize_u8": [_vp, _vp, _i64, _vp],

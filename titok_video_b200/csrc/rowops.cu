@@ -399,6 +399,74 @@ __global__ void __launch_bounds__(256) build_plan_kernel(const int64_t* __restri
   }
 }
 
+// The same expansion for a BUCKET: the launch extents (M_max rows, T_max tokens, G_max patches) are fixed -- they are
+// baked into a captured CUDA graph -- while the real sizes of this step's batch are read from device memory:
+//   hdr int64[8] = {n_clips, M, T, G, scratch element offset of a 768-element patch, 0, 0, 0}.
+// Rows / tokens / patches past the real sizes get harmless defaults: padded rows are latent-type rows in the encoder and
+// patch-type rows in the decoder (mask-token rows, nothing is gathered), padded tokens read packed row 0, padded patches
+// read and write the scratch patch behind the clips. Every kernel of the launch sequence is row-wise (attention goes by
+// its work list, whose padded records have q_valid = 0), so the padding never touches a real row.
+__global__ void __launch_bounds__(256) build_plan_bucket_kernel(const int64_t* __restrict__ desc,
+                                                                const int64_t* __restrict__ hdr, int64_t M_max, int64_t T_max,
+                                                                int64_t G_max, int P0, int P1, int P2,
+                                                                int32_t* __restrict__ enc_src, int32_t* __restrict__ dec_src,
+                                                                int32_t* __restrict__ latent_row,
+                                                                int32_t* __restrict__ patch_row, int64_t* __restrict__ geom,
+                                                                int32_t* __restrict__ rope_pos) {
+  const int B = static_cast<int>(hdr[0]);
+  const int64_t M = hdr[1], T = hdr[2], G = hdr[3], scratch = hdr[4];
+  const int64_t n = M_max > G_max ? (M_max > T_max ? M_max : T_max) : (G_max > T_max ? G_max : T_max);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (i >= T && i < T_max) latent_row[i] = 0;
+    if (i >= G && i < G_max) {
+      patch_row[i] = 0;
+      geom[i * 4 + 0] = scratch;
+      geom[i * 4 + 1] = P2;
+      geom[i * 4 + 2] = static_cast<int64_t>(P1) * P2;
+      geom[i * 4 + 3] = static_cast<int64_t>(P0) * P1 * P2;
+    }
+    if (i >= M_max) continue;
+    const int64_t row = i;
+    if (row >= M) {
+      enc_src[row] = -1;
+      dec_src[row] = -1;
+      rope_pos[row * 3 + 0] = rope_pos[row * 3 + 1] = rope_pos[row * 3 + 2] = 0;
+      continue;
+    }
+    int lo = 0, hi = B - 1;
+    while (lo < hi) {  // last clip whose row_start <= row
+      const int mid = (lo + hi + 1) >> 1;
+      if (desc[mid * 12] <= row) lo = mid; else hi = mid - 1;
+    }
+    const int64_t* d = desc + lo * 12;
+    const int64_t local = row - d[0];
+    const int64_t tc = d[3];
+    if (local < tc) {
+      const int64_t tok = d[1] + local;
+      enc_src[row] = -1;
+      dec_src[row] = static_cast<int32_t>(tok);
+      latent_row[tok] = static_cast<int32_t>(row);
+      rope_pos[row * 3 + 0] = rope_pos[row * 3 + 1] = rope_pos[row * 3 + 2] = static_cast<int32_t>(local);
+    } else {
+      const int64_t pl = local - tc;
+      const int64_t pat = d[2] + pl;
+      const int64_t g1 = d[5], g2 = d[6];
+      const int64_t d0 = pl / (g1 * g2), rem = pl - d0 * g1 * g2, d1 = rem / g2, d2 = rem - d1 * g2;
+      enc_src[row] = static_cast<int32_t>(pat);
+      dec_src[row] = -1;
+      patch_row[pat] = static_cast<int32_t>(row);
+      rope_pos[row * 3 + 0] = static_cast<int32_t>(d0 + tc);
+      rope_pos[row * 3 + 1] = static_cast<int32_t>(d1 + tc);
+      rope_pos[row * 3 + 2] = static_cast<int32_t>(d2 + tc);
+      geom[pat * 4 + 0] = d[7] + (d0 * P0) * d[9] + (d1 * P1) * d[8] + d2 * P2;
+      geom[pat * 4 + 1] = d[8];
+      geom[pat * 4 + 2] = d[9];
+      geom[pat * 4 + 3] = d[10];
+    }
+  }
+}
+
 // RoPE table of a packed batch: rope[row, (f*3 + a)*2 + {0,1}] = cs_table[pos[row, a], f, {cos, sin}].
 // pos: int32 [M,3] integer position ids (RoPE.forward, rope.py:57-71); cs_table: fp32 [n_ids, 10, 2] evaluated once on
 // the host in float64 exactly as rope.py:40-54 does. The [M,60] table never crosses PCIe. One thread per complex lane.
@@ -724,6 +792,23 @@ int ttk_build_plan(const int64_t* desc, int n_clips, int64_t M, int P0, int P1, 
   const int grid = static_cast<int>(blocks < 16LL * num_sms() ? blocks : 16LL * num_sms());
   build_plan_kernel<<<grid, 256, 0, stream>>>(desc, n_clips, M, P0, P1, P2, enc_src_row, dec_src_row, latent_row, patch_row,
                                               geom, rope_pos);
+  return launch_status();
+}
+
+// ttk_build_plan for a bucket of batch compositions (see build_plan_bucket_kernel): fixed extents by value, the real sizes
+// of the step in device memory (hdr), so that ONE captured CUDA graph serves every composition of the bucket.
+int ttk_build_plan_bucket(const int64_t* desc, const int64_t* hdr, int64_t M_max, int64_t T_max, int64_t G_max, int P0,
+                          int P1, int P2, int32_t* enc_src_row, int32_t* dec_src_row, int32_t* latent_row,
+                          int32_t* patch_row, int64_t* geom, int32_t* rope_pos, cudaStream_t stream) {
+  if (M_max <= 0) return TTK_OK;
+  if (!desc || !hdr || !enc_src_row || !dec_src_row || !latent_row || !patch_row || !geom || !rope_pos) return TTK_ERR_BAD_ARG;
+  if (int e = check_device_sm100()) return e;
+  if (T_max < 0 || G_max < 0 || P0 < 1 || P1 < 1 || P2 < 1) return TTK_ERR_BAD_SHAPE;
+  const int64_t n = M_max > G_max ? (M_max > T_max ? M_max : T_max) : (G_max > T_max ? G_max : T_max);
+  const int64_t blocks = (n + 255) / 256;
+  const int grid = static_cast<int>(blocks < 16LL * num_sms() ? blocks : 16LL * num_sms());
+  build_plan_bucket_kernel<<<grid, 256, 0, stream>>>(desc, hdr, M_max, T_max, G_max, P0, P1, P2, enc_src_row, dec_src_row,
+                                                     latent_row, patch_row, geom, rope_pos);
   return launch_status();
 }
 

@@ -211,6 +211,127 @@ def get_device_plan(grids_px, token_counts, patch_size, channels, device) -> Dev
 
 def clear_caches() -> None:
     _PLAN_CACHE.clear()  # (the workspace arenas stay: they are sized by the largest batch seen, not per plan)
+    _BUCKET_CACHE.clear()
+
+
+# --------------------------------------------------------------------------------------------------
+# shape buckets: ONE captured launch sequence for every batch composition that fits a bucket
+# --------------------------------------------------------------------------------------------------
+class _MaxPlan:
+    """The extents a bucket's launch sequence runs with (what DevicePlan.plan is to the launch functions)."""
+
+    def __init__(self, G: int, T: int, B: int, patch_size, channels: int, feat: int):
+        self.G, self.T, self.M, self.B = G, T, G + T, B
+        self.patch_size, self.channels = tuple(patch_size), channels
+        self.pixels = G * feat                # every patch is `feat` pixels-times-channels: sum 3*T*H*W == G * feat
+        self.total_numel = self.pixels + feat  # + the scratch patch of the padded patches
+        self.clip_numel = (self.pixels,) * B  # B entries (their maximum sizes the grid of ttk_clip_error)
+
+
+class BucketPlan:
+    """Device metadata + workspace of a BUCKET of batch compositions: any ragged batch with at most G patches, T latent
+    tokens and B clips (the reference's dataloader draws a new composition every step, video_dataset.py:130-172).
+
+    Extents are fixed per bucket, so the whole encoder -> FSQ -> decoder launch sequence is captured into ONE CUDA graph
+    per (model, bucket) and replayed for every composition that falls into the bucket: per step the host does the O(B)
+    planning, packs [sizes | per-clip descriptors | attention work list | clip offsets] into one pinned buffer, issues ONE
+    H2D copy and one graph launch. The per-row metadata is expanded on the device INSIDE the graph
+    (ttk_build_plan_bucket: real sizes from device memory, harmless defaults for the padding), the RoPE table is gathered
+    from it. Padded rows never touch real rows (every kernel is row-wise; attention follows its work list, whose padded
+    records are empty), so results are bit-identical to the per-composition path."""
+
+    G_STEP, T_STEP, B_STEP = 2048, 256, 8
+
+    def __init__(self, G_max: int, T_max: int, B_max: int, patch_size, channels: int, device: torch.device, heads):
+        P0, P1, P2 = patch_size
+        feat = channels * P0 * P1 * P2
+        self.plan = _MaxPlan(G_max, T_max, B_max, patch_size, channels, feat)
+        self.device = device
+        self.heads = tuple(heads)
+        M = self.plan.M
+        hq, hkv = self.heads
+        # upper bound of the attention work list: one record per (row tile, pair of query heads) -- or per (head, pair of
+        # row tiles) when the kv group is odd -- and at most M/128 + B row tiles in any composition
+        tiles = M // 128 + B_max + 1
+        self.W_max = tiles * max(hq // 2, hq)
+        i32 = dict(dtype=torch.int32, device=device)
+        self.enc_src_row = torch.empty(M, **i32)
+        self.dec_src_row = torch.empty(M, **i32)
+        self.latent_row = torch.zeros(max(T_max, 1), **i32)
+        self.patch_row = torch.zeros(max(G_max, 1), **i32)
+        self.geom = torch.zeros((max(G_max, 1), 4), dtype=torch.int64, device=device)
+        self.rope_pos = torch.zeros((M, 3), **i32)
+        self.rope = torch.empty((M, 60), dtype=torch.float32, device=device)
+        # [hdr 8 | desc B*12 | clip_offset B | clip_numel B] int64, then the work list int32 [W_max, 12]
+        self.n_i64 = 8 + 14 * B_max
+        self.meta_bytes = (self.n_i64 * 8 + self.W_max * 48 + 255) // 256 * 256
+        self._meta = torch.zeros(self.meta_bytes, dtype=torch.uint8, device=device)
+        m64 = self._meta[:self.n_i64 * 8].view(torch.int64)
+        self.hdr = m64[:8]
+        self.clip_desc = m64[8:8 + 12 * B_max].view(B_max, 12)
+        self.clip_offset = m64[8 + 12 * B_max:8 + 13 * B_max]
+        self.clip_numel = m64[8 + 13 * B_max:8 + 14 * B_max]
+        self._work = self._meta[self.n_i64 * 8:self.n_i64 * 8 + self.W_max * 48].view(torch.int32).view(self.W_max, 12)
+        self.ws: Dict[str, torch.Tensor] = {}
+        self.graphs: Dict[tuple, tuple] = {}
+        self.cs, self.n_ids = _cs_table(device, 1024)  # position ids are < token_count + max grid side << 1024
+
+    buf = DevicePlan.buf
+
+    def attn_work(self, hq: int, hkv: int) -> torch.Tensor:
+        assert (hq, hkv) == self.heads
+        return self._work
+
+    def build_launch(self) -> None:
+        """The metadata expansion + RoPE gather: the first two launches of the captured sequence."""
+        pl = self.plan
+        P0, P1, P2 = pl.patch_size
+        st = _stream()
+        _lib.call("ttk_build_plan_bucket", _ptr(self.clip_desc), _ptr(self.hdr), pl.M, pl.T, pl.G, P0, P1, P2,
+                  _ptr(self.enc_src_row), _ptr(self.dec_src_row), _ptr(self.latent_row), _ptr(self.patch_row), _ptr(self.geom),
+                  _ptr(self.rope_pos), st)
+        _lib.call("ttk_rope_table_gather", _ptr(self.rope_pos), _ptr(self.cs), self.n_ids, _ptr(self.rope), pl.M, st)
+
+    def upload(self, plan: PackedPlan) -> None:
+        """This step's composition: one pinned buffer, one asynchronous copy."""
+        mp = self.plan
+        B = len(plan.token_counts)
+        if plan.G > mp.G or plan.T > mp.T or B > mp.B:
+            raise _lib.TitokB200Error("batch does not fit this bucket")
+        if plan.max_pos + 1 > self.n_ids:
+            raise _lib.TitokB200Error("position ids exceed the bucket's RoPE table")
+        work = get_attn_work(plan, *self.heads)
+        if work.shape[0] > self.W_max:
+            raise _lib.TitokB200Error("attention work list exceeds the bucket's bound")
+        host, done = _staging(self.meta_bytes)
+        hv = host.numpy()
+        hv[:self.meta_bytes] = 0
+        h64 = hv[:self.n_i64 * 8].view(np.int64)
+        h64[0], h64[1], h64[2], h64[3], h64[4] = B, plan.M, plan.T, plan.G, mp.pixels
+        h64[8:8 + 12 * B] = plan.clip_desc.reshape(-1)
+        h64[8 + 12 * mp.B:8 + 12 * mp.B + B] = plan.clip_offset
+        h64[8 + 13 * mp.B:8 + 13 * mp.B + B] = plan.clip_numel
+        hw = hv[self.n_i64 * 8:self.n_i64 * 8 + work.size * 4].view(np.int32)
+        hw[:] = work.reshape(-1)
+        self._meta.copy_(host[:self.meta_bytes], non_blocking=True)
+        done.record()
+
+
+_BUCKET_CACHE: Dict[tuple, BucketPlan] = {}
+
+
+def _round_up(v: int, step: int) -> int:
+    return max(step, (v + step - 1) // step * step)
+
+
+def get_bucket_plan(plan: PackedPlan, device, heads) -> BucketPlan:
+    key = (_round_up(plan.G, BucketPlan.G_STEP), _round_up(plan.T, BucketPlan.T_STEP),
+           _round_up(len(plan.token_counts), BucketPlan.B_STEP), tuple(plan.patch_size), plan.channels, str(device), tuple(heads))
+    bp = _BUCKET_CACHE.get(key)
+    if bp is None:
+        bp = BucketPlan(key[0], key[1], key[2], plan.patch_size, plan.channels, device, heads)
+        _BUCKET_CACHE[key] = bp
+    return bp
 
 
 # --------------------------------------------------------------------------------------------------

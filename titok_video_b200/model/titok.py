@@ -145,3 +145,74 @@ class TiTok(nn.Module):
         if with_error:
             res["clip_error"] = err
         return engine.split_clips(out, dp.plan), res
+
+    @torch.no_grad()
+    def tokenize_reconstruct_bucketed_(self, x: Sequence[torch.Tensor], token_counts, with_error: bool = False):
+        """`tokenize_reconstruct_` for RAGGED streams (the reference's dataloader draws a new batch composition every
+        step, dataset/video_dataset.py:130-172): the launch sequence is captured ONCE per shape bucket -- (patches, latent
+        tokens, clips) rounded up to engine.BucketPlan.{G,T,B}_STEP -- and replayed for every composition that falls into
+        the bucket. Per step the host plans in O(B), uploads one small buffer and launches one graph; the per-row metadata
+        is expanded on the device inside the graph. Results are bit-identical to `tokenize_reconstruct_` / `forward`
+        (tests/test_gpu_model.py); like there, they alias workspace buffers until the next call."""
+        from ..plan import make_plan
+
+        dev = x[0].device
+        engine.require_cuda(dev)
+        enc, dec = self.encoder, self.decoder
+        if tuple(enc.heads) != tuple(dec.heads) or enc.patch_size_tuple != dec.patch_size_tuple:
+            return self.tokenize_reconstruct_(x, token_counts, with_error=with_error)  # (buckets assume one head layout)
+        grids = [tuple(v.shape[1:]) for v in x]
+        tcs = engine.to_host_ints(token_counts)
+        if len(tcs) != len(x):
+            raise ValueError("len(token_counts) must equal the number of clips")
+        plan = make_plan(grids, tcs, enc.patch_size_tuple, enc.patch_channels, arrays=False)
+        bp = engine.get_bucket_plan(plan, dev, enc.heads)
+        bp.upload(plan)
+        u8 = x[0].dtype == torch.uint8
+        if u8 and with_error:
+            raise ValueError("with_error needs float clips (the error is taken against the normalised input)")
+        consts = self.quantize._consts(dev)
+        engine.prepared(enc, "enc")
+        engine.prepared(dec, "dec")
+
+        def stage():
+            """(re)fetch the static input / output buffers of the bucket and copy this step's clips in (one cat kernel)"""
+            f = bp.buf("clips_in_u8" if u8 else "clips_in", (bp.plan.total_numel,), torch.uint8 if u8 else torch.bfloat16)
+            if u8:
+                torch.cat([v.reshape(-1) for v in x], out=f[:plan.total_numel])
+            else:
+                torch.cat([v.reshape(-1).to(torch.bfloat16) for v in x], out=f[:plan.total_numel])
+            return f, bp.buf("clips_out", (bp.plan.total_numel,))
+
+        flat, out = stage()
+
+        def launch():
+            bp.build_launch()
+            _, codes, idx = engine.encoder_launch(enc, bp, flat, consts)
+            engine.decoder_launch(dec, bp, codes, out)
+            err = engine.clip_error_launch(bp, flat, out) if with_error else None
+            return idx, err
+
+        key = ("bucketed", id(self), u8, bool(with_error))
+        entry = bp.graphs.get(key)
+        if entry is not None and entry[3] != engine.arena_generation():
+            entry = None  # a workspace arena was re-allocated since the capture: the graph's pointers are stale
+        if entry is None:
+            gen = engine.arena_generation()
+            launch()  # eager warm-up: workspace allocation, one-time function attributes
+            torch.cuda.current_stream().synchronize()
+            if engine.arena_generation() != gen:
+                flat, out = stage()  # the warm-up grew an arena: the buffers moved
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                idx, err = launch()
+            entry = (g, idx, err, engine.arena_generation(), out)
+            bp.graphs[key] = entry
+        out = entry[4]
+        entry[0].replay()
+        idx, err = entry[1][:plan.T], entry[2]
+        res = {"indices": idx}
+        if with_error:
+            res["clip_error"] = err[:len(tcs)]
+        return engine.split_clips(out[:plan.total_numel], plan), res
+
