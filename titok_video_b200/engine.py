@@ -253,7 +253,7 @@ class BucketPlan:
         # upper bound of the attention work list: one record per (row tile, pair of query heads) -- or per (head, pair of
         # row tiles) when the kv group is odd -- and at most M/128 + B row tiles in any composition
         tiles = M // 128 + B_max + 1
-        self.W_max = tiles * max(hq // 2, hq)
+        self.W_max = tiles * (hq // 2 if (hq // hkv) % 2 == 0 else hq)
         i32 = dict(dtype=torch.int32, device=device)
         self.enc_src_row = torch.empty(M, **i32)
         self.dec_src_row = torch.empty(M, **i32)
