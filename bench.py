@@ -253,24 +253,42 @@ def cpu_reference_run(steps, warmup, sample_clips=1, in_process=False):
             "sample": f"{sample_clips} clip(s) 3x16x168x168 / 128 tokens per step, {len(times)} timed steps, torch CPU oracle port"}
 
 
-def bind_to_gpu_numa_node(gpu_index):
-    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, so that the pinned staging buffers of
-    the e2e legs are allocated (first touch) on the GPU's own NUMA node. Returns a short description for the JSON line."""
-    try:
-        import pynvml
+class numa_local:
+    """Context manager for pinned host allocations: while it is active the calling thread runs on the CPUs NVML reports
+    as local to the rank's GPU, so the pinned pages are first touched on the GPU's own NUMA node; the previous affinity
+    is restored afterwards (the launch path itself is NOT pinned to a subset of the cores: on a shared host that costs
+    more than it gives). Only used for multi-GPU runs; `desc` goes into the JSON line."""
+    desc = "not bound (single GPU)"
 
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-        n_words = (os.cpu_count() + 63) // 64
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
-        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
-        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
-        if allowed:
-            os.sched_setaffinity(0, allowed)
-            return f"{len(allowed)} CPUs local to GPU {gpu_index} (NVML affinity)"
-        return "NVML affinity empty or outside the cgroup: unchanged"
-    except Exception as e:  # no NVML / not permitted: leave the affinity alone
-        return f"unchanged ({type(e).__name__})"
+    def __init__(self, gpu_index, enabled):
+        self.gpu, self.enabled, self.prev = gpu_index, enabled, None
+
+    def __enter__(self):
+        if not self.enabled:
+            return self
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+            prev = os.sched_getaffinity(0)
+            allowed = sorted(set(cpus) & set(prev))
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                self.prev = prev
+                numa_local.desc = f"pinned buffers allocated on the {len(allowed)} CPUs local to the rank's GPU (NVML affinity)"
+            else:
+                numa_local.desc = "NVML affinity empty or outside the cgroup: unchanged"
+        except Exception as e:  # no NVML / not permitted: leave the affinity alone
+            numa_local.desc = f"unchanged ({type(e).__name__})"
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            os.sched_setaffinity(0, self.prev)
+        return False
 
 
 def workload_string(B):
@@ -637,7 +655,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation: first touch decides the NUMA node
+    pin_here = lambda: numa_local(local_rank, world > 1)  # around every pinned allocation (first touch decides the node)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -664,8 +682,9 @@ def main():
     def views(flat):
         return [flat[i * clip_numel:(i + 1) * clip_numel].view(3, *CLIP_A) for i in range(B)]
 
-    host_flat = [(torch.rand((B * clip_numel,), generator=gen) * 2 - 1).to(torch.bfloat16).pin_memory()
-                 for _ in range(INPUT_SETS)]
+    with pin_here():
+        host_flat = [(torch.rand((B * clip_numel,), generator=gen) * 2 - 1).to(torch.bfloat16).pin_memory()
+                     for _ in range(INPUT_SETS)]
     dev_sets = [views(hf.to(dev)) for hf in host_flat]
     clip_bytes = 3 * CLIP_A[0] * CLIP_A[1] * CLIP_A[2] * 2
 
@@ -772,9 +791,10 @@ def main():
         out_slots = [torch.empty((B * clip_numel,) if full else (1,), dtype=torch.bfloat16, device=dev) for _ in range(SLOTS)]
         idx_slots = [torch.empty((B * TOKENS_A,), dtype=torch.int32, device=dev) for _ in range(SLOTS)]
         err_slots = [torch.empty((B, 2), dtype=torch.float64, device=dev) for _ in range(SLOTS)]
-        host_out = [torch.empty_like(out_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
-        host_idx = [torch.empty_like(idx_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
-        host_err = [torch.empty_like(err_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
+        with pin_here():
+            host_out = [torch.empty_like(out_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
+            host_idx = [torch.empty_like(idx_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
+            host_err = [torch.empty_like(err_slots[0], device="cpu").pin_memory() for _ in range(SLOTS)]
         ev_in = [torch.cuda.Event() for _ in range(SLOTS)]
         ev_compute = [torch.cuda.Event() for _ in range(SLOTS)]
         ev_out = [torch.cuda.Event() for _ in range(SLOTS)]
@@ -833,7 +853,8 @@ def main():
     # at once -- what `e2e` cannot beat (shows whether the e2e scaling curve is the platform's host<->device path)
     def copy_probe():
         dbuf = torch.empty((B * clip_numel,), dtype=torch.bfloat16, device=dev)
-        hout = torch.empty((B * clip_numel,), dtype=torch.bfloat16).pin_memory()
+        with pin_here():
+            hout = torch.empty((B * clip_numel,), dtype=torch.bfloat16).pin_memory()
         res = {}
         for name, fn in (("h2d", lambda i: dbuf.copy_(host_flat[i % INPUT_SETS], non_blocking=True)),
                          ("d2h", lambda i: hout.copy_(dbuf, non_blocking=True))):
@@ -859,7 +880,8 @@ def main():
     probe = copy_probe()
     # same leg fed with decoded uint8 frames (what the reference's dataset holds before `/255*2-1`, video_dataset.py:111-119):
     # half the PCIe bytes, normalised on the device by ttk_normalize_u8 (bit-identical to the host expression)
-    host_u8 = [torch.randint(0, 256, (B * clip_numel,), generator=gen, dtype=torch.uint8).pin_memory() for _ in range(INPUT_SETS)]
+    with pin_here():
+        host_u8 = [torch.randint(0, 256, (B * clip_numel,), generator=gen, dtype=torch.uint8).pin_memory() for _ in range(INPUT_SETS)]
     u8_ms, u8_wall_ms = e2e_leg(host_u8, torch.uint8, full)
     e2e_u8 = {"value": world * B * args.steps / (u8_ms * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": B * clip_numel,
               "d2h_bytes_per_step": (B * clip_bytes if full else 0) + B * TOKENS_A * 4 + B * 16, "ms_per_step": u8_ms / args.steps,
@@ -937,6 +959,8 @@ def main():
                     model.tokenize_reconstruct_bucketed_(clips_r, tc_r)
                 torch.cuda.synchronize()
                 wb1 = time.perf_counter()
+                _eng._PLAN_CACHE.clear()  # (evicting plans that own captured graphs from the leg above would be timed otherwise)
+                torch.cuda.synchronize()
                 we0 = time.perf_counter()
                 for clips_r, tc_r in timed:
                     model.tokenize_reconstruct_(clips_r, tc_r, use_graph=False)
@@ -1056,7 +1080,7 @@ def main():
                "l2": f"inputs rotate over {INPUT_SETS} sets ({INPUT_SETS * B * clip_bytes / 1e6:.0f} MB) and the per-step "
                      f"activation working set exceeds the 126 MB L2",
                "weights": "random init, seed 42 (reference initialiser)", "codebook_usage_percent": usage,
-               "host_affinity": numa,
+               "host_affinity": numa_local.desc,
                "whole_step_tflops": whole["tflops"], "whole_step_frac_of_tensor_peak": whole["frac_of_tensor_peak"],
                "gpu_reference": gpu_ref}
         if train:
