@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import collections
 import itertools
+import weakref
 from typing import List, Sequence, Tuple
 
 import torch
@@ -41,17 +42,26 @@ _ids = itertools.count(1)
 
 
 class _Call:
-    __slots__ = ("m", "dp", "consts", "tape", "key")
+    """(module, device plan, FSQ constants) behind a handle. The module is held weakly: the registry must not keep models
+    (and their prepared weights) alive."""
+    __slots__ = ("_m", "dp", "consts", "tape", "key")
 
     def __init__(self, m, dp, consts, key):
-        self.m, self.dp, self.consts, self.tape, self.key = m, dp, consts, None, key
+        self._m, self.dp, self.consts, self.tape, self.key = weakref.ref(m), dp, consts, None, key
+
+    @property
+    def m(self):
+        m = self._m()
+        if m is None:
+            raise RuntimeError("titok_b200: the module behind this stack handle has been freed")
+        return m
 
 
 def handle_for(module, dp, consts=None) -> int:
     """Stable integer for (module, device plan): the same batch composition maps to the same handle."""
     key = (id(module), id(dp))
     h = _by_key.get(key)
-    if h is not None and h in _calls and _calls[h].m is module and _calls[h].dp is dp:
+    if h is not None and h in _calls and _calls[h]._m() is module and _calls[h].dp is dp:
         _calls.move_to_end(h)
         if consts is not None:
             _calls[h].consts = consts
