@@ -196,13 +196,23 @@ def test_gemm_resid_norm256(mode, M, K):
 # --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("seq_lens,hq,hkv", [([128], 4, 2), ([200, 64, 513], 4, 2), ([1892, 576], 4, 2),
                                                ([300, 129], 12, 4), ([257], 8, 2)])
-def test_attn_varlen(seq_lens, hq, hkv):
+@pytest.mark.parametrize("qk_scale", [1.0, 3.5, "mixed"])
+def test_attn_varlen(seq_lens, hq, hkv, qk_scale):
+    """qk_scale 1.0: every tile takes the kernel's bounded-score loop (|q| max|k| / 8 * log2 e ~ 15 << 90); 3.5: the bound
+    is ~170, every tile takes the running-maximum loop (peaked rows: lazy rescales fire); "mixed": clips alternate, so
+    both loops run in one launch."""
     from titok_video_b200.plan import attn_work_list
 
     width, gqa = hq * 64, hkv * 64
     M = sum(seq_lens)
     qkv = randn(M, 2 * width + 2 * gqa, seed=20, scale=1.0)
     starts = np.concatenate([[0], np.cumsum(seq_lens)[:-1]]).tolist()
+    qk_cols = torch.ones(2 * width + 2 * gqa)
+    qk_cols[:width] = 0
+    qk_cols[2 * width:2 * width + gqa] = 0  # 0 where the column is q or k
+    for ci, (s0, sl) in enumerate(zip(starts, seq_lens)):
+        f = qk_scale if qk_scale != "mixed" else (3.5 if ci % 2 == 0 else 1.0)
+        qkv[s0:s0 + sl] = (qkv[s0:s0 + sl].float() * (qk_cols + (1 - qk_cols) * f)).to(BF)
     work = torch.from_numpy(attn_work_list(starts, seq_lens, hq, hkv))
     q, gate, k, v = qkv.float().split([width, width, gqa, gqa], dim=-1)
     ref = torch.empty(M, width)

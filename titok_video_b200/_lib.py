@@ -110,7 +110,7 @@ def fn(name: str):
     return getattr(_lib, name)
 
 
-LAUNCHES = 0  # kernels launched through call() since import (every kernel entry point launches exactly one)
+LAUNCHES = 0  # kernels launched through call() since import (an entry point launches one kernel unless `launches` says otherwise)
 _PROFILER = None  # optional object with begin(name) / end(name, token), see bench.py
 
 
@@ -135,7 +135,7 @@ def profiling() -> bool:
 
 def call(name: str, *args, launches: int = 1) -> None:
     """Invoke an int-returning kernel entry point and raise on a non-zero status. `launches`: kernels the entry point
-    enqueues (1 for every kernel entry point, more for the native sequencers)."""
+    enqueues (1 for most kernel entry points, 2 for the attention forward, more for the native sequencers)."""
     global LAUNCHES
     LAUNCHES += launches
     if _PROFILER is None:

@@ -140,7 +140,7 @@ def _layers_train(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torc
     if NATIVE_SEQ and not _lib.profiling():
         d = layers_desc(m, W, dp, M)
         _lib.call("ttk_layers_fwd_train", ctypes.byref(d), _ptr(x), _ptr(xn), _ptr(slab), per_layer, _vp(foffs.ctypes.data),
-                  _ptr(lse_all), st, launches=8 * L)
+                  _ptr(lse_all), st, launches=9 * L)
         return lt.view(L - 1, F_XN), lt.view(L - 1, F_XNN)
     work = dp.attn_work(hq, hkv)
     scale = 1.0 / math.sqrt(64.0)
@@ -151,7 +151,7 @@ def _layers_train(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torc
         _lib.call("ttk_gemm_qkv_rope", _ptr(xn), xn.stride(0), _ptr(T[f"to_qkv{i}"]), w, M, w, w, gqa, _ptr(dp.rope),
                   _ptr(qkv), qkv.stride(0), st)
         _lib.call("ttk_attn_varlen_fwd_train", _ptr(qkv), qkv.stride(0), M, w, gqa, _ptr(work), work.shape[0], scale,
-                  _ptr(att), att.stride(0), _ptr(o), _ptr(lse), st)
+                  _ptr(att), att.stride(0), _ptr(o), _ptr(lse), st, launches=2)  # (key-norm bound kernel + attention)
         y_a = lt.view(i, F_YA)
         _gemm(st, att, T[f"out_proj{i}"], y_a, w, w)
         x_f, xn_f = lt.view(i, F_XF), lt.view(i, F_XNF)

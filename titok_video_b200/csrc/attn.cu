@@ -8,19 +8,9 @@
 //   [0,w) q (RoPE applied) | [w,2w) gate | [2w,2w+g) k (RoPE applied) | [2w+g,2w+2g) v
 // Rows of one clip are contiguous (latent rows then patch rows); attention never crosses clips.
 //
-// Work item (one CTA): TWO 128-row query tiles that share one K/V stream (two query heads of the
-// same kv group, or two consecutive row tiles of one head). Warp roles:
-//   warp 0        TMA producer: Q tiles once, K and V tiles through 4-stage rings
-//   warp 1        MMA issuer:   S_t = Q_t K^T  (SS: M128 N128 K64)
-//                               O_t += P_t V    (TS: P read from tensor memory, V MN-major in smem, M128 N64 K128)
-//   warp 2        TMEM allocator (512 columns: S0 S1 | O0 O1 | P0 P1)
-//   warps 4-11    softmax for query tile 0: thread == (query row, half of the 128 keys of a kv tile); the two
-//   warps 12-19   softmax for query tile 1   half-row threads agree on the row maximum through shared memory
-// Pipeline: S_t(j+1) is issued as soon as the softmax warps have pulled S_t(j) into registers, so the next score
-// tile is ready before the exponentials of the current one are done; P_t(j) goes back to tensor memory as bf16
-// (tcgen05.st) and the P V product accumulates into O_t in tensor memory. The running maximum is updated lazily:
-// O_t / l are rescaled (by the softmax warps themselves) only when the row maximum grew by more than 2^8, which
-// after the first one or two kv tiles practically never happens; the final division by l makes the result exact.
+// One CTA = one 128-row query tile against the K/V stream of its clip, in 64-key sub-tiles; two CTAs per SM. The design
+// (warp roles, the two softmax groups, the two softmax loops) is described above attn_fwd_kernel. A small pre-kernel
+// (attn_kmax_kernel) provides max_j |k_j|^2 per (clip, kv head), from which every query row derives a bound on its scores.
 #include "common.cuh"
 #include "host_util.cuh"
 
@@ -33,7 +23,9 @@ struct AttnWork {
   int kv_head;
   int kv_row0;  // first packed row of the clip
   int kv_len;   // rows in the clip
-  int pad[3];
+  int kmax2;    // scratch, written by attn_kmax_kernel into the LEADER record of a (clip, kv head): float bits of max_j |k_j|^2
+  int leader;   // index of that leader record (filled in by the planner)
+  int pad;
 };
 static_assert(sizeof(AttnWork) == 48, "AttnWork is mirrored in titok_video_b200/plan.py");
 
@@ -76,6 +68,12 @@ constexpr uint32_t AT_TM_O = 128;  // O [128,192)
 constexpr uint32_t AT_TM_P = 192;  // P_a [192,224)  P_b [224,256)   (64 keys x bf16 = 32 columns)
 constexpr uint32_t AT_TM_COLS = 256;
 constexpr float AT_RESCALE_LOG2 = 8.0f;  // rescale O only when the row maximum grew by more than 2^8
+// Bounded-score path (see attn_fwd_kernel): a query row whose Cauchy-Schwarz bound B = |q| max_j|k_j| scale log2(e) on its
+// scaled scores is at most AT_BOUND_MAX uses the FIXED reference B - AT_BOUND_OFFSET for its exponentials:
+// P = 2^(s c - B + OFFSET) <= 2^OFFSET can never overflow (row sums <= 2^(OFFSET+14), O <= 2^(OFFSET+14) |v|), and since
+// the row maximum is >= -B the largest P of a row is >= 2^(OFFSET - 2 B) >= 2^-100: no underflow of the terms that matter.
+constexpr float AT_BOUND_MAX = 90.0f;
+constexpr float AT_BOUND_OFFSET = 80.0f;
 // named barriers: token hand-over between the two softmax groups, end-of-loop exchange
 constexpr uint32_t AT_BAR_TOK = 1;  // + group that WAITS on it (1, 2)
 constexpr uint32_t AT_BAR_FIN = 3;
@@ -88,6 +86,29 @@ __device__ __forceinline__ void nbar_sync256() {
 template <int ID>
 __device__ __forceinline__ void nbar_arrive256() {
   asm volatile("bar.arrive %0, 256;" ::"n"(ID) : "memory");
+}
+
+__device__ __forceinline__ int ld_global_s32(const int* ptr) {
+  int v;
+  asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+
+// AND-reduction of a predicate over the 256 threads that meet at named barrier ID
+template <int ID>
+__device__ __forceinline__ bool bar_red_and_256(bool pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n"
+      ".reg .pred pi, po;\n"
+      "setp.ne.u32 pi, %1, 0;\n"
+      "bar.red.and.pred po, %2, 256, pi;\n"
+      "selp.u32 %0, 1, 0, po;\n"
+      "}\n"
+      : "=r"(out)
+      : "r"(static_cast<uint32_t>(pred)), "n"(ID)
+      : "memory");
+  return out != 0;
 }
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -156,6 +177,15 @@ __device__ __forceinline__ void ex2_poly_pair(uint64_t t, float& o0, float& o1) 
 // allocator, warps 4-7 softmax group a (even sub-tiles), warps 8-11 softmax group b (odd sub-tiles); thread == one
 // query row x the 64 keys of a sub-tile, so a sub-tile's row maximum needs no exchange. Each group has its own S and P
 // buffers in tensor memory (S(j+2) is issued as soon as S(j) sits in registers); both accumulate into the same O.
+//
+// Two softmax loops, chosen per CTA before the first sub-tile:
+//  * bounded-score loop (the common case). By Cauchy-Schwarz a row's scaled scores never exceed
+//    B = |q| max_j |k_j| scale log2(e); with the FIXED per-row reference B - AT_BOUND_OFFSET the exponentials can neither
+//    overflow nor (for B <= AT_BOUND_MAX) lose the terms that matter, so the loop needs no row maximum, no rescale of O
+//    and no exchange between the groups: tensor-memory load, 64 exponentials, row sum, P back to tensor memory
+//    (256 instead of 372 instructions per sub-tile and warp). Floating point makes the result independent of the
+//    reference up to the rounding of s c - ref.
+//  * running-maximum loop (rows with B > AT_BOUND_MAX, i.e. logits beyond +-60 nats), described next.
 //
 // The exponential phases of the two groups are serialised by a token (named barriers): at any time at most one group
 // of a CTA is on the MUFU pipe while the other one loads / reduces / stores, which keeps the pipe that bounds the loop
@@ -337,140 +367,252 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // adopting one then scales the empty sum by 2^-inf = 0)
     float m_ref = __int_as_float(0xff800000), l_run = 0.f;
 
-    for (int j = g; j < n_sub; j += 2) {
-      const uint32_t par = (j >> 1) & 1;
-      // ---- S(j): this thread's 64 scores into registers with one wait, then hand S_g back to the tensor core
-      mbar_wait_a(a_sfull, par);
-      tc_fence_after();
-      if (threadIdx.x == 128) at_stamp(p, j >> 1, 0);
-      // the epilogue's gate values: pull this thread's 64-byte segment towards L2 a few kv tiles ahead of its use
-      if (j + 6 >= n_sub && j + 4 < n_sub) {
-        const __nv_bfloat16* gp = p.gate + static_cast<int64_t>(q_row0 + min(r, q_valid - 1)) * p.ld + q_head * AT_D + g * 32;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(gp));
-      }
-      uint32_t sv[64];
-      tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-      tmem_ld_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a(a_sempty);  // S(j+2) may overwrite the accumulator once the 4 warps arrived
-      if (threadIdx.x == 128) at_stamp(p, j >> 1, 1);
-
-      const int kv_valid = kv_len - j * AT_BN;  // < 64 only in the last sub-tile
-      if (kv_valid < 64) {
+    // ---- which loop? The bound B_r = |q_r| max_j |k_j| c on this row's scaled scores (Cauchy-Schwarz; max_j |k_j|^2 of the
+    // clip's kv head comes from attn_kmax_kernel through the leader work record). If every valid row of the tile has
+    // B_r <= AT_BOUND_MAX the CTA takes the bounded-score loop: fixed per-row reference, no row maximum, no rescale, no
+    // exchange between the groups. Otherwise (huge logits) it takes the running-maximum loop below. Both are exact up to
+    // the bf16 rounding of P; the choice depends only on the clip's own q and k, never on what it is packed with.
+    float ref_l2;  // reference of the exponentials in log2 units (bounded-score loop)
+    bool fast;
+    {
+      // (issued ahead of the wait for Q: the L2 latency of this load runs under the arrival of the Q tile)
+      const float k2 = __int_as_float(ld_global_s32(&p.work[wp->leader].kmax2));
+      mbar_wait(q_full, 0);  // Q has landed in shared memory (async proxy -> mbarrier -> generic reads)
+      float q2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i >= kv_valid) sv[i] = 0xff800000u;  // -inf: exp2 -> 0, never the max
-      }
-      float m0 = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
-      float m1 = fmaxf(__uint_as_float(sv[2]), __uint_as_float(sv[3]));
+      for (int cc = 0; cc < 8; ++cc) {
+        const uint4 v = *reinterpret_cast<const uint4*>(sQ + r * 128 + ((cc ^ (r & 7)) << 4));
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int i = 4; i < 64; i += 4) {
-        m0 = fmax3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
-        m1 = fmax3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+        for (int e = 0; e < 4; ++e) {
+          const float x0 = bf16_lo(w4[e]), x1 = bf16_hi(w4[e]);
+          q2 = fmaf(x0, x0, q2);
+          q2 = fmaf(x1, x1, q2);
+        }
       }
-      const float m_sub = fmaxf(m0, m1);  // a sub-tile always holds >= 1 valid key
-
-      // ---- take the token: the other group's exponentials of sub-tile j-1 are done, its reference is published
-      if (j == 0) {
-        m_ref = m_sub;
-        sts_f32(a_msh, m_sub);
-      } else {
-#ifndef AT_EXP_NOTOKEN  // (timing experiment only: what does the token cost? results are wrong whenever a rescale fires)
-        if (g == 0) nbar_sync256<AT_BAR_TOK>(); else nbar_sync256<AT_BAR_TOK + 1>();
+      // 1.02: bf16 rounding of the RoPE-rotated q / k and the fp32 accumulation of the score never exceed it
+      const float bound = sqrtf(q2 * k2) * c * 1.02f + 1e-3f;
+      ref_l2 = bound - AT_BOUND_OFFSET;
+      const bool row_ok = (r >= q_valid) || (bound <= AT_BOUND_MAX);  // (NaN / inf bounds fail the test)
+#ifdef AT_NO_FAST  // (experiment / test hook: always take the running-maximum loop)
+      fast = false;
+      (void)row_ok;
+#else
+      fast = bar_red_and_256<AT_BAR_FIN>(row_ok);
 #endif
-        const float m_cur = lds_f32(a_msh);
-        if (m_cur != m_ref) {  // the other group moved the reference (rare)
-          l_run *= ex2_approx((m_ref - m_cur) * c);
-          m_ref = m_cur;
-        }
-        // lazy maximum: keep the reference unless some row of this warp outgrew it by 2^8
-        // (rows past the clip's end hold another clip's queries: they must not take part in the decision, or the
-        // rounding of this clip's rows would depend on what it is packed with)
-        if (__any_sync(0xffffffffu, r < q_valid && (m_sub - m_ref) * c > AT_RESCALE_LOG2)) {
-          const float m_new = fmaxf(m_ref, m_sub);
-          const float alpha = ex2_approx((m_ref - m_new) * c);
-          // O holds every product up to sub-tile j-1 once the latest PV of either group has retired
-          mbar_wait_a(a_pvdone_o, ((j - 1) >> 1) & 1);
-          if (j >= 2) mbar_wait_a(a_pvdone, ((j - 2) >> 1) & 1);
-          tc_fence_after();
-#pragma unroll 1
-          for (int q = 0; q < 4; ++q) {
-            uint32_t o[16];
-            tmem_ld_32x32b_x16(t_o + q * 16, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32b_x16(t_o + q * 16, o);
-          }
-          tmem_st_wait();
-          tc_fence_before();
-          l_run *= alpha;
-          m_ref = m_new;
-          sts_f32(a_msh, m_new);
-        }
-      }
-      if (threadIdx.x == 128) at_stamp(p, j >> 1, 2);
+    }
+    // the epilogue's gate values: pull this thread's 64-byte segment into L2 ahead of its use
+    {
+      const __nv_bfloat16* gp = p.gate + static_cast<int64_t>(q_row0 + min(r, q_valid - 1)) * p.ld + q_head * AT_D + g * 32;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(gp));
+    }
 
-      // ---- P(j) = 2^(s*c - m*c): packed FMA, MUFU ex2 / polynomial, packed row-sum, bf16 pairs (in place, sv[0..31])
-      const float nmc = -m_ref * c;
-      const uint64_t nmc2 = f32x2_pack(nmc, nmc);
+    if (fast) {
+      // ===== bounded-score loop: P(j) = 2^(s c - ref), ref fixed per row =====
+      const float nref = -ref_l2;
+      const uint64_t nref2 = f32x2_pack(nref, nref);
       uint64_t la = f32x2_pack(0.f, 0.f), lb = la;
+      const int last_valid = kv_len - (n_sub - 1) * AT_BN;  // keys of the last sub-tile (1..64)
+      uint32_t par = 0;
+      // exponentials of 32 scores sv[0..31] -> 16 packed bf16 pairs pk[0..15], row sums into la / lb
+      auto exp32 = [&](uint32_t (&sv)[32], uint32_t (&pk)[16], const int half) {
 #pragma unroll
-      for (int i = 0; i < 64; i += 4) {
-        const uint64_t ta = f32x2_fma(f32x2_pack(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), c2, nmc2);
-        const uint64_t tb = f32x2_fma(f32x2_pack(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), c2, nmc2);
-        float a0, a1, b0, b1;
-        if ((AT_EMU_A >> (i >> 2)) & 1) {
-          ex2_poly_pair(ta, a0, a1);
-        } else {
-          f32x2_unpack(ta, a0, a1);
-          a0 = ex2_approx(a0);
-          a1 = ex2_approx(a1);
+        for (int i = 0; i < 32; i += 4) {
+          const uint64_t ta = f32x2_fma(f32x2_pack(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), c2, nref2);
+          const uint64_t tb = f32x2_fma(f32x2_pack(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), c2, nref2);
+          float a0, a1, b0, b1;
+          if ((AT_EMU_A >> ((i >> 2) + 8 * half)) & 1) {
+            ex2_poly_pair(ta, a0, a1);
+          } else {
+            f32x2_unpack(ta, a0, a1);
+            a0 = ex2_approx(a0);
+            a1 = ex2_approx(a1);
+          }
+          if ((AT_EMU_B >> ((i >> 2) + 8 * half)) & 1) {
+            ex2_poly_pair(tb, b0, b1);
+          } else {
+            f32x2_unpack(tb, b0, b1);
+            b0 = ex2_approx(b0);
+            b1 = ex2_approx(b1);
+          }
+          la = f32x2_add(la, f32x2_pack(a0, a1));
+          lb = f32x2_add(lb, f32x2_pack(b0, b1));
+          pk[i >> 1] = pack_bf16x2(a0, a1);
+          pk[(i >> 1) + 1] = pack_bf16x2(b0, b1);
         }
-        if ((AT_EMU_B >> (i >> 2)) & 1) {
-          ex2_poly_pair(tb, b0, b1);
-        } else {
-          f32x2_unpack(tb, b0, b1);
-          b0 = ex2_approx(b0);
-          b1 = ex2_approx(b1);
+      };
+      for (int j = g; j < n_sub; j += 2, par ^= 1) {
+        // ---- S(j): first 32 scores with a wait, the other 32 in flight under the first half's exponentials
+        mbar_wait_a(a_sfull, par);
+        tc_fence_after();
+        uint32_t s0[32], s1[32], pk[32];
+        tmem_ld_32x32b_x32(t_s, s0);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(t_s + 32, s1);
+        if (j == n_sub - 1 && last_valid < 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= last_valid) s0[i] = 0xff800000u;  // -inf: exp2 -> 0
         }
-        la = f32x2_add(la, f32x2_pack(a0, a1));
-        lb = f32x2_add(lb, f32x2_pack(b0, b1));
-        sv[i >> 1] = pack_bf16x2(a0, a1);
-        sv[(i >> 1) + 1] = pack_bf16x2(b0, b1);
+        exp32(s0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]), 0);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(a_sempty);  // S(j+2) may overwrite the accumulator once the 4 warps arrived
+        if (j == n_sub - 1 && last_valid < 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (32 + i >= last_valid) s1[i] = 0xff800000u;
+        }
+        exp32(s1, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]), 1);
+        // ---- P(j) -> tensor memory once this group's previous P V no longer reads the buffer
+        if (j >= 2) {
+          mbar_wait_a(a_pvdone, par ^ 1);
+          tc_fence_after();
+        }
+        tmem_st_32x32b_x32(t_p, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(a_pfull);
       }
       {
         float x0, x1;
         f32x2_unpack(f32x2_add(la, lb), x0, x1);
-        l_run += x0 + x1;
+        l_run = x0 + x1;
       }
-      // ---- hand the token over: the other group may start the exponentials of sub-tile j+1
-#ifndef AT_EXP_NOTOKEN
-      if (j + 1 < n_sub) {
-        if (g == 0) nbar_arrive256<AT_BAR_TOK + 1>(); else nbar_arrive256<AT_BAR_TOK>();
-      }
-#endif
-      if (threadIdx.x == 128) at_stamp(p, j >> 1, 3);
-      // ---- P(j) -> tensor memory once this group's previous P V no longer reads the buffer
-      if (j >= 2) {
-        mbar_wait_a(a_pvdone, ((j - 2) >> 1) & 1);
+    } else {
+      for (int j = g; j < n_sub; j += 2) {
+        const uint32_t par = (j >> 1) & 1;
+        // ---- S(j): this thread's 64 scores into registers with one wait, then hand S_g back to the tensor core
+        mbar_wait_a(a_sfull, par);
         tc_fence_after();
+        if (threadIdx.x == 128) at_stamp(p, j >> 1, 0);
+        uint32_t sv[64];
+        tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        tmem_ld_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(a_sempty);  // S(j+2) may overwrite the accumulator once the 4 warps arrived
+        if (threadIdx.x == 128) at_stamp(p, j >> 1, 1);
+
+        const int kv_valid = kv_len - j * AT_BN;  // < 64 only in the last sub-tile
+        if (kv_valid < 64) {
+  #pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i >= kv_valid) sv[i] = 0xff800000u;  // -inf: exp2 -> 0, never the max
+        }
+        float m0 = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
+        float m1 = fmaxf(__uint_as_float(sv[2]), __uint_as_float(sv[3]));
+  #pragma unroll
+        for (int i = 4; i < 64; i += 4) {
+          m0 = fmax3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+          m1 = fmax3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+        }
+        const float m_sub = fmaxf(m0, m1);  // a sub-tile always holds >= 1 valid key
+
+        // ---- take the token: the other group's exponentials of sub-tile j-1 are done, its reference is published
+        if (j == 0) {
+          m_ref = m_sub;
+          sts_f32(a_msh, m_sub);
+        } else {
+  #ifndef AT_EXP_NOTOKEN  // (timing experiment only: what does the token cost? results are wrong whenever a rescale fires)
+          if (g == 0) nbar_sync256<AT_BAR_TOK>(); else nbar_sync256<AT_BAR_TOK + 1>();
+  #endif
+          const float m_cur = lds_f32(a_msh);
+          if (m_cur != m_ref) {  // the other group moved the reference (rare)
+            l_run *= ex2_approx((m_ref - m_cur) * c);
+            m_ref = m_cur;
+          }
+          // lazy maximum: keep the reference unless some row of this warp outgrew it by 2^8
+          // (rows past the clip's end hold another clip's queries: they must not take part in the decision, or the
+          // rounding of this clip's rows would depend on what it is packed with)
+          if (__any_sync(0xffffffffu, r < q_valid && (m_sub - m_ref) * c > AT_RESCALE_LOG2)) {
+            const float m_new = fmaxf(m_ref, m_sub);
+            const float alpha = ex2_approx((m_ref - m_new) * c);
+            // O holds every product up to sub-tile j-1 once the latest PV of either group has retired
+            mbar_wait_a(a_pvdone_o, ((j - 1) >> 1) & 1);
+            if (j >= 2) mbar_wait_a(a_pvdone, ((j - 2) >> 1) & 1);
+            tc_fence_after();
+  #pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+              uint32_t o[16];
+              tmem_ld_32x32b_x16(t_o + q * 16, o);
+              tmem_ld_wait();
+  #pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x32b_x16(t_o + q * 16, o);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            l_run *= alpha;
+            m_ref = m_new;
+            sts_f32(a_msh, m_new);
+          }
+        }
+        if (threadIdx.x == 128) at_stamp(p, j >> 1, 2);
+
+        // ---- P(j) = 2^(s*c - m*c): packed FMA, MUFU ex2 / polynomial, packed row-sum, bf16 pairs (in place, sv[0..31])
+        const float nmc = -m_ref * c;
+        const uint64_t nmc2 = f32x2_pack(nmc, nmc);
+        uint64_t la = f32x2_pack(0.f, 0.f), lb = la;
+  #pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          const uint64_t ta = f32x2_fma(f32x2_pack(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), c2, nmc2);
+          const uint64_t tb = f32x2_fma(f32x2_pack(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), c2, nmc2);
+          float a0, a1, b0, b1;
+          if ((AT_EMU_A >> (i >> 2)) & 1) {
+            ex2_poly_pair(ta, a0, a1);
+          } else {
+            f32x2_unpack(ta, a0, a1);
+            a0 = ex2_approx(a0);
+            a1 = ex2_approx(a1);
+          }
+          if ((AT_EMU_B >> (i >> 2)) & 1) {
+            ex2_poly_pair(tb, b0, b1);
+          } else {
+            f32x2_unpack(tb, b0, b1);
+            b0 = ex2_approx(b0);
+            b1 = ex2_approx(b1);
+          }
+          la = f32x2_add(la, f32x2_pack(a0, a1));
+          lb = f32x2_add(lb, f32x2_pack(b0, b1));
+          sv[i >> 1] = pack_bf16x2(a0, a1);
+          sv[(i >> 1) + 1] = pack_bf16x2(b0, b1);
+        }
+        {
+          float x0, x1;
+          f32x2_unpack(f32x2_add(la, lb), x0, x1);
+          l_run += x0 + x1;
+        }
+        // ---- hand the token over: the other group may start the exponentials of sub-tile j+1
+  #ifndef AT_EXP_NOTOKEN
+        if (j + 1 < n_sub) {
+          if (g == 0) nbar_arrive256<AT_BAR_TOK + 1>(); else nbar_arrive256<AT_BAR_TOK>();
+        }
+  #endif
+        if (threadIdx.x == 128) at_stamp(p, j >> 1, 3);
+        // ---- P(j) -> tensor memory once this group's previous P V no longer reads the buffer
+        if (j >= 2) {
+          mbar_wait_a(a_pvdone, ((j - 2) >> 1) & 1);
+          tc_fence_after();
+        }
+        if (threadIdx.x == 128) at_stamp(p, j >> 1, 4);
+        tmem_st_32x32b_x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(a_pfull);
+        if (threadIdx.x == 128) at_stamp(p, j >> 1, 5);
       }
-      if (threadIdx.x == 128) at_stamp(p, j >> 1, 4);
-      tmem_st_32x32b_x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a(a_pfull);
-      if (threadIdx.x == 128) at_stamp(p, j >> 1, 5);
+
     }
 
     // ---- epilogue: out = bf16(O / l) * bf16(sigmoid(gate)); group g writes 32 of the 64 head dims
     pdl_launch_dependents();  // once the LAST CTAs of the grid are here, the successor may start setting itself up
-    nbar_sync256<AT_BAR_FIN>();  // every exponential phase is over: the reference is final
-    {
+    if (!fast) {  // (CTA-uniform)
+      nbar_sync256<AT_BAR_FIN>();  // every exponential phase is over: the reference is final
       const float m_fin = lds_f32(a_msh);
       if (m_fin != m_ref) {
         l_run *= ex2_approx((m_ref - m_fin) * c);
@@ -482,7 +624,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float l_tot = l_run + lds_f32(smem_u32(l_sh + (g ^ 1) * 128 + r));
     const float inv_l = __fdividef(1.0f, l_tot);
     if (TRAIN && g == 0 && r < q_valid)  // the backward kernels recompute P = 2^(s*c - lse)
-      p.lse[static_cast<int64_t>(q_head) * p.M + q_row0 + r] = fmaf(m_ref, c, __log2f(l_tot));
+      p.lse[static_cast<int64_t>(q_head) * p.M + q_row0 + r] = fast ? ref_l2 + __log2f(l_tot) : fmaf(m_ref, c, __log2f(l_tot));
     mbar_wait(&pv_done[(n_sub - 1) & 1], ((n_sub - 1) >> 1) & 1);  // the last product issued (in-order completion)
     tc_fence_after();
     uint32_t o[32];
@@ -522,6 +664,67 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 2) tmem_dealloc(tmem_base, AT_TM_COLS);
 }
 
+// max_j |k_j|^2 over the keys of one (clip, kv head), for the score bound of attn_fwd_kernel. A small persistent grid walks
+// the work list; only the LEADER record of each (clip, kv head) -- the one whose own index the planner stored in `leader` --
+// causes work, and its CTA keeps the result (float bits) in the record's `kmax2` field (single writer: no atomics, nothing
+// to reset between launches). 8 lanes per key row (16 bytes each), 64 rows per pass. The maximum does not depend on the
+// order of the rows: results are reproducible.
+constexpr int AT_KMAX_THREADS = 512;
+__global__ void __launch_bounds__(AT_KMAX_THREADS, 2)
+attn_kmax_kernel(AttnWork* work, int n_work, const __nv_bfloat16* kbase, int64_t ld) {
+  __shared__ float red[AT_KMAX_THREADS / 32];
+  const int sub_row = (threadIdx.x & 31) >> 3;
+  bool waited = false;
+  for (int rec = blockIdx.x; rec < n_work; rec += gridDim.x) {
+    AttnWork* w = work + rec;
+    // (the work list is plan metadata, written long before the predecessor kernel: reading it ahead of pdl_wait is safe)
+    if (w->q_valid[0] <= 0 || w->leader != rec) continue;  // (CTA-uniform)
+    if (!waited) {
+      pdl_wait();  // the keys are the predecessor's output
+      waited = true;
+    }
+    const int kv_len = w->kv_len;
+    const __nv_bfloat16* kp = kbase + static_cast<int64_t>(w->kv_row0) * ld + w->kv_head * AT_D + (threadIdx.x & 7) * 8;
+    float mx = 0.f;
+    constexpr int ROWS_PER_PASS = AT_KMAX_THREADS / 8, BATCH = 8;
+    for (int base = (threadIdx.x >> 5) * 4; base < kv_len; base += BATCH * ROWS_PER_PASS) {  // (warp-uniform trip count)
+      uint4 v[BATCH];  // all loads of a batch are in flight before the first use
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const int row = base + u * ROWS_PER_PASS + sub_row;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (row < kv_len) v[u] = ldg16(kp + static_cast<int64_t>(row) * ld);
+      }
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        float ss = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x0 = bf16_lo(w4[e]), x1 = bf16_hi(w4[e]);
+          ss = fmaf(x0, x0, ss);
+          ss = fmaf(x1, x1, ss);
+        }
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+        mx = fmaxf(mx, ss);
+      }
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    __syncthreads();  // (red[] of the previous leader has been read)
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      mx = threadIdx.x < AT_KMAX_THREADS / 32 ? red[threadIdx.x] : 0.f;
+      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (threadIdx.x == 0) w->kmax2 = __float_as_int(mx);
+    }
+  }
+  // (a CTA that found no leader never waits: harmless, some other CTA of the grid did -- every valid record has a leader)
+}
+
 }  // namespace ttk
 
 using namespace ttk;
@@ -555,6 +758,14 @@ static int attn_fwd_launch(const void* qkv, int64_t ld, int M, int width, int gq
   static PerDeviceOnce once_plain, once_train;
   if (int e = set_smem_attr_once(once_plain, reinterpret_cast<const void*>(attn_fwd_kernel<false>), AT_SMEM)) return e;
   if (int e = set_smem_attr_once(once_train, reinterpret_cast<const void*>(attn_fwd_kernel<true>), AT_SMEM)) return e;
+  // score bound of every (clip, kv head): written into the scratch field of the leader work records (the work list is the
+  // caller's device buffer; its `kmax2` fields are this library's scratch)
+  {
+    const int cap = 2 * num_sms();
+    if (int e = cuda_status(launch_pdl(attn_kmax_kernel, dim3(n_work < cap ? n_work : cap), dim3(AT_KMAX_THREADS), 0, stream,
+                                       const_cast<AttnWork*>(p.work), n_work, base + 2 * width, ld)))
+      return e;
+  }
   if (o_save)
     return cuda_status(launch_pdl(attn_fwd_kernel<true>, dim3(2 * n_work), dim3(AT_THREADS), AT_SMEM, stream, tmQ, tmK, tmV, p));
   return cuda_status(launch_pdl(attn_fwd_kernel<false>, dim3(2 * n_work), dim3(AT_THREADS), AT_SMEM, stream, tmQ, tmK, tmV, p));

@@ -587,7 +587,7 @@ def _layers(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tens
     if NATIVE_SEQ and not _lib.profiling():
         d = layers_desc(m, W, dp, M)
         _lib.call("ttk_layers_fwd", ctypes.byref(d), _ptr(x), _ptr(xn), _ptr(qkv), _ptr(att), _ptr(h), _ptr(y), st,
-                  launches=L * (5 if y is None else 7))
+                  launches=L * (6 if y is None else 8))
         return
 
     def out_update(a: torch.Tensor, wmat: torch.Tensor, K: int, mode: int, w_post, w_next) -> None:
@@ -605,7 +605,7 @@ def _layers(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tens
         _lib.call("ttk_gemm_qkv_rope", _ptr(xn), xn.stride(0), _ptr(T[f"to_qkv{i}"]), w, M, w, w, gqa, _ptr(dp.rope),
                   _ptr(qkv), qkv.stride(0), st)
         _lib.call("ttk_attn_varlen_fwd", _ptr(qkv), qkv.stride(0), M, w, gqa, _ptr(work), work.shape[0], scale,
-                  _ptr(att), att.stride(0), st)
+                  _ptr(att), att.stride(0), st, launches=2)  # (key-norm bound kernel + attention)
         out_update(att, T[f"out_proj{i}"], w, mode, T.get(f"attn_post_ln{i}"), T[f"ffn_norm{i}"])
         _lib.call("ttk_gemm_geglu", _ptr(xn), xn.stride(0), _ptr(T[f"w12_{i}"]), w, M, inner, w, _ptr(h), h.stride(0),
                   st)

@@ -123,9 +123,11 @@ def rope_table_from_int_ids(ids: np.ndarray, inv_freqs: np.ndarray) -> np.ndarra
 
 
 def attn_work_list(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: int, hkv: int) -> np.ndarray:
-    """int32 [n, 12] records {q_row0[2], q_valid[2], q_head[2], kv_head, kv_row0, kv_len, pad[3]} (csrc/attn.cu).
-    Two query tiles per record share one kv head: two heads of the same group when the group size is even,
-    otherwise two consecutive row tiles of one head. Longest sequences first (LPT) to shorten the tail."""
+    """int32 [n, 12] records {q_row0[2], q_valid[2], q_head[2], kv_head, kv_row0, kv_len, kmax2, leader, pad}
+    (csrc/attn.cu). Two query tiles per record share one kv head: two heads of the same group when the group size is
+    even, otherwise two consecutive row tiles of one head. Longest sequences first (LPT) to shorten the tail.
+    `leader` = index of the first record of the same (clip, kv head): the kernel library keeps that pair's score bound
+    in the leader's `kmax2` field (device-side scratch, zero here)."""
     ratio = hq // hkv
     if ratio % 2 == 0 and len(seq_starts):
         # vectorised: one record per (clip, row tile, pair of query heads of one kv group)
@@ -145,7 +147,7 @@ def attn_work_list(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: int, 
         rec[:, 4], rec[:, 5], rec[:, 6] = h, h + 1, h // ratio
         rec[:, 7], rec[:, 8] = rep(st[clip]), rep(sl[clip])
         order = np.argsort(-rec[:, 8], kind="stable")  # longest sequences first (LPT), ties in generation order
-        return np.ascontiguousarray(rec[order])
+        return _with_leaders(np.ascontiguousarray(rec[order]))
     recs: List[List[int]] = []
     for start, slen in zip(seq_starts, seq_lens):
         n_tiles = (slen + ATTN_TILE - 1) // ATTN_TILE
@@ -167,7 +169,16 @@ def attn_work_list(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: int, 
                         r1, v1 = r0, 0
                     recs.append([r0, r1, v0, v1, h, h, h // ratio, start, slen, 0, 0, 0])
     recs.sort(key=lambda r: -r[8])
-    return np.asarray(recs, dtype=np.int32).reshape(-1, 12)
+    return _with_leaders(np.asarray(recs, dtype=np.int32).reshape(-1, 12))
+
+
+def _with_leaders(rec: np.ndarray) -> np.ndarray:
+    """Fills column 10 (`leader`): the index of the first record with the same (kv_row0, kv_head)."""
+    if rec.shape[0]:
+        key = rec[:, 7].astype(np.int64) * 4096 + rec[:, 6]
+        _, first, inv = np.unique(key, return_index=True, return_inverse=True)
+        rec[:, 10] = first[inv.reshape(-1)]
+    return rec
 
 
 def make_plan(grids_px: Sequence[Sequence[int]], token_counts: Sequence[int], patch_size: Sequence[int],
