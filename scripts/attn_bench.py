@@ -59,3 +59,8 @@ if "--trace" in sys.argv:
     print(f"  P stored(j) -> MMA PV(j) issue: mean {seg[ok].mean().item():.0f} median {seg[ok].median().item():.0f}")
     seg = (t[:, 12] - t[:, 8]).float()
     print(f"  MMA S(j+1) issue -> S ready(j+1) seen by softmax: mean {seg[ok].mean().item():.0f} median {seg[ok].median().item():.0f}")
+    # CTA-level phases (slots 48..51: entry, loop entered, loop left, epilogue stores issued)
+    okc = (t[:, 48] > 0) & (t[:, 51] > 0)
+    for a, b, nm in ((48, 49, "entry -> loop entered (prologue)"), (49, 50, "loop"), (50, 51, "epilogue"), (48, 51, "CTA lifetime")):
+        seg = (t[:, b] - t[:, a]).float()
+        print(f"  {nm}: mean {seg[okc].mean().item():.0f} median {seg[okc].median().item():.0f} cycles")

@@ -51,6 +51,13 @@ __device__ __forceinline__ void at_stamp(const AttnParams& p, int j, int ev) {
 #endif
 }
 
+// CTA-level stamps (slots 48..): 48 kernel entry, 49 first sub-tile loop entered, 50 loop left, 51 epilogue stores issued
+__device__ __forceinline__ void at_stamp_cta(const AttnParams& p, int slot) {
+#ifdef AT_TRACE
+  if (p.trace) p.trace[blockIdx.x * 64 + slot] = clock64();
+#endif
+}
+
 constexpr int AT_BM = 128;  // query rows per tile
 constexpr int AT_BN = 64;   // keys per kv sub-tile (one S accumulator)
 constexpr int AT_D = 64;
@@ -206,6 +213,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int q_row0 = wp->q_row0[t], q_head = wp->q_head[t];
   const int kv_head = wp->kv_head, kv_row0 = wp->kv_row0, kv_len = wp->kv_len;
 
+  if (threadIdx.x == 128) at_stamp_cta(p, 48);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                       // [128][64]
@@ -318,13 +326,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(&k_empty[j]);
       }
       // Fixed issue order (S(j+2), then P(j) V(j), j ascending): the accumulation order into O is the same in every run
-      // and for every batch composition, so results are bit-reproducible. (Issuing whichever group's operation is
-      // ready first was measured: no faster, and it reorders the fp32 accumulation.)
+      // and for every batch composition, so results are bit-reproducible. (Two polled streams -- score products not waiting
+      // behind a late P -- were measured: 334 vs 321 us per launch, the polling thread costs more than the order.)
       for (int j = 0; j < n_sub; ++j) {
         const int g = j & 1;
         const uint32_t par = (j >> 1) & 1;
         if (j + 2 < n_sub) {
-          // ---- S(j+2) = Q K(j+2)^T into group g's accumulator as soon as S(j) has been read out of tensor memory
           const int sk = (j + 2) % AT_KST;
           mbar_wait(&k_full[sk], ((j + 2) / AT_KST) & 1);
           mbar_wait(&s_empty[g], par);
@@ -334,7 +341,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_commit(&s_full[g]);
           umma_commit(&k_empty[sk]);
         }
-        // ---- O += P(j) V(j)
         const int sv = j % AT_VST;
         mbar_wait(&v_full[sv], (j / AT_VST) & 1);
         mbar_wait(&p_full[g], par);
@@ -407,6 +413,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       asm volatile("prefetch.global.L2 [%0];" ::"l"(gp));
     }
 
+    if (threadIdx.x == 128) at_stamp_cta(p, 49);
     if (fast) {
       // ===== bounded-score loop: P(j) = 2^(s c - ref), ref fixed per row =====
       const float nref = -ref_l2;
@@ -442,39 +449,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       };
       for (int j = g; j < n_sub; j += 2, par ^= 1) {
-        // ---- S(j): first 32 scores with a wait, the other 32 in flight under the first half's exponentials
+        // ---- S(j): this thread's 64 scores into registers, then hand S_g back to the tensor core
         mbar_wait_a(a_sfull, par);
         tc_fence_after();
+        if (threadIdx.x == 128) at_stamp(p, j >> 1, 0);
         uint32_t s0[32], s1[32], pk[32];
         tmem_ld_32x32b_x32(t_s, s0);
-        tmem_ld_wait();
         tmem_ld_32x32b_x32(t_s + 32, s1);
-        if (j == n_sub - 1 && last_valid < 64) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i >= last_valid) s0[i] = 0xff800000u;  // -inf: exp2 -> 0
-        }
-        exp32(s0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]), 0);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_a(a_sempty);  // S(j+2) may overwrite the accumulator once the 4 warps arrived
+        if (threadIdx.x == 128) at_stamp(p, j >> 1, 1);
         if (j == n_sub - 1 && last_valid < 64) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
+          for (int i = 0; i < 32; ++i) {
+            if (i >= last_valid) s0[i] = 0xff800000u;  // -inf: exp2 -> 0
             if (32 + i >= last_valid) s1[i] = 0xff800000u;
+          }
         }
+        exp32(s0, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]), 0);
         exp32(s1, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]), 1);
+        if (threadIdx.x == 128) at_stamp(p, j >> 1, 3);
         // ---- P(j) -> tensor memory once this group's previous P V no longer reads the buffer
         if (j >= 2) {
           mbar_wait_a(a_pvdone, par ^ 1);
           tc_fence_after();
         }
+        if (threadIdx.x == 128) at_stamp(p, j >> 1, 4);
+        // (deferring this hand-over to the top of the next iteration, so that the store's latency runs under the next
+        // load, was measured: 334-341 vs 321 us per launch -- the P V product and everything queued behind it start later)
         tmem_st_32x32b_x32(t_p, pk);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_a(a_pfull);
+        if (threadIdx.x == 128) at_stamp(p, j >> 1, 5);
       }
       {
         float x0, x1;
@@ -609,8 +619,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     }
 
+    if (threadIdx.x == 128) at_stamp_cta(p, 50);
     // ---- epilogue: out = bf16(O / l) * bf16(sigmoid(gate)); group g writes 32 of the 64 head dims
     pdl_launch_dependents();  // once the LAST CTAs of the grid are here, the successor may start setting itself up
+    // this thread's gate values (prefetched into L2 before the loop): in flight while the groups meet at the barrier
+    uint4 gv4[4];
+    {
+      const __nv_bfloat16* gt0 = p.gate + static_cast<int64_t>(q_row0 + min(r, q_valid - 1)) * p.ld + q_head * AT_D + g * 32;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) gv4[q] = ldg16(gt0 + q * 8);
+    }
     if (!fast) {  // (CTA-uniform)
       nbar_sync256<AT_BAR_FIN>();  // every exponential phase is over: the reference is final
       const float m_fin = lds_f32(a_msh);
@@ -633,12 +651,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (r < q_valid) {
       const int row = q_row0 + r;
       const int col = q_head * AT_D + g * 32;
-      const __nv_bfloat16* gt = p.gate + static_cast<int64_t>(row) * p.ld + col;
       __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + col;
       __nv_bfloat16* osv = TRAIN ? p.o_save + static_cast<int64_t>(row) * p.ldo + col : nullptr;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint4 gv = ldg16(gt + q * 8);
+        const uint4 gv = gv4[q];
         const uint32_t gg[4] = {gv.x, gv.y, gv.z, gv.w};
         uint32_t ov[4], av[4];
 #pragma unroll
@@ -659,6 +676,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   }
 
+  if (threadIdx.x == 128) at_stamp_cta(p, 51);
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, AT_TM_COLS);
