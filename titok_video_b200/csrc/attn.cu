@@ -180,7 +180,8 @@ __device__ __forceinline__ void ex2_poly_pair(uint64_t t, float& o0, float& o1) 
 // memory allocation, first loads) and epilogue (gate, normalisation, stores) run under the other's kv loop, and the
 // two tiles of a record -- launched side by side -- find each other's K/V tiles in L2.
 //
-// Warp roles: warp 0 TMA producer (Q once, K and V sub-tiles through rings), warp 1 MMA issuer, warp 2 tensor-memory
+// Warp roles: warp 0 TMA producer (Q once, K and V sub-tiles through rings), warp 1 issues the score products, warp 3 the
+// P V products (two in-order streams that do not wait for each other), warp 2 tensor-memory
 // allocator, warps 4-7 softmax group a (even sub-tiles), warps 8-11 softmax group b (odd sub-tiles); thread == one
 // query row x the 64 keys of a sub-tile, so a sub-tile's row maximum needs no exchange. Each group has its own S and P
 // buffers in tensor memory (S(j+2) is issued as soon as S(j) sits in registers); both accumulate into the same O.
@@ -301,7 +302,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_D, 0, 1);   // P (tmem, K-major) x V (MN-major)
       auto issue_s = [&](int g, int st) {
         const uint32_t sa = smem_u32(sQ);
         const uint32_t sb = smem_u32(sK + st * AT_KV_BYTES);
@@ -310,43 +310,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_bf16_ss(tmem_base + AT_TM_S + g * AT_BN, umma_smem_desc_sw128(sa + k * 32, 1024, 0),
                        umma_smem_desc_sw128(sb + k * 32, 1024, 0), idesc_s, k != 0 ? 1u : 0u);
       };
-      auto issue_pv = [&](int g, int st, bool accumulate) {
-        const uint32_t sb = smem_u32(sV + st * AT_KV_BYTES);
+      // Score products S(0), S(1), S(2), ... in order, each as soon as its K sub-tile has landed and the softmax group has
+      // pulled the previous contents of its accumulator into registers. The P V products are issued by warp 3: a score
+      // product never waits behind a P that the other softmax group hands over late (with one in-order stream
+      // S(j+2), P(j) V(j) the softmax warps spent 11 % of their time waiting for scores).
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_sub; ++j) {
+        const int g = j & 1, sk = j % AT_KST;
+        mbar_wait(&k_full[sk], (j / AT_KST) & 1);
+        if (j >= 2) mbar_wait(&s_empty[g], ((j - 2) >> 1) & 1);
+        tc_fence_after();
+        if (g == 0 && j >= 2) at_stamp(p, (j - 2) >> 1, 8);
+        issue_s(g, sk);
+        umma_commit(&s_full[g]);
+        umma_commit(&k_empty[sk]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (elect_one()) {
+      // O += P(j) V(j), j ascending: the accumulation order into O is the same in every run and for every batch
+      // composition, so results are bit-reproducible.
+      constexpr uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_D, 0, 1);  // P (tmem, K-major) x V (MN-major)
+      for (int j = 0; j < n_sub; ++j) {
+        const int g = j & 1, sv = j % AT_VST;
+        mbar_wait(&v_full[sv], (j / AT_VST) & 1);
+        mbar_wait(&p_full[g], (j >> 1) & 1);
+        tc_fence_after();
+        if (g == 0) at_stamp(p, j >> 1, 10);
+        const uint32_t sb = smem_u32(sV + sv * AT_KV_BYTES);
 #pragma unroll
         for (int k = 0; k < AT_BN / 16; ++k)  // 16 keys == 8 packed columns of P
           umma_bf16_ts(tmem_base + AT_TM_O, tmem_base + AT_TM_P + g * (AT_BN / 2) + k * 8,
-                       umma_smem_desc_sw128(sb + k * 2048, 1024, 0), idesc_o, (accumulate || k != 0) ? 1u : 0u);
-      };
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < 2 && j < n_sub; ++j) {
-        mbar_wait(&k_full[j], 0);
-        tc_fence_after();
-        issue_s(j, j);
-        umma_commit(&s_full[j]);
-        umma_commit(&k_empty[j]);
-      }
-      // Fixed issue order (S(j+2), then P(j) V(j), j ascending): the accumulation order into O is the same in every run
-      // and for every batch composition, so results are bit-reproducible. (Two polled streams -- score products not waiting
-      // behind a late P -- were measured: 334 vs 321 us per launch, the polling thread costs more than the order.)
-      for (int j = 0; j < n_sub; ++j) {
-        const int g = j & 1;
-        const uint32_t par = (j >> 1) & 1;
-        if (j + 2 < n_sub) {
-          const int sk = (j + 2) % AT_KST;
-          mbar_wait(&k_full[sk], ((j + 2) / AT_KST) & 1);
-          mbar_wait(&s_empty[g], par);
-          tc_fence_after();
-          if (g == 0) at_stamp(p, j >> 1, 8);
-          issue_s(g, sk);
-          umma_commit(&s_full[g]);
-          umma_commit(&k_empty[sk]);
-        }
-        const int sv = j % AT_VST;
-        mbar_wait(&v_full[sv], (j / AT_VST) & 1);
-        mbar_wait(&p_full[g], par);
-        tc_fence_after();
-        if (g == 0) at_stamp(p, j >> 1, 10);
-        issue_pv(g, sv, j > 0);
+                       umma_smem_desc_sw128(sb + k * 2048, 1024, 0), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
         umma_commit(&pv_done[g]);
         umma_commit(&v_empty[sv]);
       }
