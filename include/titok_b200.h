@@ -128,8 +128,8 @@ int ttk_gemm_resid_norm256(const void* A, int64_t lda, const void* W, int64_t ld
 /* ---------------------------------------------------------------------------------------------
  * Attention: flash_attn_varlen_func(...) * sigmoid(gate) (transformer.py:100-103).
  * qkv is the output of ttk_gemm_qkv_rope. work: device array of n_work 48-byte records
- * {q_row0[2], q_valid[2], q_head[2], kv_head, kv_row0, kv_len, kmax2, leader, pad} (int32) built by the host planner
- * from cu_seqlens (blocks.py:81-83); leader = index of the first record of the same (clip, kv head); kmax2 is SCRATCH
+ * {q_row0[2], q_valid[2], q_head[2], kv_head, kv_row0, kv_len, kmax2, leader, kmax2b} (int32) built by the host planner
+ * from cu_seqlens (blocks.py:81-83); leader = index of the first record of the same (clip, kv head); kmax2 / kmax2b are SCRATCH
  * of the library (the call writes max_j |k_j|^2 of that clip / kv head into the leader records: the work list must be
  * writable device memory, and concurrent calls on different streams need their own copy). out [M, width].
  * Enqueues two kernels: the key-norm bound, then the attention kernel proper.

@@ -23,9 +23,10 @@ struct AttnWork {
   int kv_head;
   int kv_row0;  // first packed row of the clip
   int kv_len;   // rows in the clip
-  int kmax2;    // scratch, written by attn_kmax_kernel into the LEADER record of a (clip, kv head): float bits of max_j |k_j|^2
+  int kmax2;    // scratch, written by attn_kmax_kernel into the LEADER record of a (clip, kv head): float bits of
+                //   max_j |k_j|^2 over the first half of the clip's keys ...
   int leader;   // index of that leader record (filled in by the planner)
-  int pad;
+  int kmax2b;   // ... and over the second half (two single-writer slots: two CTAs share the work, no atomics)
 };
 static_assert(sizeof(AttnWork) == 48, "AttnWork is mirrored in titok_video_b200/plan.py");
 
@@ -379,7 +380,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     bool fast;
     {
       // (issued ahead of the wait for Q: the L2 latency of this load runs under the arrival of the Q tile)
-      const float k2 = __int_as_float(ld_global_s32(&p.work[wp->leader].kmax2));
+      const AttnWork* lead = p.work + wp->leader;
+      const float k2 = fmaxf(__int_as_float(ld_global_s32(&lead->kmax2)), __int_as_float(ld_global_s32(&lead->kmax2b)));
       mbar_wait(q_full, 0);  // Q has landed in shared memory (async proxy -> mbarrier -> generic reads)
       float q2 = 0.f;
 #pragma unroll
@@ -681,8 +683,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 // max_j |k_j|^2 over the keys of one (clip, kv head), for the score bound of attn_fwd_kernel. A small persistent grid walks
 // the work list; only the LEADER record of each (clip, kv head) -- the one whose own index the planner stored in `leader` --
-// causes work, and its CTA keeps the result (float bits) in the record's `kmax2` field (single writer: no atomics, nothing
-// to reset between launches). 8 lanes per key row (16 bytes each), 64 rows per pass. The maximum does not depend on the
+// causes work: two CTAs take one half of the clip's keys each and keep their results (float bits) in the record's `kmax2`
+// / `kmax2b` fields (single writers: no atomics, nothing to reset between launches). 8 lanes per key row (16 bytes each), 64 rows per pass. The maximum does not depend on the
 // order of the rows: results are reproducible.
 constexpr int AT_KMAX_THREADS = 512;
 __global__ void __launch_bounds__(AT_KMAX_THREADS, 2)
@@ -690,7 +692,8 @@ attn_kmax_kernel(AttnWork* work, int n_work, const __nv_bfloat16* kbase, int64_t
   __shared__ float red[AT_KMAX_THREADS / 32];
   const int sub_row = (threadIdx.x & 31) >> 3;
   bool waited = false;
-  for (int rec = blockIdx.x; rec < n_work; rec += gridDim.x) {
+  for (int item = blockIdx.x; item < 2 * n_work; item += gridDim.x) {
+    const int rec = item >> 1, half = item & 1;
     AttnWork* w = work + rec;
     // (the work list is plan metadata, written long before the predecessor kernel: reading it ahead of pdl_wait is safe)
     if (w->q_valid[0] <= 0 || w->leader != rec) continue;  // (CTA-uniform)
@@ -698,8 +701,11 @@ attn_kmax_kernel(AttnWork* work, int n_work, const __nv_bfloat16* kbase, int64_t
       pdl_wait();  // the keys are the predecessor's output
       waited = true;
     }
-    const int kv_len = w->kv_len;
-    const __nv_bfloat16* kp = kbase + static_cast<int64_t>(w->kv_row0) * ld + w->kv_head * AT_D + (threadIdx.x & 7) * 8;
+    // this CTA's half of the clip's keys (the first half is rounded up to whole warps' rows)
+    const int len = w->kv_len, split = ((len + 1) / 2 + 3) & ~3;
+    const int row_begin = half ? split : 0;
+    const int kv_len = (half ? len : (split < len ? split : len)) - row_begin;  // rows of this half (<= 0: nothing to do)
+    const __nv_bfloat16* kp = kbase + static_cast<int64_t>(w->kv_row0 + row_begin) * ld + w->kv_head * AT_D + (threadIdx.x & 7) * 8;
     float mx = 0.f;
     constexpr int ROWS_PER_PASS = AT_KMAX_THREADS / 8, BATCH = 8;
     for (int base = (threadIdx.x >> 5) * 4; base < kv_len; base += BATCH * ROWS_PER_PASS) {  // (warp-uniform trip count)
@@ -734,7 +740,7 @@ attn_kmax_kernel(AttnWork* work, int n_work, const __nv_bfloat16* kbase, int64_t
     if (threadIdx.x < 32) {
       mx = threadIdx.x < AT_KMAX_THREADS / 32 ? red[threadIdx.x] : 0.f;
       for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      if (threadIdx.x == 0) w->kmax2 = __float_as_int(mx);
+      if (threadIdx.x == 0) (half ? w->kmax2b : w->kmax2) = __float_as_int(mx);
     }
   }
   // (a CTA that found no leader never waits: harmless, some other CTA of the grid did -- every valid record has a leader)
@@ -777,7 +783,7 @@ static int attn_fwd_launch(const void* qkv, int64_t ld, int M, int width, int gq
   // caller's device buffer; its `kmax2` fields are this library's scratch)
   {
     const int cap = 2 * num_sms();
-    if (int e = cuda_status(launch_pdl(attn_kmax_kernel, dim3(n_work < cap ? n_work : cap), dim3(AT_KMAX_THREADS), 0, stream,
+    if (int e = cuda_status(launch_pdl(attn_kmax_kernel, dim3(2 * n_work < cap ? 2 * n_work : cap), dim3(AT_KMAX_THREADS), 0, stream,
                                        const_cast<AttnWork*>(p.work), n_work, base + 2 * width, ld)))
       return e;
   }

@@ -123,11 +123,11 @@ def rope_table_from_int_ids(ids: np.ndarray, inv_freqs: np.ndarray) -> np.ndarra
 
 
 def attn_work_list(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: int, hkv: int) -> np.ndarray:
-    """int32 [n, 12] records {q_row0[2], q_valid[2], q_head[2], kv_head, kv_row0, kv_len, kmax2, leader, pad}
+    """int32 [n, 12] records {q_row0[2], q_valid[2], q_head[2], kv_head, kv_row0, kv_len, kmax2, leader, kmax2b}
     (csrc/attn.cu). Two query tiles per record share one kv head: two heads of the same group when the group size is
     even, otherwise two consecutive row tiles of one head. Longest sequences first (LPT) to shorten the tail.
     `leader` = index of the first record of the same (clip, kv head): the kernel library keeps that pair's score bound
-    in the leader's `kmax2` field (device-side scratch, zero here)."""
+    in the leader's `kmax2` / `kmax2b` fields (device-side scratch, zero here)."""
     ratio = hq // hkv
     if ratio % 2 == 0 and len(seq_starts):
         # vectorised: one record per (clip, row tile, pair of query heads of one kv group)
