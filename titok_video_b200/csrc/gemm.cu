@@ -32,6 +32,8 @@ __host__ __device__ constexpr int epi_warps(int epi, int bn = 256) {
 }
 constexpr int BOX_BYTES = 32 * 128;  // one [32 rows x 64 bf16] staging box
 
+constexpr int WS_MAX_N = 12;  // n blocks a weight-stationary launch may have (K <= 256 shapes: N <= 3072)
+
 struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, num_k_blocks;
@@ -53,6 +55,8 @@ struct GemmParams {
   float alpha;
   int mode;  // 0: x + y ; 1: RMSNorm(alpha*x + y)*w_post
   long long* trace;  // optional [gridDim][64] clock64 stamps (ttk_debug_set_trace), null in production
+  // weight-stationary kernels: CTAs [ws_begin[n], ws_begin[n+1]) share n block n (sized by the block's share of the work)
+  int ws_begin[WS_MAX_N + 1];
 };
 
 // development aid: per-CTA timeline of the three pipelines (slot = 1 + 8 * local tile + event)
@@ -85,15 +89,18 @@ struct GemmSmem {
 };
 
 // Which tiles a CTA walks. Streaming kernels: tile = blockIdx.x + i * gridDim.x over the (m, n) grid. Weight-stationary
-// kernels: n block = blockIdx.x % num_n_tiles for the CTA's lifetime, m blocks strided over the CTAs of that n block.
+// kernels: one n block for the CTA's lifetime (CTAs [ws_begin[n], ws_begin[n+1]) own n block n: a partly filled last block
+// -- GEGLU: inner = 704 = 5.5 blocks of 128 -- gets fewer CTAs), m blocks strided over the CTAs of that n block.
 template <bool WS>
 struct TileWalk {
   int m_blk, n_blk, step, num_m, num_n, tile;
-  __device__ __forceinline__ TileWalk(int num_m_tiles, int num_n_tiles) : num_m(num_m_tiles), num_n(num_n_tiles) {
+  __device__ __forceinline__ TileWalk(int num_m_tiles, int num_n_tiles, const int* ws_begin)
+      : num_m(num_m_tiles), num_n(num_n_tiles) {
     if (WS) {
-      n_blk = blockIdx.x % num_n;
-      m_blk = blockIdx.x / num_n;
-      step = (gridDim.x - n_blk + num_n - 1) / num_n;  // CTAs that share this n block
+      n_blk = 0;
+      while (n_blk + 1 < num_n && static_cast<int>(blockIdx.x) >= ws_begin[n_blk + 1]) ++n_blk;
+      m_blk = blockIdx.x - ws_begin[n_blk];
+      step = ws_begin[n_blk + 1] - ws_begin[n_blk];  // CTAs that share this n block
     } else {
       tile = blockIdx.x;
       step = gridDim.x;
@@ -243,7 +250,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      TileWalk<WS> tw(p.num_m_tiles, p.num_n_tiles);
+      TileWalk<WS> tw(p.num_m_tiles, p.num_n_tiles, p.ws_begin);
       if constexpr (WS) {
         // the CTA's weight tile: all k blocks of its n block, once
         if (tw.valid()) {
@@ -293,6 +300,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // residual tile of this M block. First tile: right behind the first operand stage (nothing to wait for).
             // Later tiles: behind the LAST operand stage, because the load has to wait until the previous tile's
             // epilogue has stored its rows and must not hold back the operands that let this tile's MMAs overlap it.
+            // (the load of a later tile is issued up to a whole epilogue after this point: an L2 prefetch four k blocks
+            // ahead takes the HBM latency out of the chain residual load -> epilogue -> store that paces the kernel;
+            // K = 256: 57.8 -> 54.6 us per launch at 64 clips. Prefetching earlier than that at K = 704 cost 1.5 %.)
+            if (it != 0 && kb == (p.num_k_blocks > 4 ? p.num_k_blocks - 4 : 0)) {
+#pragma unroll
+              for (int b = 0; b < 4; ++b) tma_prefetch_l2_2d(&tmR, b * 64, m_blk * BM);
+            }
             if (kb == (it == 0 ? 0 : p.num_k_blocks - 1)) {
               mbar_wait(resid_empty, (it & 1) ^ 1);
               mbar_arrive_expect_tx(resid_full, BM * 256 * 2);
@@ -313,7 +327,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int as = 0;
       uint32_t aphase = 0;
       int itm = 0;
-      TileWalk<WS> tw(p.num_m_tiles, p.num_n_tiles);
+      TileWalk<WS> tw(p.num_m_tiles, p.num_n_tiles, p.ws_begin);
       if constexpr (WS) {
         if (tw.valid()) mbar_wait(res_full, 0);
       }
@@ -369,7 +383,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int as = 0;
     uint32_t aphase = 0;
     uint32_t it = 0;
-    for (TileWalk<WS> tw(p.num_m_tiles, p.num_n_tiles); tw.valid(); tw.next(), ++it) {
+    for (TileWalk<WS> tw(p.num_m_tiles, p.num_n_tiles, p.ws_begin); tw.valid(); tw.next(), ++it) {
       const int m_blk = tw.m_blk;
       const int n_blk = tw.n_blk;
       const int row0 = m_blk * BM + quarter * 32;  // first row of this warp's 32-row slice
@@ -682,6 +696,10 @@ struct GemmIo {
   int64_t ldr = 0;
 };
 
+#ifndef GEGLU_TAIL_BASE
+#define GEGLU_TAIL_BASE 0.6  // share of a tile's cost that does not shrink with its valid columns (GEGLU, 64 clips: 0.0 122 us, 0.3 94.7, 0.6 88.9; equal shares 91.6)
+#endif
+
 template <int BN, int EPI, bool B_MN, bool WS = false>
 static int launch_gemm(const GemmIo& io, GemmParams& p, cudaStream_t stream) {
   using S = GemmSmem<BN, EPI, WS>;
@@ -723,6 +741,30 @@ static int launch_gemm(const GemmIo& io, GemmParams& p, cudaStream_t stream) {
   if (int e = set_smem_attr_once(once, reinterpret_cast<const void*>(kern), S::TOTAL)) return e;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  if (WS) {
+    // CTAs per n block in proportion to the block's work. A partly valid last block (GEGLU: columns past `inner`) keeps the
+    // MMA and the barrier traffic of a full tile but only part of the epilogue: weight = GEGLU_TAIL_BASE + the rest by columns.
+    if (p.num_n_tiles > WS_MAX_N || grid < p.num_n_tiles) return TTK_ERR_BAD_SHAPE;
+    const int bw = (EPI == EPI_GEGLU) ? BN / 2 : BN, cols = (EPI == EPI_GEGLU) ? p.inner : p.N;
+    double wt[WS_MAX_N], tot = 0;
+    for (int n = 0; n < p.num_n_tiles; ++n) {
+      const int valid = cols - n * bw < bw ? cols - n * bw : bw;
+      wt[n] = GEGLU_TAIL_BASE + (1.0 - GEGLU_TAIL_BASE) * valid / bw;
+      tot += wt[n];
+    }
+    int used = 0;
+    double acc = 0;
+    p.ws_begin[0] = 0;
+    for (int n = 0; n < p.num_n_tiles; ++n) {
+      acc += wt[n];
+      int end = static_cast<int>(acc / tot * grid + 0.5);
+      const int left = p.num_n_tiles - 1 - n;
+      if (end < used + 1) end = used + 1;
+      if (end > grid - left) end = grid - left;
+      p.ws_begin[n + 1] = used = end;
+    }
+    p.ws_begin[p.num_n_tiles] = grid;
+  }
   return cuda_status(launch_pdl(kern, dim3(grid), dim3(128 + 32 * epi_warps(EPI, BN)), S::TOTAL, stream, tmA, tmB, tmO, tmO2, tmR, p));
 }
 
