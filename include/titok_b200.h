@@ -110,9 +110,10 @@ int ttk_debug_set_trace(void* buf);
 
 /* Attn.to_qkv + split + apply_rotary_emb(q), (k) (transformer.py:85-98, rope.py:19-27).
  * rope: fp32 [M,60] (cos,sin) of the 30 rotated complex lanes per token (RoPE.forward, rope.py:57-71).
- * out [M, 2*width+2*gqa] = [rope(q) | gate | rope(k) | v]. */
+ * out [M, 2*width+2*gqa] = [rope(q) | gate | rope(k) | v]. k_norm2 (optional, fp32 [gqa/64][M]): |k|^2 of every row and
+ * kv head, a by-product of the epilogue that ttk_attn_varlen_fwd turns into its score bound. */
 int ttk_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int K, int width, int gqa,
-                      const float* rope, void* out, int64_t ldo, ttk_stream_t stream);
+                      const float* rope, void* out, int64_t ldo, float* k_norm2, ttk_stream_t stream);
 
 /* GEGLU.w12 + chunk + gelu(gate)*x (transformer.py:47-52). W12 [2*inner, K]; out [M, inner]. */
 int ttk_gemm_geglu(const void* A, int64_t lda, const void* W12, int64_t ldw, int M, int inner, int K, void* out,
@@ -132,10 +133,11 @@ int ttk_gemm_resid_norm256(const void* A, int64_t lda, const void* W, int64_t ld
  * from cu_seqlens (blocks.py:81-83); leader = index of the first record of the same (clip, kv head); kmax2 / kmax2b are SCRATCH
  * of the library (the call writes max_j |k_j|^2 of that clip / kv head into the leader records: the work list must be
  * writable device memory, and concurrent calls on different streams need their own copy). out [M, width].
- * Enqueues two kernels: the key-norm bound, then the attention kernel proper.
+ * k_norm2 (optional): the by-product of ttk_gemm_qkv_rope; with it the call enqueues ONE kernel and does not touch the
+ * work list. Without it, it enqueues two kernels: the key-norm bound (reads K again), then the attention kernel proper.
  * ------------------------------------------------------------------------------------------- */
 int ttk_attn_varlen_fwd(const void* qkv, int64_t ld, int M, int width, int gqa, const void* work, int n_work,
-                        float softmax_scale, void* out, int64_t ldo, ttk_stream_t stream);
+                        float softmax_scale, void* out, int64_t ldo, const float* k_norm2, ttk_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Row kernels (width in {256,512,768,1024}; norm weights fp32 [width]; mask_token fp32 [1]).
@@ -223,7 +225,7 @@ int ttk_unpatchify(const void* proj, int64_t ldp, const int32_t* patch_row, cons
 /* ttk_attn_varlen_fwd that also saves what the backward needs: o_save [M, ldo] = attention output before the gate,
  * lse fp32 [width/64][M] = log2-domain log-sum-exp of the scaled scores. */
 int ttk_attn_varlen_fwd_train(const void* qkv, int64_t ld, int M, int width, int gqa, const void* work, int n_work,
-                              float softmax_scale, void* out, int64_t ldo, void* o_save, float* lse,
+                              float softmax_scale, void* out, int64_t ldo, void* o_save, float* lse, const float* k_norm2,
                               ttk_stream_t stream);
 
 /* Backward of `attn * sigmoid(gate)` (transformer.py:101-103) + the row sums flash-attn's backward needs:
@@ -305,6 +307,7 @@ typedef struct ttk_layers_desc {
   const void* dkv_work;   /* ttk_attn_bwd_dkv work list (backward only) */
   const void* dq_work;    /* ttk_attn_bwd_dq work list (backward only) */
   const int64_t* weights; /* host */
+  float* k_norm2;         /* scratch fp32 [gqa/64][M]: key norms from the qkv GEMM to the attention kernel (may be null) */
 } ttk_layers_desc;
 
 /* Inference: x, xn [M,width] updated in place; qkv [M,2w+2g], att [M,w], h [M,inner] scratch; y [M,w] scratch selects the

@@ -14,7 +14,10 @@ qkv = (torch.randn(M, 2 * w + 2 * gqa, device=dev) * 1.0).to(torch.bfloat16)
 out = torch.empty(M, w, device=dev, dtype=torch.bfloat16)
 work = torch.from_numpy(np.ascontiguousarray(attn_work_list([i * s for i in range(B)], [s] * B, 4, 2))).to(dev)
 st = _stream()
-run = lambda: _lib.call("ttk_attn_varlen_fwd", _ptr(qkv), qkv.stride(0), M, w, gqa, _ptr(work), work.shape[0], 0.125, _ptr(out), w, st)
+from titok_video_b200.engine import _vp
+kn = (qkv[:, 2 * w:2 * w + gqa].float() ** 2).reshape(M, gqa // 64, 64).sum(-1).t().contiguous()  # what ttk_gemm_qkv_rope leaves behind
+kn_ptr = _vp(0) if "--no-knorm" in sys.argv else _ptr(kn)
+run = lambda: _lib.call("ttk_attn_varlen_fwd", _ptr(qkv), qkv.stride(0), M, w, gqa, _ptr(work), work.shape[0], 0.125, _ptr(out), w, kn_ptr, st)
 for _ in range(3):
     run()
 torch.cuda.synchronize()

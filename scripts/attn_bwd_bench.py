@@ -18,7 +18,7 @@ def main(B=16, s=1892, hq=4, hkv=2, reps=10):
     lse = torch.empty(hq, M, device=dev); delta = torch.empty(hq, M, device=dev); dqkv = torch.empty_like(qkv)
     rope = torch.zeros(M, 60, device=dev); rope[:, 0::2] = 1
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    def fwd(): _lib.call("ttk_attn_varlen_fwd_train", P(qkv), ld, M, w, g, P(work), work.shape[0], 0.125, P(out), w, P(o), P(lse), st)
+    def fwd(): _lib.call("ttk_attn_varlen_fwd_train", P(qkv), ld, M, w, g, P(work), work.shape[0], 0.125, P(out), w, P(o), P(lse), ctypes.c_void_p(0), st)
     def prep(): _lib.call("ttk_attn_bwd_prep", P(dOut), w, P(o), w, P(qkv), ld, M, w, P(dO), w, P(dqkv), ld, P(delta), st)
     def bw(name, k): _lib.call(name, P(qkv), ld, P(dO), w, M, w, g, P(k), k.shape[0], P(lse), P(delta), P(rope), 0.125, P(dqkv), ld, st)
     fl = B * 4.0 * s * s * w  # forward FLOPs

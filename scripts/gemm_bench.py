@@ -20,10 +20,11 @@ Wo = (torch.randn(w, w, device=dev) * 0.05).to(bf)
 rope = torch.rand(M, 60, device=dev)
 qkv = torch.empty(M, 2 * w + 2 * gqa, device=dev, dtype=bf)
 hout = torch.empty(M, inner, device=dev, dtype=bf)
+knorm = torch.empty(gqa // 64, M, device=dev, dtype=torch.float32)
 wn = torch.ones(w, device=dev)
 st = _stream()
 runs = {
-    "qkv": (lambda: _lib.call("ttk_gemm_qkv_rope", _ptr(A), w, _ptr(Wqkv), w, M, w, w, gqa, _ptr(rope), _ptr(qkv), qkv.stride(0), st),
+    "qkv": (lambda: _lib.call("ttk_gemm_qkv_rope", _ptr(A), w, _ptr(Wqkv), w, M, w, w, gqa, _ptr(rope), _ptr(qkv), qkv.stride(0), _ptr(knorm), st),
             2.0 * M * w * (2 * w + 2 * gqa), M * (w + 2 * w + 2 * gqa) * 2),
     "geglu": (lambda: _lib.call("ttk_gemm_geglu", _ptr(A), w, _ptr(W12), w, M, inner, w, _ptr(hout), inner, st),
               2.0 * M * w * 2 * inner, M * (w + inner) * 2),

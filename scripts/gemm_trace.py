@@ -29,7 +29,7 @@ st = _stream()
 
 def run(name):
     if name == "qkv":
-        _lib.call("ttk_gemm_qkv_rope", _ptr(A), w, _ptr(Wqkv), w, M, w, w, gqa, _ptr(rope), _ptr(qkv), qkv.stride(0), st)
+        _lib.call("ttk_gemm_qkv_rope", _ptr(A), w, _ptr(Wqkv), w, M, w, w, gqa, _ptr(rope), _ptr(qkv), qkv.stride(0), _vp(0), st)
     elif name == "geglu":
         _lib.call("ttk_gemm_geglu", _ptr(A), w, _ptr(W12), w, M, inner, w, _ptr(hout), inner, st)
     elif name == "resid256":

@@ -77,6 +77,6 @@ def test_sequencers_reject_null_arguments_without_a_gpu():
     assert _lib.fn("ttk_layers_fwd_train")(z, z, z, z, 0, z, z, z) == -1
     assert _lib.fn("ttk_layers_bwd")(z, z, z, z, 0, z, z, z, z, z, z, z, z, z) == -1
     d = _lib.LayersDesc()
-    assert ctypes.sizeof(d) == 8 * 4 + 2 * 4 + 5 * 8  # layout of ttk_layers_desc in include/titok_b200.h
+    assert ctypes.sizeof(d) == 8 * 4 + 2 * 4 + 6 * 8  # layout of ttk_layers_desc in include/titok_b200.h
     with pytest.raises(_lib.TitokB200Error):
         _lib.call("ttk_layers_fwd", ctypes.byref(d), z, z, z, z, z, z, z)

@@ -143,7 +143,7 @@ def test_attn_backward(seq_lens, hq, hkv):
     o_save = torch.empty((M, width), dtype=BF, device=DEV)
     lse = torch.full((hq, M), float("nan"), dtype=torch.float32, device=DEV)
     lib().call("ttk_attn_varlen_fwd_train", P(qkv), ld, M, width, gqa, P(work), work.shape[0], 0.125, P(out), width,
-               P(o_save), P(lse), ST())
+               P(o_save), P(lse), P(None), ST())
     torch.cuda.synchronize()
     assert rel_err(out, out_ref) < 2e-2
     assert torch.isfinite(lse).all()

@@ -144,11 +144,24 @@ def test_gemm_qkv_rope(M, width, gqa):
     k = O.apply_rope(k.reshape(M, -1, 64), cos, sin).reshape(M, -1)
     ref = torch.cat([q, gate, k, v], dim=-1)
     out = torch.empty((M, 2 * width + 2 * gqa), dtype=BF, device=DEV)
+    knorm = torch.full((gqa // 64, M), float("nan"), dtype=torch.float32, device=DEV)
     lib().call("ttk_gemm_qkv_rope", G(A), K, G(W), K, M, K, width, gqa, G(rope), P(out),
-               out.stride(0), ST())
+               out.stride(0), P(knorm), ST())
     torch.cuda.synchronize()
     # the rotation is done on bf16-rounded GEMM outputs: a 1-ulp difference of an input moves the output by ~1 ulp of it
     close_bf16(out, ref, ulps=3.0, atol=2.0 ** -8 * ref.abs().max().item() * 0.5, what="qkv+rope")
+    # by-product: |k|^2 per row and kv head of the (pre-rotation, bf16) keys -- the rotation preserves the norm up to its
+    # own rounding, which is why the attention kernel's bound carries a 2 % margin
+    k_dev = out.float().cpu()[:, 2 * width:2 * width + gqa].reshape(M, gqa // 64, 64)
+    n2 = (k_dev ** 2).sum(-1).t()
+    got = knorm.cpu()
+    assert torch.isfinite(got).all()
+    assert ((got - n2).abs() <= 1.5e-2 * n2 + 1e-6).all(), "key norms"
+    # without the by-product the call is unchanged
+    out2 = torch.empty_like(out)
+    lib().call("ttk_gemm_qkv_rope", G(A), K, G(W), K, M, K, width, gqa, G(rope), P(out2), out2.stride(0), P(None), ST())
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out)
 
 
 @pytest.mark.parametrize("M,inner,K", [(300, 704, 256), (1000, 1376, 512), (64, 704, 256),
@@ -222,10 +235,18 @@ def test_attn_varlen(seq_lens, hq, hkv, qk_scale):
         ref[s0:s0 + sl] = O.r(o * O.r(torch.sigmoid(gate[s0:s0 + sl])))
     out = torch.full((M, width), float("nan"), dtype=BF, device=DEV)
     qd = qkv.to(DEV)
+    # with the key norms that ttk_gemm_qkv_rope leaves behind (one launch) ...
+    knorm = (k ** 2).reshape(M, hkv, 64).sum(-1).t().contiguous().to(DEV)
     lib().call("ttk_attn_varlen_fwd", P(qd), qd.stride(0), M, width, gqa, G(work), work.shape[0], 0.125, P(out),
-               width, ST())
+               width, P(knorm), ST())
+    # ... and without them (the library derives the bound from K with its own pre-kernel): same loop, same reference
+    # up to the rounding of s c - ref
+    out_nk = torch.full((M, width), float("nan"), dtype=BF, device=DEV)
+    lib().call("ttk_attn_varlen_fwd", P(qd), qd.stride(0), M, width, gqa, G(work), work.shape[0], 0.125, P(out_nk),
+               width, P(None), ST())
     torch.cuda.synchronize()
     o = out.float().cpu()
+    assert (out_nk.float().cpu() - o).abs().max().item() <= 2.0 ** -7 * o.abs().max().item()
     assert torch.isfinite(o).all()
     d = (o - ref).abs()
     # P is rounded to bf16 before P.V (as in flash-attention): errors ~2^-9 relative to the value scale

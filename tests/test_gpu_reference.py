@@ -122,7 +122,7 @@ def test_kernels_match_flash_attn_and_triton_rmsnorm(tmp_path):
         qkv = torch.cat([q, torch.full((M, 256), 30.0, dtype=torch.bfloat16), kk, v], dim=1).contiguous().cuda()
         o_dev = torch.full((M, 256), float("nan"), dtype=torch.bfloat16, device="cuda")
         _lib.call("ttk_attn_varlen_fwd", engine._ptr(qkv), qkv.stride(0), M, 256, 128, engine._ptr(work), work.shape[0], 0.125,
-                  engine._ptr(o_dev), 256, engine._stream())
+                  engine._ptr(o_dev), 256, engine._vp(0), engine._stream())
         torch.cuda.synchronize()
         o = o_dev.float().cpu()
         o_ref = from_bits(k[f"{tag}_o"]).reshape(M, 256).float()

@@ -51,10 +51,10 @@ SIGNATURES = {
     "ttk_vq_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _f, _f, _vp, _vp, _i64, _vp, _i64, _vp],
     "ttk_gemm_bf16": [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _i64, _vp, _i, _vp],
     "ttk_debug_set_trace": [_vp],
-    "ttk_gemm_qkv_rope": [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _vp],
+    "ttk_gemm_qkv_rope": [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _vp, _vp],
     "ttk_gemm_geglu": [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i64, _vp],
     "ttk_gemm_resid_norm256": [_vp, _i64, _vp, _i64, _i, _i, _vp, _i64, _i, _f, _vp, _vp, _vp, _vp, _i64, _vp],
-    "ttk_attn_varlen_fwd": [_vp, _i64, _i, _i, _i, _vp, _i, _f, _vp, _i64, _vp],
+    "ttk_attn_varlen_fwd": [_vp, _i64, _i, _i, _i, _vp, _i, _f, _vp, _i64, _vp, _vp],
     "ttk_rmsnorm_fwd": [_vp, _i64, _vp, _vp, _i64, _i, _i, _vp],
     "ttk_resid_norm": [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i64, _vp],
     "ttk_enc_embed": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp],
@@ -69,7 +69,7 @@ SIGNATURES = {
     "ttk_patchify_u8": [_vp, _vp, _i, _i, _i, _i, _vp, _i64, _i64, _vp],
     "ttk_unpatchify": [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp, _i64, _vp],
     # ---- training path (backward kernels)
-    "ttk_attn_varlen_fwd_train": [_vp, _i64, _i, _i, _i, _vp, _i, _f, _vp, _i64, _vp, _vp, _vp],
+    "ttk_attn_varlen_fwd_train": [_vp, _i64, _i, _i, _i, _vp, _i, _f, _vp, _i64, _vp, _vp, _vp, _vp],
     "ttk_attn_bwd_prep": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp],
     "ttk_attn_bwd_dkv": [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _f, _vp, _i64, _vp],
     "ttk_attn_bwd_dq": [_vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _f, _vp, _i64, _vp],
@@ -125,7 +125,7 @@ class LayersDesc(ctypes.Structure):
                 ("n_attn_work", c_int32), ("n_dkv_work", c_int32), ("n_dq_work", c_int32),
                 ("alpha", c_float), ("softmax_scale", c_float),
                 ("rope", c_void_p), ("attn_work", c_void_p), ("dkv_work", c_void_p), ("dq_work", c_void_p),
-                ("weights", c_void_p)]
+                ("weights", c_void_p), ("k_norm2", c_void_p)]
 
 
 def profiling() -> bool:
@@ -135,7 +135,7 @@ def profiling() -> bool:
 
 def call(name: str, *args, launches: int = 1) -> None:
     """Invoke an int-returning kernel entry point and raise on a non-zero status. `launches`: kernels the entry point
-    enqueues (1 for most kernel entry points, 2 for the attention forward, more for the native sequencers)."""
+    enqueues (1 for the kernel entry points -- 2 for the attention forward without key norms --, more for the native sequencers)."""
     global LAUNCHES
     LAUNCHES += launches
     if _PROFILER is None:

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import NATIVE_SEQ, DevicePlan, cached_named_params, PreparedStack, _ptr, _stream, _vp, layers_desc, patch_feature_perm_on, prepared
+from .engine import NATIVE_SEQ, DevicePlan, cached_named_params, PreparedStack, _ptr, _stream, _vp, key_norms, layers_desc, patch_feature_perm_on, prepared
 
 bf16 = torch.bfloat16
 
@@ -140,18 +140,19 @@ def _layers_train(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torc
     if NATIVE_SEQ and not _lib.profiling():
         d = layers_desc(m, W, dp, M)
         _lib.call("ttk_layers_fwd_train", ctypes.byref(d), _ptr(x), _ptr(xn), _ptr(slab), per_layer, _vp(foffs.ctypes.data),
-                  _ptr(lse_all), st, launches=9 * L)
+                  _ptr(lse_all), st, launches=8 * L)
         return lt.view(L - 1, F_XN), lt.view(L - 1, F_XNN)
     work = dp.attn_work(hq, hkv)
+    knorm = key_norms(dp, M, hkv)
     scale = 1.0 / math.sqrt(64.0)
     T = W.t
     for i in range(L):
         mode = 0 if i == 0 else 1
         qkv, att, o, lse = lt.view(i, F_QKV), lt.view(i, F_ATT), lt.view(i, F_O), lse_all[i]
         _lib.call("ttk_gemm_qkv_rope", _ptr(xn), xn.stride(0), _ptr(T[f"to_qkv{i}"]), w, M, w, w, gqa, _ptr(dp.rope),
-                  _ptr(qkv), qkv.stride(0), st)
+                  _ptr(qkv), qkv.stride(0), _ptr(knorm), st)
         _lib.call("ttk_attn_varlen_fwd_train", _ptr(qkv), qkv.stride(0), M, w, gqa, _ptr(work), work.shape[0], scale,
-                  _ptr(att), att.stride(0), _ptr(o), _ptr(lse), st, launches=2)  # (key-norm bound kernel + attention)
+                  _ptr(att), att.stride(0), _ptr(o), _ptr(lse), _ptr(knorm), st)
         y_a = lt.view(i, F_YA)
         _gemm(st, att, T[f"out_proj{i}"], y_a, w, w)
         x_f, xn_f = lt.view(i, F_XF), lt.view(i, F_XNF)

@@ -40,6 +40,8 @@ struct AttnParams {
   __nv_bfloat16* o_save;  // training: un-gated attention output [M, ldo] (null in inference)
   float* lse;             // training: [heads][M] log2-domain log-sum-exp of the scaled scores (null in inference)
   int M;
+  const float* knorm2;  // optional [gqa / 64][M]: |k|^2 per row and kv head (written by the qkv GEMM epilogue); null: the
+                        //   bound comes from attn_kmax_kernel through the leader work records
   long long* trace;  // development aid (ttk_debug_set_trace): [CTA][64] clock64 stamps of kv iterations 3..7
 };
 
@@ -379,9 +381,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float ref_l2;  // reference of the exponentials in log2 units (bounded-score loop)
     bool fast;
     {
-      // (issued ahead of the wait for Q: the L2 latency of this load runs under the arrival of the Q tile)
-      const AttnWork* lead = p.work + wp->leader;
-      const float k2 = fmaxf(__int_as_float(ld_global_s32(&lead->kmax2)), __int_as_float(ld_global_s32(&lead->kmax2b)));
+      // max_j |k_j|^2 (issued ahead of the wait for Q: the L2 latency of these loads runs under the arrival of the Q tile)
+      float k2;
+      if (p.knorm2) {
+        // the qkv GEMM left |k|^2 of every row: the 256 softmax threads stride over the clip's rows
+        const float* kn = p.knorm2 + static_cast<int64_t>(kv_head) * p.M + kv_row0;
+        float mx = 0.f;
+#pragma unroll 4
+        for (int i = threadIdx.x - 128; i < kv_len; i += 256) mx = fmaxf(mx, __int_as_float(ld_global_s32(reinterpret_cast<const int*>(kn + i))));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) l_sh[warp - 4] = mx;
+        nbar_sync256<AT_BAR_FIN>();
+        const float4 m0 = *reinterpret_cast<const float4*>(l_sh), m1 = *reinterpret_cast<const float4*>(l_sh + 4);
+        k2 = fmaxf(fmaxf(fmaxf(m0.x, m0.y), fmaxf(m0.z, m0.w)), fmaxf(fmaxf(m1.x, m1.y), fmaxf(m1.z, m1.w)));
+        // (l_sh is written again in the epilogue, behind the vote barrier below)
+      } else {
+        const AttnWork* lead = p.work + wp->leader;
+        k2 = fmaxf(__int_as_float(ld_global_s32(&lead->kmax2)), __int_as_float(ld_global_s32(&lead->kmax2b)));
+      }
       mbar_wait(q_full, 0);  // Q has landed in shared memory (async proxy -> mbarrier -> generic reads)
       float q2 = 0.f;
 #pragma unroll
@@ -755,7 +773,8 @@ extern "C" {
 // qkv: packed [M, ld] bf16 (see header). work: device array of n_work AttnWork records (built by the
 // host planner). out: [M, ldo] bf16 = attention(q,k,v) * sigmoid(gate).
 static int attn_fwd_launch(const void* qkv, int64_t ld, int M, int width, int gqa, const void* work, int n_work,
-                           float softmax_scale, void* out, int64_t ldo, void* o_save, float* lse, cudaStream_t stream) {
+                           float softmax_scale, void* out, int64_t ldo, void* o_save, float* lse, const float* k_norm2,
+                           cudaStream_t stream) {
   if (!qkv || !work || !out) return TTK_ERR_BAD_ARG;
   if (int e = check_device_sm100()) return e;
   if (width % 64 != 0 || gqa % 64 != 0 || ld % 8 != 0 || ldo % 8 != 0) return TTK_ERR_BAD_SHAPE;
@@ -776,12 +795,13 @@ static int attn_fwd_launch(const void* qkv, int64_t ld, int M, int width, int gq
   p.o_save = static_cast<__nv_bfloat16*>(o_save);
   p.lse = lse;
   p.M = M;
+  p.knorm2 = k_norm2;
   static PerDeviceOnce once_plain, once_train;
   if (int e = set_smem_attr_once(once_plain, reinterpret_cast<const void*>(attn_fwd_kernel<false>), AT_SMEM)) return e;
   if (int e = set_smem_attr_once(once_train, reinterpret_cast<const void*>(attn_fwd_kernel<true>), AT_SMEM)) return e;
   // score bound of every (clip, kv head): written into the scratch field of the leader work records (the work list is the
   // caller's device buffer; its `kmax2` fields are this library's scratch)
-  {
+  if (!k_norm2) {
     const int cap = 2 * num_sms();
     if (int e = cuda_status(launch_pdl(attn_kmax_kernel, dim3(2 * n_work < cap ? 2 * n_work : cap), dim3(AT_KMAX_THREADS), 0, stream,
                                        const_cast<AttnWork*>(p.work), n_work, base + 2 * width, ld)))
@@ -793,17 +813,17 @@ static int attn_fwd_launch(const void* qkv, int64_t ld, int M, int width, int gq
 }
 
 int ttk_attn_varlen_fwd(const void* qkv, int64_t ld, int M, int width, int gqa, const void* work, int n_work,
-                        float softmax_scale, void* out, int64_t ldo, cudaStream_t stream) {
-  return attn_fwd_launch(qkv, ld, M, width, gqa, work, n_work, softmax_scale, out, ldo, nullptr, nullptr, stream);
+                        float softmax_scale, void* out, int64_t ldo, const float* k_norm2, cudaStream_t stream) {
+  return attn_fwd_launch(qkv, ld, M, width, gqa, work, n_work, softmax_scale, out, ldo, nullptr, nullptr, k_norm2, stream);
 }
 
 // Training forward: additionally saves what the backward kernels (attn_bwd.cu) need: o_save [M, ldo] = the attention
 // output before the gate, lse fp32 [width/64][M] = log2-domain log-sum-exp of the scaled scores.
 int ttk_attn_varlen_fwd_train(const void* qkv, int64_t ld, int M, int width, int gqa, const void* work, int n_work,
                               float softmax_scale, void* out, int64_t ldo, void* o_save, float* lse,
-                              cudaStream_t stream) {
+                              const float* k_norm2, cudaStream_t stream) {
   if (!o_save || !lse) return TTK_ERR_BAD_ARG;
-  return attn_fwd_launch(qkv, ld, M, width, gqa, work, n_work, softmax_scale, out, ldo, o_save, lse, stream);
+  return attn_fwd_launch(qkv, ld, M, width, gqa, work, n_work, softmax_scale, out, ldo, o_save, lse, k_norm2, stream);
 }
 
 }  // extern "C"

@@ -47,6 +47,7 @@ struct GemmParams {
   const float* rope;  // [M, 60] (cos,sin) pairs for the first 30 complex lanes of every head
   int width;          // q width (= gate width)
   int gqa;            // k width (= v width)
+  float* knorm2;      // optional [gqa / 64][M]: |k|^2 of every row and kv head (for the attention kernel's score bound)
   // EPI_GEGLU
   int inner;
   // EPI_RESID  (N == BN == 256)
@@ -485,6 +486,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             pk[j] = pack_bf16x2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
             pk[16 + j] = pack_bf16x2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
           }
+          if (p.knorm2 && col0 >= 2 * p.width && col0 < 2 * p.width + p.gqa) {
+            // |k|^2 of this row's head (one box == one head), from the bf16 values. (The rotation that follows preserves
+            // the norm up to its own bf16 rounding; the consumer's bound carries a 2 % margin.)
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float k0 = bf16_lo(pk[j]), k1 = bf16_hi(pk[j]);
+              ss = fmaf(k0, k0, ss);
+              ss = fmaf(k1, k1, ss);
+            }
+            if (row_ok) p.knorm2[static_cast<int64_t>((col0 - 2 * p.width) >> 6) * p.M + row] = ss;
+          }
           uint8_t* box = stg.acquire(lane);
           box_write_row(box, lane, pk);
           const bool is_rope = (col0 < p.width) || (col0 >= 2 * p.width && col0 < 2 * p.width + p.gqa);
@@ -831,7 +844,7 @@ int ttk_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M,
 
 // Attn.to_qkv + split + RoPE(q), RoPE(k): out[M, 2w+2g] = [rope(q) | gate | rope(k) | v]
 int ttk_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int K, int width, int gqa,
-                      const float* rope, void* out, int64_t ldo, cudaStream_t stream) {
+                      const float* rope, void* out, int64_t ldo, float* k_norm2, cudaStream_t stream) {
   if (!A || !W || !out || !rope) return TTK_ERR_BAD_ARG;
   if (width % 64 != 0 || gqa % 64 != 0 || ldo % 8 != 0) return TTK_ERR_BAD_SHAPE;
   if ((reinterpret_cast<uintptr_t>(rope) & 7u) != 0) return TTK_ERR_ALIGNMENT;
@@ -844,6 +857,7 @@ int ttk_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldw, in
   p.rope = rope;
   p.width = width;
   p.gqa = gqa;
+  p.knorm2 = k_norm2;
   GemmIo io{A, lda, W, ldw};
   // Weight-stationary variants measured slower here, twice: 256-wide tiles (two boxes per warp through one staging buffer
   // serialise the RoPE pass and the store) and 192-wide tiles with a warp per head box (0.78 ms vs 0.53 ms per step: four

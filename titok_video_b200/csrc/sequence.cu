@@ -40,8 +40,8 @@ int ttk_layers_fwd(const ttk_layers_desc* d, void* x, void* xn, void* qkv, void*
   for (int i = 0; i < L; ++i) {
     const int64_t* W = d->weights + (int64_t)i * W_COLS;
     const int mode = i == 0 ? 0 : 1;
-    TTK_TRY(ttk_gemm_qkv_rope(xn, w, P(W[W_QKV]), w, M, w, w, g, d->rope, qkv, ldq, st));
-    TTK_TRY(ttk_attn_varlen_fwd(qkv, ldq, M, w, g, d->attn_work, d->n_attn_work, d->softmax_scale, att, w, st));
+    TTK_TRY(ttk_gemm_qkv_rope(xn, w, P(W[W_QKV]), w, M, w, w, g, d->rope, qkv, ldq, d->k_norm2, st));
+    TTK_TRY(ttk_attn_varlen_fwd(qkv, ldq, M, w, g, d->attn_work, d->n_attn_work, d->softmax_scale, att, w, d->k_norm2, st));
     if (fused) {
       TTK_TRY(ttk_gemm_resid_norm256(att, w, P(W[W_OUT]), w, M, w, x, w, mode, d->alpha, PF(W[LN_ATTN_POST]), PF(W[LN_FFN]), x,
                                      xn, w, st));
@@ -78,9 +78,9 @@ int ttk_layers_fwd_train(const ttk_layers_desc* d, const void* x0, const void* x
     const int64_t* W = d->weights + (int64_t)i * W_COLS;
     const int mode = i == 0 ? 0 : 1;
     float* lse_i = lse + (int64_t)i * hq * M;
-    TTK_TRY(ttk_gemm_qkv_rope(xn, w, P(W[W_QKV]), w, M, w, w, g, d->rope, B(i, F_QKV), ldq, st));
+    TTK_TRY(ttk_gemm_qkv_rope(xn, w, P(W[W_QKV]), w, M, w, w, g, d->rope, B(i, F_QKV), ldq, d->k_norm2, st));
     TTK_TRY(ttk_attn_varlen_fwd_train(B(i, F_QKV), ldq, M, w, g, d->attn_work, d->n_attn_work, d->softmax_scale, B(i, F_ATT), w,
-                                      B(i, F_O), lse_i, st));
+                                      B(i, F_O), lse_i, d->k_norm2, st));
     TTK_TRY(ttk_gemm_bf16(B(i, F_ATT), w, P(W[W_OUT]), w, M, w, w, nullptr, B(i, F_YA), w, nullptr, 0, st));
     TTK_TRY(ttk_resid_norm(x, B(i, F_YA), B(i, F_XF), B(i, F_XNF), PF(W[LN_ATTN_POST]), PF(W[LN_FFN]), d->alpha, mode, M, w, w, st));
     TTK_TRY(ttk_gemm_bf16(B(i, F_XNF), w, P(W[W_12]), w, M, 2 * inner, w, nullptr, B(i, F_H12), 2 * (int64_t)inner, nullptr, 0, st));

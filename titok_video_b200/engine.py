@@ -550,6 +550,12 @@ FUSE_RESID_256 = os.environ.get("TTK_FUSE_RESID", "1") != "0"
 NATIVE_SEQ = os.environ.get("TTK_NATIVE_SEQ", "1") != "0"  # 0: enqueue the layers kernel by kernel from Python
 
 
+def key_norms(dp: DevicePlan, M: int, hkv: int) -> torch.Tensor:
+    """fp32 [kv heads, M] scratch: |k|^2 of every packed row, written by the qkv GEMM epilogue and read by the attention
+    kernel of the same layer (its score bound)."""
+    return dp.buf("knorm", (hkv, M), torch.float32)
+
+
 def layers_desc(m, W: PreparedStack, dp: DevicePlan, M: int, backward: bool = False) -> "_lib.LayersDesc":
     """ttk_layers_desc for one stack and one packed batch (the weight table and the work lists stay referenced by W / dp)."""
     hq, hkv = m.heads
@@ -559,6 +565,7 @@ def layers_desc(m, W: PreparedStack, dp: DevicePlan, M: int, backward: bool = Fa
     d.n_attn_work = work.shape[0]
     d.alpha, d.softmax_scale = float(2 * m.num_layers), 1.0 / math.sqrt(64.0)
     d.rope, d.attn_work = dp.rope.data_ptr(), work.data_ptr()
+    d.k_norm2 = key_norms(dp, M, hkv).data_ptr()
     if backward:
         wk_dkv, wk_dq = dp.attn_bwd_work(hq, hkv)
         d.n_dkv_work, d.n_dq_work = wk_dkv.shape[0], wk_dq.shape[0]
@@ -582,12 +589,13 @@ def _layers(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tens
     h = dp.buf("h", (M, inner))
     y = None if (FUSE_RESID_256 and w == 256) else dp.buf("y", (M, w))
     work = dp.attn_work(hq, hkv)
+    knorm = key_norms(dp, M, hkv)
     scale = 1.0 / math.sqrt(64.0)
     T = W.t
     if NATIVE_SEQ and not _lib.profiling():
         d = layers_desc(m, W, dp, M)
         _lib.call("ttk_layers_fwd", ctypes.byref(d), _ptr(x), _ptr(xn), _ptr(qkv), _ptr(att), _ptr(h), _ptr(y), st,
-                  launches=L * (6 if y is None else 8))
+                  launches=L * (5 if y is None else 7))
         return
 
     def out_update(a: torch.Tensor, wmat: torch.Tensor, K: int, mode: int, w_post, w_next) -> None:
@@ -603,9 +611,9 @@ def _layers(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tens
     for i in range(L):
         mode = 0 if i == 0 else 1
         _lib.call("ttk_gemm_qkv_rope", _ptr(xn), xn.stride(0), _ptr(T[f"to_qkv{i}"]), w, M, w, w, gqa, _ptr(dp.rope),
-                  _ptr(qkv), qkv.stride(0), st)
+                  _ptr(qkv), qkv.stride(0), _ptr(knorm), st)
         _lib.call("ttk_attn_varlen_fwd", _ptr(qkv), qkv.stride(0), M, w, gqa, _ptr(work), work.shape[0], scale,
-                  _ptr(att), att.stride(0), st, launches=2)  # (key-norm bound kernel + attention)
+                  _ptr(att), att.stride(0), _ptr(knorm), st)
         out_update(att, T[f"out_proj{i}"], w, mode, T.get(f"attn_post_ln{i}"), T[f"ffn_norm{i}"])
         _lib.call("ttk_gemm_geglu", _ptr(xn), xn.stride(0), _ptr(T[f"w12_{i}"]), w, M, inner, w, _ptr(h), h.stride(0),
                   st)
