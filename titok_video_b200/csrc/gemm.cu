@@ -487,15 +487,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             pk[16 + j] = pack_bf16x2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
           }
           if (p.knorm2 && col0 >= 2 * p.width && col0 < 2 * p.width + p.gqa) {
-            // |k|^2 of this row's head (one box == one head), from the bf16 values. (The rotation that follows preserves
-            // the norm up to its own bf16 rounding; the consumer's bound carries a 2 % margin.)
-            float ss = 0.f;
+            // |k|^2 of this row's head (one box == one head), from the fp32 accumulators. (The bf16 rounding and the
+            // rotation that follow move the norm by < 2^-8 relative; the consumer's bound carries a 2 % margin.)
+            float ss = 0.f, ss1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float k0 = bf16_lo(pk[j]), k1 = bf16_hi(pk[j]);
-              ss = fmaf(k0, k0, ss);
-              ss = fmaf(k1, k1, ss);
+              ss = fmaf(__uint_as_float(v0[j]), __uint_as_float(v0[j]), ss);
+              ss1 = fmaf(__uint_as_float(v1[j]), __uint_as_float(v1[j]), ss1);
             }
+            ss += ss1;
             if (row_ok) p.knorm2[static_cast<int64_t>((col0 - 2 * p.width) >> 6) * p.M + row] = ss;
           }
           uint8_t* box = stg.acquire(lane);
