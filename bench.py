@@ -1031,7 +1031,9 @@ def main():
                     "avg_launch_ms": avg_ms, "share_of_step": ksum[top][0] / tot_k,
                     "mufu_bound_tflops": 16 * 148 * 1.965e9 * 256 / 1e12,
                     "note": "head dim 64: 256 FLOP per exponential; the XU pipe's 16 ex2/clk/SM caps the kernel at 1191 TFLOP/s "
-                            "(75 % of the burst tensor peak) before any other limit"}
+                            "(75 % of the burst tensor peak; 1361 with the 12.5 % of the exponentials this kernel evaluates on the "
+                            "FMA pipes) before any other limit. One launch per call: the score bound of the bounded-score "
+                            "softmax comes from key norms that the qkv GEMM epilogue leaves behind"}
     whole = {"tflops": value * flops_clip / 1e12, "frac_of_tensor_peak": value * flops_clip / 1e12 / pk["bf16_tflops_sustained"]}
 
     vq = None
