@@ -170,7 +170,8 @@ __device__ __forceinline__ void ex2_poly_pair(uint64_t t, float& o0, float& o1) 
 // which of the 16 groups of four scores per thread take the polynomial: bit g of AT_EMU_B -> elements 4g+2, 4g+3,
 // bit g of AT_EMU_A -> elements 4g, 4g+1. Default: 8 of 64 exponentials (12.5 %) off the MUFU pipe -- the loop is
 // bound by instruction issue almost as much as by MUFU, and a polynomial pair costs ~14 issue slots against 5
-// (measured at 64 clips: 0 % 366 us, 12.5 % 355 us, 25 % 371 us, 37.5 % 379 us, 50 % 405 us per launch).
+// (measured at 64 clips, us per launch -- running-maximum loop: 0 % 366, 12.5 % 355, 25 % 371, 37.5 % 379, 50 % 405;
+// bounded-score loop: 0 % 363, 12.5 % 332, 25 % 338, 37.5 % 336).
 #ifndef AT_EMU_A
 #define AT_EMU_A 0x0000
 #endif
@@ -198,7 +199,7 @@ __device__ __forceinline__ void ex2_poly_pair(uint64_t t, float& o0, float& o1) 
 //    reference up to the rounding of s c - ref.
 //  * running-maximum loop (rows with B > AT_BOUND_MAX, i.e. logits beyond +-60 nats), described next.
 //
-// The exponential phases of the two groups are serialised by a token (named barriers): at any time at most one group
+// Running-maximum loop: the exponential phases of the two groups are serialised by a token (named barriers): at any time at most one group
 // of a CTA is on the MUFU pipe while the other one loads / reduces / stores, which keeps the pipe that bounds the loop
 // busy instead of having all warps of a scheduler hit it in phase and then leave it idle together. The token also
 // carries the per-row reference maximum (shared memory): the holder decides about the lazy rescale (only when a row
