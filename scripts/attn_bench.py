@@ -7,7 +7,7 @@ from titok_video_b200.engine import _ptr, _stream
 from titok_video_b200.plan import attn_work_list
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-s, w, gqa = 1892, 256, 128
+s, w, gqa = int(os.environ.get("ATTN_S", "1892")), 256, 128
 dev = torch.device("cuda:0")
 M = B * s
 qkv = (torch.randn(M, 2 * w + 2 * gqa, device=dev) * 1.0).to(torch.bfloat16)
