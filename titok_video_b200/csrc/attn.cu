@@ -73,9 +73,12 @@ constexpr int AT_XCH_BYTES = 4 * 128 * 4;  // per-row reference maximum, the two
 constexpr int AT_SMEM = AT_Q_BYTES + (AT_KST + AT_VST) * AT_KV_BYTES + 512 + AT_XCH_BYTES + 1024;
 constexpr int AT_THREADS = 128 + 8 * 32;
 // TMEM columns (256 per CTA)
-constexpr uint32_t AT_TM_S = 0;    // S_a [0,64)  S_b [64,128)   (even / odd kv sub-tiles)
-constexpr uint32_t AT_TM_O = 128;  // O [128,192)
-constexpr uint32_t AT_TM_P = 192;  // P_a [192,224)  P_b [224,256)   (64 keys x bf16 = 32 columns)
+// group g (even / odd kv sub-tiles): S_g [96 g, 96 g + 64), P_g [96 g + 64, 96 g + 96) (64 keys x bf16 = 32 columns): P sits
+// at the same distance behind S for both groups, so the softmax loop addresses both from one register
+constexpr uint32_t AT_TM_S = 0;
+constexpr uint32_t AT_TM_P = 64;
+constexpr uint32_t AT_TM_GROUP = 96;
+constexpr uint32_t AT_TM_O = 192;  // O [192,256)
 constexpr uint32_t AT_TM_COLS = 256;
 constexpr float AT_RESCALE_LOG2 = 8.0f;  // rescale O only when the row maximum grew by more than 2^8
 // Bounded-score path (see attn_fwd_kernel): a query row whose Cauchy-Schwarz bound B = |q| max_j|k_j| scale log2(e) on its
@@ -316,7 +319,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t sb = smem_u32(sK + st * AT_KV_BYTES);
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16_ss(tmem_base + AT_TM_S + g * AT_BN, umma_smem_desc_sw128(sa + k * 32, 1024, 0),
+          umma_bf16_ss(tmem_base + AT_TM_S + g * AT_TM_GROUP, umma_smem_desc_sw128(sa + k * 32, 1024, 0),
                        umma_smem_desc_sw128(sb + k * 32, 1024, 0), idesc_s, k != 0 ? 1u : 0u);
       };
       // Score products S(0), S(1), S(2), ... in order, each as soon as its K sub-tile has landed and the softmax group has
@@ -351,7 +354,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t sb = smem_u32(sV + sv * AT_KV_BYTES);
 #pragma unroll
         for (int k = 0; k < AT_BN / 16; ++k)  // 16 keys == 8 packed columns of P
-          umma_bf16_ts(tmem_base + AT_TM_O, tmem_base + AT_TM_P + g * (AT_BN / 2) + k * 8,
+          umma_bf16_ts(tmem_base + AT_TM_O, tmem_base + AT_TM_P + g * AT_TM_GROUP + k * 8,
                        umma_smem_desc_sw128(sb + k * 2048, 1024, 0), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
         umma_commit(&pv_done[g]);
         umma_commit(&v_empty[sv]);
@@ -366,14 +369,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row within the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_off + AT_TM_S + g * AT_BN;
+    // (pinned: left to itself the compiler re-derives these addresses from the thread index in every kv iteration -- the
+    // loop is 250 instructions long and every one of them is worth 0.2 % of the launch)
+    uint32_t t_s = tmem_base + lane_off + AT_TM_S + g * AT_TM_GROUP;
     const uint32_t t_o = tmem_base + lane_off + AT_TM_O;
-    const uint32_t t_p = tmem_base + lane_off + AT_TM_P + g * (AT_BN / 2);
+    asm volatile("" : "+r"(t_s));
+    const uint32_t t_p = t_s + (AT_TM_P - AT_TM_S);
     const float c = p.scale_log2;
     const uint64_t c2 = f32x2_pack(c, c);
     // shared-memory addresses of this group's barriers and of this row's exchange slots, converted once
-    const uint32_t a_sfull = smem_u32(&s_full[g]), a_sempty = smem_u32(&s_empty[g]), a_pfull = smem_u32(&p_full[g]);
-    const uint32_t a_pvdone = smem_u32(&pv_done[g]), a_pvdone_o = smem_u32(&pv_done[g ^ 1]);
+    uint32_t a_sfull = smem_u32(&s_full[g]);
+    asm volatile("" : "+r"(a_sfull));
+    // the group's other barriers sit at fixed distances: s_full[2] | s_empty[2] | p_full[2] | pv_done[2] (8 bytes each)
+    const uint32_t a_sempty = a_sfull + 16, a_pfull = a_sfull + 32, a_pvdone = a_sfull + 48;
+    const uint32_t a_pvdone_o = a_pvdone + (g ? -8 : 8);
     const uint32_t a_msh = smem_u32(m_sh + r);
     // l_run: this group's share of the row sum, relative to m_ref (-inf until the group has seen a reference:
     // adopting one then scales the empty sum by 2^-inf = 0)
@@ -495,10 +504,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         exp32(s1, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]), 1);
         if (threadIdx.x == 128) at_stamp(p, j >> 1, 3);
         // ---- P(j) -> tensor memory once this group's previous P V no longer reads the buffer
-        if (j >= 2) {
-          mbar_wait_a(a_pvdone, par ^ 1);
-          tc_fence_after();
-        }
+        // (first pass: the wait for the phase before the barrier's first returns at once)
+        mbar_wait_a(a_pvdone, par ^ 1);
+        tc_fence_after();
         if (threadIdx.x == 128) at_stamp(p, j >> 1, 4);
         // (deferring this hand-over to the top of the next iteration, so that the store's latency runs under the next
         // load, was measured: 334-341 vs 321 us per launch -- the P V product and everything queued behind it start later)
