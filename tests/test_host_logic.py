@@ -91,6 +91,16 @@ def test_attention_work_list_covers_every_query_tile_once(hq, hkv):
     want = sum(((s + 127) // 128) * hq for s in seq)
     assert len(seen) == want
     assert w[:, 8].tolist() == sorted(w[:, 8].tolist(), reverse=True)  # longest sequences first
+    # leader records: every record names the FIRST record of its (clip, kv head) -- that record is its own leader and is
+    # where the kernel library keeps the pair's score bound (kmax2 / kmax2b: scratch, zero in the plan)
+    rows = w.tolist()
+    first = {}
+    for i, r in enumerate(rows):
+        first.setdefault((r[7], r[6]), i)
+    for i, r in enumerate(rows):
+        assert r[10] == first[(r[7], r[6])] and rows[r[10]][10] == r[10]
+        assert r[9] == 0 and r[11] == 0
+    assert len(first) == len(seq) * hkv
 
 
 def test_plan_rejects_bad_shapes():
