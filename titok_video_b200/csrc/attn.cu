@@ -684,25 +684,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int col = q_head * AT_D + g * 32;
       __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + col;
       __nv_bfloat16* osv = TRAIN ? p.o_save + static_cast<int64_t>(row) * p.ldo + col : nullptr;
+      // this thread's 32 head dims = two full 32-byte sectors of its row: 256-bit stores (a 128-bit store whose 32 lanes
+      // hit 32 different rows costs the same 32 L1 wavefronts for half the bytes)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 gv = gv4[q];
-        const uint32_t gg[4] = {gv.x, gv.y, gv.z, gv.w};
-        uint32_t ov[4], av[4];
+      for (int q2 = 0; q2 < 2; ++q2) {
+        uint32_t ov[8], av[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float g0 = bf16_lo(gg[e]), g1 = bf16_hi(gg[e]);
-          // sigmoid(x) = 0.5 tanh(0.5 x) + 0.5: one MUFU op per value instead of two (exp + reciprocal); the epilogue's
-          // MUFU work was one extra kv sub-tile per row. tanh.approx is good to 2^-11, the result is rounded to bf16 (2^-9)
-          const float s0 = bf16r(fmaf(0.5f, tanh_approx(0.5f * g0), 0.5f));
-          const float s1 = bf16r(fmaf(0.5f, tanh_approx(0.5f * g1), 0.5f));
-          const float a0 = bf16r(__uint_as_float(o[q * 8 + 2 * e]) * inv_l);
-          const float a1 = bf16r(__uint_as_float(o[q * 8 + 2 * e + 1]) * inv_l);
-          ov[e] = pack_bf16x2(a0 * s0, a1 * s1);
-          av[e] = pack_bf16x2(a0, a1);
+        for (int qq = 0; qq < 2; ++qq) {
+          const int q = 2 * q2 + qq;
+          const uint4 gv = gv4[q];
+          const uint32_t gg[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float g0 = bf16_lo(gg[e]), g1 = bf16_hi(gg[e]);
+            // sigmoid(x) = 0.5 tanh(0.5 x) + 0.5: one MUFU op per value instead of two (exp + reciprocal); the epilogue's
+            // MUFU work was one extra kv sub-tile per row. tanh.approx is good to 2^-11, the result is rounded to bf16 (2^-9)
+            const float s0 = bf16r(fmaf(0.5f, tanh_approx(0.5f * g0), 0.5f));
+            const float s1 = bf16r(fmaf(0.5f, tanh_approx(0.5f * g1), 0.5f));
+            const float a0 = bf16r(__uint_as_float(o[q * 8 + 2 * e]) * inv_l);
+            const float a1 = bf16r(__uint_as_float(o[q * 8 + 2 * e + 1]) * inv_l);
+            ov[qq * 4 + e] = pack_bf16x2(a0 * s0, a1 * s1);
+            av[qq * 4 + e] = pack_bf16x2(a0, a1);
+          }
         }
-        stg16(dst + q * 8, make_uint4(ov[0], ov[1], ov[2], ov[3]));
-        if (TRAIN) stg16(osv + q * 8, make_uint4(av[0], av[1], av[2], av[3]));
+        stg32(dst + q2 * 16, ov);
+        if (TRAIN) stg32(osv + q2 * 16, av);
       }
     }
   }
@@ -791,7 +797,9 @@ static int attn_fwd_launch(const void* qkv, int64_t ld, int M, int width, int gq
                            cudaStream_t stream) {
   if (!qkv || !work || !out) return TTK_ERR_BAD_ARG;
   if (int e = check_device_sm100()) return e;
-  if (width % 64 != 0 || gqa % 64 != 0 || ld % 8 != 0 || ldo % 8 != 0) return TTK_ERR_BAD_SHAPE;
+  if (width % 64 != 0 || gqa % 64 != 0 || ld % 8 != 0 || ldo % 16 != 0) return TTK_ERR_BAD_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(out) & 31u) != 0 || (reinterpret_cast<uintptr_t>(o_save) & 31u) != 0)
+    return TTK_ERR_ALIGNMENT;  // 256-bit stores
   if (n_work <= 0) return TTK_OK;
   const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
   CUtensorMap tmQ, tmK, tmV;

@@ -72,6 +72,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // 16-byte global accesses
 __device__ __forceinline__ uint4 ldg16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+// 256-bit global store (sm_100: STG.E.ENL2.256): one full 32-byte sector per thread. p must be 32-byte aligned.
+__device__ __forceinline__ void stg32(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void stg16(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
 __device__ __forceinline__ uint4 ldg16_stream(const void* p) {
   uint4 r;
