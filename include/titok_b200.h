@@ -135,6 +135,7 @@ int ttk_gemm_resid_norm256(const void* A, int64_t lda, const void* W, int64_t ld
  * writable device memory, and concurrent calls on different streams need their own copy). out [M, width].
  * k_norm2 (optional): the by-product of ttk_gemm_qkv_rope; with it the call enqueues ONE kernel and does not touch the
  * work list. Without it, it enqueues two kernels: the key-norm bound (reads K again), then the attention kernel proper.
+ * out must be 32-byte aligned with ldo % 16 == 0 (256-bit row stores).
  * ------------------------------------------------------------------------------------------- */
 int ttk_attn_varlen_fwd(const void* qkv, int64_t ld, int M, int width, int gqa, const void* work, int n_work,
                         float softmax_scale, void* out, int64_t ldo, const float* k_norm2, ttk_stream_t stream);
