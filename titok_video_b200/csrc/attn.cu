@@ -393,9 +393,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // B_r <= AT_BOUND_MAX the CTA takes the bounded-score loop: fixed per-row reference, no row maximum, no rescale, no
     // exchange between the groups. Otherwise (huge logits) it takes the running-maximum loop below. Both are exact up to
     // the bf16 rounding of P; the choice depends only on the clip's own q and k, never on what it is packed with.
-    float ref_l2;  // reference of the exponentials in log2 units (bounded-score loop)
-    bool fast;
-    {
+    // The training forward (TRAIN) always takes the running-maximum loop: there the dominant probability of a row is
+    // exactly 1, as in flash-attention, so its bf16 rounding pattern -- and with it the gradients of a chaotic network
+    // (wide "stress" weights) -- follows the reference's (cosine 0.95..0.99 per parameter against 0.3..0.99 with the
+    // bounded-score loop, whose dominant probability carries an ordinary 2^-9 rounding error; absolute accuracy of the two
+    // loops against an fp64 softmax differs by 11 % at most, see profiles/r2_bench.md).
+    float ref_l2 = 0.f;  // reference of the exponentials in log2 units (bounded-score loop)
+    bool fast = false;
+    if constexpr (!TRAIN) {
       // max_j |k_j|^2 (issued ahead of the wait for Q: the L2 latency of these loads runs under the arrival of the Q tile)
       float k2;
       if (p.knorm2) {
@@ -823,7 +828,7 @@ static int attn_fwd_launch(const void* qkv, int64_t ld, int M, int width, int gq
   if (int e = set_smem_attr_once(once_train, reinterpret_cast<const void*>(attn_fwd_kernel<true>), AT_SMEM)) return e;
   // score bound of every (clip, kv head): written into the scratch field of the leader work records (the work list is the
   // caller's device buffer; its `kmax2` fields are this library's scratch)
-  if (!k_norm2) {
+  if (!k_norm2 && !o_save) {  // (the training forward does not use the bound)
     const int cap = 2 * num_sms();
     if (int e = cuda_status(launch_pdl(attn_kmax_kernel, dim3(2 * n_work < cap ? 2 * n_work : cap), dim3(AT_KMAX_THREADS), 0, stream,
                                        const_cast<AttnWork*>(p.work), n_work, base + 2 * width, ld)))
