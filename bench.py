@@ -80,6 +80,17 @@ def clip_flops(shape=CLIP_A, t=TOKENS_A):
     return 2 * (lin + attn) + io, s, g
 
 
+def latent_tail_savings(s, t, w, inner):
+    """FLOPs of the reference's algorithm that this implementation does NOT execute: the encoder's last layer carries only
+    the t latent rows past its attention (engine._layer_latent; the head reads nothing else, blocks.py:101) -- the other
+    s - t rows skip attention as queries, out_proj, w12 and w3. 0 when the engine runs all rows (TTK_LATENT_TAIL=0)."""
+    from titok_video_b200 import engine
+
+    if not engine.LATENT_TAIL:
+        return 0.0
+    return float((s - t) * 2 * (w * w + 3 * w * inner) + 4 * s * (s - t) * w)
+
+
 # ----------------------------------------------------------------------------------------------------
 # per-kernel device timing (CUDA events on the launching stream, inside the timed region)
 # ----------------------------------------------------------------------------------------------------
@@ -546,7 +557,7 @@ def model_flops(size, shape, t):
     lin = layers * s * 2 * (w * (2 * w + 2 * hkv * 64) + w * w + 3 * w * inner)
     attn = layers * 4 * s * s * w
     io = 2 * 768 * w * g * 2 + 2 * 5 * w * t * 2
-    return 2 * (lin + attn) + io, s
+    return 2 * (lin + attn) + io - latent_tail_savings(s, t, w, inner), s
 
 
 def scaled_leg(T, dev, world, rank, dist, steps, warmup, size="tiny", clips_per_gpu=4):
@@ -1034,7 +1045,12 @@ def main():
                             "(75 % of the burst tensor peak; 1361 with the 12.5 % of the exponentials this kernel evaluates on the "
                             "FMA pipes) before any other limit. One launch per call: the score bound of the bounded-score "
                             "softmax comes from key norms that the qkv GEMM epilogue leaves behind"}
-    whole = {"tflops": value * flops_clip / 1e12, "frac_of_tensor_peak": value * flops_clip / 1e12 / pk["bf16_tflops_sustained"]}
+    # FLOPs the GPU executes per clip: the reference's algorithm minus the rows the last encoder layer skips
+    exec_clip = flops_clip - latent_tail_savings(s, TOKENS_A, WIDTH, INNER)
+    whole = {"tflops": value * exec_clip / 1e12, "frac_of_tensor_peak": value * exec_clip / 1e12 / pk["bf16_tflops_sustained"],
+             "gflop_per_clip_executed": exec_clip / 1e9, "gflop_per_clip_reference_algorithm": flops_clip / 1e9,
+             "note": "executed FLOPs: the encoder's last layer runs attention queries, out_proj and the GEGLU block on the latent "
+                     "rows only (the head reads nothing else; results bit-identical to running every row)"}
 
     vq = None
     if rank == 0 and not args.no_vq:

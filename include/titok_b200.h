@@ -199,7 +199,8 @@ int ttk_dec_embed(const void* codes, int token_size, const int32_t* src_row, con
                   void* xn_out, int M, int width, int64_t ld, ttk_stream_t stream);
 
 /* Encoder head + quantizer (blocks.py:101-103 -> titok.py:49 -> fsq.py:123-135).
- * w_out bf16 [token_size, width], b_out bf16 [token_size]. Outputs z/codes bf16 [T, token_size], idx int32 [T]. */
+ * w_out bf16 [token_size, width], b_out bf16 [token_size]. Outputs z/codes bf16 [T, token_size], idx int32 [T].
+ * latent_row int32 [T]: packed row of every latent token; NULL: x holds the latent rows only, in token order. */
 int ttk_enc_head_fsq(const void* x, int64_t ld, const int32_t* latent_row, const float* w_post, int pre_normed,
                      const void* w_out, const void* b_out, int token_size, void* z_out, void* codes_out,
                      int32_t* idx_out, int T, int width, const float* half_l, const float* offset, const float* shift,
@@ -314,6 +315,18 @@ typedef struct ttk_layers_desc {
 /* Inference: x, xn [M,width] updated in place; qkv [M,2w+2g], att [M,w], h [M,inner] scratch; y [M,w] scratch selects the
  * unfused residual path (required unless width == 256). */
 int ttk_layers_fwd(const ttk_layers_desc* d, void* x, void* xn, void* qkv, void* att, void* h, void* y, ttk_stream_t stream);
+
+/* The encoder's LAST layer, restricted to what the head reads (blocks.py:101 `x[latent_mask]`): every row-wise step of
+ * ResidualAttentionBlock.forward (transformer.py:126-146) acts on a packed row alone and attention output row i depends on
+ * query row i only, so after the last qkv projection (keys / values of ALL rows are still needed) only the latent rows have
+ * to be carried on. Runs layer `layer` of the stack described by d: qkv GEMM + RoPE on all M rows, attention for the query
+ * tiles of `tail_work` (planner: the tiles that hold latent rows), gathers the T latent rows (latent_row int32 [T]) of att
+ * and x into the compact xc / attc [T,width], then out_proj, GEGLU and w3 (+ residual / KEEL / norms) on T rows. On return
+ * xc = x[latent_row] after the layer and xnc = RMSNorm(xc) * next norm weight, bit-identical to those rows of
+ * ttk_layers_fwd. hc [T,inner] scratch; yc [T,width] scratch selects the unfused residual path (required unless width == 256). */
+int ttk_layer_fwd_latent(const ttk_layers_desc* d, int layer, const void* x, const void* xn, void* qkv, void* att,
+                         const void* tail_work, int n_tail_work, const int32_t* latent_row, int T, void* xc, void* xnc,
+                         void* attc, void* hc, void* yc, ttk_stream_t stream);
 
 /* Training forward: slab bf16 [n_layers][per_layer]; offs HOST int64 [11] = element offsets of {qkv, att, o, y_a, x_f, xn_f,
  * h12, h, y_f, x_n, xn_n} in a layer's block; lse fp32 [n_layers][width/64][M]. */

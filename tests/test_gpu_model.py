@@ -170,6 +170,84 @@ def test_fused_and_unfused_residual_paths_agree(golden_stress, monkeypatch):
     _check(z1, z2, True, "fused vs unfused residual epilogue")
 
 
+@pytest.mark.parametrize("size,native", [("tiny", True), ("tiny", False), ("small", True), ("base", False)])
+def test_latent_tail_of_the_last_encoder_layer_is_bit_identical(size, native, monkeypatch):
+    """The encoder's head reads the latent rows only (blocks.py:101), so the last layer carries nothing else past its
+    attention (engine._layer_latent / ttk_layer_fwd_latent: attention for the query tiles that hold latent rows, the rest
+    of the layer on the gathered latent rows). Every step is row-wise, so z, the codes and the indices must equal the
+    all-rows path (TTK_LATENT_TAIL=0, what the reference computes) BIT FOR BIT -- fused (width 256) and unfused residual
+    kernels, even and odd query-head groups, through the native sequencer and kernel by kernel; clips with 0 tokens, with
+    latent rows spilling into a second query tile, and with exactly one tile of them."""
+    from titok_video_b200 import engine
+
+    shapes, tcs = [(8, 64, 64), (4, 32, 48), (8, 96, 64), (4, 16, 16)], [200, 0, 37, 128]
+    clips = [c.cuda() for c in O.make_clips(shapes, 17)]
+    model = build_model(True, enc=size, dec=size).cuda().eval()
+    monkeypatch.setattr(engine, "NATIVE_SEQ", native)
+    out = {}
+    with torch.no_grad():
+        for tail in (False, True):
+            monkeypatch.setattr(engine, "LATENT_TAIL", tail)
+            engine.clear_caches()
+            _poison_workspace()  # (the all-rows run must not leave the right values behind for the tail run to find)
+            z = model.encoder(clips, tcs).clone()
+            _poison_workspace()
+            rec, d = model(clips, tcs)
+            out[tail] = (z, d["indices"].clone(), [r.clone() for r in rec])
+    z0, i0, r0 = out[False]
+    z1, i1, r1 = out[True]
+    assert z0.shape == (sum(tcs), 5) and torch.isfinite(z0.float()).all()
+    assert torch.equal(z0, z1), f"z differs: max|d| {(z0.float() - z1.float()).abs().max().item():.4g}"
+    assert torch.equal(i0, i1), f"{int((i0 != i1).sum())} indices differ"
+    assert all(torch.equal(a, b) for a, b in zip(r0, r1))
+    assert len(torch.unique(i0)) > 8  # (the stress initialiser spreads the tokens: the comparison is not vacuous)
+
+
+def _poison_workspace():
+    """Every byte of the device-wide workspace arenas becomes 0xFF: NaN as bf16 / fp32, -1 as int32. A launch sequence that
+    reads anything it did not write itself (stale results of an earlier call used to mask exactly that) shows up as NaN."""
+    from titok_video_b200 import engine
+
+    torch.cuda.synchronize()
+    for t in engine._ARENA.values():
+        t.fill_(0xFF)
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("tail", [True, False])
+def test_results_do_not_depend_on_what_the_workspace_held(tail, monkeypatch):
+    """The launch sequences share device-wide workspace arenas, so a call always finds the leftovers of earlier calls there
+    -- often the right values of the very same batch, which would hide a kernel that fails to write (or reads past) its
+    rows. With the arenas poisoned (NaN everywhere) before each call, the eager launches, the per-composition graph replay
+    and the bucketed graph replay must still return the same tokens and reconstructions, bit for bit. Covers the latent
+    tail of the last encoder layer (rows of `att` it leaves unwritten are never read) and the padded rows of a bucket (the
+    attention kernel's last key box of the last clip reads into them: they must hold finite values)."""
+    from titok_video_b200 import engine
+
+    monkeypatch.setattr(engine, "LATENT_TAIL", tail)
+    engine.clear_caches()
+    model = build_model(True).cuda().eval()
+    comps = [([(16, 168, 168), (8, 96, 64), (16, 168, 168)], [128, 37, 64]),   # multi-tile clips, s = 1892 / 229 / 1828
+             ([(8, 64, 64), (4, 16, 16), (8, 64, 48)], [200, 128, 16])]
+    for shapes, tcs in comps:
+        clips = [c.cuda() for c in O.make_clips(shapes, 23)]
+        with torch.no_grad():
+            rec, d = model.tokenize_reconstruct_(clips, tcs, use_graph=False)
+            ref_idx, ref_rec = d["indices"].clone(), [r.clone() for r in rec]
+            assert len(torch.unique(ref_idx)) > 8 and all(torch.isfinite(r.float()).all() for r in ref_rec)
+            for what, run in [("eager", lambda: model.tokenize_reconstruct_(clips, tcs, use_graph=False)),
+                              ("graph", lambda: model.tokenize_reconstruct_(clips, tcs, use_graph=True)),
+                              ("graph replay", lambda: model.tokenize_reconstruct_(clips, tcs, use_graph=True)),
+                              ("bucketed", lambda: model.tokenize_reconstruct_bucketed_(clips, tcs)),
+                              ("bucketed replay", lambda: model.tokenize_reconstruct_bucketed_(clips, tcs))]:
+                _poison_workspace()
+                rec, d = run()
+                bad = int((d["indices"] != ref_idx).sum())
+                assert bad == 0, f"{what}: {bad} of {ref_idx.numel()} indices differ after poisoning the workspace"
+                for a, b in zip(rec, ref_rec):
+                    assert torch.equal(a, b), f"{what}: reconstruction differs after poisoning the workspace"
+
+
 def test_other_model_sizes_run_and_match_oracle():
     """'small' (width 512, 8 layers, heads 8/2) exercises the generic-width path (unfused residual kernels)."""
     shapes, tcs = [(4, 32, 32), (8, 16, 24)], [4, 9]

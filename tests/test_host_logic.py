@@ -344,3 +344,35 @@ def test_bench_reference_arm_prints_the_contract_line():
             "r = bench.cpu_reference_run(1, 1); print(r['kind'], r['clips_per_s'] > 0)" % ROOT)
     fb = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
     assert fb.stdout.strip() == "port True", fb.stdout[-300:] + fb.stderr[-800:]
+
+
+def test_latent_work_list_is_the_leading_tiles_of_the_full_list():
+    """The encoder's last layer needs attention output for latent rows only (blocks.py:101); they lead every clip. Its
+    work list must consist of records of the full list restricted to the tiles that hold latent rows, cover every latent
+    row, hold nothing for clips without tokens, and carry valid leader indices."""
+    from titok_video_b200.plan import ATTN_TILE, get_attn_work, get_attn_work_latent, make_plan
+
+    rng = np.random.default_rng(3)
+    for _ in range(6):
+        B = int(rng.integers(1, 7))
+        shapes = [(4 * int(rng.integers(1, 5)), 8 * int(rng.integers(1, 12)), 8 * int(rng.integers(1, 12))) for _ in range(B)]
+        tcs = [int(rng.choice([0, 1, 37, 128, 129, 256, 300])) for _ in range(B)]
+        pl = make_plan(shapes, tcs, (4, 8, 8), arrays=True)
+        starts = pl.cu_seqlens[:-1].tolist()
+        for hq, hkv in [(4, 2), (8, 2), (12, 4), (16, 16)]:
+            full, lat = get_attn_work(pl, hq, hkv), get_attn_work_latent(pl, hq, hkv)
+            # (head, first row, valid rows, kv head, clip start, clip length) of every used query tile
+            tiles = lambda w: {(int(r[4 + j]), int(r[j]), int(r[2 + j]), int(r[6]), int(r[7]), int(r[8]))
+                               for r in w for j in (0, 1) if r[2 + j] > 0}
+            tf, tl = tiles(full), tiles(lat)
+            assert tl <= tf
+            want = {t for t in tf if t[1] - t[4] < tcs[starts.index(t[4])]}
+            assert tl == want
+            covered = np.zeros(pl.M, dtype=np.int64)
+            for (h, r0, v, _, _, _) in tl:
+                covered[r0:r0 + v] += 1
+            assert (covered[pl.latent_row] == hq).all()
+            assert lat.shape[0] <= (pl.T // ATTN_TILE + B + 1) * (hq // 2 if (hq // hkv) % 2 == 0 else hq)  # BucketPlan.W_lat_max
+            for i, r in enumerate(lat):
+                lead = lat[r[10]]
+                assert r[10] <= i and lead[6] == r[6] and lead[7] == r[7] and lat[r[10]][10] == r[10]

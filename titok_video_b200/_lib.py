@@ -85,6 +85,7 @@ SIGNATURES = {
     "ttk_dec_in_bwd": [_vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "ttk_enc_embed_train": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp],
     "ttk_layers_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ttk_layer_fwd_latent": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "ttk_layers_fwd_train": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "ttk_layers_bwd": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ttk_dec_embed_train": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp],
@@ -133,17 +134,18 @@ def profiling() -> bool:
     return _PROFILER is not None
 
 
-def call(name: str, *args, launches: int = 1) -> None:
+def call(name: str, *args, launches: int = 1, label: str = None) -> None:
     """Invoke an int-returning kernel entry point and raise on a non-zero status. `launches`: kernels the entry point
-    enqueues (1 for the kernel entry points -- 2 for the attention forward without key norms --, more for the native sequencers)."""
+    enqueues (1 for the kernel entry points -- 2 for the attention forward without key norms --, more for the native sequencers).
+    `label`: the name a per-kernel profiler files this launch under (default: the entry point's)."""
     global LAUNCHES
     LAUNCHES += launches
     if _PROFILER is None:
         check(getattr(_lib, name)(*args), name)
     else:
-        tok = _PROFILER.begin(name)
+        tok = _PROFILER.begin(label or name)
         check(getattr(_lib, name)(*args), name)
-        _PROFILER.end(name, tok)
+        _PROFILER.end(label or name, tok)
 
 
 def version() -> int:

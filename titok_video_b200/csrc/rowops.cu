@@ -211,7 +211,7 @@ enc_head_fsq_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, const int32
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (t >= T) return;
-  const int row = latent_row[t];
+  const int row = latent_row ? latent_row[t] : t;  // (null map: x holds the latent rows only, in token order)
   RowVec<NV> a;
   a.load(x + row * ld, lane);
   if (!pre_normed) a.norm(w_post, lane, rstd_of(a.sumsq(), NV * 256));
@@ -672,7 +672,7 @@ int ttk_enc_head_fsq(const void* x, int64_t ld, const int32_t* latent_row, const
                      const void* w_out, const void* b_out, int token_size, void* z_out, void* codes_out,
                      int32_t* idx_out, int T, int width, const float* half_l, const float* offset, const float* shift,
                      const float* half_width, const int32_t* basis, const int32_t* levels, cudaStream_t stream) {
-  if (!x || !latent_row || !w_out || !b_out || !z_out || !codes_out || !idx_out) return TTK_ERR_BAD_ARG;
+  if (!x || !w_out || !b_out || !z_out || !codes_out || !idx_out) return TTK_ERR_BAD_ARG;
   if (!pre_normed && !w_post) return TTK_ERR_BAD_ARG;
   if (int e = check_device_sm100()) return e;
   if (!width_ok(width) || ld % 8) return TTK_ERR_BAD_SHAPE;

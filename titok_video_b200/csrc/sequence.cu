@@ -61,6 +61,41 @@ int ttk_layers_fwd(const ttk_layers_desc* d, void* x, void* xn, void* qkv, void*
   return TTK_OK;
 }
 
+// Last encoder layer on the latent rows only (engine._layer_latent): see include/titok_b200.h.
+int ttk_layer_fwd_latent(const ttk_layers_desc* d, int layer, const void* x, const void* xn, void* qkv, void* att,
+                         const void* tail_work, int n_tail_work, const int32_t* latent_row, int T, void* xc, void* xnc,
+                         void* attc, void* hc, void* yc, ttk_stream_t st) {
+  if (!d || !d->weights || !x || !xn || !qkv || !att || !tail_work || !latent_row || !xc || !xnc || !attc || !hc)
+    return TTK_ERR_BAD_ARG;
+  const int M = d->M, w = d->width, g = d->gqa, inner = d->inner;
+  if (layer < 0 || layer >= d->n_layers || T <= 0) return TTK_ERR_BAD_ARG;
+  const int64_t ldq = 2 * (int64_t)w + 2 * g;
+  const bool fused = (yc == nullptr);
+  if (fused && w != 256) return TTK_ERR_BAD_SHAPE;
+  const int64_t* W = d->weights + (int64_t)layer * W_COLS;
+  const int mode = layer == 0 ? 0 : 1;
+  TTK_TRY(ttk_gemm_qkv_rope(xn, w, P(W[W_QKV]), w, M, w, w, g, d->rope, qkv, ldq, d->k_norm2, st));
+  TTK_TRY(ttk_attn_varlen_fwd(qkv, ldq, M, w, g, tail_work, n_tail_work, d->softmax_scale, att, w, d->k_norm2, st));
+  TTK_TRY(ttk_gather_rows(att, w, latent_row, attc, w, T, w, st));
+  TTK_TRY(ttk_gather_rows(x, w, latent_row, xc, w, T, w, st));
+  if (fused) {
+    TTK_TRY(ttk_gemm_resid_norm256(attc, w, P(W[W_OUT]), w, T, w, xc, w, mode, d->alpha, PF(W[LN_ATTN_POST]), PF(W[LN_FFN]), xc,
+                                   xnc, w, st));
+  } else {
+    TTK_TRY(ttk_gemm_bf16(attc, w, P(W[W_OUT]), w, T, w, w, nullptr, yc, w, nullptr, 0, st));
+    TTK_TRY(ttk_resid_norm(xc, yc, xc, xnc, PF(W[LN_ATTN_POST]), PF(W[LN_FFN]), d->alpha, mode, T, w, w, st));
+  }
+  TTK_TRY(ttk_gemm_geglu(xnc, w, P(W[W_12]), w, T, inner, w, hc, inner, st));
+  if (fused) {
+    TTK_TRY(ttk_gemm_resid_norm256(hc, inner, P(W[W_3]), inner, T, inner, xc, w, mode, d->alpha, PF(W[LN_FFD_POST]),
+                                   PF(W[LN_NEXT]), xc, xnc, w, st));
+  } else {
+    TTK_TRY(ttk_gemm_bf16(hc, inner, P(W[W_3]), inner, T, w, inner, nullptr, yc, w, nullptr, 0, st));
+    TTK_TRY(ttk_resid_norm(xc, yc, xc, xnc, PF(W[LN_FFD_POST]), PF(W[LN_NEXT]), d->alpha, mode, T, w, w, st));
+  }
+  return TTK_OK;
+}
+
 // Training forward (backward._layers_train). slab: bf16 [n_layers][per_layer]; offs: HOST int64 [11] element offsets of
 // {qkv, att, o, y_a, x_f, xn_f, h12, h, y_f, x_n, xn_n} inside a layer's block; lse: fp32 [n_layers][width/64][M].
 // Layer i reads x_n / xn_n of layer i-1 (x0 / xn0 for layer 0).

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .plan import PackedPlan, get_attn_bwd_work, get_attn_work, make_plan
+from .plan import PackedPlan, get_attn_bwd_work, get_attn_work, get_attn_work_latent, make_plan
 
 _vp = ctypes.c_void_p
 
@@ -102,6 +102,13 @@ class DevicePlan:
             dev.copy_(host[:dev.numel()], non_blocking=True)
             done.record()
             self._attn[k] = dev[:w.nbytes].view(torch.int32).view(w.shape)
+        return self._attn[k]
+
+    def attn_work_latent(self, hq: int, hkv: int) -> torch.Tensor:
+        """Work list of the encoder's last layer: only the query tiles that hold latent rows (plan.get_attn_work_latent)."""
+        k = ("latent", hq, hkv)
+        if k not in self._attn:
+            self._attn[k] = self._upload_i32(get_attn_work_latent(self.plan, hq, hkv))
         return self._attn[k]
 
     def _upload_i32(self, w: np.ndarray) -> torch.Tensor:
@@ -262,9 +269,11 @@ class BucketPlan:
         self.geom = torch.zeros((max(G_max, 1), 4), dtype=torch.int64, device=device)
         self.rope_pos = torch.zeros((M, 3), **i32)
         self.rope = torch.empty((M, 60), dtype=torch.float32, device=device)
-        # [hdr 8 | desc B*12 | clip_offset B | clip_numel B] int64, then the work list int32 [W_max, 12]
+        # the last encoder layer's list (query tiles that hold latent rows): at most T/128 + B row tiles
+        self.W_lat_max = (T_max // 128 + B_max + 1) * (hq // 2 if (hq // hkv) % 2 == 0 else hq)
+        # [hdr 8 | desc B*12 | clip_offset B | clip_numel B] int64, then the work lists int32 [W_max, 12], [W_lat_max, 12]
         self.n_i64 = 8 + 14 * B_max
-        self.meta_bytes = (self.n_i64 * 8 + self.W_max * 48 + 255) // 256 * 256
+        self.meta_bytes = (self.n_i64 * 8 + (self.W_max + self.W_lat_max) * 48 + 255) // 256 * 256
         self._meta = torch.zeros(self.meta_bytes, dtype=torch.uint8, device=device)
         m64 = self._meta[:self.n_i64 * 8].view(torch.int64)
         self.hdr = m64[:8]
@@ -272,6 +281,8 @@ class BucketPlan:
         self.clip_offset = m64[8 + 12 * B_max:8 + 13 * B_max]
         self.clip_numel = m64[8 + 13 * B_max:8 + 14 * B_max]
         self._work = self._meta[self.n_i64 * 8:self.n_i64 * 8 + self.W_max * 48].view(torch.int32).view(self.W_max, 12)
+        o_lat = self.n_i64 * 8 + self.W_max * 48
+        self._work_lat = self._meta[o_lat:o_lat + self.W_lat_max * 48].view(torch.int32).view(self.W_lat_max, 12)
         self.ws: Dict[str, torch.Tensor] = {}
         self.graphs: Dict[tuple, tuple] = {}
         self.cs, self.n_ids = _cs_table(device, 1024)  # position ids are < token_count + max grid side << 1024
@@ -281,6 +292,10 @@ class BucketPlan:
     def attn_work(self, hq: int, hkv: int) -> torch.Tensor:
         assert (hq, hkv) == self.heads
         return self._work
+
+    def attn_work_latent(self, hq: int, hkv: int) -> torch.Tensor:
+        assert (hq, hkv) == self.heads
+        return self._work_lat
 
     def build_launch(self) -> None:
         """The metadata expansion + RoPE gather: the first two launches of the captured sequence."""
@@ -301,7 +316,8 @@ class BucketPlan:
         if plan.max_pos + 1 > self.n_ids:
             raise _lib.TitokB200Error("position ids exceed the bucket's RoPE table")
         work = get_attn_work(plan, *self.heads)
-        if work.shape[0] > self.W_max:
+        work_lat = get_attn_work_latent(plan, *self.heads)
+        if work.shape[0] > self.W_max or work_lat.shape[0] > self.W_lat_max:
             raise _lib.TitokB200Error("attention work list exceeds the bucket's bound")
         host, done = _staging(self.meta_bytes)
         hv = host.numpy()
@@ -313,6 +329,8 @@ class BucketPlan:
         h64[8 + 13 * mp.B:8 + 13 * mp.B + B] = plan.clip_numel
         hw = hv[self.n_i64 * 8:self.n_i64 * 8 + work.size * 4].view(np.int32)
         hw[:] = work.reshape(-1)
+        o_lat = self.n_i64 * 8 + self.W_max * 48
+        hv[o_lat:o_lat + work_lat.size * 4].view(np.int32)[:] = work_lat.reshape(-1)
         self._meta.copy_(host[:self.meta_bytes], non_blocking=True)
         done.record()
 
@@ -548,6 +566,11 @@ except Exception:  # pragma: no cover  (very old torch: training forwards still 
 # --------------------------------------------------------------------------------------------------
 FUSE_RESID_256 = os.environ.get("TTK_FUSE_RESID", "1") != "0"
 NATIVE_SEQ = os.environ.get("TTK_NATIVE_SEQ", "1") != "0"  # 0: enqueue the layers kernel by kernel from Python
+# The encoder's last layer carries only the latent rows past its attention (blocks.py:101 reads `x[latent_mask]` alone;
+# every other step of the layer is row-wise): 0 runs all rows through it, as the reference does -- same results bit for bit.
+LATENT_TAIL = os.environ.get("TTK_LATENT_TAIL", "1") != "0"
+# (test hook) 0: a bucket's launch sequence does not clear the attention output of its padded rows -- see _clear_padding
+BUCKET_CLEAR_ATT = os.environ.get("TTK_BUCKET_CLEAR_ATT", "1") != "0"
 
 
 def key_norms(dp: DevicePlan, M: int, hkv: int) -> torch.Tensor:
@@ -574,15 +597,31 @@ def layers_desc(m, W: PreparedStack, dp: DevicePlan, M: int, backward: bool = Fa
     return d
 
 
-def _layers(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tensor) -> None:
+def _clear_padding(dp, M: int, w: int) -> None:
+    """A bucket's launch sequence runs with the bucket's extents: packed rows past the step's real M are padding. No
+    attention record covers them, so their rows of `att` are never written, and whatever the arena held there would reach
+    `x` / `qkv` of the padded rows through out_proj. Padded rows never write real rows -- but the attention kernel READS
+    them: the last 64-key box of the last real clip extends into the rows behind it, and although those keys are masked
+    (P = 0), a NaN in their value rows survives the product (0 x NaN). In the per-composition path the rows behind the last
+    clip are past the tensor map's extent (TMA fills zeros); here they are padded rows, so `att` is cleared once per launch
+    sequence (one memset node in the captured graph), which keeps every padded row finite through both stacks."""
+    if isinstance(dp, BucketPlan) and BUCKET_CLEAR_ATT:
+        dp.buf("att", (M, w)).zero_()
+
+
+def _layers(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tensor, n_run: Optional[int] = None) -> None:
     """ResidualAttentionBlock.forward (transformer.py:126-146). x, xn are updated in place; on return xn holds
-    RMSNorm(x) * ln_post.weight for every packed row."""
+    RMSNorm(x) * ln_post.weight for every packed row. n_run: run only the first n_run layers (xn then holds the pre-norm
+    of layer n_run)."""
     M, w = x.shape
     hq, hkv = m.heads
     gqa = hkv * 64
     inner = m.inner_dim
     L = m.num_layers
     alpha = float(2 * L)
+    n_run = L if n_run is None else n_run
+    if n_run <= 0:
+        return
     st = _stream()
     qkv = dp.buf("qkv", (M, 2 * w + 2 * gqa))
     att = dp.buf("att", (M, w))
@@ -594,8 +633,9 @@ def _layers(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tens
     T = W.t
     if NATIVE_SEQ and not _lib.profiling():
         d = layers_desc(m, W, dp, M)
+        d.n_layers = n_run
         _lib.call("ttk_layers_fwd", ctypes.byref(d), _ptr(x), _ptr(xn), _ptr(qkv), _ptr(att), _ptr(h), _ptr(y), st,
-                  launches=L * (5 if y is None else 7))
+                  launches=n_run * (5 if y is None else 7))
         return
 
     def out_update(a: torch.Tensor, wmat: torch.Tensor, K: int, mode: int, w_post, w_next) -> None:
@@ -608,7 +648,7 @@ def _layers(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tens
             _lib.call("ttk_resid_norm", _ptr(x), _ptr(y), _ptr(x), _ptr(xn), _ptr(w_post), _ptr(w_next), alpha, mode,
                       M, w, x.stride(0), st)
 
-    for i in range(L):
+    for i in range(n_run):
         mode = 0 if i == 0 else 1
         _lib.call("ttk_gemm_qkv_rope", _ptr(xn), xn.stride(0), _ptr(T[f"to_qkv{i}"]), w, M, w, w, gqa, _ptr(dp.rope),
                   _ptr(qkv), qkv.stride(0), _ptr(knorm), st)
@@ -619,6 +659,61 @@ def _layers(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tens
                   st)
         w_next = T[f"pre_ln{i + 1}"] if i + 1 < L else T["ln_post"]
         out_update(h, T[f"w3_{i}"], inner, mode, T.get(f"ffd_post_ln{i}"), w_next)
+
+
+def _layer_latent(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tensor, Tn: int) -> torch.Tensor:
+    """The encoder's last layer on what the head reads. The qkv projection runs on all rows (every row is a key), attention
+    only for the query tiles that hold latent rows, and everything behind it on the Tn latent rows gathered into compact
+    [Tn, w] buffers. Returns xnc = RMSNorm(x_out[latent rows]) * ln_post.weight, bit-identical to those rows of _layers."""
+    M, w = x.shape
+    hq, hkv = m.heads
+    gqa = hkv * 64
+    inner = m.inner_dim
+    L = m.num_layers
+    i = L - 1
+    alpha = float(2 * L)
+    st = _stream()
+    qkv = dp.buf("qkv", (M, 2 * w + 2 * gqa))
+    att = dp.buf("att", (M, w))
+    xc = dp.buf("x_lat", (Tn, w))
+    xnc = dp.buf("xn_lat", (Tn, w))
+    attc = dp.buf("att_lat", (Tn, w))
+    hc = dp.buf("h_lat", (Tn, inner))
+    yc = None if (FUSE_RESID_256 and w == 256) else dp.buf("y_lat", (Tn, w))
+    work = dp.attn_work_latent(hq, hkv)
+    knorm = key_norms(dp, M, hkv)
+    scale = 1.0 / math.sqrt(64.0)
+    T = W.t
+    if NATIVE_SEQ and not _lib.profiling():
+        d = layers_desc(m, W, dp, M)
+        _lib.call("ttk_layer_fwd_latent", ctypes.byref(d), i, _ptr(x), _ptr(xn), _ptr(qkv), _ptr(att), _ptr(work),
+                  work.shape[0], _ptr(dp.latent_row), Tn, _ptr(xc), _ptr(xnc), _ptr(attc), _ptr(hc), _ptr(yc), st,
+                  launches=4 + (3 if yc is None else 5))
+        return xnc
+    mode = 0 if i == 0 else 1
+    tag = "[latent rows]"  # (the per-kernel profiler keeps these launches apart from the full-size ones)
+
+    def out_update(a: torch.Tensor, wmat: torch.Tensor, K: int, w_post, w_next) -> None:
+        if yc is None:
+            _lib.call("ttk_gemm_resid_norm256", _ptr(a), a.stride(0), _ptr(wmat), wmat.stride(0), Tn, K, _ptr(xc), w, mode,
+                      alpha, _ptr(w_post), _ptr(w_next), _ptr(xc), _ptr(xnc), w, st, label="ttk_gemm_resid_norm256" + tag)
+        else:
+            _lib.call("ttk_gemm_bf16", _ptr(a), a.stride(0), _ptr(wmat), wmat.stride(0), Tn, w, K, _vp(0), _ptr(yc), w,
+                      _vp(0), 0, st, label="ttk_gemm_bf16" + tag)
+            _lib.call("ttk_resid_norm", _ptr(xc), _ptr(yc), _ptr(xc), _ptr(xnc), _ptr(w_post), _ptr(w_next), alpha, mode,
+                      Tn, w, w, st, label="ttk_resid_norm" + tag)
+
+    _lib.call("ttk_gemm_qkv_rope", _ptr(xn), xn.stride(0), _ptr(T[f"to_qkv{i}"]), w, M, w, w, gqa, _ptr(dp.rope),
+              _ptr(qkv), qkv.stride(0), _ptr(knorm), st)
+    _lib.call("ttk_attn_varlen_fwd", _ptr(qkv), qkv.stride(0), M, w, gqa, _ptr(work), work.shape[0], scale, _ptr(att),
+              att.stride(0), _ptr(knorm), st, label="ttk_attn_varlen_fwd" + tag)
+    _lib.call("ttk_gather_rows", _ptr(att), w, _ptr(dp.latent_row), _ptr(attc), w, Tn, w, st)
+    _lib.call("ttk_gather_rows", _ptr(x), w, _ptr(dp.latent_row), _ptr(xc), w, Tn, w, st)
+    out_update(attc, T[f"out_proj{i}"], w, T.get(f"attn_post_ln{i}"), T[f"ffn_norm{i}"])
+    _lib.call("ttk_gemm_geglu", _ptr(xnc), w, _ptr(T[f"w12_{i}"]), w, Tn, inner, w, _ptr(hc), inner, st,
+              label="ttk_gemm_geglu" + tag)
+    out_update(hc, T[f"w3_{i}"], inner, T.get(f"ffd_post_ln{i}"), T["ln_post"])
+    return xnc
 
 
 def encoder_launch(m, dp: DevicePlan, clips_flat: torch.Tensor, fsq_consts) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -646,9 +741,16 @@ def encoder_launch(m, dp: DevicePlan, clips_flat: torch.Tensor, fsq_consts) -> T
               _ptr(proj), w, _vp(0), 0, st)
     _lib.call("ttk_enc_embed", _ptr(proj), w, _ptr(dp.enc_src_row), _ptr(T["mask_token"]), _ptr(T["ln_pre_t"]),
               _ptr(T["ln_pre_p"]), _ptr(T["pre_ln0"]), _ptr(x), _ptr(xn), M, w, w, st)
-    _layers(m, W, dp, x, xn)
+    _clear_padding(dp, M, w)
     half_l, offset, shift, half_width, basis, levels = fsq_consts
-    _lib.call("ttk_enc_head_fsq", _ptr(xn), w, _ptr(dp.latent_row), _ptr(T["ln_post"]), 1, _ptr(T["proj_out_w"]),
+    if LATENT_TAIL and Tn > 0:
+        # the head reads the latent rows only: the last layer carries nothing else past its attention
+        _layers(m, W, dp, x, xn, n_run=m.num_layers - 1)
+        head_in, head_map = _layer_latent(m, W, dp, x, xn, Tn), None
+    else:
+        _layers(m, W, dp, x, xn)
+        head_in, head_map = xn, dp.latent_row
+    _lib.call("ttk_enc_head_fsq", _ptr(head_in), w, _ptr(head_map), _ptr(T["ln_post"]), 1, _ptr(T["proj_out_w"]),
               _ptr(T["proj_out_b"]), ts, _ptr(z), _ptr(codes), _ptr(idx), Tn, w, half_l, offset, shift, half_width,
               basis, levels, st)
     return z[:Tn], codes[:Tn], idx[:Tn]
@@ -669,6 +771,7 @@ def decoder_launch(m, dp: DevicePlan, codes: torch.Tensor, out_flat: torch.Tenso
     _lib.call("ttk_dec_embed", _ptr(codes), m.token_size, _ptr(dp.dec_src_row), _ptr(T["proj_in_w"]),
               _ptr(T["proj_in_b"]), _ptr(T["mask_token"]), _ptr(T["ln_pre_t"]), _ptr(T["ln_pre_p"]), _ptr(T["pre_ln0"]),
               _ptr(x), _ptr(xn), M, w, w, st)
+    _clear_padding(dp, M, w)
     _layers(m, W, dp, x, xn)
     _lib.call("ttk_gemm_bf16", _ptr(xn), w, _ptr(T["proj_out_w"]), w, M, feat, w, _ptr(T["proj_out_b"]), _ptr(rows),
               feat, _vp(0), 0, st)

@@ -122,18 +122,24 @@ def rope_table_from_int_ids(ids: np.ndarray, inv_freqs: np.ndarray) -> np.ndarra
     return np.ascontiguousarray(out.transpose(0, 2, 1, 3)).reshape(ids.shape[0], -1)
 
 
-def attn_work_list(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: int, hkv: int) -> np.ndarray:
+def attn_work_list(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: int, hkv: int,
+                   q_lens: Sequence[int] = None) -> np.ndarray:
     """int32 [n, 12] records {q_row0[2], q_valid[2], q_head[2], kv_head, kv_row0, kv_len, kmax2, leader, kmax2b}
     (csrc/attn.cu). Two query tiles per record share one kv head: two heads of the same group when the group size is
     even, otherwise two consecutive row tiles of one head. Longest sequences first (LPT) to shorten the tail.
     `leader` = index of the first record of the same (clip, kv head): the kernel library keeps that pair's score bound
-    in the leader's `kmax2` / `kmax2b` fields (device-side scratch, zero here)."""
+    in the leader's `kmax2` / `kmax2b` fields (device-side scratch, zero here).
+    `q_lens` (optional, per clip): only the row tiles that hold a clip's first `q_lens[i]` rows get a record -- the
+    encoder's last layer needs attention output for the latent rows alone (blocks.py:101: `x[latent_mask]`), which lead
+    every clip. The tiles that remain are exactly the records of the full list (same rows, same valid counts)."""
     ratio = hq // hkv
+    if q_lens is None:
+        q_lens = seq_lens
     if ratio % 2 == 0 and len(seq_starts):
         # vectorised: one record per (clip, row tile, pair of query heads of one kv group)
         st = np.asarray(seq_starts, dtype=np.int64)
         sl = np.asarray(seq_lens, dtype=np.int64)
-        nt = (sl + ATTN_TILE - 1) // ATTN_TILE
+        nt = (np.minimum(np.asarray(q_lens, dtype=np.int64), sl) + ATTN_TILE - 1) // ATTN_TILE
         clip = np.repeat(np.arange(len(sl)), nt)
         ti = np.arange(int(nt.sum()), dtype=np.int64) - np.repeat(np.concatenate([[0], np.cumsum(nt)[:-1]]), nt)
         r0 = st[clip] + ti * ATTN_TILE
@@ -149,8 +155,8 @@ def attn_work_list(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: int, 
         order = np.argsort(-rec[:, 8], kind="stable")  # longest sequences first (LPT), ties in generation order
         return _with_leaders(np.ascontiguousarray(rec[order]))
     recs: List[List[int]] = []
-    for start, slen in zip(seq_starts, seq_lens):
-        n_tiles = (slen + ATTN_TILE - 1) // ATTN_TILE
+    for start, slen, qlen in zip(seq_starts, seq_lens, q_lens):
+        n_tiles = (min(slen, qlen) + ATTN_TILE - 1) // ATTN_TILE
         if ratio % 2 == 0:
             for ti in range(n_tiles):
                 r0 = start + ti * ATTN_TILE
@@ -284,6 +290,14 @@ def get_attn_work(plan: PackedPlan, hq: int, hkv: int) -> np.ndarray:
     k = (hq, hkv)
     if k not in plan.attn_work:
         plan.attn_work[k] = attn_work_list(plan.cu_seqlens[:-1].tolist(), plan.seq_lens, hq, hkv)
+    return plan.attn_work[k]
+
+
+def get_attn_work_latent(plan: PackedPlan, hq: int, hkv: int) -> np.ndarray:
+    """Work list of the encoder's LAST layer: only the query tiles that hold latent rows (they lead every clip)."""
+    k = ("latent", hq, hkv)
+    if k not in plan.attn_work:
+        plan.attn_work[k] = attn_work_list(plan.cu_seqlens[:-1].tolist(), plan.seq_lens, hq, hkv, q_lens=plan.token_counts)
     return plan.attn_work[k]
 
 
