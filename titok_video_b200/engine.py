@@ -93,22 +93,19 @@ class DevicePlan:
         self.graphs: Dict[tuple, "torch.cuda.CUDAGraph"] = {}
 
     def attn_work(self, hq: int, hkv: int) -> torch.Tensor:
-        k = (hq, hkv)
-        if k not in self._attn:
-            w = np.ascontiguousarray(get_attn_work(self.plan, hq, hkv))
-            host, done = _staging(max(w.nbytes, 256))
-            host.numpy()[:w.nbytes] = w.view(np.uint8).reshape(-1)
-            dev = torch.empty(max(w.nbytes, 256), dtype=torch.uint8, device=self.device)
-            dev.copy_(host[:dev.numel()], non_blocking=True)
-            done.record()
-            self._attn[k] = dev[:w.nbytes].view(torch.int32).view(w.shape)
-        return self._attn[k]
+        return self._attn_lists(hq, hkv)[0]
 
     def attn_work_latent(self, hq: int, hkv: int) -> torch.Tensor:
         """Work list of the encoder's last layer: only the query tiles that hold latent rows (plan.get_attn_work_latent)."""
-        k = ("latent", hq, hkv)
+        return self._attn_lists(hq, hkv)[1]
+
+    def _attn_lists(self, hq: int, hkv: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(all query tiles, query tiles that hold latent rows): both lists travel in one staging buffer / one copy."""
+        k = (hq, hkv)
         if k not in self._attn:
-            self._attn[k] = self._upload_i32(get_attn_work_latent(self.plan, hq, hkv))
+            full, lat = get_attn_work(self.plan, hq, hkv), get_attn_work_latent(self.plan, hq, hkv)
+            both = self._upload_i32(np.concatenate([full, lat], axis=0))
+            self._attn[k] = (both[:full.shape[0]], both[full.shape[0]:])
         return self._attn[k]
 
     def _upload_i32(self, w: np.ndarray) -> torch.Tensor:
@@ -137,13 +134,15 @@ class DevicePlan:
         hit = self.ws.get(key)
         if hit is not None and hit[0] == _ARENA_GEN:
             return hit[1]
-        nbytes = max(1, math.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        nbytes = max(1, math.prod(shape)) * _ELEM_SIZE[dtype]
         base = _arena(self.device, name, nbytes)
         t = base[:nbytes].view(dtype)[:math.prod(shape)].view(shape)
         self.ws[key] = (_ARENA_GEN, t)
         return t
 
 
+_ELEM_SIZE = {torch.bfloat16: 2, torch.float16: 2, torch.float32: 4, torch.float64: 8, torch.int32: 4, torch.int64: 8,
+              torch.uint8: 1, torch.int8: 1, torch.int16: 2, torch.bool: 1}
 _ARENA: Dict[Tuple[str, str], torch.Tensor] = {}
 _ARENA_GEN = 0  # bumped whenever an arena is re-allocated: cached views and captured CUDA graphs of older generations are stale
 
