@@ -80,13 +80,15 @@ def clip_flops(shape=CLIP_A, t=TOKENS_A):
     return 2 * (lin + attn) + io, s, g
 
 
-def latent_tail_savings(s, t, w, inner):
+def latent_tail_savings(s, t, w, inner, enabled=None):
     """FLOPs of the reference's algorithm that this implementation does NOT execute: the encoder's last layer carries only
     the t latent rows past its attention (engine._layer_latent; the head reads nothing else, blocks.py:101) -- the other
     s - t rows skip attention as queries, out_proj, w12 and w3. 0 when the engine runs all rows (TTK_LATENT_TAIL=0)."""
-    from titok_video_b200 import engine
+    if enabled is None:
+        from titok_video_b200 import engine
 
-    if not engine.LATENT_TAIL:
+        enabled = engine.LATENT_TAIL
+    if not enabled:
         return 0.0
     return float((s - t) * 2 * (w * w + 3 * w * inner) + 4 * s * (s - t) * w)
 
@@ -314,7 +316,11 @@ def workload_string(B):
 def train_flops(B):
     """Algorithmic FLOPs of one training step on B clips A: forward + backward (2x forward: dgrad + wgrad; the attention
     backward's recomputation of S and dP is NOT counted)."""
-    f, _, _ = clip_flops()
+    f, s_rows, _ = clip_flops()
+    from titok_video_b200 import backward
+
+    # (with the encoder's last layer carried on the latent rows only, those FLOPs are not executed, forward or backward)
+    f -= latent_tail_savings(s_rows, TOKENS_A, WIDTH, INNER, enabled=backward.TRAIN_LATENT_TAIL)
     return 3.0 * B * f
 
 
@@ -409,6 +415,7 @@ def train_leg(T, _lib, dev, world, rank, dist, batch, steps, warmup, graphed=Fal
     return {"clips_per_s": world * batch / (ms_step * 1e-3), "ms_per_step": ms_step, "clips_per_gpu_per_step": batch,
             "packed_rows_per_gpu": batch * clip_flops()[1], "loss": float(loss.detach()), "gpu_launches_per_step": launches / steps,
             "tflops_algorithmic": tf, "frac_of_tensor_peak": tf / pk["bf16_tflops_sustained"],
+            "latent_tail": bool(__import__("titok_video_b200.backward", fromlist=["x"]).TRAIN_LATENT_TAIL),
             "ms_per_step_mean": mean_ms, "timing": "median of the per-step CUDA-event times, max over ranks",
             "wall_ms_per_step": wall_ms, "kernel_ms_per_step": sum(v[0] for v in ks.values()) / prof_steps, "kernels": kernels,
             "graph_replays": (gstep.replays if gstep is not None else 0),

@@ -606,6 +606,40 @@ def test_native_sequencer_equals_per_kernel_launches(monkeypatch):
         assert torch.allclose(a[4][k], b[4][k], rtol=1e-3, atol=1e-6 + 1e-4 * float(b[4][k].abs().max())), k
 
 
+@pytest.mark.parametrize("size", ["tiny", "base"])
+def test_training_latent_tail_equals_all_rows(size, monkeypatch):
+    """Training with the encoder's last layer carried on the latent rows only (backward.TRAIN_LATENT_TAIL: forward AND
+    backward of that layer behind its attention run on T rows, the attention backward follows work lists restricted to the
+    latent query rows) against every row going through it, as in the reference: tokens and reconstructions bit-exact,
+    every parameter gradient -- encoder, decoder, and the pixel gradient -- equal up to the fp32 order of the atomic
+    reductions. Clips with 0 tokens, with latent rows spilling into a second query tile, with exactly one tile."""
+    from titok_video_b200 import backward
+
+    shapes, tcs = [(8, 64, 64), (4, 32, 48), (8, 96, 64), (4, 16, 16)], [200, 0, 37, 128]
+    base = [c.to(DEV) for c in O.make_clips(shapes, 19)]
+
+    def run(tail):
+        monkeypatch.setattr(backward, "TRAIN_LATENT_TAIL", tail)
+        model = build_model(True, enc=size, dec=size).to(DEV).train()
+        clips = [c.clone().float().requires_grad_(True) for c in base]
+        rec, d = model(clips, tcs)
+        torch.stack([(r_.float() - c.detach().float()).abs().mean() for c, r_ in zip(clips, rec)]).mean().backward()
+        torch.cuda.synchronize()
+        g = {k: p.grad.clone() for k, p in model.named_parameters()}
+        for j, c in enumerate(clips):
+            g[f"pixels{j}"] = c.grad.float().clone()
+        return [r_.detach().clone() for r_ in rec], d["indices"].clone(), g
+
+    a, b = run(True), run(False)
+    assert torch.equal(a[1], b[1]) and len(torch.unique(b[1])) > 8
+    for x, y in zip(a[0], b[0]):
+        assert torch.equal(x, y)
+    for k in b[2]:
+        assert torch.isfinite(a[2][k]).all(), k
+        assert torch.allclose(a[2][k], b[2][k], rtol=1e-3, atol=1e-6 + 1e-4 * float(b[2][k].abs().max())), \
+            f"{k}: max|d| {float((a[2][k] - b[2][k]).abs().max()):.3g} vs scale {float(b[2][k].abs().max()):.3g}"
+
+
 def test_inference_sees_weights_updated_by_a_fused_optimizer_or_through_data():
     """Weights changed by a fused optimizer step (no version bump) are picked up by the next no-grad forward through the
     optimizer-step hook; edits through `p.data` need engine.invalidate()."""

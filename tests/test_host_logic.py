@@ -376,3 +376,26 @@ def test_latent_work_list_is_the_leading_tiles_of_the_full_list():
             for i, r in enumerate(lat):
                 lead = lat[r[10]]
                 assert r[10] <= i and lead[6] == r[6] and lead[7] == r[7] and lat[r[10]][10] == r[10]
+
+
+def test_latent_backward_work_lists():
+    """Attention backward of the encoder's last layer in training: only the latent rows carry an output gradient. dq keeps
+    the full list's records of the query tiles that hold latent rows; dkv keeps every key tile of the clips that have
+    tokens and streams just their latent query rows (`clip_len` = token count); nothing for clips without tokens."""
+    from titok_video_b200.plan import ATTN_TILE, get_attn_bwd_work, get_attn_bwd_work_latent, make_plan
+
+    rng = np.random.default_rng(5)
+    for _ in range(6):
+        B = int(rng.integers(1, 7))
+        shapes = [(4 * int(rng.integers(1, 5)), 8 * int(rng.integers(1, 12)), 8 * int(rng.integers(1, 12))) for _ in range(B)]
+        tcs = [int(rng.choice([0, 1, 37, 128, 129, 256, 300])) for _ in range(B)]
+        pl = make_plan(shapes, tcs, (4, 8, 8), arrays=True)
+        starts = pl.cu_seqlens[:-1].tolist()
+        tok = {st: t for st, t in zip(starts, tcs)}
+        for hq, hkv in [(4, 2), (12, 4), (16, 16)]:
+            (a, b), (al, bl) = get_attn_bwd_work(pl, hq, hkv), get_attn_bwd_work_latent(pl, hq, hkv)
+            rows = lambda w: {tuple(int(v) for v in r) for r in w}
+            assert rows(bl) == {r for r in rows(b) if r[0] - r[5] < tok[r[5]]}
+            want = {r[:6] + (tok[r[5]], 0) for r in rows(a) if tok[r[5]] > 0}
+            assert rows(al) == want
+            assert all(r[6] <= pl.seq_lens[starts.index(r[5])] for r in rows(al))

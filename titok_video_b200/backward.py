@@ -25,6 +25,25 @@ from .engine import NATIVE_SEQ, DevicePlan, cached_named_params, PreparedStack, 
 
 bf16 = torch.bfloat16
 
+# Training forward + backward of the ENCODER's last layer on the latent rows only (the head reads nothing else,
+# blocks.py:101; see engine._layer_latent for the inference side): 0 = every packed row goes through the layer, as in
+# the reference. The layers before it run through the native sequencers as before (n_layers - 1 of them).
+import os as _os
+
+TRAIN_LATENT_TAIL = _os.environ.get("TTK_TRAIN_LATENT_TAIL", "0") != "0"
+_IDENT: Dict[str, torch.Tensor] = {}
+
+
+def _ident(n: int, device) -> torch.Tensor:
+    """int32 [n] = 0..n-1 on `device` (row map of compact buffers), cached."""
+    t = _IDENT.get(str(device))
+    if t is None or t.numel() < n:
+        if torch.cuda.is_current_stream_capturing():  # (memory allocated under capture belongs to the graph: not cached)
+            return torch.arange(n, dtype=torch.int32, device=device)
+        t = torch.arange(max(n, 4096), dtype=torch.int32, device=device)
+        _IDENT[str(device)] = t
+    return t[:n]
+
 
 def _new(shape, device, dtype=bf16) -> torch.Tensor:
     return torch.empty(shape, dtype=dtype, device=device)
@@ -35,6 +54,8 @@ class Tape:
 
     def __init__(self):
         self.lt = None  # LayerTape of the transformer layers
+        self.tail = None  # encoder with TRAIN_LATENT_TAIL: tensors of the last layer (_last_layer_train)
+        self.latent_tail = False
         self.t: Dict[str, torch.Tensor] = {}
         self.weights_sig = None  # (parameter signature, optimizer-step counter) the forward ran with
 
@@ -122,31 +143,37 @@ class LayerTape:
         return self.slab[o:o + self.M * self.cols[col]].view(self.M, self.cols[col])
 
 
-def _layers_train(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tensor, tape: Tape):
-    """ResidualAttentionBlock.forward (transformer.py:126-146), recording per-layer activations."""
+def _layers_train(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torch.Tensor, tape: Tape,
+                  n_run: Optional[int] = None):
+    """ResidualAttentionBlock.forward (transformer.py:126-146), recording per-layer activations. n_run: only the first
+    n_run layers (the encoder's last layer then follows in _last_layer_train)."""
     M, w = x.shape
     dev = x.device
     hq, hkv = m.heads
     gqa = hkv * 64
     inner = m.inner_dim
     L = m.num_layers
+    n_run = L if n_run is None else n_run
     alpha = float(2 * L)
     st = _stream()
     fcols, foffs, per_layer, _, _, _ = _layouts(M, w, gqa, inner)
-    slab = torch.empty(L * per_layer, dtype=bf16, device=dev)
+    slab = torch.empty(max(n_run, 1) * per_layer, dtype=bf16, device=dev)
     lse_all = torch.empty((L, hq, M), dtype=torch.float32, device=dev)
     lt = LayerTape(slab, per_layer, fcols, foffs, lse_all, x, xn, M)
     tape.lt = lt
+    if n_run <= 0:
+        return x, xn
     if NATIVE_SEQ and not _lib.profiling():
         d = layers_desc(m, W, dp, M)
+        d.n_layers = n_run
         _lib.call("ttk_layers_fwd_train", ctypes.byref(d), _ptr(x), _ptr(xn), _ptr(slab), per_layer, _vp(foffs.ctypes.data),
-                  _ptr(lse_all), st, launches=8 * L)
-        return lt.view(L - 1, F_XN), lt.view(L - 1, F_XNN)
+                  _ptr(lse_all), st, launches=8 * n_run)
+        return lt.view(n_run - 1, F_XN), lt.view(n_run - 1, F_XNN)
     work = dp.attn_work(hq, hkv)
     knorm = key_norms(dp, M, hkv)
     scale = 1.0 / math.sqrt(64.0)
     T = W.t
-    for i in range(L):
+    for i in range(n_run):
         mode = 0 if i == 0 else 1
         qkv, att, o, lse = lt.view(i, F_QKV), lt.view(i, F_ATT), lt.view(i, F_O), lse_all[i]
         _lib.call("ttk_gemm_qkv_rope", _ptr(xn), xn.stride(0), _ptr(T[f"to_qkv{i}"]), w, M, w, w, gqa, _ptr(dp.rope),
@@ -172,6 +199,130 @@ def _layers_train(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torc
     return x, xn
 
 
+def _use_latent_tail(m, dp: DevicePlan) -> bool:
+    return TRAIN_LATENT_TAIL and dp.plan.T > 0 and m.num_layers > 1
+
+
+def _last_layer_train(m, W: PreparedStack, dp: DevicePlan, x_a: torch.Tensor, xn_a: torch.Tensor, tape: Tape):
+    """The encoder's last layer, recorded for the backward, on what the head reads: qkv projection on all M rows (every row
+    is a key), attention for the query tiles that hold latent rows, everything behind it on the T latent rows gathered
+    into compact [T, .] tensors. Returns (x_out, RMSNorm(x_out) * ln_post.weight) of the latent rows, in token order."""
+    M, w = x_a.shape
+    dev = x_a.device
+    hq, hkv = m.heads
+    gqa = hkv * 64
+    inner = m.inner_dim
+    L = m.num_layers
+    i = L - 1
+    mode = 0 if i == 0 else 1
+    alpha = float(2 * L)
+    Tn = dp.plan.T
+    st = _stream()
+    T = W.t
+    ldq = 2 * w + 2 * gqa
+    qkv = _new((M, ldq), dev)
+    att = _new((M, w), dev)                                   # only its latent rows are written and read
+    o = torch.zeros((M, w), dtype=bf16, device=dev)           # the backward's row pass reads every row: zeros elsewhere
+    lse = tape.lt.lse[i]
+    lse.zero_()
+    work = dp.attn_work_latent(hq, hkv)
+    knorm = key_norms(dp, M, hkv)
+    _lib.call("ttk_gemm_qkv_rope", _ptr(xn_a), xn_a.stride(0), _ptr(T[f"to_qkv{i}"]), w, M, w, w, gqa, _ptr(dp.rope),
+              _ptr(qkv), ldq, _ptr(knorm), st)
+    _lib.call("ttk_attn_varlen_fwd_train", _ptr(qkv), ldq, M, w, gqa, _ptr(work), work.shape[0], 1.0 / math.sqrt(64.0),
+              _ptr(att), w, _ptr(o), _ptr(lse), _ptr(knorm), st)
+    att_c, x_c = _new((Tn, w), dev), _new((Tn, w), dev)
+    _lib.call("ttk_gather_rows", _ptr(att), w, _ptr(dp.latent_row), _ptr(att_c), w, Tn, w, st)
+    _lib.call("ttk_gather_rows", _ptr(x_a), x_a.stride(0), _ptr(dp.latent_row), _ptr(x_c), w, Tn, w, st)
+    y_a = _new((Tn, w), dev)
+    _gemm(st, att_c, T[f"out_proj{i}"], y_a, w, w)
+    x_f, xn_f = _new((Tn, w), dev), _new((Tn, w), dev)
+    _lib.call("ttk_resid_norm", _ptr(x_c), _ptr(y_a), _ptr(x_f), _ptr(xn_f), _ptr(T.get(f"attn_post_ln{i}")),
+              _ptr(T[f"ffn_norm{i}"]), alpha, mode, Tn, w, w, st)
+    h12 = _new((Tn, 2 * inner), dev)
+    _gemm(st, xn_f, T[f"w12_{i}"], h12, 2 * inner, w)
+    h = _new((Tn, inner), dev)
+    _lib.call("ttk_geglu_fwd", _ptr(h12), 2 * inner, inner, _ptr(h), inner, Tn, st)
+    y_f = _new((Tn, w), dev)
+    _gemm(st, h, T[f"w3_{i}"], y_f, w, inner)
+    x_n, xn_n = _new((Tn, w), dev), _new((Tn, w), dev)
+    _lib.call("ttk_resid_norm", _ptr(x_f), _ptr(y_f), _ptr(x_n), _ptr(xn_n), _ptr(T.get(f"ffd_post_ln{i}")),
+              _ptr(T["ln_post"]), alpha, mode, Tn, w, w, st)
+    tape.tail = dict(qkv=qkv, o=o, att_c=att_c, x_a=x_a, xn_a=xn_a, x_c=x_c, y_a=y_a, x_f=x_f, xn_f=xn_f, h12=h12, h=h,
+                     y_f=y_f)
+    return x_n, xn_n
+
+
+def _last_layer_backward(m, W: PreparedStack, dp: DevicePlan, tape: Tape, g: torch.Tensor, grads) -> torch.Tensor:
+    """g = dL/dx_out of the latent rows [T, w] -> dL/dx at the input of the last layer for all M packed rows. The part
+    behind the attention runs on T rows (same kernels and order as _layers_backward); its two results -- the gradient of
+    the attention output and of the residual branch -- go back to their packed rows (zeros elsewhere), the attention
+    backward follows work lists restricted to the latent query rows (dK / dV of every key row, dQ of the latent tiles), and
+    the qkv projection's backward runs on all rows again."""
+    Tn, w = g.shape
+    dev = g.device
+    hq, hkv = m.heads
+    gqa = hkv * 64
+    inner = m.inner_dim
+    L = m.num_layers
+    i = L - 1
+    mode = 0 if i == 0 else 1
+    alpha = float(2 * L)
+    c = alpha if mode == 1 else 1.0
+    st = _stream()
+    T = W.t
+    t = tape.tail
+    x_a, xn_a, qkv = t["x_a"], t["xn_a"], t["qkv"]
+    M = x_a.shape[0]
+    ldq = 2 * w + 2 * gqa
+    # ---- GEGLU block
+    if mode == 1:
+        du = _new((Tn, w), dev)
+        _rmsnorm_bwd(st, t["x_f"], T[f"ffd_post_ln{i}"], g, du, grads[f"ffd_post_ln{i}"], y=t["y_f"], alpha=alpha)
+    else:
+        du = g
+    dh = _new((Tn, inner), dev)
+    _gemm(st, du, T[f"w3_{i}"], dh, inner, w, kn=1)
+    _wgrad(st, du, t["h"], grads[f"w3_{i}"])
+    dh12 = _new((Tn, 2 * inner), dev)
+    _lib.call("ttk_geglu_bwd", _ptr(t["h12"]), 2 * inner, inner, _ptr(dh), inner, _ptr(dh12), 2 * inner, Tn, st)
+    dxn = _new((Tn, w), dev)
+    _gemm(st, dh12, T[f"w12_{i}"], dxn, w, 2 * inner, kn=1)
+    _wgrad(st, dh12, t["xn_f"], grads[f"w12_{i}"])
+    g_f = _new((Tn, w), dev)
+    _rmsnorm_bwd(st, t["x_f"], T[f"ffn_norm{i}"], dxn, g_f, grads[f"ffn_norm{i}"], add=du, add_scale=c)
+    # ---- attention block
+    if mode == 1:
+        du_a = _new((Tn, w), dev)
+        _rmsnorm_bwd(st, t["x_c"], T[f"attn_post_ln{i}"], g_f, du_a, grads[f"attn_post_ln{i}"], y=t["y_a"], alpha=alpha)
+    else:
+        du_a = g_f
+    d_att_c = _new((Tn, w), dev)
+    _gemm(st, du_a, T[f"out_proj{i}"], d_att_c, w, w, kn=1)
+    _wgrad(st, du_a, t["att_c"], grads[f"out_proj{i}"])
+    # ---- back to the packed rows: zeros wherever no gradient arrives
+    d_att = torch.zeros((M, w), dtype=bf16, device=dev)
+    du_full = torch.zeros((M, w), dtype=bf16, device=dev)
+    _lib.call("ttk_scatter_rows", _ptr(d_att_c), w, _ptr(dp.latent_row), _ptr(d_att), w, Tn, w, st)
+    _lib.call("ttk_scatter_rows", _ptr(du_a), w, _ptr(dp.latent_row), _ptr(du_full), w, Tn, w, st)
+    dqkv = torch.zeros((M, ldq), dtype=bf16, device=dev)  # dQ of the other query tiles, dK / dV of clips without tokens
+    dO = _new((M, w), dev)
+    delta = _new((hq, M), dev, torch.float32)
+    lse = tape.lt.lse[i]
+    _lib.call("ttk_attn_bwd_prep", _ptr(d_att), w, _ptr(t["o"]), w, _ptr(qkv), ldq, M, w, _ptr(dO), w, _ptr(dqkv), ldq,
+              _ptr(delta), st)
+    wk_dkv, wk_dq = dp.attn_bwd_work_latent(hq, hkv)
+    for name, wk in (("ttk_attn_bwd_dkv", wk_dkv), ("ttk_attn_bwd_dq", wk_dq)):
+        _lib.call(name, _ptr(qkv), ldq, _ptr(dO), w, M, w, gqa, _ptr(wk), wk.shape[0], _ptr(lse), _ptr(delta),
+                  _ptr(dp.rope), 1.0 / math.sqrt(64.0), _ptr(dqkv), ldq, st)
+    dxn_full = _new((M, w), dev)
+    _gemm(st, dqkv, T[f"to_qkv{i}"], dxn_full, w, ldq, kn=1)
+    _wgrad(st, dqkv, xn_a, grads[f"to_qkv{i}"])
+    g_next = _new((M, w), dev)
+    _rmsnorm_bwd(st, x_a, T[f"pre_ln{i}"], dxn_full, g_next, grads[f"pre_ln{i}"], add=du_full, add_scale=c)
+    return g_next
+
+
 def encoder_forward_train(m, dp: DevicePlan, clips_flat: torch.Tensor, fsq_consts):
     """TiTokEncoder.forward recording a tape. Returns (z, codes, idx, tape); z/codes bf16 [T, ts]."""
     W = prepared(m, "enc", force=True)  # a training step always re-reads the parameters (see PreparedStack.refresh)
@@ -190,16 +341,22 @@ def encoder_forward_train(m, dp: DevicePlan, clips_flat: torch.Tensor, fsq_const
     _gemm(st, patches, T["proj_in_w"], proj, w, feat, bias=T["proj_in_b"])
     _lib.call("ttk_enc_embed_train", _ptr(proj), w, _ptr(dp.enc_src_row), _ptr(T["mask_token"]), _ptr(T["ln_pre_t"]),
               _ptr(T["ln_pre_p"]), _ptr(T["pre_ln0"]), _ptr(x), _ptr(xn), _ptr(e0), M, w, w, st)
-    x_fin, xn_fin = _layers_train(m, W, dp, x, xn, tape)
+    tail = _use_latent_tail(m, dp)
+    if tail:
+        x_a, xn_a = _layers_train(m, W, dp, x, xn, tape, n_run=m.num_layers - 1)
+        x_fin, xn_fin = _last_layer_train(m, W, dp, x_a, xn_a, tape)  # latent rows only, in token order
+    else:
+        x_fin, xn_fin = _layers_train(m, W, dp, x, xn, tape)
     ts = m.token_size
     z = _new((max(Tn, 1), ts), dev)
     codes = _new((max(Tn, 1), ts), dev)
     idx = _new((max(Tn, 1),), dev, torch.int32)
     half_l, offset, shift, half_width, basis, levels = fsq_consts
-    _lib.call("ttk_enc_head_fsq", _ptr(xn_fin), w, _ptr(dp.latent_row), _ptr(T["ln_post"]), 1, _ptr(T["proj_out_w"]),
+    _lib.call("ttk_enc_head_fsq", _ptr(xn_fin), w, _vp(0) if tail else _ptr(dp.latent_row), _ptr(T["ln_post"]), 1, _ptr(T["proj_out_w"]),
               _ptr(T["proj_out_b"]), ts, _ptr(z), _ptr(codes), _ptr(idx), Tn, w, half_l, offset, shift, half_width,
               basis, levels, st)
     tape.t.update(patches=patches, e0=e0, x_fin=x_fin, xn_fin=xn_fin)
+    tape.latent_tail = tail
     tape.weights_sig = _weights_sig(m)
     return z[:Tn], codes[:Tn], idx[:Tn], tape
 
@@ -262,14 +419,19 @@ def _zero_grads(W: PreparedStack) -> Dict[str, torch.Tensor]:
     return grads
 
 
-def _layers_backward(m, W: PreparedStack, dp: DevicePlan, tape: Tape, g: torch.Tensor, grads) -> torch.Tensor:
-    """g = dL/dx at the output of the last layer -> dL/dx at the input of layer 0."""
+def _layers_backward(m, W: PreparedStack, dp: DevicePlan, tape: Tape, g: torch.Tensor, grads,
+                     n_run: Optional[int] = None) -> torch.Tensor:
+    """g = dL/dx at the output of the last layer -> dL/dx at the input of layer 0. n_run: g belongs to the output of layer
+    n_run - 1 (the forward ran its last layer through _last_layer_train)."""
     M, w = g.shape
     dev = g.device
     hq, hkv = m.heads
     gqa = hkv * 64
     inner = m.inner_dim
     L = m.num_layers
+    n_run = L if n_run is None else n_run
+    if n_run <= 0:
+        return g
     alpha = float(2 * L)
     st = _stream()
     lt: LayerTape = tape.lt
@@ -283,11 +445,12 @@ def _layers_backward(m, W: PreparedStack, dp: DevicePlan, tape: Tape, g: torch.T
 
     if NATIVE_SEQ and not _lib.profiling():
         d = layers_desc(m, W, dp, M, backward=True)
+        d.n_layers = n_run
         flat = grads["__flat__"]
         tab = W._grad_layout[3]
         gptr = np.where(tab >= 0, flat.data_ptr() + 4 * tab, 0).astype(np.int64)
         g_out = ctypes.c_void_p(0)
-        n_launch = sum(14 + (2 if i > 0 else 0) for i in range(L))
+        n_launch = sum(14 + (2 if i > 0 else 0) for i in range(n_run))
         _lib.call("ttk_layers_bwd", ctypes.byref(d), _ptr(lt.x0), _ptr(lt.xn0), _ptr(lt.slab), lt.per_layer,
                   _vp(lt.offs.ctypes.data), _ptr(lt.lse), _ptr(g), _ptr(work), _vp(boffs.ctypes.data), _ptr(delta),
                   _vp(gptr.ctypes.data), ctypes.byref(g_out), st, launches=n_launch)
@@ -297,7 +460,7 @@ def _layers_backward(m, W: PreparedStack, dp: DevicePlan, tape: Tape, g: torch.T
     scale = 1.0 / math.sqrt(64.0)
     T = W.t
     wk_dkv, wk_dq = dp.attn_bwd_work(hq, hkv)
-    for i in reversed(range(L)):
+    for i in reversed(range(n_run)):
         mode = 0 if i == 0 else 1
         c = alpha if mode == 1 else 1.0
         x_a = lt.x0 if i == 0 else lt.view(i - 1, F_XN)
@@ -355,12 +518,22 @@ def encoder_backward(m, dp: DevicePlan, tape: Tape, dz: torch.Tensor, need_input
     st = _stream()
     T = W.t
     grads = _zero_grads(W)
-    dxn = torch.zeros((M, w), dtype=bf16, device=dev)
-    _lib.call("ttk_head_bwd", _ptr(dz), m.token_size, _ptr(tape.t["xn_fin"]), w, _ptr(dp.latent_row), _ptr(T["proj_out_w"]),
-              _ptr(dxn), _ptr(grads["proj_out_w"]), _ptr(grads["proj_out_b"]), Tn, w, st)
-    g = _new((M, w), dev)
-    _rmsnorm_bwd(st, tape.t["x_fin"], T["ln_post"], dxn, g, grads["ln_post"])
-    g0 = _layers_backward(m, W, dp, tape, g, grads)
+    if getattr(tape, "latent_tail", False):
+        # the forward carried only the latent rows through the last layer: x_fin / xn_fin are [T, w] in token order
+        dxn = torch.zeros((Tn, w), dtype=bf16, device=dev)
+        _lib.call("ttk_head_bwd", _ptr(dz), m.token_size, _ptr(tape.t["xn_fin"]), w, _ptr(_ident(Tn, dev)), _ptr(T["proj_out_w"]),
+                  _ptr(dxn), _ptr(grads["proj_out_w"]), _ptr(grads["proj_out_b"]), Tn, w, st)
+        g_c = _new((Tn, w), dev)
+        _rmsnorm_bwd(st, tape.t["x_fin"], T["ln_post"], dxn, g_c, grads["ln_post"])
+        g = _last_layer_backward(m, W, dp, tape, g_c, grads)
+        g0 = _layers_backward(m, W, dp, tape, g, grads, n_run=m.num_layers - 1)
+    else:
+        dxn = torch.zeros((M, w), dtype=bf16, device=dev)
+        _lib.call("ttk_head_bwd", _ptr(dz), m.token_size, _ptr(tape.t["xn_fin"]), w, _ptr(dp.latent_row), _ptr(T["proj_out_w"]),
+                  _ptr(dxn), _ptr(grads["proj_out_w"]), _ptr(grads["proj_out_b"]), Tn, w, st)
+        g = _new((M, w), dev)
+        _rmsnorm_bwd(st, tape.t["x_fin"], T["ln_post"], dxn, g, grads["ln_post"])
+        g0 = _layers_backward(m, W, dp, tape, g, grads)
     # embed: latent rows (enc_src_row < 0) went through ln_pre_t, patch rows through ln_pre_p (blocks.py:95-97)
     d_e0 = _new((M, w), dev)
     _rmsnorm_bwd(st, tape.t["e0"], T["ln_pre_p"], g0, d_e0, grads["ln_pre_p"], sel=dp.enc_src_row, w2=T["ln_pre_t"],

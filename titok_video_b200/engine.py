@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .plan import PackedPlan, get_attn_bwd_work, get_attn_work, get_attn_work_latent, make_plan
+from .plan import PackedPlan, get_attn_bwd_work, get_attn_bwd_work_latent, get_attn_work, get_attn_work_latent, make_plan
 
 _vp = ctypes.c_void_p
 
@@ -122,6 +122,14 @@ class DevicePlan:
         k = ("bwd", hq, hkv)
         if k not in self._attn:
             a, b = get_attn_bwd_work(self.plan, hq, hkv)
+            self._attn[k] = (self._upload_i32(a), self._upload_i32(b))
+        return self._attn[k]
+
+    def attn_bwd_work_latent(self, hq: int, hkv: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(dkv, dq) work lists of the encoder's last layer when only the latent rows carry a gradient."""
+        k = ("bwd_latent", hq, hkv)
+        if k not in self._attn:
+            a, b = get_attn_bwd_work_latent(self.plan, hq, hkv)
             self._attn[k] = (self._upload_i32(a), self._upload_i32(b))
         return self._attn[k]
 

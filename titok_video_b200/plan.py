@@ -301,35 +301,41 @@ def get_attn_work_latent(plan: PackedPlan, hq: int, hkv: int) -> np.ndarray:
     return plan.attn_work[k]
 
 
-def attn_bwd_work_lists(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: int, hkv: int):
+def attn_bwd_work_lists(seq_starts: Sequence[int], seq_lens: Sequence[int], hq: int, hkv: int,
+                        q_lens: Sequence[int] = None):
     """Work lists of the attention backward kernels (csrc/attn_bwd.cu), int32 [n, 8] records
     {st_row0, st_valid, st_head, o_head0, n_heads, clip_row0, clip_len, 0}, longest work first:
       dkv: one record per (128-key tile, kv head); streams the clip's query tiles of the `hq // hkv` grouped query heads
-      dq : one record per (128-row query tile, query head); streams the clip's key tiles of kv head `h // (hq // hkv)`."""
+      dq : one record per (128-row query tile, query head); streams the clip's key tiles of kv head `h // (hq // hkv)`.
+    `q_lens` (optional, per clip): only a clip's first `q_lens[i]` rows carry an output gradient (the encoder's last layer:
+    the head reads the latent rows alone, blocks.py:101). dkv then streams just those query rows (its records' `clip_len`
+    is the streamed range) and clips without such rows get no record (their dK / dV are zero); dq keeps only the query
+    tiles that hold such rows (they stream all keys of the clip)."""
     grp = hq // hkv
     st = np.asarray(seq_starts, dtype=np.int64).reshape(-1)
     sl = np.asarray(seq_lens, dtype=np.int64).reshape(-1)
     if len(sl) == 0:
         return np.zeros((0, 8), dtype=np.int32), np.zeros((0, 8), dtype=np.int32)
+    ql = sl if q_lens is None else np.minimum(np.asarray(q_lens, dtype=np.int64).reshape(-1), sl)
     # vectorised over all 128-row tiles of the batch (a ragged stream builds these lists every step)
     nt = (sl + ATTN_TILE - 1) // ATTN_TILE
     clip = np.repeat(np.arange(len(sl)), nt)
     ti = np.arange(int(nt.sum()), dtype=np.int64) - np.repeat(np.cumsum(nt) - nt, nt)
     row0 = st[clip] + ti * ATTN_TILE
     valid = np.minimum(ATTN_TILE, sl[clip] - ti * ATTN_TILE)
-    n_t = len(ti)
 
-    def records(n_heads_out, head, other0, n_heads):
+    def records(sel, n_heads_out, other_of, n_heads, stream_len):
+        """one record per (selected tile, head < n_heads_out); other_of(head) -> o_head0; stream_len: per clip"""
+        n_t = int(sel.sum())
         rec = np.zeros((n_t * n_heads_out, 8), dtype=np.int32)
-        rep = lambda v: np.repeat(v, n_heads_out)
-        rec[:, 0], rec[:, 1], rec[:, 2], rec[:, 3], rec[:, 4] = rep(row0), rep(valid), head, other0, n_heads
-        rec[:, 5], rec[:, 6] = rep(st[clip]), rep(sl[clip])
+        rep = lambda v: np.repeat(v[sel], n_heads_out)
+        head = np.tile(np.arange(n_heads_out), n_t)
+        rec[:, 0], rec[:, 1], rec[:, 2], rec[:, 3], rec[:, 4] = rep(row0), rep(valid), head, other_of(head), n_heads
+        rec[:, 5], rec[:, 6] = rep(st[clip]), rep(stream_len[clip])
         return rec
 
-    kh = np.tile(np.arange(hkv), n_t)
-    qh = np.tile(np.arange(hq), n_t)
-    a = records(hkv, kh, kh * grp, grp)
-    b = records(hq, qh, qh // grp, 1)
+    a = records(ql[clip] > 0, hkv, lambda h: h * grp, grp, ql)
+    b = records(ti * ATTN_TILE < ql[clip], hq, lambda h: h // grp, 1, sl)
     a = a[np.argsort(-(a[:, 4].astype(np.int64) * ((a[:, 6] + 127) // 128)), kind="stable")]
     b = b[np.argsort(-((b[:, 6] + 127) // 128), kind="stable")]
     return np.ascontiguousarray(a), np.ascontiguousarray(b)
@@ -339,6 +345,14 @@ def get_attn_bwd_work(plan: PackedPlan, hq: int, hkv: int):
     k = ("bwd", hq, hkv)
     if k not in plan.attn_work:
         plan.attn_work[k] = attn_bwd_work_lists(plan.cu_seqlens[:-1].tolist(), plan.seq_lens, hq, hkv)
+    return plan.attn_work[k]
+
+
+def get_attn_bwd_work_latent(plan: PackedPlan, hq: int, hkv: int):
+    """(dkv, dq) lists of the encoder's LAST layer in training: only the latent rows carry an output gradient."""
+    k = ("bwd_latent", hq, hkv)
+    if k not in plan.attn_work:
+        plan.attn_work[k] = attn_bwd_work_lists(plan.cu_seqlens[:-1].tolist(), plan.seq_lens, hq, hkv, q_lens=plan.token_counts)
     return plan.attn_work[k]
 
 
