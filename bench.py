@@ -320,7 +320,7 @@ def train_flops(B):
     from titok_video_b200 import backward
 
     # (with the encoder's last layer carried on the latent rows only, those FLOPs are not executed, forward or backward)
-    f -= latent_tail_savings(s_rows, TOKENS_A, WIDTH, INNER, enabled=backward.TRAIN_LATENT_TAIL)
+    f -= latent_tail_savings(s_rows, TOKENS_A, WIDTH, INNER, enabled=backward.latent_tail_active(B * s_rows))
     return 3.0 * B * f
 
 
@@ -415,7 +415,7 @@ def train_leg(T, _lib, dev, world, rank, dist, batch, steps, warmup, graphed=Fal
     return {"clips_per_s": world * batch / (ms_step * 1e-3), "ms_per_step": ms_step, "clips_per_gpu_per_step": batch,
             "packed_rows_per_gpu": batch * clip_flops()[1], "loss": float(loss.detach()), "gpu_launches_per_step": launches / steps,
             "tflops_algorithmic": tf, "frac_of_tensor_peak": tf / pk["bf16_tflops_sustained"],
-            "latent_tail": bool(__import__("titok_video_b200.backward", fromlist=["x"]).TRAIN_LATENT_TAIL),
+            "latent_tail": bool(__import__("titok_video_b200.backward", fromlist=["x"]).latent_tail_active(batch * clip_flops()[1])),
             "ms_per_step_mean": mean_ms, "timing": "median of the per-step CUDA-event times, max over ranks",
             "wall_ms_per_step": wall_ms, "kernel_ms_per_step": sum(v[0] for v in ks.values()) / prof_steps, "kernels": kernels,
             "graph_replays": (gstep.replays if gstep is not None else 0),

@@ -15,9 +15,14 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--graph", action="store_true", help="also run the leg with forward + loss + backward replayed as one CUDA graph")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     r = bench.train_leg(T, _lib, dev, 1, 0, None, a.batch, a.steps, 3)
     r.pop("what")
     print(json.dumps(r))
+    if a.graph:
+        r = bench.train_leg(T, _lib, dev, 1, 0, None, a.batch, a.steps, 3, graphed=True)
+        r.pop("what")
+        print(json.dumps(r))

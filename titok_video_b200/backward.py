@@ -26,11 +26,25 @@ from .engine import NATIVE_SEQ, DevicePlan, cached_named_params, PreparedStack, 
 bf16 = torch.bfloat16
 
 # Training forward + backward of the ENCODER's last layer on the latent rows only (the head reads nothing else,
-# blocks.py:101; see engine._layer_latent for the inference side): 0 = every packed row goes through the layer, as in
-# the reference. The layers before it run through the native sequencers as before (n_layers - 1 of them).
+# blocks.py:101; see engine._layer_latent for the inference side). The layers before it run through the native sequencers
+# as before (n_layers - 1 of them); the last layer is enqueued kernel by kernel from Python (about 45 launches, forward +
+# backward), which costs host time: "auto" (default) takes this path when the packed batch has at least
+# TRAIN_TAIL_MIN_ROWS rows -- where the step is bound by the GPU (16 clips A per GPU: 8.38 -> 7.87 ms per step) -- and
+# runs every row through the layer, as the reference does, for small host-bound batches. True / False (env 1 / 0) force it.
 import os as _os
 
-TRAIN_LATENT_TAIL = _os.environ.get("TTK_TRAIN_LATENT_TAIL", "0") != "0"
+_env_tail = _os.environ.get("TTK_TRAIN_LATENT_TAIL", "auto")
+TRAIN_LATENT_TAIL = {"0": False, "1": True}.get(_env_tail, "auto")
+TRAIN_TAIL_MIN_ROWS = int(_os.environ.get("TTK_TRAIN_TAIL_MIN_ROWS", "24000"))
+
+
+def latent_tail_active(packed_rows: int) -> bool:
+    """Whether a training forward over `packed_rows` rows carries only the latent rows through the encoder's last layer."""
+    if TRAIN_LATENT_TAIL == "auto":
+        return packed_rows >= TRAIN_TAIL_MIN_ROWS
+    return bool(TRAIN_LATENT_TAIL)
+
+
 _IDENT: Dict[str, torch.Tensor] = {}
 
 
@@ -200,7 +214,7 @@ def _layers_train(m, W: PreparedStack, dp: DevicePlan, x: torch.Tensor, xn: torc
 
 
 def _use_latent_tail(m, dp: DevicePlan) -> bool:
-    return TRAIN_LATENT_TAIL and dp.plan.T > 0 and m.num_layers > 1
+    return latent_tail_active(dp.plan.M) and dp.plan.T > 0 and m.num_layers > 1
 
 
 def _last_layer_train(m, W: PreparedStack, dp: DevicePlan, x_a: torch.Tensor, xn_a: torch.Tensor, tape: Tape):
