@@ -399,3 +399,17 @@ def test_latent_backward_work_lists():
             want = {r[:6] + (tok[r[5]], 0) for r in rows(a) if tok[r[5]] > 0}
             assert rows(al) == want
             assert all(r[6] <= pl.seq_lens[starts.index(r[5])] for r in rows(al))
+
+
+def test_training_latent_tail_is_chosen_by_batch_size(monkeypatch):
+    """backward.latent_tail_active: "auto" takes the latent-tail training path for packed batches of at least
+    TRAIN_TAIL_MIN_ROWS rows (GPU-bound steps: its last layer is enqueued from Python), True / False force it."""
+    from titok_video_b200 import backward
+
+    monkeypatch.setattr(backward, "TRAIN_LATENT_TAIL", "auto")
+    monkeypatch.setattr(backward, "TRAIN_TAIL_MIN_ROWS", 24000)
+    assert backward.latent_tail_active(16 * 1892) and not backward.latent_tail_active(3 * 1892)
+    monkeypatch.setattr(backward, "TRAIN_LATENT_TAIL", True)
+    assert backward.latent_tail_active(1)
+    monkeypatch.setattr(backward, "TRAIN_LATENT_TAIL", False)
+    assert not backward.latent_tail_active(10 ** 6)
