@@ -361,6 +361,9 @@ def test_latent_work_list_is_the_leading_tiles_of_the_full_list():
         starts = pl.cu_seqlens[:-1].tolist()
         for hq, hkv in [(4, 2), (8, 2), (12, 4), (16, 16)]:
             full, lat = get_attn_work(pl, hq, hkv), get_attn_work_latent(pl, hq, hkv)
+            # (even head groups take a row filter of the full list: it must equal the generic construction)
+            from titok_video_b200.plan import attn_work_list
+            assert np.array_equal(lat, attn_work_list(starts, pl.seq_lens, hq, hkv, q_lens=pl.token_counts))
             # (head, first row, valid rows, kv head, clip start, clip length) of every used query tile
             tiles = lambda w: {(int(r[4 + j]), int(r[j]), int(r[2 + j]), int(r[6]), int(r[7]), int(r[8]))
                                for r in w for j in (0, 1) if r[2 + j] > 0}

@@ -297,7 +297,13 @@ def get_attn_work_latent(plan: PackedPlan, hq: int, hkv: int) -> np.ndarray:
     """Work list of the encoder's LAST layer: only the query tiles that hold latent rows (they lead every clip)."""
     k = ("latent", hq, hkv)
     if k not in plan.attn_work:
-        plan.attn_work[k] = attn_work_list(plan.cu_seqlens[:-1].tolist(), plan.seq_lens, hq, hkv, q_lens=plan.token_counts)
+        if (hq // hkv) % 2 == 0 and len(plan.token_counts):
+            # one record per (row tile, pair of heads): the latent list is a row filter of the full list (same order)
+            full = get_attn_work(plan, hq, hkv)
+            tok = np.asarray(plan.token_counts, dtype=np.int64)[np.searchsorted(plan.cu_seqlens[:-1], full[:, 7])]
+            plan.attn_work[k] = _with_leaders(np.ascontiguousarray(full[(full[:, 0] - full[:, 7]) < tok]))
+        else:
+            plan.attn_work[k] = attn_work_list(plan.cu_seqlens[:-1].tolist(), plan.seq_lens, hq, hkv, q_lens=plan.token_counts)
     return plan.attn_work[k]
 
 
