@@ -93,7 +93,7 @@ class TiTok(nn.Module):
         """forward() without the output clones: the returned clips / indices alias workspace buffers that the next
         call with the same shapes overwrites. Used by bench.py and batch jobs that consume results immediately.
 
-        The 47 kernel launches of encoder + FSQ + decoder are captured once per (shapes, token_counts) signature into
+        The 49 kernel launches of encoder + FSQ + decoder are captured once per (shapes, token_counts) signature into
         a CUDA graph and replayed (`use_graph=False` or TTK_CUDA_GRAPH=0 launches them one by one). Inputs are copied
         into the plan's static clip buffer first; weights are refreshed in place, so a captured graph stays valid
         across optimizer steps.
