@@ -716,6 +716,13 @@ def main():
         return recon, d
 
     # ---------------- value: inputs resident in HBM ----------------
+    # the objects that exist now (torch, the model, the input sets) move to the collector's permanent generation: a full
+    # collection of Python's cyclic GC over them takes 20-40 ms and would otherwise land at random inside the host-bound
+    # legs (ragged stream, 3-clip training step); what a serving / training process does once after start-up
+    import gc
+
+    gc.collect()
+    gc.freeze()
     sampler = ClockSampler(local_rank)  # started ahead of the warm-up: nvidia-smi needs ~0.3 s to deliver its first sample
     sampler.start()
     for i in range(args.warmup):
